@@ -1,0 +1,166 @@
+"""Deterministic synthetic frames for the parity tests and bench.py (numpy only).
+
+Follows SURVEY.md section 8(d): markers of a predefined ArUco dictionary with a white quiet
+zone, laid on a grid, each warped by a random in-plane rotation plus per-corner jitter, on a
+light background with a slow sinusoidal gradient, Gaussian blur (sigma 1) and +-4 integer
+noise, gray replicated to BGR8.  Camera intrinsics mimic the reference test's CameraInfo
+(aruco_detect/test/aruco_images_test.cpp:20-29): fx = fy = 0.73 W, principal point at the
+centre, plumb_bob distortion D from that test.
+"""
+from __future__ import annotations
+
+import math
+import os
+
+import numpy as np
+
+_DICT_NPZ = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dictionaries.npz")
+_dict_cache: dict = {}
+
+# aruco_detect/test/aruco_images_test.cpp:24-27
+REFERENCE_TEST_D = (0.1349735087283542, -0.2335869827451621, 0.0006697030315075139, 0.004846737465872353, 0.0)
+
+# BASELINE.json configs: name -> (W, H, n_markers, dictionary enum)
+CONFIGS = {
+    "C1": (640, 480, 4, 6),
+    "C2": (1920, 1080, 16, 10),
+    "C3": (1280, 720, 8, 6),
+    "C4": (3840, 2160, 64, 10),
+}
+
+
+def dictionary_info(dict_id: int):
+    """(marker_size, n_markers, max_correction_bits, bytes uint8[n, 4*nbytes])."""
+    if not _dict_cache:
+        z = np.load(_DICT_NPZ)
+        _dict_cache["info"] = {int(r[0]): (int(r[1]), int(r[2]), int(r[3])) for r in z["info"]}
+        _dict_cache[5] = z["bytes_5x5"]
+        _dict_cache[6] = z["bytes_6x6"]
+    if dict_id not in _dict_cache["info"]:
+        raise ValueError("unsupported dictionary enum %d (supported: 4..11)" % dict_id)
+    ms, n, mc = _dict_cache["info"][dict_id]
+    return ms, n, mc, _dict_cache[ms][:n]
+
+
+def marker_bits(dict_id: int, marker_id: int) -> np.ndarray:
+    """(ms+2) x (ms+2) uint8 cell image incl. the black border: 1 = white cell."""
+    ms, n, _, tab = dictionary_info(dict_id)
+    nb = tab.shape[1] // 4
+    rot0 = tab[marker_id, :nb]
+    bits = np.zeros(ms * ms, np.uint8)
+    full = (ms * ms) // 8
+    k = 0
+    for byte_i in range(nb):
+        nbits = 8 if byte_i < full else ms * ms - 8 * full
+        for j in range(nbits):
+            bits[k] = (int(rot0[byte_i]) >> (nbits - 1 - j)) & 1
+            k += 1
+    out = np.zeros((ms + 2, ms + 2), np.uint8)
+    out[1:-1, 1:-1] = bits.reshape(ms, ms)
+    return out
+
+
+def camera_for(W: int, H: int):
+    f = 0.73 * W
+    K = np.array([[f, 0.0, W / 2.0], [0.0, f, H / 2.0], [0.0, 0.0, 1.0]], np.float64)
+    return K, np.array(REFERENCE_TEST_D, np.float64)
+
+
+def _homography(src, dst):
+    A = []
+    b = []
+    for (x, y), (u, v) in zip(src, dst):
+        A.append([x, y, 1, 0, 0, 0, -u * x, -u * y])
+        A.append([0, 0, 0, x, y, 1, -v * x, -v * y])
+        b += [u, v]
+    h = np.linalg.solve(np.array(A, np.float64), np.array(b, np.float64))
+    return np.append(h, 1.0).reshape(3, 3)
+
+
+def _blur(img: np.ndarray, sigma: float) -> np.ndarray:
+    r = int(math.ceil(3 * sigma))
+    k = np.exp(-0.5 * (np.arange(-r, r + 1) / sigma) ** 2).astype(np.float32)
+    k /= k.sum()
+    H, W = img.shape
+    p = np.pad(img, ((0, 0), (r, r)), mode="edge")
+    t = np.zeros_like(img)
+    for i, w in enumerate(k):
+        t += w * p[:, i : i + W]
+    p = np.pad(t, ((r, r), (0, 0)), mode="edge")
+    out = np.zeros_like(img)
+    for i, w in enumerate(k):
+        out += w * p[i : i + H, :]
+    return out
+
+
+def make_frame(W: int, H: int, n_markers: int, dict_id: int, seed: int = 0, jitter: float = 0.08, first_id: int = 0, supersample: int = 2):
+    """Returns (bgr uint8[H,W,3], truth list of (id, float64[4,2] TL,TR,BR,BL image corners))."""
+    rng = np.random.default_rng(seed)
+    ms, nmk, _, _ = dictionary_info(dict_id)
+    cells = ms + 2
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    phase = rng.uniform(0, 2 * math.pi, 2)
+    img = 190.0 + 20.0 * np.sin(2 * math.pi * xx / (1.7 * W) + phase[0]) * np.cos(2 * math.pi * yy / (1.3 * H) + phase[1])
+    img = img.astype(np.float32)
+    cols = int(math.ceil(math.sqrt(n_markers * W / H)))
+    rows = int(math.ceil(n_markers / cols))
+    cw, ch = W / cols, H / rows
+    truth = []
+    ss = supersample
+    offs = (np.arange(ss) + 0.5) / ss - 0.5
+    for i in range(n_markers):
+        mid = (first_id + i) % nmk
+        bits = marker_bits(dict_id, mid)
+        side = 0.55 * min(cw, ch)
+        cx = (i % cols + 0.5) * cw + rng.uniform(-0.05, 0.05) * cw
+        cy = (i // cols + 0.5) * ch + rng.uniform(-0.05, 0.05) * ch
+        ang = rng.uniform(0, 2 * math.pi)
+        ca, sa = math.cos(ang), math.sin(ang)
+        base = np.array([[-0.5, -0.5], [0.5, -0.5], [0.5, 0.5], [-0.5, 0.5]]) * side
+        quad = np.stack([cx + ca * base[:, 0] - sa * base[:, 1], cy + sa * base[:, 0] + ca * base[:, 1]], 1)
+        quad += rng.uniform(-jitter, jitter, (4, 2)) * side
+        truth.append((mid, quad.copy()))
+        # marker plane coordinates: marker occupies [0,1]^2, quiet zone extends by q on every side
+        q = 1.0 / 6.0
+        Hm = _homography([(0, 0), (1, 0), (1, 1), (0, 1)], quad)
+        Hinv = np.linalg.inv(Hm)
+        outer = (Hm @ np.array([[-q, -q, 1], [1 + q, -q, 1], [1 + q, 1 + q, 1], [-q, 1 + q, 1]]).T).T
+        outer = outer[:, :2] / outer[:, 2:3]
+        x0 = max(int(math.floor(outer[:, 0].min())) - 1, 0)
+        x1 = min(int(math.ceil(outer[:, 0].max())) + 2, W)
+        y0 = max(int(math.floor(outer[:, 1].min())) - 1, 0)
+        y1 = min(int(math.ceil(outer[:, 1].max())) + 2, H)
+        if x1 <= x0 or y1 <= y0:
+            continue
+        py, px = np.mgrid[y0:y1, x0:x1].astype(np.float64)
+        acc = np.zeros(py.shape, np.float64)
+        cov = np.zeros(py.shape, np.float64)
+        for oy in offs:
+            for ox in offs:
+                X = px + ox
+                Y = py + oy
+                w = Hinv[2, 0] * X + Hinv[2, 1] * Y + Hinv[2, 2]
+                u = (Hinv[0, 0] * X + Hinv[0, 1] * Y + Hinv[0, 2]) / w
+                v = (Hinv[1, 0] * X + Hinv[1, 1] * Y + Hinv[1, 2]) / w
+                inside_q = (u >= -q) & (u < 1 + q) & (v >= -q) & (v < 1 + q)
+                inside_m = (u >= 0) & (u < 1) & (v >= 0) & (v < 1)
+                ci = np.clip((u * cells).astype(np.int64), 0, cells - 1)
+                cj = np.clip((v * cells).astype(np.int64), 0, cells - 1)
+                val = np.where(inside_m, np.where(bits[cj, ci] > 0, 235.0, 20.0), 235.0)
+                acc += np.where(inside_q, val, 0.0)
+                cov += inside_q
+        n_s = float(ss * ss)
+        a = cov / n_s
+        region = img[y0:y1, x0:x1]
+        img[y0:y1, x0:x1] = (region * (1.0 - a) + acc / n_s).astype(np.float32)
+    img = _blur(img, 1.0)
+    img += rng.integers(-4, 5, img.shape).astype(np.float32)
+    g = np.clip(np.rint(img), 0, 255).astype(np.uint8)
+    return np.repeat(g[:, :, None], 3, axis=2), truth
+
+
+def make_config_frame(name: str, seed: int = 0):
+    W, H, n, d = CONFIGS[name]
+    bgr, truth = make_frame(W, H, n, d, seed)
+    K, D = camera_for(W, H)
+    return bgr, truth, K, D, d
