@@ -91,8 +91,8 @@ def test_create_map_aruco_expectations(kat):
     for _ in range(40):
         robot = m.update(so.observations_from_transforms(transforms), ident, ident)
     q = so.m_to_q(robot.R)
-    exp_pose = [0.73, 0.11, 1.0, 0.98, -0.01, -0.18, 0.07]  # x y z qw qx qy qz (map_test.py order)
-    got = robot.t + [q[3], q[0], q[1], q[2]]
+    exp_pose = [0.73, 0.11, 1.0, 0.98, -0.01, -0.18, 0.07]  # x y z qx qy qz qw (map_test.py order)
+    got = robot.t + [q[0], q[1], q[2], q[3]]
     for v, g in zip(got, exp_pose):
         assert abs(v - g) < 0.1
     expect = {
@@ -115,24 +115,43 @@ def test_create_map_aruco_expectations(kat):
             assert abs(d) < 0.1 * 180 / math.pi + 0.1  # map_test.py compares degrees with EPSILON on radians-ish; keep loose
 
 
-# --- fiducial_slam/test/transform_var_test.cpp (property tests, no numeric goldens) ------
-def _twv(x, var):
-    return so.TWV.from_qt([0, 0, 0, 1], [x, 0, 0], var)
+# --- fiducial_slam/test/transform_var_test.cpp (5 property tests, inequalities only) -----
+def _twv(x, var, rpy=(0.0, 0.0, 0.0)):
+    return so.TWV.from_qt(so.q_from_rpy(*rpy), [x, 0, 0], var)
 
 
-def test_transform_var_properties():
-    a, b = _twv(0.0, 0.1), _twv(1.0, 0.1)
-    c = so.average_transforms(a, b)
-    assert 0.0 < c.t[0] < 1.0 and c.var < 0.1 + 1e-12  # :15-49
-    t = _twv(0.0, 0.3)
-    for _ in range(10000):  # :51-77
-        t.update(_twv(0.0, 0.3))
-        assert 1e-9 < t.var <= 0.3 + 1e-12
-    base = _twv(0.0, 0.1)
-    base.update(_twv(10.0, 1e3))  # :79-107 outlier with huge variance barely moves the mean
-    assert abs(base.t[0]) < 0.01
-    d1 = _twv(0.0, 0.1)
-    d1.update(_twv(0.0, 0.1))
-    d2 = _twv(0.0, 0.1)
-    d2.update(_twv(5.0, 0.1))  # :109-126 disagreeing data inflates variance
-    assert d2.var > d1.var
+def _angle(t):
+    """tf2::Quaternion::getAngle = 2 acos(w)."""
+    return 2.0 * math.acos(max(-1.0, min(1.0, so.m_to_q(t.R)[3])))
+
+
+def test_tv_simple_fusion():  # transform_var_test.cpp:15-31
+    out = so.average_transforms(_twv(0.0, 0.3), _twv(0.1, 0.3))
+    assert 0 < out.t[0] < 0.1 and 0 < out.var < 0.3
+
+
+def test_tv_simple_rotation_fusion():  # :33-49
+    out = so.average_transforms(_twv(0.0, 0.3), _twv(0.0, 0.3, (0.1, 0, 0)))
+    assert 0 < _angle(out) < 0.1 and 0 < out.var < 0.3
+
+
+def test_tv_same_fusion_iterative():  # :51-77
+    tv2 = _twv(0.0, 0.3)
+    out = so.average_transforms(_twv(0.0, 0.3), tv2)
+    assert out.t[0] == 0 and 0 < out.var < 0.3
+    for _ in range(10000):
+        out.update(tv2)
+        assert out.t[0] == 0 and 1e-9 < out.var < 0.3
+
+
+def test_tv_outlier_with_large_variance():  # :79-107
+    out = so.average_transforms(_twv(0.0, 0.2), _twv(0.1, 0.2))
+    out = so.average_transforms(out, _twv(0.1, 0.2))
+    out = so.average_transforms(out, _twv(1.0, 2.0, (0, 1, 0)))
+    assert 0 < out.t[0] < 1.0 and 0 < _angle(out) < 1.0 and 0 < out.var < 1.0
+    assert abs(out.t[0] - 0.1) < 0.05 and abs(_angle(out)) < 0.1
+
+
+def test_tv_different_with_similar_variance():  # :109-126
+    out = so.average_transforms(_twv(0.0, 0.1), _twv(1.0, 0.2, (1, 0, 0)))
+    assert 0 < out.t[0] < 1.0 and 0 < _angle(out) < 1.0 and out.var > 0.2
