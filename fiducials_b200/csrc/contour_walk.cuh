@@ -1,0 +1,144 @@
+// Mark-free border following on an immutable neighbour-mask plane.
+//
+// Replaces the findContours(RETR_LIST, CHAIN_APPROX_NONE) pass that cv::aruco::detectMarkers
+// (called at aruco_detect/src/aruco_detect.cpp:350) runs on each of the 13 threshold planes.
+// OpenCV's Suzuki-Abe scan is sequential (it marks visited pixels); here every border is found
+// independently:
+//
+//  * the plane is stored as one byte per pixel holding the 8-neighbour occupancy of that pixel
+//    (bit k set <=> neighbour in direction k is foreground; pixels outside the image are
+//    background, which is OpenCV 4.13's zero padding).  Direction codes (y down):
+//        0:(+1,0) 1:(+1,-1) 2:(0,-1) 3:(-1,-1) 4:(-1,0) 5:(-1,+1) 6:(0,+1) 7:(+1,+1)
+//  * a border is a cycle of states (pixel, dir to previous pixel a, dir to next pixel b) where b is
+//    the first foreground neighbour counter-clockwise after a.  The zero neighbours strictly
+//    between a and b are the ones Suzuki "examines" in that step; if code 4 (left) or 0 (right) is
+//    among them the state owns the pixel's left / right crack.
+//  * Suzuki starts an outer border at a foreground pixel whose left neighbour is zero and a hole
+//    border at one whose right neighbour is zero, the first time the raster scan meets an
+//    untraced border; equivalently the start is the raster-minimum pixel over all left/right
+//    cracks of the cycle (left wins a tie) and the border is "outer" iff that crack is a left one.
+//  * so: every left/right crack walks its cycle BACKWARDS (clockwise search) and gives up as soon
+//    as it meets a crack with a raster-smaller pixel; only the canonical start survives a full
+//    lap, and it then knows the contour length n.  Walking backwards kills the typical
+//    non-canonical crack of a convex outline within a step or two.
+#pragma once
+#include "common.cuh"
+
+namespace fid {
+
+FID_HD int dir_dx(int k) { return (int)((0x901Au >> (2 * k)) & 3u) - 1; }
+FID_HD int dir_dy(int k) { return (int)((0xA901u >> (2 * k)) & 3u) - 1; }
+
+FID_HD int rotr8(int m, int s) {
+    s &= 7;
+    return ((m >> s) | (m << (8 - s))) & 0xFF;
+}
+// first set code searching a+1, a+2, ..., a+8 (counter-clockwise); m != 0
+FID_HD int next_ccw(int m, int a) {
+    int t = rotr8(m, a + 1);
+    return (a + 1 + fid_ctz((uint32_t)t)) & 7;
+}
+// first set code searching b-1, b-2, ..., b-8 (clockwise); m != 0
+FID_HD int prev_cw(int m, int b) {
+    int t = rotr8(m, b);
+    return (b + 31 - fid_clz((uint32_t)t)) & 7;
+}
+
+enum { WALK_ABORT = 0, WALK_CANONICAL = 1, WALK_TOO_LONG = 2 };
+
+// Walk the border owning the left (is_right=0) or right (is_right=1) crack of foreground pixel
+// (x0,y0) backwards.  Returns WALK_CANONICAL with *n_out = contour point count if (x0,y0) is the
+// Suzuki start pixel of that border (outer border for a left crack, hole border for a right one).
+FID_HD int walk_reverse(const uint8_t* mask, int pitch, int x0, int y0, int is_right, int max_len, int* n_out) {
+    int m = mask[(size_t)y0 * pitch + x0];
+    if (m == 0) return WALK_ABORT;  // isolated pixel: 1-point contour, never long enough to matter
+    const int crack = is_right ? 0 : 4;
+    int a = prev_cw(m, crack);
+    const int b0 = next_ccw(m, crack);
+    if (is_right) {  // the same state also owns the left crack -> the left-crack walker wins the tie
+        int d = (b0 - a - 1) & 7;
+        if (((4 - a - 1) & 7) < d) return WALK_ABORT;
+    }
+    int x = x0, y = y0, n = 0;
+    for (;;) {
+        x += dir_dx(a);
+        y += dir_dy(a);
+        n++;
+        const int bq = (a + 4) & 7;
+        if (x == x0 && y == y0 && bq == b0) {
+            *n_out = n;
+            return WALK_CANONICAL;
+        }
+        if (n > max_len) return WALK_TOO_LONG;
+        m = mask[(size_t)y * pitch + x];
+        a = prev_cw(m, bq);
+        const int d = (bq - a - 1) & 7;
+        const bool exL = ((4 - a - 1) & 7) < d;
+        const bool exR = ((0 - a - 1) & 7) < d;
+        if (exL || exR) {
+            if (y < y0 || (y == y0 && x < x0)) return WALK_ABORT;
+            if (is_right && exL && y == y0 && x == x0) return WALK_ABORT;
+        }
+    }
+}
+
+// Emit the n contour points in OpenCV order (start pixel first, then Suzuki's direction).
+FID_HD void trace_forward(const uint8_t* mask, int pitch, int x0, int y0, int is_right, int n, Pt16* out) {
+    int m = mask[(size_t)y0 * pitch + x0];
+    int x = x0, y = y0;
+    if (m == 0) {
+        out[0].x = (int16_t)x;
+        out[0].y = (int16_t)y;
+        return;
+    }
+    int a = prev_cw(m, is_right ? 0 : 4);
+    for (int i = 0; i < n; i++) {
+        out[i].x = (int16_t)x;
+        out[i].y = (int16_t)y;
+        const int b = next_ccw(m, a);
+        x += dir_dx(b);
+        y += dir_dy(b);
+        a = (b + 4) & 7;
+        m = mask[(size_t)y * pitch + x];
+    }
+}
+
+// ---- neighbour masks and start cracks from bit-packed planes ------------------------------------
+// A threshold plane is bit-packed 32 pixels per word, LSB = lowest x.  For the word holding pixels
+// [32w, 32w+32) of row y, up/mid/down are the words of rows y-1,y,y+1 (0 outside the image) and
+// *_l / *_r the neighbouring words to the left / right (0 outside).
+struct NbrWords {
+    uint32_t d[8];  // d[k] bit i set <=> neighbour k of pixel i is foreground
+};
+
+FID_HD uint32_t shl_in(uint32_t w, uint32_t left) { return (w << 1) | (left >> 31); }   // value at x-1
+FID_HD uint32_t shr_in(uint32_t w, uint32_t right) { return (w >> 1) | (right << 31); }  // value at x+1
+
+FID_HD NbrWords nbr_words(uint32_t up_l, uint32_t up, uint32_t up_r, uint32_t mid_l, uint32_t mid, uint32_t mid_r, uint32_t dn_l, uint32_t dn,
+                          uint32_t dn_r) {
+    NbrWords n;
+    n.d[0] = shr_in(mid, mid_r);
+    n.d[1] = shr_in(up, up_r);
+    n.d[2] = up;
+    n.d[3] = shl_in(up, up_l);
+    n.d[4] = shl_in(mid, mid_l);
+    n.d[5] = shl_in(dn, dn_l);
+    n.d[6] = dn;
+    n.d[7] = shr_in(dn, dn_r);
+    return n;
+}
+
+// Start cracks that survive the exact local prune: a left crack of (x,y) is dominated when (x,y-1)
+// is foreground with a zero left neighbour (that crack lies on the same border and is raster
+// smaller); same for right cracks.
+FID_HD uint32_t left_crack_starts(uint32_t mid, const NbrWords& n) { return mid & ~n.d[4] & ~(n.d[2] & ~n.d[3]); }
+FID_HD uint32_t right_crack_starts(uint32_t mid, const NbrWords& n) { return mid & ~n.d[0] & ~(n.d[2] & ~n.d[1]); }
+
+FID_HD uint8_t mask_byte(const NbrWords& n, int i) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) v |= ((n.d[k] >> i) & 1u) << k;
+    return (uint8_t)v;
+}
+
+}  // namespace fid

@@ -1,0 +1,154 @@
+// Candidate ordering and grouping: the float arithmetic of cv::aruco's MarkerCandidateTree /
+// filterTooCloseCandidates (OpenCV 4.13 semantics), executed by the reference at
+// aruco_detect/src/aruco_detect.cpp:350.  All quantities are float32 exactly as in OpenCV
+// (Point2f corners, float perimeter, float distances); the library is compiled with --fmad=false.
+#pragma once
+#include "common.cuh"
+
+namespace fid {
+
+struct QuadF {
+    float x[4], y[4];
+};
+
+// Raw candidate emitted by the approximation kernel.
+struct RawQuad {
+    int16_t x[4], y[4];  // approxPolyDP vertex order
+    int32_t n_contour;   // contour length (points)
+    uint32_t order_hi;   // scale index
+    uint32_t order_lo;   // 0xFFFFFFFF - (2*raster(start)+is_hole): ascending == OpenCV's list order
+};
+
+// _reorderCandidatesCorners: make the quad clockwise.
+FID_HD QuadF quad_clockwise(const RawQuad& r) {
+    QuadF q;
+    for (int i = 0; i < 4; i++) {
+        q.x[i] = (float)r.x[i];
+        q.y[i] = (float)r.y[i];
+    }
+    const double dx1 = q.x[1] - q.x[0], dy1 = q.y[1] - q.y[0];
+    const double dx2 = q.x[2] - q.x[0], dy2 = q.y[2] - q.y[0];
+    if (dx1 * dy2 - dy1 * dx2 < 0.0) {
+        float t = q.x[1];
+        q.x[1] = q.x[3];
+        q.x[3] = t;
+        t = q.y[1];
+        q.y[1] = q.y[3];
+        q.y[3] = t;
+    }
+    return q;
+}
+
+FID_HD float quad_perimeter(const QuadF& q) {
+    float p = 0.f;
+    for (int i = 0; i < 4; i++) {
+        const float dx = q.x[i] - q.x[(i + 1) & 3], dy = q.y[i] - q.y[(i + 1) & 3];
+        p += sqrtf(dx * dx + dy * dy);
+    }
+    return p;
+}
+
+// getAverageDistance: sqrt(min over the 4 cyclic corner alignments of the mean squared distance).
+FID_HD float quad_avg_distance(const QuadF& a, const QuadF& b) {
+    float best = 3.402823466e+38f;
+    for (int fc = 0; fc < 4; fc++) {
+        float d = 0.f;
+        for (int c = 0; c < 4; c++) {
+            const int mc = (c + fc) & 3;
+            const float dx = a.x[mc] - b.x[c], dy = a.y[mc] - b.y[c];
+            d += dx * dx + dy * dy;
+        }
+        d /= 4.f;
+        best = d < best ? d : best;
+    }
+    return sqrtf(best);
+}
+
+// getAverageModuleSize
+FID_HD float quad_module_size(const QuadF& q, int marker_size, int border_bits) {
+    float s = quad_perimeter(q);
+    const int modules = marker_size + 2 * border_bits;
+    s /= (4.f * (float)modules);
+    return s;
+}
+
+// Serial grouping over candidates already sorted by descending perimeter (stable).  `close(i,j)` is
+// the pair predicate avgDist(i,j) < perimeter[j]*minMarkerDistanceRate evaluated by the caller (in
+// parallel on the GPU, as a bit matrix).  Outputs: selected[i] and, for group leaders, the list of
+// close contours (indices) in close_idx[close_off[i] .. close_off[i+1]).
+// Scratch: group_id[n], group_of[..] arrays supplied by the caller.
+template <class ClosePred>
+FID_HD void group_candidates(int n, const QuadF* quads, int marker_size, int border_bits, float min_group_dist, const ClosePred& close, uint8_t* selected,
+                             int* group_id,        // [n]
+                             int* group_members,   // [n]   members of all groups, appended per group via linked lists
+                             int* next_in_group,   // [n]   linked list
+                             int* group_head,      // [n]   head per group
+                             int* group_tail,      // [n]
+                             int* close_count,     // [n]   number of close contours per candidate
+                             int* close_idx,       // [n]   flat storage
+                             int* close_off)       // [n+1]
+{
+    int n_groups = 0;
+    for (int i = 0; i < n; i++) {
+        selected[i] = 1;
+        group_id[i] = -1;
+        next_in_group[i] = -1;
+        close_count[i] = 0;
+    }
+    for (int i = 0; i < n; i++) {
+        for (int j = i + 1; j < n; j++) {
+            if (!close(i, j)) continue;
+            selected[i] = 0;
+            selected[j] = 0;
+            if (group_id[i] < 0 && group_id[j] < 0) {
+                const int g = n_groups++;
+                group_id[i] = group_id[j] = g;
+                group_head[g] = i;
+                next_in_group[i] = j;
+                group_tail[g] = j;
+            } else if (group_id[i] > -1 && group_id[j] == -1) {
+                const int g = group_id[i];
+                group_id[j] = g;
+                next_in_group[group_tail[g]] = j;
+                group_tail[g] = j;
+            } else if (group_id[j] > -1 && group_id[i] == -1) {
+                const int g = group_id[j];
+                group_id[i] = g;
+                next_in_group[group_tail[g]] = i;
+                group_tail[g] = i;
+            }
+        }
+    }
+    // per group: sort members ascending (largest perimeter first), keep the first, collect the
+    // "close contours" that differ enough from the running reference.
+    int total_close = 0;
+    for (int g = 0; g < n_groups; g++) {
+        int m = 0;
+        for (int k = group_head[g]; k >= 0; k = next_in_group[k]) group_members[m++] = k;
+        for (int a = 1; a < m; a++) {  // insertion sort (groups are small)
+            const int v = group_members[a];
+            int b = a - 1;
+            while (b >= 0 && group_members[b] > v) {
+                group_members[b + 1] = group_members[b];
+                b--;
+            }
+            group_members[b + 1] = v;
+        }
+        const int lead = group_members[0];
+        int cur = lead;
+        selected[lead] = 1;
+        close_off[lead] = total_close;
+        for (int a = 1; a < m; a++) {
+            const int id = group_members[a];
+            const float dist = quad_avg_distance(quads[id], quads[cur]);
+            const float module = quad_module_size(quads[id], marker_size, border_bits);
+            if (dist > min_group_dist * module) {
+                cur = id;
+                close_idx[total_close++] = id;
+                close_count[lead]++;
+            }
+        }
+    }
+}
+
+}  // namespace fid

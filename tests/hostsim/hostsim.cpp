@@ -1,0 +1,375 @@
+// tests/hostsim -- CPU unit-test harness for the FID_HD device functions of fiducials_b200/csrc.
+//
+// TEST INFRASTRUCTURE ONLY.  This file compiles the *same headers* the CUDA kernels are built
+// from with g++, and drives them with serial loops so that the per-element logic (border walk,
+// polygon approximation, grouping, bit extraction, sub-pixel refinement, PnP, map update) can be
+// checked against the cv2 oracle in the GPU-less authoring container.  It is a separate shared
+// object (tests/hostsim/libfid_hostsim.so), it is not linked into libfiducials_b200.so, and the
+// C-ABI has no way to reach it: the product fails loudly without a CUDA device.
+#include <stdint.h>
+#include <string.h>
+#include <algorithm>
+#include <vector>
+
+#include "../../fiducials_b200/csrc/common.cuh"
+#include "../../fiducials_b200/csrc/contour_walk.cuh"
+#include "../../fiducials_b200/csrc/approx_quad.cuh"
+#include "../../fiducials_b200/csrc/quad_group.cuh"
+#include "../../fiducials_b200/csrc/identify.cuh"
+#include "../../fiducials_b200/csrc/subpix.cuh"
+#include "../../fiducials_b200/csrc/pnp.cuh"
+#include "../../fiducials_b200/csrc/slam.cuh"
+#include "../../fiducials_b200/csrc/params_host.h"
+
+using namespace fid;
+
+static void pack_plane(const uint8_t* plane, int W, int H, std::vector<uint32_t>& bits, int& wpr) {
+    wpr = (W + 31) / 32;
+    bits.assign((size_t)wpr * H, 0u);
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++)
+            if (plane[(size_t)y * W + x]) bits[(size_t)y * wpr + (x >> 5)] |= 1u << (x & 31);
+}
+
+struct Start {
+    int x, y, is_right;
+};
+
+static void masks_and_starts(const std::vector<uint32_t>& bits, int wpr, int W, int H, std::vector<uint8_t>& mask, std::vector<Start>& starts) {
+    mask.assign((size_t)W * H, 0);
+    auto word = [&](int y, int w) -> uint32_t { return (y < 0 || y >= H || w < 0 || w >= wpr) ? 0u : bits[(size_t)y * wpr + w]; };
+    for (int y = 0; y < H; y++)
+        for (int w = 0; w < wpr; w++) {
+            const uint32_t mid = word(y, w);
+            NbrWords nw = nbr_words(word(y - 1, w - 1), word(y - 1, w), word(y - 1, w + 1), word(y, w - 1), mid, word(y, w + 1), word(y + 1, w - 1), word(y + 1, w),
+                                    word(y + 1, w + 1));
+            uint32_t L = left_crack_starts(mid, nw), R = right_crack_starts(mid, nw);
+            for (int i = 0; i < 32 && 32 * w + i < W; i++) {
+                mask[(size_t)y * W + 32 * w + i] = mask_byte(nw, i);
+                if ((L >> i) & 1) starts.push_back({32 * w + i, y, 0});
+                if ((R >> i) & 1) starts.push_back({32 * w + i, y, 1});
+            }
+        }
+}
+
+extern "C" {
+
+// All contours of a {0,!=0} plane with min_len <= n <= max_len, in cv2.findContours list order.
+// out_pts: (x,y) int16 pairs, out_len: per-contour lengths.  Returns the number of contours, or
+// -1 if a buffer is too small.  *n_walk_steps returns the total number of reverse-walk steps taken.
+int hs_find_contours(const uint8_t* plane, int W, int H, int min_len, int max_len, int16_t* out_pts, int64_t max_pts, int32_t* out_len, int max_contours,
+                     int64_t* n_starts_out) {
+    std::vector<uint32_t> bits;
+    int wpr;
+    pack_plane(plane, W, H, bits, wpr);
+    std::vector<uint8_t> mask;
+    std::vector<Start> starts;
+    masks_and_starts(bits, wpr, W, H, mask, starts);
+    if (n_starts_out) *n_starts_out = (int64_t)starts.size();
+    struct Chain {
+        int64_t key;
+        int x, y, is_right, n;
+    };
+    std::vector<Chain> chains;
+    for (const Start& s : starts) {
+        int n = 0;
+        int st = walk_reverse(mask.data(), W, s.x, s.y, s.is_right, max_len, &n);
+        if (st == WALK_CANONICAL && n >= min_len) chains.push_back({((int64_t)s.y * W + s.x) * 2 + s.is_right, s.x, s.y, s.is_right, n});
+    }
+    if (min_len <= 1) {  // isolated pixels are 1-point outer contours
+        for (int y = 0; y < H; y++)
+            for (int x = 0; x < W; x++)
+                if (plane[(size_t)y * W + x] && mask[(size_t)y * W + x] == 0) chains.push_back({((int64_t)y * W + x) * 2, x, y, 0, 1});
+    }
+    std::sort(chains.begin(), chains.end(), [](const Chain& a, const Chain& b) { return a.key > b.key; });  // reverse discovery order
+    if ((int)chains.size() > max_contours) return -1;
+    int64_t off = 0;
+    for (size_t i = 0; i < chains.size(); i++) {
+        const Chain& c = chains[i];
+        if (off + c.n > max_pts) return -1;
+        trace_forward(mask.data(), W, c.x, c.y, c.is_right, c.n, reinterpret_cast<Pt16*>(out_pts) + off);
+        out_len[i] = c.n;
+        off += c.n;
+    }
+    return (int)chains.size();
+}
+
+// approxPolyDP (closed) of one contour; returns vertex count (-1 = more than 8 before clean-up).
+int hs_approx_poly(const int16_t* pts, int n, double eps, int16_t* out) {
+    SerialReducer red;
+    return approx_poly_closed(red, reinterpret_cast<const Pt16*>(pts), n, eps, reinterpret_cast<Pt16*>(out));
+}
+
+int hs_is_convex(const int16_t* pts, int n) { return is_convex_int(reinterpret_cast<const Pt16*>(pts), n) ? 1 : 0; }
+
+
+// Raw quad candidates of all scales from precomputed threshold planes (n_scales x H x W, {0,!=0}),
+// in OpenCV's concatenation order.  quads: n x 8 int32 (x0,y0,..), scale[n], clen[n].
+static void raw_candidates(const uint8_t* planes, int W, int H, const DevParams& P, std::vector<RawQuad>& out) {
+    const int mx = W > H ? W : H;
+    const int min_len = (int)(P.min_perimeter_rate * mx), max_len = (int)(P.max_perimeter_rate * mx);
+    for (int s = 0; s < P.n_scales; s++) {
+        std::vector<uint32_t> bits;
+        int wpr;
+        pack_plane(planes + (size_t)s * W * H, W, H, bits, wpr);
+        std::vector<uint8_t> mask;
+        std::vector<Start> starts;
+        masks_and_starts(bits, wpr, W, H, mask, starts);
+        std::vector<RawQuad> found;
+        std::vector<Pt16> pts;
+        for (const Start& st : starts) {
+            int n = 0;
+            if (walk_reverse(mask.data(), W, st.x, st.y, st.is_right, max_len, &n) != WALK_CANONICAL) continue;
+            if (n < min_len || n > max_len) continue;
+            pts.resize(n);
+            trace_forward(mask.data(), W, st.x, st.y, st.is_right, n, pts.data());
+            Pt16 q[FID_APPROX_MAX_V];
+            SerialReducer red;
+            if (approx_poly_closed(red, pts.data(), n, (double)n * P.poly_accuracy_rate, q) != 4) continue;
+            if (!quad_passes_filters(q, n, W, H, P.min_corner_dist_rate, P.min_dist_to_border)) continue;
+            RawQuad r;
+            for (int k = 0; k < 4; k++) {
+                r.x[k] = q[k].x;
+                r.y[k] = q[k].y;
+            }
+            r.n_contour = n;
+            r.order_hi = (uint32_t)s;
+            r.order_lo = 0xFFFFFFFFu - (uint32_t)(((uint32_t)st.y * (uint32_t)W + (uint32_t)st.x) * 2u + (uint32_t)st.is_right);
+            found.push_back(r);
+        }
+        std::sort(found.begin(), found.end(), [](const RawQuad& a, const RawQuad& b) { return a.order_lo < b.order_lo; });
+        out.insert(out.end(), found.begin(), found.end());
+    }
+}
+
+int hs_candidates(const uint8_t* planes, int W, int H, int dict_id, int32_t* quads, int32_t* scale, int32_t* clen, int max_out) {
+    fid_params fp;
+    default_params(&fp);
+    fp.dictionary = dict_id;
+    DevParams P;
+    if (make_dev_params(fp, &P) != FID_OK) return -2;
+    std::vector<RawQuad> raw;
+    raw_candidates(planes, W, H, P, raw);
+    if ((int)raw.size() > max_out) return -1;
+    for (size_t i = 0; i < raw.size(); i++) {
+        for (int k = 0; k < 4; k++) {
+            quads[i * 8 + 2 * k] = raw[i].x[k];
+            quads[i * 8 + 2 * k + 1] = raw[i].y[k];
+        }
+        scale[i] = (int)raw[i].order_hi;
+        clen[i] = raw[i].n_contour;
+    }
+    return (int)raw.size();
+}
+
+// Full detect from gray + threshold planes: ids/corners in OpenCV order.  refine: apply cornerSubPix.
+int hs_detect(const uint8_t* gray, const uint8_t* planes, int W, int H, int dict_id, int refine, int32_t* ids, float* corners, int max_out, int32_t* stats) {
+    fid_params fp;
+    default_params(&fp);
+    fp.dictionary = dict_id;
+    DevParams P;
+    if (make_dev_params(fp, &P) != FID_OK) return -2;
+    std::vector<RawQuad> raw;
+    raw_candidates(planes, W, H, P, raw);
+    const int n = (int)raw.size();
+    // stable sort by descending float perimeter
+    std::vector<QuadF> q(n);
+    std::vector<float> per(n);
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) {
+        q[i] = quad_clockwise(raw[i]);
+        per[i] = quad_perimeter(q[i]);
+        order[i] = i;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return per[a] > per[b]; });
+    std::vector<QuadF> sq(n);
+    std::vector<float> sper(n);
+    for (int i = 0; i < n; i++) {
+        sq[i] = q[order[i]];
+        sper[i] = per[order[i]];
+    }
+    std::vector<uint8_t> selected(n);
+    std::vector<int> gid(n), gmem(n), nxt(n), ghead(n), gtail(n), ccount(n), cidx(n), coff(n + 1);
+    const float rate = (float)P.min_marker_dist_rate;
+    auto close = [&](int i, int j) { return quad_avg_distance(sq[i], sq[j]) < sper[j] * rate; };
+    group_candidates(n, sq.data(), P.marker_size, P.marker_border_bits, (float)P.min_group_dist, close, selected.data(), gid.data(), gmem.data(), nxt.data(),
+                     ghead.data(), gtail.data(), ccount.data(), cidx.data(), coff.data());
+    std::vector<unsigned long long> dict;
+    pack_dictionary(P, &dict);
+    SerialLanes L;
+    std::vector<uint8_t> img(64 * 64);
+    int hist[256];
+    int n_out = 0, n_sel = 0;
+    float mask[121];
+    std::vector<float> patch(13 * 13);
+    for (int i = 0; i < n; i++) {
+        if (!selected[i]) continue;
+        n_sel++;
+        QuadF use = sq[i];
+        IdentifyResult r = identify_candidate(L, gray, W, H, (size_t)W, use, P, dict.data(), img.data(), hist);
+        if (r.id < 0) {
+            for (int k = 0; k < ccount[i]; k++) {
+                const QuadF& alt = sq[cidx[coff[i] + k]];
+                r = identify_candidate(L, gray, W, H, (size_t)W, alt, P, dict.data(), img.data(), hist);
+                if (r.id >= 0) {
+                    use = alt;
+                    break;
+                }
+            }
+        }
+        if (r.id < 0) continue;
+        if (n_out >= max_out) return -1;
+        // correctCornerPosition: std::rotate(begin, begin + 4 - rotation, end)
+        float cx[4], cy[4];
+        for (int k = 0; k < 4; k++) {
+            cx[k] = use.x[(k + 4 - r.rotation) & 3];
+            cy[k] = use.y[(k + 4 - r.rotation) & 3];
+        }
+        if (refine && P.corner_refine) {
+            QuadF rq;
+            for (int k = 0; k < 4; k++) {
+                rq.x[k] = cx[k];
+                rq.y[k] = cy[k];
+            }
+            const float module = quad_module_size(rq, P.marker_size, P.marker_border_bits);
+            int win = (int)nearbyintf((float)P.rel_refine_win * module);
+            win = win < 1 ? 1 : win;
+            win = win < P.refine_win ? win : P.refine_win;
+            subpix_mask(win, mask);
+            for (int k = 0; k < 4; k++)
+                corner_subpix(gray, W, H, (size_t)W, &cx[k], &cy[k], win, mask, P.refine_max_iter, P.refine_min_acc * P.refine_min_acc, patch.data());
+        }
+        ids[n_out] = r.id;
+        for (int k = 0; k < 4; k++) {
+            corners[n_out * 8 + 2 * k] = cx[k];
+            corners[n_out * 8 + 2 * k + 1] = cy[k];
+        }
+        n_out++;
+    }
+    if (stats) {
+        stats[0] = n;
+        stats[1] = n_sel;
+    }
+    return n_out;
+}
+
+// cornerSubPix of n points (x,y interleaved, in place).
+void hs_corner_subpix(const uint8_t* gray, int W, int H, float* pts, int n, int win, int max_iters, double eps) {
+    float mask[121];
+    float patch[13 * 13];
+    subpix_mask(win, mask);
+    for (int i = 0; i < n; i++) corner_subpix(gray, W, H, (size_t)W, &pts[2 * i], &pts[2 * i + 1], win, mask, max_iters, eps * eps, patch);
+}
+
+// Pose of n markers; out: n x 19 doubles (rvec3 tvec3 image_error object_error area quat4 iters pad..)
+void hs_pose(int n, const float* corners, const double* K, const double* D, const float* lens, double default_len, double* out) {
+    Camera cam = {K[0], K[4], K[2], K[5], D[0], D[1], D[2], D[3], D[4]};
+    for (int i = 0; i < n; i++) {
+        PoseOut po;
+        solve_marker_pose(corners + 8 * i, cam, lens[i], default_len, &po);
+        double* o = out + 16 * i;
+        for (int k = 0; k < 3; k++) {
+            o[k] = po.rvec[k];
+            o[3 + k] = po.tvec[k];
+        }
+        o[6] = po.image_error;
+        o[7] = po.object_error;
+        o[8] = po.area;
+        for (int k = 0; k < 4; k++) o[9 + k] = po.quat[k];
+        o[13] = po.lm_iters;
+    }
+}
+
+// --- map ---------------------------------------------------------------------------------------
+struct HsMap {
+    MapState st;
+    std::vector<MapEntry> e;
+    std::vector<uint32_t> links;
+};
+
+void* hs_map_create(int capacity, int read_only) {
+    HsMap* m = new HsMap();
+    memset(&m->st, 0, sizeof(m->st));
+    m->st.capacity = capacity;
+    m->st.origin_fid = -1;
+    m->st.read_only = read_only;
+    m->e.resize(capacity);
+    m->links.assign((size_t)capacity * ((capacity + 31) / 32), 0u);
+    return m;
+}
+void hs_map_destroy(void* h) { delete (HsMap*)h; }
+// obs: n x (id as double, t3, q4, object_error, area) = 10 doubles; tf: 7 doubles (t3 q4) or null
+int hs_map_update(void* h, int n, const double* obs, const double* baseCam, const double* camBase, double* robot /* valid,n,t3,q4,var = 10 */) {
+    HsMap* m = (HsMap*)h;
+    std::vector<Obs> o(n);
+    for (int i = 0; i < n; i++) {
+        o[i].id = (int)obs[10 * i];
+        for (int k = 0; k < 3; k++) o[i].t[k] = obs[10 * i + 1 + k];
+        for (int k = 0; k < 4; k++) o[i].q[k] = obs[10 * i + 4 + k];
+        o[i].object_error = obs[10 * i + 8];
+        o[i].area = obs[10 * i + 9];
+    }
+    Twv bc, cb;
+    if (baseCam) {
+        q_to_m(baseCam + 3, bc.R);
+        bc.t[0] = baseCam[0];
+        bc.t[1] = baseCam[1];
+        bc.t[2] = baseCam[2];
+        bc.var = 0;
+    }
+    if (camBase) {
+        q_to_m(camBase + 3, cb.R);
+        cb.t[0] = camBase[0];
+        cb.t[1] = camBase[1];
+        cb.t[2] = camBase[2];
+        cb.var = 0;
+    }
+    RobotPose rp;
+    map_update(m->st, m->e.data(), m->links.data(), o.data(), n, baseCam ? &bc : nullptr, camBase ? &cb : nullptr, 1e9, 0, 0.01, &rp);
+    robot[0] = rp.valid;
+    robot[1] = rp.n_estimates;
+    for (int k = 0; k < 3; k++) robot[2 + k] = rp.t[k];
+    for (int k = 0; k < 4; k++) robot[5 + k] = rp.q[k];
+    robot[9] = rp.var;
+    return m->st.n;
+}
+void hs_map_load(void* h, int id, double x, double y, double z, double r_deg, double p_deg, double y_deg, double var, int num_obs) {
+    HsMap* m = (HsMap*)h;
+    const double d2r = 3.14159265358979323846 / 180.0;
+    const double hr = r_deg * d2r * 0.5, hp = p_deg * d2r * 0.5, hy = y_deg * d2r * 0.5;
+    const double cy = cos(hy), sy = sin(hy), cp = cos(hp), sp = sin(hp), cr = cos(hr), sr = sin(hr);
+    const double q[4] = {sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy, cr * cp * cy + sr * sp * sy};
+    MapEntry& e = m->e[m->st.n++];
+    e.id = id;
+    e.num_obs = num_obs;
+    q_to_m(q, e.pose.R);
+    e.pose.t[0] = x;
+    e.pose.t[1] = y;
+    e.pose.t[2] = z;
+    e.pose.var = var;
+}
+// entries: n x (id, x,y,z, rx,ry,rz, var, numObs) = 9 doubles, ascending id
+int hs_map_entries(void* h, double* out) {
+    HsMap* m = (HsMap*)h;
+    std::vector<int> idx(m->st.n);
+    for (int i = 0; i < m->st.n; i++) idx[i] = i;
+    std::sort(idx.begin(), idx.end(), [&](int a, int b) { return m->e[a].id < m->e[b].id; });
+    for (int k = 0; k < m->st.n; k++) {
+        const MapEntry& e = m->e[idx[k]];
+        double r, p, y;
+        get_rpy(e.pose.R, &r, &p, &y);
+        double* o = out + 9 * k;
+        o[0] = e.id;
+        o[1] = e.pose.t[0];
+        o[2] = e.pose.t[1];
+        o[3] = e.pose.t[2];
+        o[4] = r;
+        o[5] = p;
+        o[6] = y;
+        o[7] = e.pose.var;
+        o[8] = e.num_obs;
+    }
+    return m->st.n;
+}
+
+}  // extern "C"
