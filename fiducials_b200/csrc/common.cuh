@@ -19,6 +19,9 @@
 namespace fid {
 
 #define FID_MAX_SCALES 16
+#define FID_MAX_WIN_RADIUS 31   // adaptive-threshold window <= 63
+#define FID_MAX_WARP_SIDE 64    // (markerSize + 2*border) * pixelPerCell <= 64
+#define FID_MAX_WARP_SIDE_SQ (FID_MAX_WARP_SIDE * FID_MAX_WARP_SIDE)
 
 struct Pt16 {
     int16_t x, y;

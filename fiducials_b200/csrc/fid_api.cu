@@ -1,0 +1,764 @@
+// C-ABI of the detector (include/fiducials_b200.h): handle management, batch orchestration on CUDA
+// streams, stage timing.  No CPU fallback: every entry point that computes needs a CUDA device.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/fiducials_b200.h"
+#include "kernels_contour.cuh"
+#include "kernels_marker.cuh"
+#include "params_host.h"
+
+using namespace fid;
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            fprintf(stderr, "[fiducials_b200] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return FID_ERR_CUDA;                                                                       \
+        }                                                                                              \
+    } while (0)
+
+enum { ST_H2D = 0, ST_THRESH, ST_MASKS, ST_WALK, ST_EMIT, ST_APPROX, ST_GROUP, ST_IDENT, ST_SUBPIX_POSE, ST_POSE_UNUSED, ST_D2H, ST_COUNT };
+
+struct Slot {
+    uint8_t* d_bgr = nullptr;
+    uint8_t* d_gray = nullptr;
+    uint32_t* d_bits = nullptr;
+    uint8_t* d_mask = nullptr;
+    StartRec* d_starts = nullptr;
+    ChainRec* d_chains = nullptr;
+    Pt16* d_points = nullptr;
+    Counters* d_counters = nullptr;
+    RawQuad* d_raw = nullptr;
+    unsigned int* d_nraw = nullptr;
+    FrameScratch fs{};
+    int* d_nsel = nullptr;
+    int* d_nrawc = nullptr;
+    int* d_cand_id = nullptr;
+    float* d_cand_corners = nullptr;
+    int32_t* d_out_count = nullptr;
+    int32_t* d_out_ids = nullptr;
+    float* d_out_corners = nullptr;
+    fid_transform* d_out_tf = nullptr;
+    // pinned host mirrors
+    int32_t* h_out_count = nullptr;
+    int32_t* h_out_ids = nullptr;
+    float* h_out_corners = nullptr;
+    fid_transform* h_out_tf = nullptr;
+    Counters* h_counters = nullptr;
+    int* h_nsel = nullptr;
+    int* h_nrawc = nullptr;
+    cudaEvent_t ev[ST_COUNT + 1]{};
+    cudaEvent_t done = nullptr;
+    cudaEvent_t copied = nullptr;
+};
+
+struct fid_detector {
+    int device = 0;
+    int sm_count = 148;
+    fid_params params{};
+    DevParams P{};
+    int max_w = 0, max_h = 0, max_batch = 0;
+    int max_raw = 4096, close_wpr = 128, max_sel = 512, max_markers = FID_MAX_MARKERS;
+    unsigned int max_starts = 0, max_chains = 0, max_points = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    Slot slot[2];
+    float* d_subpix_masks = nullptr;
+    int32_t* d_override_ids = nullptr;
+    double* d_override_lens = nullptr;
+    int32_t* d_pose_ids = nullptr;
+    float* d_pose_corners = nullptr;
+    fid_transform* d_pose_out = nullptr;
+    float stage_ms[ST_COUNT]{};
+    int64_t counters[8]{};
+    // last geometry (for debug calls)
+    int last_w = 0, last_h = 0, last_frames = 0;
+};
+
+static const char* kErr[] = {"ok", "invalid argument", "no usable CUDA device (this library has no CPU fallback)", "CUDA runtime error", "unsupported parameter or dictionary",
+                             "capacity exceeded", "out of memory"};
+
+extern "C" const char* fid_strerror(int status) {
+    const int i = -status;
+    if (i < 0 || i > 6) return "unknown status";
+    return kErr[i];
+}
+extern "C" const char* fid_version(void) { return "0.1.0"; }
+
+extern "C" int fid_default_params(fid_params* p) {
+    if (!p) return FID_ERR_INVALID_ARG;
+    default_params(p);
+    return FID_OK;
+}
+
+template <class T>
+static int dalloc(T** p, size_t count) {
+    if (cudaMalloc((void**)p, count * sizeof(T)) != cudaSuccess) {
+        cudaGetLastError();
+        return FID_ERR_NO_MEMORY;
+    }
+    return FID_OK;
+}
+template <class T>
+static int halloc(T** p, size_t count) {
+    if (cudaMallocHost((void**)p, count * sizeof(T)) != cudaSuccess) {
+        cudaGetLastError();
+        return FID_ERR_NO_MEMORY;
+    }
+    return FID_OK;
+}
+
+static FrameGeom make_geom(const fid_detector* h, int W, int H, size_t row_stride, size_t frame_stride) {
+    FrameGeom g;
+    g.W = W;
+    g.H = H;
+    g.wpr = (W + 31) / 32;
+    g.gray_pitch = g.wpr * 32;
+    g.mask_pitch = g.wpr * 32;
+    g.bgr_row_stride = row_stride;
+    g.bgr_frame_stride = frame_stride;
+    g.gray_frame_stride = (size_t)g.gray_pitch * H;
+    g.bits_scale_stride = (size_t)g.wpr * H;
+    g.bits_frame_stride = g.bits_scale_stride * h->P.n_scales;
+    g.mask_scale_stride = (size_t)g.mask_pitch * H;
+    g.mask_frame_stride = g.mask_scale_stride * h->P.n_scales;
+    return g;
+}
+
+static int upload_constants() {
+    static bool done[64] = {false};
+    int dev = 0;
+    CK(cudaGetDevice(&dev));
+    if (dev < 64 && done[dev]) return FID_OK;
+    std::vector<uint32_t> d5(4000);
+    std::vector<unsigned long long> d6(4000);
+    for (int m = 0; m < 1000; m++)
+        for (int r = 0; r < 4; r++) {
+            uint32_t v5 = 0;
+            for (int k = 0; k < 4; k++) v5 |= (uint32_t)kDictBytes5x5[m * 16 + r * 4 + k] << (8 * k);
+            d5[m * 4 + r] = v5;
+            unsigned long long v6 = 0;
+            for (int k = 0; k < 5; k++) v6 |= (unsigned long long)kDictBytes6x6[m * 20 + r * 5 + k] << (8 * k);
+            d6[m * 4 + r] = v6;
+        }
+    CK(cudaMemcpyToSymbol(c_dict5, d5.data(), sizeof(uint32_t) * 4000));
+    CK(cudaMemcpyToSymbol(c_dict6, d6.data(), sizeof(unsigned long long) * 4000));
+    if (dev < 64) done[dev] = true;
+    return FID_OK;
+}
+
+static size_t thresh_smem(int r_max) {
+    const int RW = THR_TW + 2 * r_max, RH = THR_TH + 2 * r_max;
+    return (size_t)(RH + 1) * (RW + 1) * 4 + THR_TW * THR_TH;
+}
+static size_t ident_smem(const DevParams& P) { return (size_t)P.n_markers * 4 * 8 + IDENT_WARPS * 256 * 4 + IDENT_WARPS * FID_MAX_WARP_SIDE_SQ; }
+
+static int r_max_of(const DevParams& P) {
+    int r = 1;
+    for (int i = 0; i < P.n_scales; i++) r = std::max(r, P.win[i] / 2);
+    return r;
+}
+
+static int configure_kernels(fid_detector* h) {
+    CK(cudaFuncSetAttribute(k_threshold, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thresh_smem(FID_MAX_WIN_RADIUS)));
+    CK(cudaFuncSetAttribute(k_identify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1000 * 4 * 8 + IDENT_WARPS * 256 * 4 + IDENT_WARPS * FID_MAX_WARP_SIDE_SQ)));
+    return FID_OK;
+}
+
+static int alloc_slot(fid_detector* h, Slot& s) {
+    const size_t F = h->max_batch;
+    const int W = h->max_w, H = h->max_h;
+    const size_t wpr = (W + 31) / 32, pitch = wpr * 32;
+    const int S = FID_MAX_SCALES;  // params may change between frames (fid_set_params)
+    int rc;
+#define A(expr)                  \
+    if ((rc = (expr)) != FID_OK) return rc;
+    A(dalloc(&s.d_bgr, F * (size_t)W * H * 3));
+    A(dalloc(&s.d_gray, F * pitch * H));
+    A(dalloc(&s.d_bits, F * (size_t)S * wpr * H));
+    A(dalloc(&s.d_mask, F * (size_t)S * pitch * H));
+    A(dalloc(&s.d_starts, (size_t)h->max_starts));
+    A(dalloc(&s.d_chains, (size_t)h->max_chains));
+    A(dalloc(&s.d_points, (size_t)h->max_points));
+    A(dalloc(&s.d_counters, 1));
+    const size_t R = F * h->max_raw;
+    A(dalloc(&s.d_raw, R));
+    A(dalloc(&s.d_nraw, F));
+    A(dalloc(&s.fs.quads_tmp, R));
+    A(dalloc(&s.fs.per_tmp, R));
+    A(dalloc(&s.fs.quads, R));
+    A(dalloc(&s.fs.per, R));
+    A(dalloc(&s.fs.close_bits, R * h->close_wpr));
+    A(dalloc(&s.fs.group_id, R));
+    A(dalloc(&s.fs.group_members, R));
+    A(dalloc(&s.fs.next_in_group, R));
+    A(dalloc(&s.fs.group_head, R));
+    A(dalloc(&s.fs.group_tail, R));
+    A(dalloc(&s.fs.close_count, R));
+    A(dalloc(&s.fs.close_idx, R));
+    A(dalloc(&s.fs.close_off, R));
+    A(dalloc(&s.fs.selected, R));
+    A(dalloc(&s.fs.sel_idx, R));
+    A(dalloc(&s.d_nsel, F));
+    A(dalloc(&s.d_nrawc, F));
+    A(dalloc(&s.d_cand_id, F * h->max_sel));
+    A(dalloc(&s.d_cand_corners, F * h->max_sel * 8));
+    const size_t M = F * h->max_markers;
+    A(dalloc(&s.d_out_count, F));
+    A(dalloc(&s.d_out_ids, M));
+    A(dalloc(&s.d_out_corners, M * 8));
+    A(dalloc(&s.d_out_tf, M));
+    A(halloc(&s.h_out_count, F));
+    A(halloc(&s.h_out_ids, M));
+    A(halloc(&s.h_out_corners, M * 8));
+    A(halloc(&s.h_out_tf, M));
+    A(halloc(&s.h_counters, 1));
+    A(halloc(&s.h_nsel, F));
+    A(halloc(&s.h_nrawc, F));
+#undef A
+    for (int i = 0; i <= ST_COUNT; i++) CK(cudaEventCreate(&s.ev[i]));
+    CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
+    return FID_OK;
+}
+
+static void free_slot(Slot& s) {
+    void* dptrs[] = {s.d_bgr,         s.d_gray,          s.d_bits,          s.d_mask,         s.d_starts,       s.d_chains,       s.d_points,      s.d_counters,
+                     s.d_raw,         s.d_nraw,          s.fs.quads_tmp,    s.fs.per_tmp,     s.fs.quads,       s.fs.per,         s.fs.close_bits, s.fs.group_id,
+                     s.fs.group_members, s.fs.next_in_group, s.fs.group_head, s.fs.group_tail, s.fs.close_count, s.fs.close_idx,   s.fs.close_off,  s.fs.selected,
+                     s.fs.sel_idx,    s.d_nsel,          s.d_nrawc,         s.d_cand_id,      s.d_cand_corners, s.d_out_count,    s.d_out_ids,     s.d_out_corners,
+                     s.d_out_tf};
+    for (void* p : dptrs)
+        if (p) cudaFree(p);
+    void* hptrs[] = {s.h_out_count, s.h_out_ids, s.h_out_corners, s.h_out_tf, s.h_counters, s.h_nsel, s.h_nrawc};
+    for (void* p : hptrs)
+        if (p) cudaFreeHost(p);
+    for (int i = 0; i <= ST_COUNT; i++)
+        if (s.ev[i]) cudaEventDestroy(s.ev[i]);
+    if (s.done) cudaEventDestroy(s.done);
+    if (s.copied) cudaEventDestroy(s.copied);
+}
+
+extern "C" int fid_create(const fid_params* params, int device, int max_width, int max_height, int max_batch, fid_detector** out) {
+    if (!params || !out || max_width < 16 || max_height < 16 || max_batch < 1 || max_width > 16384 || max_height > 16384) return FID_ERR_INVALID_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return FID_ERR_NO_DEVICE;
+    }
+    DevParams P;
+    int rc = make_dev_params(*params, &P);
+    if (rc != FID_OK) return rc;
+    CK(cudaSetDevice(device));
+    fid_detector* h = new fid_detector();
+    h->device = device;
+    h->params = *params;
+    h->P = P;
+    h->max_w = max_width;
+    h->max_h = max_height;
+    h->max_batch = max_batch;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    h->sm_count = prop.multiProcessorCount;
+    const size_t px = (size_t)max_width * max_height * max_batch;
+    h->max_starts = (unsigned int)std::min<size_t>(px / 2 + 65536, 0x7fffffffu);
+    h->max_chains = (unsigned int)std::min<size_t>((size_t)max_batch * 32768, 0x7fffffffu);
+    h->max_points = (unsigned int)std::min<size_t>(px + 65536, 0x7fffffffu);
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if ((rc = upload_constants()) != FID_OK || (rc = configure_kernels(h)) != FID_OK) {
+        fid_destroy(h);
+        return rc;
+    }
+    for (int i = 0; i < 2; i++)
+        if ((rc = alloc_slot(h, h->slot[i])) != FID_OK) {
+            fid_destroy(h);
+            return rc;
+        }
+    // cornerSubPix windows 1..5 (host libm, like OpenCV)
+    {
+        std::vector<float> masks;
+        for (int w = 1; w <= 5; w++) {
+            std::vector<float> m((2 * w + 1) * (2 * w + 1));
+            subpix_mask(w, m.data());
+            masks.insert(masks.end(), m.begin(), m.end());
+        }
+        if ((rc = dalloc(&h->d_subpix_masks, masks.size())) != FID_OK) {
+            fid_destroy(h);
+            return rc;
+        }
+        CK(cudaMemcpy(h->d_subpix_masks, masks.data(), masks.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    if ((rc = dalloc(&h->d_override_ids, 1024)) != FID_OK || (rc = dalloc(&h->d_override_lens, 1024)) != FID_OK || (rc = dalloc(&h->d_pose_ids, 4096)) != FID_OK ||
+        (rc = dalloc(&h->d_pose_corners, 4096 * 8)) != FID_OK || (rc = dalloc(&h->d_pose_out, 4096)) != FID_OK) {
+        fid_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return FID_OK;
+}
+
+extern "C" int fid_destroy(fid_detector* h) {
+    if (!h) return FID_ERR_INVALID_ARG;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < 2; i++) free_slot(h->slot[i]);
+    void* ptrs[] = {h->d_subpix_masks, h->d_override_ids, h->d_override_lens, h->d_pose_ids, h->d_pose_corners, h->d_pose_out};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    delete h;
+    return FID_OK;
+}
+
+extern "C" int fid_set_params(fid_detector* h, const fid_params* params) {
+    if (!h || !params) return FID_ERR_INVALID_ARG;
+    DevParams P;
+    const int rc = make_dev_params(*params, &P);
+    if (rc != FID_OK) return rc;
+    h->params = *params;
+    h->P = P;
+    return FID_OK;
+}
+
+static Camera make_camera(const fid_camera* c) {
+    Camera cam{};
+    if (c) {
+        cam.fx = c->K[0];
+        cam.fy = c->K[4];
+        cam.cx = c->K[2];
+        cam.cy = c->K[5];
+        cam.k1 = c->D[0];
+        cam.k2 = c->D[1];
+        cam.p1 = c->D[2];
+        cam.p2 = c->D[3];
+        cam.k3 = c->D[4];
+    }
+    return cam;
+}
+
+// Enqueue the whole pipeline for `nf` frames resident in s.d_bgr (geometry g) on h->stream.
+static int enqueue_pipeline(fid_detector* h, Slot& s, int nf, const FrameGeom& g, const uint8_t* d_bgr, const fid_camera* cam, double fiducial_len, int n_override,
+                            int stop_after /* -1 = all */) {
+    cudaStream_t st = h->stream;
+    const DevParams& P = h->P;
+    const int W = g.W, H = g.H;
+    int launches = 0;
+    CK(cudaMemsetAsync(s.d_counters, 0, sizeof(Counters), st));
+    CK(cudaMemsetAsync(s.d_nraw, 0, sizeof(unsigned int) * nf, st));
+    CK(cudaEventRecord(s.ev[ST_THRESH], st));
+    {  // threshold
+        ThreshArgs a{};
+        a.bgr = d_bgr;
+        a.gray = s.d_gray;
+        a.bits = s.d_bits;
+        a.g = g;
+        a.n_scales = P.n_scales;
+        a.r_max = r_max_of(P);
+        a.thresh_c = P.thresh_c;
+        for (int i = 0; i < P.n_scales; i++) a.win[i] = P.win[i];
+        dim3 grid((W + THR_TW - 1) / THR_TW, (H + THR_TH - 1) / THR_TH, nf);
+        k_threshold<<<grid, THR_THREADS, thresh_smem(a.r_max), st>>>(a);
+        launches++;
+    }
+    CK(cudaEventRecord(s.ev[ST_MASKS], st));
+    if (stop_after == ST_THRESH) return FID_OK;
+    {  // masks + starts
+        MaskArgs a{};
+        a.bits = s.d_bits;
+        a.mask = s.d_mask;
+        a.starts = s.d_starts;
+        a.counters = s.d_counters;
+        a.max_starts = h->max_starts;
+        a.g = g;
+        a.n_scales = P.n_scales;
+        a.n_frames = nf;
+        const long long total = (long long)nf * P.n_scales * H * g.wpr;
+        k_masks_starts<<<(unsigned int)((total + 255) / 256), 256, 0, st>>>(a);
+        launches++;
+    }
+    CK(cudaEventRecord(s.ev[ST_WALK], st));
+    const int mx = W > H ? W : H;
+    const int min_len = (int)(P.min_perimeter_rate * mx), max_len = (int)(P.max_perimeter_rate * mx);
+    {  // walk
+        WalkArgs a{};
+        a.mask = s.d_mask;
+        a.starts = s.d_starts;
+        a.chains = s.d_chains;
+        a.counters = s.d_counters;
+        a.max_starts = h->max_starts;
+        a.max_chains = h->max_chains;
+        a.max_points = h->max_points;
+        a.g = g;
+        a.min_len = min_len;
+        a.max_len = max_len;
+        k_walk<<<h->sm_count * 8, 256, 0, st>>>(a);
+        launches++;
+    }
+    CK(cudaEventRecord(s.ev[ST_EMIT], st));
+    {  // emit
+        EmitArgs a{};
+        a.mask = s.d_mask;
+        a.chains = s.d_chains;
+        a.points = s.d_points;
+        a.counters = s.d_counters;
+        a.max_chains = h->max_chains;
+        a.g = g;
+        k_emit<<<h->sm_count * 4, 128, 0, st>>>(a);
+        launches++;
+    }
+    CK(cudaEventRecord(s.ev[ST_APPROX], st));
+    {  // approx
+        ApproxArgs a{};
+        a.chains = s.d_chains;
+        a.points = s.d_points;
+        a.counters = s.d_counters;
+        a.raw = s.d_raw;
+        a.n_raw = s.d_nraw;
+        a.counters_rw = s.d_counters;
+        a.max_chains = h->max_chains;
+        a.max_raw = h->max_raw;
+        a.W = W;
+        a.H = H;
+        a.poly_accuracy_rate = P.poly_accuracy_rate;
+        a.min_corner_dist_rate = P.min_corner_dist_rate;
+        a.min_dist_to_border = P.min_dist_to_border;
+        k_approx<<<h->sm_count * 8, APPROX_THREADS, 0, st>>>(a);
+        launches++;
+    }
+    CK(cudaEventRecord(s.ev[ST_GROUP], st));
+    if (stop_after == ST_APPROX) return FID_OK;
+    {  // sort + group
+        GroupArgs a{};
+        a.raw = s.d_raw;
+        a.n_raw = s.d_nraw;
+        a.fs = s.fs;
+        a.n_sel = s.d_nsel;
+        a.n_raw_clamped = s.d_nrawc;
+        a.max_raw = h->max_raw;
+        a.close_wpr = h->close_wpr;
+        a.max_sel = h->max_sel;
+        a.marker_size = P.marker_size;
+        a.border_bits = P.marker_border_bits;
+        a.min_marker_dist_rate = (float)P.min_marker_dist_rate;
+        a.min_group_dist = (float)P.min_group_dist;
+        a.counters = s.d_counters;
+        k_sort_group<<<nf, GROUP_THREADS, 0, st>>>(a);
+        launches++;
+    }
+    CK(cudaEventRecord(s.ev[ST_IDENT], st));
+    {  // identify
+        IdentifyArgs a{};
+        a.gray = s.d_gray;
+        a.gray_frame_stride = g.gray_frame_stride;
+        a.gray_pitch = g.gray_pitch;
+        a.W = W;
+        a.H = H;
+        a.fs = s.fs;
+        a.n_sel = s.d_nsel;
+        a.max_raw = h->max_raw;
+        a.max_sel = h->max_sel;
+        a.P = P;
+        a.cand_id = s.d_cand_id;
+        a.cand_corners = s.d_cand_corners;
+        dim3 grid((h->max_sel + IDENT_WARPS - 1) / IDENT_WARPS, nf);
+        k_identify<<<grid, IDENT_WARPS * 32, ident_smem(P), st>>>(a);
+        launches++;
+    }
+    CK(cudaEventRecord(s.ev[ST_SUBPIX_POSE], st));
+    {  // finish
+        FinishArgs a{};
+        a.gray = s.d_gray;
+        a.gray_frame_stride = g.gray_frame_stride;
+        a.gray_pitch = g.gray_pitch;
+        a.W = W;
+        a.H = H;
+        a.n_sel = s.d_nsel;
+        a.cand_id = s.d_cand_id;
+        a.cand_corners = s.d_cand_corners;
+        a.max_sel = h->max_sel;
+        a.max_markers = h->max_markers;
+        a.P = P;
+        a.subpix_masks = h->d_subpix_masks;
+        a.do_pose = cam ? 1 : 0;
+        a.cam = make_camera(cam);
+        a.fiducial_len = fiducial_len;
+        a.n_override = n_override;
+        a.override_ids = h->d_override_ids;
+        a.override_lens = h->d_override_lens;
+        a.out_count = s.d_out_count;
+        a.out_ids = s.d_out_ids;
+        a.out_corners = s.d_out_corners;
+        a.out_tf = s.d_out_tf;
+        a.counters = s.d_counters;
+        k_finish<<<nf, FINISH_THREADS, 0, st>>>(a);
+        launches++;
+    }
+    CK(cudaEventRecord(s.ev[ST_D2H], st));
+    h->counters[6] += launches;
+    CK(cudaGetLastError());
+    return FID_OK;
+}
+
+static int enqueue_d2h(fid_detector* h, Slot& s, int nf, bool with_pose) {
+    cudaStream_t st = h->stream;
+    const size_t M = (size_t)nf * h->max_markers;
+    CK(cudaMemcpyAsync(s.h_out_count, s.d_out_count, sizeof(int32_t) * nf, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s.h_out_ids, s.d_out_ids, sizeof(int32_t) * M, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s.h_out_corners, s.d_out_corners, sizeof(float) * 8 * M, cudaMemcpyDeviceToHost, st));
+    if (with_pose) CK(cudaMemcpyAsync(s.h_out_tf, s.d_out_tf, sizeof(fid_transform) * M, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s.h_counters, s.d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s.h_nsel, s.d_nsel, sizeof(int) * nf, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(s.h_nrawc, s.d_nrawc, sizeof(int) * nf, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(s.ev[ST_COUNT], st));
+    CK(cudaEventRecord(s.done, st));
+    return FID_OK;
+}
+
+static int collect(fid_detector* h, Slot& s, int nf, int max_markers, int32_t* counts, int32_t* ids, float* corners, fid_transform* tfs, bool first_chunk) {
+    CK(cudaEventSynchronize(s.done));
+    int status = FID_OK;
+    if (s.h_counters->overflow) status = FID_ERR_CAPACITY;
+    for (int f = 0; f < nf; f++) {
+        int n = s.h_out_count[f];
+        if (n > max_markers) {
+            n = max_markers;
+            status = FID_ERR_CAPACITY;
+        }
+        counts[f] = n;
+        if (ids) memcpy(ids + (size_t)f * max_markers, s.h_out_ids + (size_t)f * h->max_markers, sizeof(int32_t) * n);
+        if (corners) memcpy(corners + (size_t)f * max_markers * 8, s.h_out_corners + (size_t)f * h->max_markers * 8, sizeof(float) * 8 * n);
+        if (tfs) memcpy(tfs + (size_t)f * max_markers, s.h_out_tf + (size_t)f * h->max_markers, sizeof(fid_transform) * n);
+    }
+    // statistics
+    float ms = 0;
+    static const int order[] = {ST_THRESH, ST_MASKS, ST_WALK, ST_EMIT, ST_APPROX, ST_GROUP, ST_IDENT, ST_SUBPIX_POSE, ST_D2H, ST_COUNT};
+    if (first_chunk) {
+        for (int i = 0; i < ST_COUNT; i++) h->stage_ms[i] = 0;
+        for (int i = 0; i < 6; i++) h->counters[i] = 0;
+    }
+    for (int i = 0; i + 1 < (int)(sizeof(order) / sizeof(order[0])); i++) {
+        if (cudaEventElapsedTime(&ms, s.ev[order[i]], s.ev[order[i + 1]]) == cudaSuccess) {
+            const int dst = order[i] == ST_D2H ? ST_D2H : order[i];
+            h->stage_ms[dst] += ms;
+        } else {
+            cudaGetLastError();
+        }
+    }
+    h->counters[0] += s.h_counters->n_starts;
+    h->counters[1] += s.h_counters->n_chains;
+    h->counters[2] += s.h_counters->n_points;
+    for (int f = 0; f < nf; f++) {
+        h->counters[3] += s.h_nrawc[f];
+        h->counters[4] += s.h_nsel[f];
+        h->counters[5] += s.h_out_count[f];
+    }
+    return status;
+}
+
+static int upload_overrides(fid_detector* h, int n_override, const int32_t* ids, const double* lens) {
+    if (n_override < 0 || n_override > 1024 || (n_override > 0 && (!ids || !lens))) return FID_ERR_INVALID_ARG;
+    if (n_override > 0) {
+        CK(cudaMemcpyAsync(h->d_override_ids, ids, sizeof(int32_t) * n_override, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->d_override_lens, lens, sizeof(double) * n_override, cudaMemcpyHostToDevice, h->stream));
+    }
+    return FID_OK;
+}
+
+extern "C" int fid_detect_pose_batch(fid_detector* h, int n_frames, const uint8_t* bgr, int bgr_on_device, int width, int height, size_t row_stride, size_t frame_stride,
+                                     const fid_camera* cam, double fiducial_len, int n_override, const int32_t* override_ids, const double* override_lens,
+                                     int max_markers, int32_t* counts, int32_t* ids, float* corners, fid_transform* transforms) {
+    if (!h || !bgr || !counts || n_frames < 0 || width < 16 || height < 16 || width > h->max_w || height > h->max_h || max_markers < 0) return FID_ERR_INVALID_ARG;
+    if (row_stride < (size_t)width * 3 || frame_stride < row_stride * (size_t)height) return FID_ERR_INVALID_ARG;
+    if (cam && !(fiducial_len > 0)) return FID_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    int rc = upload_overrides(h, n_override, override_ids, override_lens);
+    if (rc != FID_OK) return rc;
+    h->last_w = width;
+    h->last_h = height;
+    int status = FID_OK;
+    const int B = h->max_batch;
+    const int n_chunks = (n_frames + B - 1) / B;
+    h->counters[6] = 0;
+    h->stage_ms[ST_H2D] = 0;
+    // software pipeline over chunks: copy(c+1) overlaps compute(c); two slots
+    for (int c = 0; c <= n_chunks; c++) {
+        if (c < n_chunks) {
+            Slot& s = h->slot[c & 1];
+            const int nf = std::min(B, n_frames - c * B);
+            const uint8_t* src = bgr + (size_t)c * B * frame_stride;
+            const uint8_t* d_in;
+            FrameGeom g;
+            if (bgr_on_device) {
+                d_in = src;
+                g = make_geom(h, width, height, row_stride, frame_stride);
+            } else {
+                // slot reuse: its previous results must have been collected (done below) before overwrite
+                if (row_stride == (size_t)width * 3 && frame_stride == row_stride * height) {
+                    CK(cudaMemcpyAsync(s.d_bgr, src, (size_t)nf * frame_stride, cudaMemcpyHostToDevice, h->copy_stream));
+                } else {
+                    for (int f = 0; f < nf; f++)
+                        CK(cudaMemcpy2DAsync(s.d_bgr + (size_t)f * width * 3 * height, (size_t)width * 3, src + (size_t)f * frame_stride, row_stride, (size_t)width * 3, height,
+                                             cudaMemcpyHostToDevice, h->copy_stream));
+                }
+                CK(cudaEventRecord(s.copied, h->copy_stream));
+                CK(cudaStreamWaitEvent(h->stream, s.copied, 0));
+                d_in = s.d_bgr;
+                g = make_geom(h, width, height, (size_t)width * 3, (size_t)width * 3 * height);
+            }
+            rc = enqueue_pipeline(h, s, nf, g, d_in, cam, fiducial_len, n_override, -1);
+            if (rc != FID_OK) return rc;
+            rc = enqueue_d2h(h, s, nf, cam != nullptr);
+            if (rc != FID_OK) return rc;
+            h->last_frames = nf;
+        }
+        if (c > 0) {
+            const int pc = c - 1;
+            Slot& s = h->slot[pc & 1];
+            const int nf = std::min(B, n_frames - pc * B);
+            rc = collect(h, s, nf, max_markers, counts + (size_t)pc * B, ids ? ids + (size_t)pc * B * max_markers : nullptr,
+                         corners ? corners + (size_t)pc * B * max_markers * 8 : nullptr, (transforms && cam) ? transforms + (size_t)pc * B * max_markers : nullptr, pc == 0);
+            if (rc != FID_OK) status = rc;
+        }
+    }
+    return status;
+}
+
+extern "C" int fid_detect(fid_detector* h, const uint8_t* bgr, int width, int height, size_t stride, int max_markers, int* n, int32_t* ids, float* corners) {
+    if (!n) return FID_ERR_INVALID_ARG;
+    int32_t count = 0;
+    const int rc = fid_detect_pose_batch(h, 1, bgr, 0, width, height, stride, stride * (size_t)height, nullptr, 0.0, 0, nullptr, nullptr, max_markers, &count, ids, corners, nullptr);
+    *n = count;
+    return rc;
+}
+
+extern "C" int fid_pose(fid_detector* h, int n, const int32_t* ids, const float* corners, const fid_camera* cam, double fiducial_len, int n_override,
+                        const int32_t* override_ids, const double* override_lens, fid_transform* out) {
+    if (!h || n < 0 || n > 4096 || !cam || !(fiducial_len > 0) || (n > 0 && (!ids || !corners || !out))) return FID_ERR_INVALID_ARG;
+    if (n == 0) return FID_OK;
+    CK(cudaSetDevice(h->device));
+    int rc = upload_overrides(h, n_override, override_ids, override_lens);
+    if (rc != FID_OK) return rc;
+    CK(cudaMemcpyAsync(h->d_pose_ids, ids, sizeof(int32_t) * n, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(h->d_pose_corners, corners, sizeof(float) * 8 * n, cudaMemcpyHostToDevice, h->stream));
+    PoseArgs a{};
+    a.n = n;
+    a.ids = h->d_pose_ids;
+    a.corners = h->d_pose_corners;
+    a.cam = make_camera(cam);
+    a.fiducial_len = fiducial_len;
+    a.n_override = n_override;
+    a.override_ids = h->d_override_ids;
+    a.override_lens = h->d_override_lens;
+    a.out = h->d_pose_out;
+    k_pose<<<(n + 63) / 64, 64, 0, h->stream>>>(a);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, h->d_pose_out, sizeof(fid_transform) * n, cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return FID_OK;
+}
+
+extern "C" int fid_host_alloc(size_t bytes, void** out) {
+    if (!out) return FID_ERR_INVALID_ARG;
+    if (cudaMallocHost(out, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return FID_ERR_NO_MEMORY;
+    }
+    return FID_OK;
+}
+extern "C" int fid_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+    return FID_OK;
+}
+extern "C" int fid_device_alloc(fid_detector* h, size_t bytes, void** out) {
+    if (!h || !out) return FID_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    if (cudaMalloc(out, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return FID_ERR_NO_MEMORY;
+    }
+    return FID_OK;
+}
+extern "C" int fid_device_free(fid_detector* h, void* p) {
+    if (!h) return FID_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    if (p) cudaFree(p);
+    return FID_OK;
+}
+extern "C" int fid_memcpy_h2d(fid_detector* h, void* dst_device, const void* src_host, size_t bytes) {
+    if (!h || !dst_device || !src_host) return FID_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpy(dst_device, src_host, bytes, cudaMemcpyHostToDevice));
+    return FID_OK;
+}
+
+extern "C" int fid_debug_threshold(fid_detector* h, const uint8_t* bgr, int width, int height, size_t stride, uint8_t* gray, uint8_t* planes, int* n_scales) {
+    if (!h || !bgr || width < 16 || height < 16 || width > h->max_w || height > h->max_h || stride < (size_t)width * 3) return FID_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    Slot& s = h->slot[0];
+    CK(cudaMemcpy2DAsync(s.d_bgr, (size_t)width * 3, bgr, stride, (size_t)width * 3, height, cudaMemcpyHostToDevice, h->stream));
+    const FrameGeom g = make_geom(h, width, height, (size_t)width * 3, (size_t)width * 3 * height);
+    const int rc = enqueue_pipeline(h, s, 1, g, s.d_bgr, nullptr, 0.0, 0, ST_THRESH);
+    if (rc != FID_OK) return rc;
+    CK(cudaStreamSynchronize(h->stream));
+    if (gray) CK(cudaMemcpy2D(gray, width, s.d_gray, g.gray_pitch, width, height, cudaMemcpyDeviceToHost));
+    if (planes) {
+        std::vector<uint32_t> bits((size_t)h->P.n_scales * g.wpr * height);
+        CK(cudaMemcpy(bits.data(), s.d_bits, bits.size() * 4, cudaMemcpyDeviceToHost));
+        for (int sc = 0; sc < h->P.n_scales; sc++)
+            for (int y = 0; y < height; y++)
+                for (int x = 0; x < width; x++)
+                    planes[((size_t)sc * height + y) * width + x] = (bits[(size_t)sc * g.bits_scale_stride + (size_t)y * g.wpr + (x >> 5)] >> (x & 31)) & 1u;
+    }
+    if (n_scales) *n_scales = h->P.n_scales;
+    return FID_OK;
+}
+
+extern "C" int fid_debug_candidates(fid_detector* h, int max_candidates, int* n, int32_t* quads, int32_t* scale, int32_t* contour_len) {
+    if (!h || !n) return FID_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    Slot& s = h->slot[0];
+    unsigned int cnt = 0;
+    CK(cudaMemcpy(&cnt, s.d_nraw, sizeof(cnt), cudaMemcpyDeviceToHost));
+    cnt = std::min<unsigned int>(cnt, (unsigned int)h->max_raw);
+    std::vector<RawQuad> raw(cnt);
+    if (cnt) CK(cudaMemcpy(raw.data(), s.d_raw, sizeof(RawQuad) * cnt, cudaMemcpyDeviceToHost));
+    std::sort(raw.begin(), raw.end(), [](const RawQuad& a, const RawQuad& b) { return a.order_hi != b.order_hi ? a.order_hi < b.order_hi : a.order_lo < b.order_lo; });
+    *n = (int)cnt;
+    if ((int)cnt > max_candidates) return FID_ERR_CAPACITY;
+    for (unsigned int i = 0; i < cnt; i++) {
+        for (int k = 0; k < 4; k++) {
+            if (quads) {
+                quads[i * 8 + 2 * k] = raw[i].x[k];
+                quads[i * 8 + 2 * k + 1] = raw[i].y[k];
+            }
+        }
+        if (scale) scale[i] = (int)raw[i].order_hi;
+        if (contour_len) contour_len[i] = raw[i].n_contour;
+    }
+    return FID_OK;
+}
+
+extern "C" int fid_last_stage_ms(fid_detector* h, float* ms, int max_stages, int* n_stages) {
+    if (!h || !ms) return FID_ERR_INVALID_ARG;
+    const int n = std::min(max_stages, (int)ST_COUNT);
+    for (int i = 0; i < n; i++) ms[i] = h->stage_ms[i];
+    if (n_stages) *n_stages = ST_COUNT;
+    return FID_OK;
+}
+
+extern "C" int fid_last_counters(fid_detector* h, int64_t* counters, int max_counters, int* n_counters) {
+    if (!h || !counters) return FID_ERR_INVALID_ARG;
+    const int n = std::min(max_counters, 7);
+    for (int i = 0; i < n; i++) counters[i] = h->counters[i];
+    if (n_counters) *n_counters = 7;
+    return FID_OK;
+}

@@ -1,0 +1,422 @@
+// C-ABI of the fiducial_slam map update (include/fiducials_b200.h, "Map" section).
+// One CUDA thread per map instance runs the reference's sequential fold (slam.cuh); a whole
+// sequence of messages can be replayed in a single launch.  The merge step for multi-GPU runs is
+// new and deterministic: tables are folded in rank order, ids ascending.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/fiducials_b200.h"
+#include "slam.cuh"
+
+using namespace fid;
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            fprintf(stderr, "[fiducials_b200] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return FID_ERR_CUDA;                                                                       \
+        }                                                                                              \
+    } while (0)
+
+struct fid_map {
+    int device = 0;
+    fid_map_params p{};
+    cudaStream_t stream = nullptr;
+    MapState* d_state = nullptr;      // [n_instances]
+    MapEntry* d_entries = nullptr;    // [n_instances][cap]
+    uint32_t* d_links = nullptr;      // [n_instances][cap][ceil(cap/32)]
+    fid_map_record* d_export = nullptr;  // [n_instances][cap]
+    Obs* d_obs = nullptr;
+    size_t obs_cap = 0;
+    int32_t* d_offsets = nullptr;
+    size_t off_cap = 0;
+    RobotPose* d_robot = nullptr;
+    size_t robot_cap = 0;
+    Twv* d_tf = nullptr;  // [2]: baseCam, camBase
+    fid_map_record* d_merge_in = nullptr;
+    size_t merge_cap = 0;
+};
+
+struct SeqArgs {
+    MapState* state;
+    MapEntry* entries;
+    uint32_t* links;
+    int cap, links_wpr;
+    int n_instances, n_msgs;
+    const int32_t* offsets;  // [n_instances][n_msgs+1]
+    const Obs* obs;
+    const Twv* tf;  // [0] baseCam [1] camBase
+    int have_base_cam, have_cam_base;
+    double weighting_scale, systematic_error;
+    int use_area;
+    RobotPose* robot;  // [n_instances][n_msgs] or null
+};
+
+__global__ void k_map_sequence(const SeqArgs a) {
+    const int inst = blockIdx.x * blockDim.x + threadIdx.x;
+    if (inst >= a.n_instances) return;
+    MapState st = a.state[inst];
+    MapEntry* e = a.entries + (size_t)inst * a.cap;
+    uint32_t* links = a.links ? a.links + (size_t)inst * a.cap * a.links_wpr : nullptr;
+    const int32_t* off = a.offsets + (size_t)inst * (a.n_msgs + 1);
+    for (int k = 0; k < a.n_msgs; k++) {
+        RobotPose rp;
+        map_update(st, e, links, a.obs + off[k], off[k + 1] - off[k], a.have_base_cam ? &a.tf[0] : nullptr, a.have_cam_base ? &a.tf[1] : nullptr, a.weighting_scale,
+                   a.use_area, a.systematic_error, &rp);
+        if (a.robot) a.robot[(size_t)inst * a.n_msgs + k] = rp;
+    }
+    a.state[inst] = st;
+}
+
+// export: slot i of the table = i-th fiducial in ascending id order; unused slots id = -1
+__global__ void k_map_export(const MapState* state, const MapEntry* entries, int cap, int inst, fid_map_record* table) {
+    const MapState st = state[inst];
+    const MapEntry* e = entries + (size_t)inst * cap;
+    for (int i = threadIdx.x; i < cap; i += blockDim.x) {
+        fid_map_record r;
+        r.fiducial_id = -1;
+        r.num_obs = 0;
+        r.t[0] = r.t[1] = r.t[2] = 0;
+        r.q[0] = r.q[1] = r.q[2] = 0;
+        r.q[3] = 1;
+        r.variance = 0;
+        if (i < st.n) {
+            int rank = 0;
+            for (int j = 0; j < st.n; j++) rank += e[j].id < e[i].id ? 1 : 0;
+            r.fiducial_id = e[i].id;
+            r.num_obs = e[i].num_obs;
+            r.t[0] = e[i].pose.t[0];
+            r.t[1] = e[i].pose.t[1];
+            r.t[2] = e[i].pose.t[2];
+            m_to_q(e[i].pose.R, r.q);
+            r.variance = e[i].pose.var;
+            table[rank] = r;
+        }
+        if (i >= st.n) table[i] = r;
+    }
+}
+
+// merge: single thread (tables are tiny); replaces the instance's content with the merged map
+__global__ void k_map_merge(MapState* state, MapEntry* entries, int cap, int inst, int n_tables, const fid_map_record* tables) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    MapState st = state[inst];
+    MapEntry* e = entries + (size_t)inst * cap;
+    st.n = 0;
+    for (int t = 0; t < n_tables; t++) {
+        const fid_map_record* tab = tables + (size_t)t * cap;
+        for (int i = 0; i < cap; i++) {  // exported tables are id-ascending
+            if (tab[i].fiducial_id < 0) continue;
+            Twv pose;
+            q_to_m(tab[i].q, pose.R);
+            pose.t[0] = tab[i].t[0];
+            pose.t[1] = tab[i].t[1];
+            pose.t[2] = tab[i].t[2];
+            pose.var = tab[i].variance;
+            const int slot = map_find(st, e, tab[i].fiducial_id);
+            if (slot < 0) {
+                if (st.n >= cap) {
+                    st.overflow = 1;
+                    continue;
+                }
+                e[st.n].id = tab[i].fiducial_id;
+                e[st.n].num_obs = tab[i].num_obs;
+                e[st.n].pose = pose;
+                st.n++;
+            } else {
+                e[slot].num_obs += tab[i].num_obs;
+                if (e[slot].pose.var == 0.0) {
+                    // pinned entry wins
+                } else if (pose.var == 0.0) {
+                    e[slot].pose = pose;
+                } else {
+                    twv_update(e[slot].pose, pose);
+                }
+            }
+        }
+    }
+    state[inst] = st;
+}
+
+extern "C" int fid_map_default_params(fid_map_params* p) {
+    if (!p) return FID_ERR_INVALID_ARG;
+    p->weighting_scale = 1e9;
+    p->use_fiducial_area_as_weight = 0;
+    p->read_only_map = 0;
+    p->systematic_error = 0.01;
+    p->max_fiducials = 512;
+    p->n_instances = 1;
+    return FID_OK;
+}
+
+static int reset_state(fid_map* m, int inst_lo, int inst_hi) {
+    std::vector<MapState> st(inst_hi - inst_lo);
+    for (auto& s : st) {
+        memset(&s, 0, sizeof(s));
+        s.capacity = m->p.max_fiducials;
+        s.origin_fid = -1;
+        s.read_only = m->p.read_only_map;
+    }
+    CK(cudaMemcpy(m->d_state + inst_lo, st.data(), sizeof(MapState) * st.size(), cudaMemcpyHostToDevice));
+    const size_t wpr = (m->p.max_fiducials + 31) / 32;
+    CK(cudaMemset(m->d_links + (size_t)inst_lo * m->p.max_fiducials * wpr, 0, sizeof(uint32_t) * (size_t)(inst_hi - inst_lo) * m->p.max_fiducials * wpr));
+    return FID_OK;
+}
+
+extern "C" int fid_map_create(const fid_map_params* p, int device, fid_map** out) {
+    if (!p || !out || p->max_fiducials < 1 || p->max_fiducials > 65536 || p->n_instances < 1) return FID_ERR_INVALID_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return FID_ERR_NO_DEVICE;
+    }
+    CK(cudaSetDevice(device));
+    fid_map* m = new fid_map();
+    m->device = device;
+    m->p = *p;
+    const size_t cap = p->max_fiducials, ni = p->n_instances, wpr = (cap + 31) / 32;
+    if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess || cudaMalloc((void**)&m->d_state, sizeof(MapState) * ni) != cudaSuccess ||
+        cudaMalloc((void**)&m->d_entries, sizeof(MapEntry) * ni * cap) != cudaSuccess || cudaMalloc((void**)&m->d_links, sizeof(uint32_t) * ni * cap * wpr) != cudaSuccess ||
+        cudaMalloc((void**)&m->d_export, sizeof(fid_map_record) * ni * cap) != cudaSuccess || cudaMalloc((void**)&m->d_tf, sizeof(Twv) * 2) != cudaSuccess) {
+        cudaGetLastError();
+        fid_map_destroy(m);
+        return FID_ERR_NO_MEMORY;
+    }
+    const int rc = reset_state(m, 0, p->n_instances);
+    if (rc != FID_OK) {
+        fid_map_destroy(m);
+        return rc;
+    }
+    *out = m;
+    return FID_OK;
+}
+
+extern "C" int fid_map_destroy(fid_map* m) {
+    if (!m) return FID_ERR_INVALID_ARG;
+    cudaSetDevice(m->device);
+    cudaDeviceSynchronize();
+    void* ptrs[] = {m->d_state, m->d_entries, m->d_links, m->d_export, m->d_obs, m->d_offsets, m->d_robot, m->d_tf, m->d_merge_in};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+    return FID_OK;
+}
+
+extern "C" int fid_map_clear(fid_map* m, int instance) {
+    if (!m || instance < 0 || instance >= m->p.n_instances) return FID_ERR_INVALID_ARG;
+    CK(cudaSetDevice(m->device));
+    // clearCallback (map.cpp:809-817): fiducials.clear(); initialFrameNum = frameNum; originFid = -1
+    MapState st;
+    CK(cudaMemcpy(&st, m->d_state + instance, sizeof(st), cudaMemcpyDeviceToHost));
+    st.n = 0;
+    st.initial_frame_num = st.frame_num;
+    st.origin_fid = -1;
+    st.initializing = 0;
+    st.overflow = 0;
+    CK(cudaMemcpy(m->d_state + instance, &st, sizeof(st), cudaMemcpyHostToDevice));
+    return FID_OK;
+}
+
+static void tf_to_twv(const fid_tf& t, Twv* o) {
+    q_to_m(t.q, o->R);
+    o->t[0] = t.t[0];
+    o->t[1] = t.t[1];
+    o->t[2] = t.t[2];
+    o->var = 0.0;
+}
+
+extern "C" int fid_map_load(fid_map* m, int instance, int n, const fid_map_file_entry* entries) {
+    if (!m || instance < 0 || instance >= m->p.n_instances || n < 0 || (n > 0 && !entries)) return FID_ERR_INVALID_ARG;
+    CK(cudaSetDevice(m->device));
+    MapState st;
+    CK(cudaMemcpy(&st, m->d_state + instance, sizeof(st), cudaMemcpyDeviceToHost));
+    std::vector<MapEntry> e(st.capacity);
+    if (st.n) CK(cudaMemcpy(e.data(), m->d_entries + (size_t)instance * st.capacity, sizeof(MapEntry) * st.n, cudaMemcpyDeviceToHost));
+    const double d2r = 3.14159265358979323846 / 180.0;
+    for (int i = 0; i < n; i++) {
+        // loadMap (map.cpp:595-606): tf2::Quaternion::setRPY(deg2rad(roll), deg2rad(pitch), deg2rad(yaw))
+        const double hr = entries[i].roll_deg * d2r * 0.5, hp = entries[i].pitch_deg * d2r * 0.5, hy = entries[i].yaw_deg * d2r * 0.5;
+        const double cy = cos(hy), sy = sin(hy), cp = cos(hp), sp = sin(hp), cr = cos(hr), sr = sin(hr);
+        const double q[4] = {sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy, cr * cp * cy + sr * sp * sy};
+        int slot = -1;
+        for (int j = 0; j < st.n; j++)
+            if (e[j].id == entries[i].fiducial_id) slot = j;
+        if (slot < 0) {
+            if (st.n >= st.capacity) return FID_ERR_CAPACITY;
+            slot = st.n++;
+        }
+        e[slot].id = entries[i].fiducial_id;
+        e[slot].num_obs = entries[i].num_obs;
+        q_to_m(q, e[slot].pose.R);
+        e[slot].pose.t[0] = entries[i].x;
+        e[slot].pose.t[1] = entries[i].y;
+        e[slot].pose.t[2] = entries[i].z;
+        e[slot].pose.var = entries[i].variance;
+    }
+    if (st.n) CK(cudaMemcpy(m->d_entries + (size_t)instance * st.capacity, e.data(), sizeof(MapEntry) * st.n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(m->d_state + instance, &st, sizeof(st), cudaMemcpyHostToDevice));
+    return FID_OK;
+}
+
+template <class T>
+static int ensure(T** p, size_t* cap, size_t need) {
+    if (need <= *cap) return FID_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    const size_t n = std::max<size_t>(need, 1024);
+    if (cudaMalloc((void**)p, sizeof(T) * n) != cudaSuccess) {
+        cudaGetLastError();
+        return FID_ERR_NO_MEMORY;
+    }
+    *cap = n;
+    return FID_OK;
+}
+
+static int run_sequence(fid_map* m, int inst_lo, int n_inst, int n_msgs, const int32_t* offsets, const fid_transform* obs, const fid_tf* T_baseCam,
+                        const fid_tf* T_camBase, fid_robot_pose* robot) {
+    CK(cudaSetDevice(m->device));
+    const size_t n_off = (size_t)n_inst * (n_msgs + 1);
+    size_t total_obs = 0;
+    for (size_t i = 0; i < n_off; i++) total_obs = std::max<size_t>(total_obs, (size_t)offsets[i]);
+    int rc;
+    if ((rc = ensure(&m->d_obs, &m->obs_cap, total_obs + 1)) != FID_OK || (rc = ensure(&m->d_offsets, &m->off_cap, n_off)) != FID_OK ||
+        (rc = ensure(&m->d_robot, &m->robot_cap, (size_t)n_inst * n_msgs + 1)) != FID_OK)
+        return rc;
+    std::vector<Obs> ho(total_obs);
+    for (size_t i = 0; i < total_obs; i++) {
+        ho[i].id = obs[i].fiducial_id;
+        ho[i].pad = 0;
+        for (int k = 0; k < 3; k++) ho[i].t[k] = obs[i].translation[k];
+        for (int k = 0; k < 4; k++) ho[i].q[k] = obs[i].rotation[k];
+        ho[i].object_error = obs[i].object_error;
+        ho[i].area = obs[i].fiducial_area;
+    }
+    if (total_obs) CK(cudaMemcpyAsync(m->d_obs, ho.data(), sizeof(Obs) * total_obs, cudaMemcpyHostToDevice, m->stream));
+    CK(cudaMemcpyAsync(m->d_offsets, offsets, sizeof(int32_t) * n_off, cudaMemcpyHostToDevice, m->stream));
+    Twv tf[2];
+    memset(tf, 0, sizeof(tf));
+    if (T_baseCam) tf_to_twv(*T_baseCam, &tf[0]);
+    if (T_camBase) tf_to_twv(*T_camBase, &tf[1]);
+    CK(cudaMemcpyAsync(m->d_tf, tf, sizeof(tf), cudaMemcpyHostToDevice, m->stream));
+    SeqArgs a{};
+    const int cap = m->p.max_fiducials;
+    a.state = m->d_state + inst_lo;
+    a.entries = m->d_entries + (size_t)inst_lo * cap;
+    a.links_wpr = (cap + 31) / 32;
+    a.links = m->d_links + (size_t)inst_lo * cap * a.links_wpr;
+    a.cap = cap;
+    a.n_instances = n_inst;
+    a.n_msgs = n_msgs;
+    a.offsets = m->d_offsets;
+    a.obs = m->d_obs;
+    a.tf = m->d_tf;
+    a.have_base_cam = T_baseCam ? 1 : 0;
+    a.have_cam_base = T_camBase ? 1 : 0;
+    a.weighting_scale = m->p.weighting_scale;
+    a.systematic_error = m->p.systematic_error;
+    a.use_area = m->p.use_fiducial_area_as_weight;
+    a.robot = m->d_robot;
+    k_map_sequence<<<(n_inst + 31) / 32, 32, 0, m->stream>>>(a);
+    CK(cudaGetLastError());
+    std::vector<RobotPose> hr((size_t)n_inst * n_msgs);
+    CK(cudaMemcpyAsync(hr.data(), m->d_robot, sizeof(RobotPose) * hr.size(), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    if (robot)
+        for (size_t i = 0; i < hr.size(); i++) {
+            robot[i].valid = hr[i].valid;
+            robot[i].n_estimates = hr[i].n_estimates;
+            for (int k = 0; k < 3; k++) robot[i].t[k] = hr[i].t[k];
+            for (int k = 0; k < 4; k++) robot[i].q[k] = hr[i].q[k];
+            robot[i].variance = hr[i].var;
+        }
+    return FID_OK;
+}
+
+extern "C" int fid_map_update(fid_map* m, int instance, int n_obs, const fid_transform* obs, const fid_tf* T_baseCam, const fid_tf* T_camBase, fid_robot_pose* robot) {
+    if (!m || instance < 0 || instance >= m->p.n_instances || n_obs < 0 || n_obs > FID_MAX_OBS || (n_obs > 0 && !obs)) return FID_ERR_INVALID_ARG;
+    const int32_t off[2] = {0, n_obs};
+    return run_sequence(m, instance, 1, 1, off, obs, T_baseCam, T_camBase, robot);
+}
+
+extern "C" int fid_map_update_sequence(fid_map* m, int n_msgs, const int32_t* offsets, const fid_transform* obs, const fid_tf* T_baseCam, const fid_tf* T_camBase,
+                                       fid_robot_pose* robot) {
+    if (!m || n_msgs < 1 || !offsets) return FID_ERR_INVALID_ARG;
+    const size_t n_off = (size_t)m->p.n_instances * (n_msgs + 1);
+    for (size_t i = 0; i + 1 < n_off; i++) {
+        if ((i + 1) % (n_msgs + 1) == 0) continue;
+        const int d = offsets[i + 1] - offsets[i];
+        if (d < 0 || d > FID_MAX_OBS) return FID_ERR_INVALID_ARG;
+    }
+    return run_sequence(m, 0, m->p.n_instances, n_msgs, offsets, obs, T_baseCam, T_camBase, robot);
+}
+
+extern "C" int fid_map_entries(fid_map* m, int instance, int max_entries, int* n, fid_map_entry* entries) {
+    if (!m || instance < 0 || instance >= m->p.n_instances || !n) return FID_ERR_INVALID_ARG;
+    CK(cudaSetDevice(m->device));
+    MapState st;
+    CK(cudaMemcpy(&st, m->d_state + instance, sizeof(st), cudaMemcpyDeviceToHost));
+    std::vector<MapEntry> e(st.n);
+    if (st.n) CK(cudaMemcpy(e.data(), m->d_entries + (size_t)instance * st.capacity, sizeof(MapEntry) * st.n, cudaMemcpyDeviceToHost));
+    std::sort(e.begin(), e.end(), [](const MapEntry& a, const MapEntry& b) { return a.id < b.id; });
+    *n = st.n;
+    if (st.n > max_entries) return FID_ERR_CAPACITY;
+    for (int i = 0; i < st.n && entries; i++) {
+        // publishMap (map.cpp:629-654): origin + getRPY
+        entries[i].fiducial_id = e[i].id;
+        entries[i].num_obs = e[i].num_obs;
+        entries[i].x = e[i].pose.t[0];
+        entries[i].y = e[i].pose.t[1];
+        entries[i].z = e[i].pose.t[2];
+        get_rpy(e[i].pose.R, &entries[i].rx, &entries[i].ry, &entries[i].rz);
+        entries[i].variance = e[i].pose.var;
+    }
+    return st.overflow ? FID_ERR_CAPACITY : FID_OK;
+}
+
+extern "C" int fid_map_export_device(fid_map* m, int instance, void** device_table, size_t* bytes) {
+    if (!m || instance < 0 || instance >= m->p.n_instances || !device_table || !bytes) return FID_ERR_INVALID_ARG;
+    CK(cudaSetDevice(m->device));
+    fid_map_record* tab = m->d_export + (size_t)instance * m->p.max_fiducials;
+    k_map_export<<<1, 256, 0, m->stream>>>(m->d_state, m->d_entries, m->p.max_fiducials, instance, tab);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(m->stream));
+    *device_table = tab;
+    *bytes = sizeof(fid_map_record) * (size_t)m->p.max_fiducials;
+    return FID_OK;
+}
+
+extern "C" int fid_map_export(fid_map* m, int instance, fid_map_record* table) {
+    if (!table) return FID_ERR_INVALID_ARG;
+    void* d = nullptr;
+    size_t bytes = 0;
+    const int rc = fid_map_export_device(m, instance, &d, &bytes);
+    if (rc != FID_OK) return rc;
+    CK(cudaMemcpy(table, d, bytes, cudaMemcpyDeviceToHost));
+    return FID_OK;
+}
+
+extern "C" int fid_map_merge_device(fid_map* m, int instance, int n_tables, const void* device_tables) {
+    if (!m || instance < 0 || instance >= m->p.n_instances || n_tables < 1 || !device_tables) return FID_ERR_INVALID_ARG;
+    CK(cudaSetDevice(m->device));
+    k_map_merge<<<1, 32, 0, m->stream>>>(m->d_state, m->d_entries, m->p.max_fiducials, instance, n_tables, (const fid_map_record*)device_tables);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(m->stream));
+    return FID_OK;
+}
+
+extern "C" int fid_map_merge(fid_map* m, int instance, int n_tables, const fid_map_record* tables) {
+    if (!m || n_tables < 1 || !tables) return FID_ERR_INVALID_ARG;
+    CK(cudaSetDevice(m->device));
+    const size_t need = (size_t)n_tables * m->p.max_fiducials;
+    const int rc = ensure(&m->d_merge_in, &m->merge_cap, need);
+    if (rc != FID_OK) return rc;
+    CK(cudaMemcpy(m->d_merge_in, tables, sizeof(fid_map_record) * need, cudaMemcpyHostToDevice));
+    return fid_map_merge_device(m, instance, n_tables, m->d_merge_in);
+}

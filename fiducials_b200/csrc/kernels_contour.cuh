@@ -1,0 +1,439 @@
+// CUDA kernels, front half of the per-frame pipeline (sm_100a):
+//   k_threshold     BGR8 -> gray + n_scales bit-packed adaptive-threshold planes   
+//   k_masks_starts  bit planes -> 8-neighbour mask bytes + start-crack queue       (A.3b)
+//   k_walk          one thread per start crack: backwards border walk, canonical test, length
+//   k_emit          one thread per surviving border: ordered contour points
+//   k_approx        one block per contour: approxPolyDP + quad filters             (A.4)
+// All kernels take a batch of frames (blockIdx.z / queue entries carry the frame index) so that a
+// launch has enough independent work to fill 148 SMs.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "approx_quad.cuh"
+#include "common.cuh"
+#include "contour_walk.cuh"
+#include "quad_group.cuh"
+
+namespace fid {
+
+// ---- batch-wide work queues ------------------------------------------------------------------------
+struct Counters {
+    unsigned int n_starts;
+    unsigned int n_chains;
+    unsigned int n_points;
+    unsigned int overflow;  // bit0 starts, bit1 chains, bit2 points, bit3 raw quads, bit4 selected
+    unsigned int walk_steps_lo, walk_steps_hi;  // optional statistics
+    unsigned int pad[2];
+};
+
+struct StartRec {
+    uint32_t xy;    // x | y << 16
+    uint32_t meta;  // frame << 8 | scale << 1 | is_right
+};
+
+struct ChainRec {
+    uint32_t xy;
+    uint32_t meta;
+    uint32_t n;
+    uint32_t offset;  // into the batch point buffer
+};
+
+struct FrameGeom {
+    int W, H;
+    int wpr;            // 32-bit words per bit-plane row
+    int gray_pitch;     // bytes
+    int mask_pitch;     // bytes (== W rounded up to 32)
+    size_t bgr_row_stride, bgr_frame_stride;
+    size_t gray_frame_stride;
+    size_t bits_scale_stride, bits_frame_stride;  // in words
+    size_t mask_scale_stride, mask_frame_stride;  // in bytes
+};
+
+// ---------------------------------------------------------------------------------------------------
+// k_threshold: one CTA per 128x64 output tile.  The tile plus a halo of r_max pixels is converted to
+// gray once (15-bit fixed point, cv::cvtColor BGR2GRAY), a summed-area table of the region is built
+// in shared memory, and every scale's box sum is 4 table look-ups.  BINARY_INV with the mean
+// rounded half-to-even and no ties for odd windows reduces to the integer test
+//     2*S >= (2*g + 2*C - 1) * k^2          
+// A warp covers 32 consecutive pixels, so __ballot_sync yields the packed plane word directly.
+// Algorithmic HBM traffic per frame: 3*W*H read + W*H (gray) + n_scales*W*H/8 written.
+// ---------------------------------------------------------------------------------------------------
+#define THR_TW 128
+#define THR_TH 64
+#define THR_THREADS 256
+
+struct ThreshArgs {
+    const uint8_t* bgr;
+    uint8_t* gray;
+    uint32_t* bits;
+    FrameGeom g;
+    int n_scales;
+    int r_max;
+    int thresh_c;
+    int win[FID_MAX_SCALES];
+};
+
+__global__ void __launch_bounds__(THR_THREADS, 2) k_threshold(const ThreshArgs a) {
+    extern __shared__ uint32_t smem_u32[];
+    const int R = a.r_max;
+    const int RW = THR_TW + 2 * R, RH = THR_TH + 2 * R;
+    const int SP = RW + 1;                                // SAT pitch (with a zero first row/column)
+    uint32_t* sat = smem_u32;                             // (RH+1) x SP
+    uint8_t* tile_gray = (uint8_t*)(sat + (RH + 1) * SP);  // THR_TH x THR_TW
+
+    const int f = blockIdx.z;
+    const int tx0 = blockIdx.x * THR_TW, ty0 = blockIdx.y * THR_TH;
+    const int W = a.g.W, H = a.g.H;
+    const uint8_t* bgr = a.bgr + (size_t)f * a.g.bgr_frame_stride;
+    const int tid = threadIdx.x;
+
+    // zero first row / column
+    for (int i = tid; i < SP; i += THR_THREADS) sat[i] = 0;
+    for (int i = tid; i <= RH; i += THR_THREADS) sat[i * SP] = 0;
+    // A. gray of the region (replicate border)
+    for (int p = tid; p < RW * RH; p += THR_THREADS) {
+        const int ry = p / RW, rx = p - ry * RW;
+        int x = tx0 - R + rx, y = ty0 - R + ry;
+        x = x < 0 ? 0 : (x > W - 1 ? W - 1 : x);
+        y = y < 0 ? 0 : (y > H - 1 ? H - 1 : y);
+        const uint8_t* px = bgr + (size_t)y * a.g.bgr_row_stride + 3 * x;
+        const uint32_t gv = (3735u * px[0] + 19235u * px[1] + 9798u * px[2] + 16384u) >> 15;
+        sat[(ry + 1) * SP + rx + 1] = gv;
+        const int ix = rx - R, iy = ry - R;
+        if (ix >= 0 && ix < THR_TW && iy >= 0 && iy < THR_TH) tile_gray[iy * THR_TW + ix] = (uint8_t)gv;
+    }
+    __syncthreads();
+    // gray plane out (coalesced 4-byte stores)
+    {
+        uint8_t* gout = a.gray + (size_t)f * a.g.gray_frame_stride;
+        for (int p = tid; p < THR_TW * THR_TH / 4; p += THR_THREADS) {
+            const int iy = p / (THR_TW / 4), ix = (p - iy * (THR_TW / 4)) * 4;
+            const int x = tx0 + ix, y = ty0 + iy;
+            if (y < H && x < W) {
+                if (x + 3 < W && (a.g.gray_pitch & 3) == 0) {
+                    *reinterpret_cast<uint32_t*>(gout + (size_t)y * a.g.gray_pitch + x) = *reinterpret_cast<const uint32_t*>(tile_gray + iy * THR_TW + ix);
+                } else {
+                    for (int k = 0; k < 4 && x + k < W; k++) gout[(size_t)y * a.g.gray_pitch + x + k] = tile_gray[iy * THR_TW + ix + k];
+                }
+            }
+        }
+    }
+    // B. row prefix sums: one warp per row, 32-wide shuffle scans with carry
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int ry = warp; ry < RH; ry += THR_THREADS / 32) {
+        uint32_t* row = sat + (ry + 1) * SP + 1;
+        uint32_t carry = 0;
+        for (int c0 = 0; c0 < RW; c0 += 32) {
+            const int c = c0 + lane;
+            uint32_t v = c < RW ? row[c] : 0u;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+                if (lane >= d) v += t;
+            }
+            v += carry;
+            if (c < RW) row[c] = v;
+            carry = __shfl_sync(0xffffffffu, v, 31);
+        }
+    }
+    __syncthreads();
+    // C. column prefix sums: one thread per column
+    for (int c = tid; c < RW; c += THR_THREADS) {
+        uint32_t acc = 0;
+        uint32_t* col = sat + SP + 1 + c;
+        for (int ry = 0; ry < RH; ry++) {
+            acc += col[ry * SP];
+            col[ry * SP] = acc;
+        }
+    }
+    __syncthreads();
+    // D. thresholds: unit = (row, 32-pixel segment)
+    uint32_t* bits = a.bits + (size_t)f * a.g.bits_frame_stride;
+    const int twoC = 2 * a.thresh_c - 1;
+    for (int u = warp; u < THR_TH * (THR_TW / 32); u += THR_THREADS / 32) {
+        const int iy = u / (THR_TW / 32), seg = u - iy * (THR_TW / 32);
+        const int ix = seg * 32 + lane;
+        const int x = tx0 + ix, y = ty0 + iy;
+        if (y >= H || tx0 + seg * 32 >= W) continue;  // warp-uniform
+        const bool valid = x < W;
+        const int g2 = 2 * (int)tile_gray[iy * THR_TW + ix] + twoC;
+        const int cx = ix + R, cy = iy + R;  // region coordinates of the pixel
+        for (int s = 0; s < a.n_scales; s++) {
+            const int k = a.win[s], r = k >> 1;
+            const uint32_t* top = sat + (cy - r) * SP;
+            const uint32_t* bot = sat + (cy + r + 1) * SP;
+            const int S = (int)(bot[cx + r + 1] - bot[cx - r] - top[cx + r + 1] + top[cx - r]);
+            const bool on = valid && (2 * S >= g2 * k * k);
+            const uint32_t word = __ballot_sync(0xffffffffu, on);
+            if (lane == 0) bits[(size_t)s * a.g.bits_scale_stride + (size_t)y * a.g.wpr + (x >> 5)] = word;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_masks_starts: one thread per (frame, scale, row, word).
+// ---------------------------------------------------------------------------------------------------
+struct MaskArgs {
+    const uint32_t* bits;
+    uint8_t* mask;
+    StartRec* starts;
+    Counters* counters;
+    unsigned int max_starts;
+    FrameGeom g;
+    int n_scales;
+    int n_frames;
+};
+
+__global__ void __launch_bounds__(256) k_masks_starts(const MaskArgs a) {
+    const int wpr = a.g.wpr, H = a.g.H, W = a.g.W;
+    const long long total = (long long)a.n_frames * a.n_scales * H * wpr;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    uint32_t L = 0, Rr = 0;
+    int f = 0, s = 0, y = 0, w = 0;
+    if (gid < total) {
+        long long t = gid;
+        w = (int)(t % wpr);
+        t /= wpr;
+        y = (int)(t % H);
+        t /= H;
+        s = (int)(t % a.n_scales);
+        f = (int)(t / a.n_scales);
+        const uint32_t* plane = a.bits + (size_t)f * a.g.bits_frame_stride + (size_t)s * a.g.bits_scale_stride;
+        auto word = [&](int yy, int ww) -> uint32_t { return (yy < 0 || yy >= H || ww < 0 || ww >= wpr) ? 0u : __ldg(plane + (size_t)yy * wpr + ww); };
+        const uint32_t mid = word(y, w);
+        const NbrWords nw = nbr_words(word(y - 1, w - 1), word(y - 1, w), word(y - 1, w + 1), word(y, w - 1), mid, word(y, w + 1), word(y + 1, w - 1),
+                                      word(y + 1, w), word(y + 1, w + 1));
+        L = left_crack_starts(mid, nw);
+        Rr = right_crack_starts(mid, nw);
+        // 32 mask bytes -> 8 words
+        uint8_t* mrow = a.mask + (size_t)f * a.g.mask_frame_stride + (size_t)s * a.g.mask_scale_stride + (size_t)y * a.g.mask_pitch + 32 * w;
+        uint32_t out[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            uint32_t v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) v |= (uint32_t)mask_byte(nw, 4 * q + b) << (8 * b);
+            out[q] = v;
+        }
+        uint4* dst = reinterpret_cast<uint4*>(mrow);
+        dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+        dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+        (void)W;
+    }
+    // warp-aggregated append of the start cracks
+    const int cnt = __popc(L) + __popc(Rr);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+    unsigned int base = 0;
+    if (warp_total > 0) {
+        if (lane == 31) base = atomicAdd(&a.counters->n_starts, (unsigned int)warp_total);
+        base = __shfl_sync(0xffffffffu, base, 31);
+    }
+    if (cnt > 0) {
+        unsigned int pos = base + (unsigned int)(incl - cnt);
+        const uint32_t meta_base = ((uint32_t)f << 8) | ((uint32_t)s << 1);
+        while (L) {
+            const int i = __ffs(L) - 1;
+            L &= L - 1;
+            if (pos < a.max_starts) a.starts[pos] = StartRec{(uint32_t)(32 * w + i) | ((uint32_t)y << 16), meta_base};
+            pos++;
+        }
+        while (Rr) {
+            const int i = __ffs(Rr) - 1;
+            Rr &= Rr - 1;
+            if (pos < a.max_starts) a.starts[pos] = StartRec{(uint32_t)(32 * w + i) | ((uint32_t)y << 16), meta_base | 1u};
+            pos++;
+        }
+        if (pos > a.max_starts) atomicOr(&a.counters->overflow, 1u);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_walk: grid-stride over the start queue.
+// ---------------------------------------------------------------------------------------------------
+struct WalkArgs {
+    const uint8_t* mask;
+    const StartRec* starts;
+    ChainRec* chains;
+    Counters* counters;
+    unsigned int max_starts, max_chains, max_points;
+    FrameGeom g;
+    int min_len, max_len;
+};
+
+__global__ void __launch_bounds__(256) k_walk(const WalkArgs a) {
+    unsigned int n = a.counters->n_starts;
+    n = n < a.max_starts ? n : a.max_starts;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const StartRec st = a.starts[i];
+        const int x = st.xy & 0xFFFF, y = st.xy >> 16;
+        const int f = st.meta >> 8, s = (st.meta >> 1) & 0x7F, is_right = st.meta & 1;
+        const uint8_t* plane = a.mask + (size_t)f * a.g.mask_frame_stride + (size_t)s * a.g.mask_scale_stride;
+        int len = 0;
+        const int r = walk_reverse(plane, a.g.mask_pitch, x, y, is_right, a.max_len, &len);
+        if (r == WALK_CANONICAL && len >= a.min_len && len <= a.max_len) {
+            const unsigned int slot = atomicAdd(&a.counters->n_chains, 1u);
+            const unsigned int off = atomicAdd(&a.counters->n_points, (unsigned int)len);
+            if (slot < a.max_chains && off + (unsigned int)len <= a.max_points) {
+                a.chains[slot] = ChainRec{st.xy, st.meta, (uint32_t)len, off};
+            } else {
+                if (slot < a.max_chains) a.chains[slot] = ChainRec{st.xy, st.meta, 0u, 0u};
+                atomicOr(&a.counters->overflow, slot >= a.max_chains ? 2u : 4u);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_emit: one thread per surviving border writes its ordered points.
+// ---------------------------------------------------------------------------------------------------
+struct EmitArgs {
+    const uint8_t* mask;
+    const ChainRec* chains;
+    Pt16* points;
+    const Counters* counters;
+    unsigned int max_chains;
+    FrameGeom g;
+};
+
+__global__ void __launch_bounds__(128) k_emit(const EmitArgs a) {
+    unsigned int n = a.counters->n_chains;
+    n = n < a.max_chains ? n : a.max_chains;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const ChainRec c = a.chains[i];
+        if (c.n == 0) continue;
+        const int f = c.meta >> 8, s = (c.meta >> 1) & 0x7F, is_right = c.meta & 1;
+        const uint8_t* plane = a.mask + (size_t)f * a.g.mask_frame_stride + (size_t)s * a.g.mask_scale_stride;
+        trace_forward(plane, a.g.mask_pitch, c.xy & 0xFFFF, c.xy >> 16, is_right, (int)c.n, a.points + c.offset);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_approx: one block per contour.
+// ---------------------------------------------------------------------------------------------------
+#define APPROX_THREADS 128
+
+struct BlockReducer {
+    int* sh_val;  // [APPROX_THREADS/32]
+    int* sh_idx;
+    __device__ ArgMax reduce(int best_v, int best_j) const {
+        // max value, ties -> smallest index (first maximum wins)
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const int ov = __shfl_xor_sync(0xffffffffu, best_v, d);
+            const int oj = __shfl_xor_sync(0xffffffffu, best_j, d);
+            if (ov > best_v || (ov == best_v && oj < best_j)) {
+                best_v = ov;
+                best_j = oj;
+            }
+        }
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        __syncthreads();  // protect sh_* from the previous call
+        if (lane == 0) {
+            sh_val[warp] = best_v;
+            sh_idx[warp] = best_j;
+        }
+        __syncthreads();
+        ArgMax r = {sh_val[0], sh_idx[0]};
+#pragma unroll
+        for (int w = 1; w < APPROX_THREADS / 32; w++) {
+            const int ov = sh_val[w], oj = sh_idx[w];
+            if (ov > r.value || (ov == r.value && oj < r.index)) {
+                r.value = ov;
+                r.index = oj;
+            }
+        }
+        if (r.value == 0) r.index = 0;
+        return r;
+    }
+    __device__ ArgMax farthest(const Pt16* p, int n, int pos0, int len) const {
+        const int sx = p[pos0].x, sy = p[pos0].y;
+        int bv = 0, bj = 0x7fffffff;
+        for (int j = 1 + threadIdx.x; j < len; j += APPROX_THREADS) {
+            int pos = pos0 + j;
+            pos = pos >= n ? pos - n : pos;
+            const Pt16 q = p[pos];
+            const int dx = q.x - sx, dy = q.y - sy;
+            const int d = dx * dx + dy * dy;
+            if (d > bv) {
+                bv = d;
+                bj = j;
+            }
+        }
+        return reduce(bv, bj);
+    }
+    __device__ ArgMax off_chord(const Pt16* p, int n, int s0, int s1) const {
+        const int sx = p[s0].x, sy = p[s0].y;
+        const int dx = p[s1].x - sx, dy = p[s1].y - sy;
+        int len = s1 - s0;
+        len = len <= 0 ? len + n : len;  // interior points are j = 1 .. len-1
+        int bv = 0, bj = 0x7fffffff;
+        for (int j = 1 + threadIdx.x; j < len; j += APPROX_THREADS) {
+            int pos = s0 + j;
+            pos = pos >= n ? pos - n : pos;
+            const Pt16 q = p[pos];
+            int d = (q.y - sy) * dx - (q.x - sx) * dy;
+            d = d < 0 ? -d : d;
+            if (d > bv) {
+                bv = d;
+                bj = j;
+            }
+        }
+        return reduce(bv, bj);
+    }
+};
+
+struct ApproxArgs {
+    const ChainRec* chains;
+    const Pt16* points;
+    const Counters* counters;
+    RawQuad* raw;           // [n_frames][max_raw]
+    unsigned int* n_raw;    // [n_frames]
+    Counters* counters_rw;
+    unsigned int max_chains;
+    int max_raw;
+    int W, H;
+    double poly_accuracy_rate, min_corner_dist_rate;
+    int min_dist_to_border;
+};
+
+__global__ void __launch_bounds__(APPROX_THREADS) k_approx(const ApproxArgs a) {
+    __shared__ int sh_val[APPROX_THREADS / 32], sh_idx[APPROX_THREADS / 32];
+    unsigned int n = a.counters->n_chains;
+    n = n < a.max_chains ? n : a.max_chains;
+    BlockReducer red{sh_val, sh_idx};
+    for (unsigned int i = blockIdx.x; i < n; i += gridDim.x) {
+        const ChainRec c = a.chains[i];
+        if (c.n == 0) continue;
+        const Pt16* p = a.points + c.offset;
+        Pt16 q[FID_APPROX_MAX_V];
+        const int nv = approx_poly_closed(red, p, (int)c.n, (double)c.n * a.poly_accuracy_rate, q);
+        if (nv != 4) continue;
+        if (threadIdx.x == 0 && quad_passes_filters(q, (int)c.n, a.W, a.H, a.min_corner_dist_rate, a.min_dist_to_border)) {
+            const int f = c.meta >> 8, s = (c.meta >> 1) & 0x7F, is_right = c.meta & 1;
+            const unsigned int slot = atomicAdd(&a.n_raw[f], 1u);
+            if (slot < (unsigned int)a.max_raw) {
+                RawQuad r;
+                for (int k = 0; k < 4; k++) {
+                    r.x[k] = q[k].x;
+                    r.y[k] = q[k].y;
+                }
+                r.n_contour = (int)c.n;
+                r.order_hi = (uint32_t)s;
+                const uint32_t x = c.xy & 0xFFFF, y = c.xy >> 16;
+                r.order_lo = 0xFFFFFFFFu - ((y * (uint32_t)a.W + x) * 2u + (uint32_t)is_right);
+                a.raw[(size_t)f * a.max_raw + slot] = r;
+            } else {
+                atomicOr(&a.counters_rw->overflow, 8u);
+            }
+        }
+    }
+}
+
+}  // namespace fid

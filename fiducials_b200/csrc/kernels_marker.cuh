@@ -1,0 +1,360 @@
+// CUDA kernels, back half of the per-frame pipeline (sm_100a):
+//   k_sort_group  one block per frame: clockwise fix, stable descending-perimeter order, pairwise
+//                 "too close" matrix, OpenCV's order-dependent grouping                  
+//   k_identify    one warp per selected candidate: perspective removal, Otsu, cell votes, border
+//                 check, first-match dictionary search (+ close-contour retry)           (A.6, A.7)
+//   k_finish      one block per frame: compaction in OpenCV's output order, cornerSubPix (A.8),
+//                 solvePnP(ITERATIVE) + FiducialTransform arithmetic                     (A.9)
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/fiducials_b200.h"
+#include "common.cuh"
+#include "identify.cuh"
+#include "pnp.cuh"
+#include "quad_group.cuh"
+#include "subpix.cuh"
+
+namespace fid {
+
+// Dictionaries live in constant memory (immutable, shared by every handle): 5x5 family as 25-bit
+// words, 6x6 family as 36-bit words; both hold 1000 markers x 4 rotations (prefix property of
+// OpenCV's predefined dictionaries, tools/gen_dict_tables.py).
+__constant__ uint32_t c_dict5[1000 * 4];
+__constant__ unsigned long long c_dict6[1000 * 4];
+
+struct FrameScratch {     // per-frame global scratch, all arrays sized max_raw
+    QuadF* quads_tmp;     // clockwise quads, unsorted
+    float* per_tmp;
+    QuadF* quads;         // sorted
+    float* per;           // sorted
+    uint32_t* close_bits; // max_raw x close_wpr
+    int* group_id;
+    int* group_members;
+    int* next_in_group;
+    int* group_head;
+    int* group_tail;
+    int* close_count;
+    int* close_idx;
+    int* close_off;
+    uint8_t* selected;
+    int* sel_idx;         // selected candidates (sorted indices), in order
+};
+
+struct GroupArgs {
+    const RawQuad* raw;          // [F][max_raw]
+    const unsigned int* n_raw;   // [F]
+    FrameScratch fs;             // base pointers; frame f uses offset f*max_raw (close_bits: f*max_raw*close_wpr)
+    int* n_sel;                  // [F]
+    int* n_raw_clamped;          // [F]
+    int max_raw, close_wpr, max_sel;
+    int marker_size, border_bits;
+    float min_marker_dist_rate, min_group_dist;
+    Counters* counters;
+};
+
+#define GROUP_THREADS 256
+
+__global__ void __launch_bounds__(GROUP_THREADS) k_sort_group(const GroupArgs a) {
+    const int f = blockIdx.x;
+    const int tid = threadIdx.x;
+    int n = (int)a.n_raw[f];
+    n = n < a.max_raw ? n : a.max_raw;
+    const size_t fo = (size_t)f * a.max_raw;
+    const RawQuad* raw = a.raw + fo;
+    QuadF* qt = a.fs.quads_tmp + fo;
+    float* pt = a.fs.per_tmp + fo;
+    QuadF* qs = a.fs.quads + fo;
+    float* ps = a.fs.per + fo;
+    uint32_t* cb = a.fs.close_bits + fo * a.close_wpr;
+    if (tid == 0) a.n_raw_clamped[f] = n;
+    // a. clockwise + perimeter
+    for (int i = tid; i < n; i += GROUP_THREADS) {
+        const QuadF q = quad_clockwise(raw[i]);
+        qt[i] = q;
+        pt[i] = quad_perimeter(q);
+    }
+    __syncthreads();
+    // b. rank = position under std::stable_sort(descending perimeter) of OpenCV's candidate order
+    for (int i = tid; i < n; i += GROUP_THREADS) {
+        const float pi = pt[i];
+        const uint32_t hi = raw[i].order_hi, lo = raw[i].order_lo;
+        int rank = 0;
+        for (int j = 0; j < n; j++) {
+            const float pj = pt[j];
+            const bool before = pj > pi || (pj == pi && (raw[j].order_hi < hi || (raw[j].order_hi == hi && raw[j].order_lo < lo)));
+            rank += before ? 1 : 0;
+        }
+        qs[rank] = qt[i];
+        ps[rank] = pi;
+    }
+    __syncthreads();
+    // c. close-pair matrix, upper triangle; unit = (row i, 32-column word)
+    const int wpr = (n + 31) >> 5;
+    for (int u = tid; u < n * wpr; u += GROUP_THREADS) {
+        const int i = u / wpr, w = u - i * wpr;
+        uint32_t bits = 0;
+        const int j0 = w << 5;
+        if (j0 + 31 > i) {
+            const QuadF qi = qs[i];
+            const float cix = (qi.x[0] + qi.x[1] + qi.x[2] + qi.x[3]) * 0.25f, ciy = (qi.y[0] + qi.y[1] + qi.y[2] + qi.y[3]) * 0.25f;
+            for (int b = 0; b < 32; b++) {
+                const int j = j0 + b;
+                if (j <= i || j >= n) continue;
+                const QuadF qj = qs[j];
+                const float thr = ps[j] * a.min_marker_dist_rate;
+                // the mean squared corner distance is >= the squared centroid distance for every
+                // corner alignment, so a far centroid can never be "close" (conservative margin)
+                const float cjx = (qj.x[0] + qj.x[1] + qj.x[2] + qj.x[3]) * 0.25f, cjy = (qj.y[0] + qj.y[1] + qj.y[2] + qj.y[3]) * 0.25f;
+                const float cd2 = (cix - cjx) * (cix - cjx) + (ciy - cjy) * (ciy - cjy);
+                const float lim = thr * 1.01f + 1.0f;
+                if (cd2 > lim * lim) continue;
+                if (quad_avg_distance(qi, qj) < thr) bits |= 1u << b;
+            }
+        }
+        cb[(size_t)i * a.close_wpr + w] = bits;
+    }
+    __syncthreads();
+    // d. order-dependent grouping (serial; the pair list is sparse)
+    if (tid == 0) {
+        const uint32_t* cbc = cb;
+        const int cw = a.close_wpr;
+        auto close = [cbc, cw](int i, int j) -> bool { return (cbc[(size_t)i * cw + (j >> 5)] >> (j & 31)) & 1u; };
+        group_candidates(n, qs, a.marker_size, a.border_bits, a.min_group_dist, close, a.fs.selected + fo, a.fs.group_id + fo, a.fs.group_members + fo,
+                         a.fs.next_in_group + fo, a.fs.group_head + fo, a.fs.group_tail + fo, a.fs.close_count + fo, a.fs.close_idx + fo, a.fs.close_off + fo);
+        int ns = 0;
+        for (int i = 0; i < n; i++) {
+            if (!a.fs.selected[fo + i]) continue;
+            if (ns < a.max_sel) {
+                a.fs.sel_idx[fo + ns] = i;
+                ns++;
+            } else {
+                atomicOr(&a.counters->overflow, 16u);
+            }
+        }
+        a.n_sel[f] = ns;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct WarpLanes {
+    __device__ int lane() const { return threadIdx.x & 31; }
+    __device__ int count() const { return 32; }
+    __device__ void sync() const { __syncwarp(); }
+    __device__ long long sum(long long v) const {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        return v;
+    }
+    __device__ int min_i(int v) const {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const int o = __shfl_xor_sync(0xffffffffu, v, d);
+            v = o < v ? o : v;
+        }
+        return v;
+    }
+    __device__ unsigned long long or_u64(unsigned long long v) const {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, d);
+        return v;
+    }
+    __device__ void hist_add(int* h, int bin) const { atomicAdd(h + bin, 1); }
+};
+
+struct IdentifyArgs {
+    const uint8_t* gray;
+    size_t gray_frame_stride;
+    int gray_pitch, W, H;
+    FrameScratch fs;
+    const int* n_sel;
+    int max_raw;
+    int max_sel;
+    DevParams P;
+    int* cand_id;        // [F][max_sel]  -1 rejected
+    float* cand_corners; // [F][max_sel][8] rotated to marker order
+};
+
+#define IDENT_WARPS 4
+
+__global__ void __launch_bounds__(IDENT_WARPS * 32) k_identify(const IdentifyArgs a) {
+    extern __shared__ unsigned long long sm_dict[];  // n_markers*4 words, then per-warp scratch
+    const int n_words = a.P.n_markers * 4;
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) sm_dict[i] = a.P.marker_size == 5 ? (unsigned long long)c_dict5[i] : c_dict6[i];
+    const int warp = threadIdx.x >> 5;
+    int* hist = reinterpret_cast<int*>(sm_dict + n_words) + warp * 256;
+    uint8_t* img = reinterpret_cast<uint8_t*>(reinterpret_cast<int*>(sm_dict + n_words) + IDENT_WARPS * 256) + warp * (FID_MAX_WARP_SIDE_SQ);
+    __syncthreads();
+    const int f = blockIdx.y;
+    const int k = blockIdx.x * IDENT_WARPS + warp;
+    if (k >= a.n_sel[f]) return;
+    const size_t fo = (size_t)f * a.max_raw;
+    const int si = a.fs.sel_idx[fo + k];
+    const uint8_t* gray = a.gray + (size_t)f * a.gray_frame_stride;
+    WarpLanes L;
+    QuadF use = a.fs.quads[fo + si];
+    IdentifyResult r = identify_candidate(L, gray, a.W, a.H, (size_t)a.gray_pitch, use, a.P, sm_dict, img, hist);
+    if (r.id < 0) {
+        const int nc = a.fs.close_count[fo + si], co = a.fs.close_off[fo + si];
+        for (int c = 0; c < nc; c++) {
+            __syncwarp();
+            const QuadF alt = a.fs.quads[fo + a.fs.close_idx[fo + co + c]];
+            r = identify_candidate(L, gray, a.W, a.H, (size_t)a.gray_pitch, alt, a.P, sm_dict, img, hist);
+            if (r.id >= 0) {
+                use = alt;
+                break;
+            }
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+        const size_t o = (size_t)f * a.max_sel + k;
+        a.cand_id[o] = r.id;
+        if (r.id >= 0) {
+            for (int c = 0; c < 4; c++) {  // correctCornerPosition: std::rotate(begin, begin + 4 - rotation, end)
+                a.cand_corners[o * 8 + 2 * c] = use.x[(c + 4 - r.rotation) & 3];
+                a.cand_corners[o * 8 + 2 * c + 1] = use.y[(c + 4 - r.rotation) & 3];
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+struct FinishArgs {
+    const uint8_t* gray;
+    size_t gray_frame_stride;
+    int gray_pitch, W, H;
+    const int* n_sel;
+    const int* cand_id;
+    const float* cand_corners;
+    int max_sel, max_markers;
+    DevParams P;
+    const float* subpix_masks;  // windows 1..5 concatenated: offsets 0, 9, 34, 83, 164
+    int do_pose;
+    Camera cam;
+    double fiducial_len;
+    int n_override;
+    const int32_t* override_ids;
+    const double* override_lens;
+    int32_t* out_count;     // [F]
+    int32_t* out_ids;       // [F][max_markers]
+    float* out_corners;     // [F][max_markers][8]
+    fid_transform* out_tf;  // [F][max_markers]
+    Counters* counters;
+};
+
+#define FINISH_THREADS 128
+
+__device__ __forceinline__ int subpix_mask_offset(int win) {
+    int off = 0;
+    for (int w = 1; w < win; w++) off += (2 * w + 1) * (2 * w + 1);
+    return off;
+}
+
+__global__ void __launch_bounds__(FINISH_THREADS) k_finish(const FinishArgs a) {
+    __shared__ int s_n;
+    __shared__ int s_src[FID_MAX_MARKERS];
+    const int f = blockIdx.x, tid = threadIdx.x;
+    if (tid == 0) {
+        int n = 0;
+        const int ns = a.n_sel[f];
+        for (int k = 0; k < ns; k++) {
+            if (a.cand_id[(size_t)f * a.max_sel + k] < 0) continue;
+            if (n < a.max_markers && n < FID_MAX_MARKERS) {
+                s_src[n++] = k;
+            } else {
+                atomicOr(&a.counters->overflow, 32u);
+            }
+        }
+        s_n = n;
+        a.out_count[f] = n;
+    }
+    __syncthreads();
+    const int n = s_n;
+    const uint8_t* gray = a.gray + (size_t)f * a.gray_frame_stride;
+    float* oc = a.out_corners + (size_t)f * a.max_markers * 8;
+    // corners (+ sub-pixel refinement), one thread per corner
+    for (int c = tid; c < 4 * n; c += FINISH_THREADS) {
+        const int m = c >> 2, ci = c & 3;
+        const size_t src = ((size_t)f * a.max_sel + s_src[m]) * 8;
+        float x = a.cand_corners[src + 2 * ci], y = a.cand_corners[src + 2 * ci + 1];
+        if (a.P.corner_refine) {
+            QuadF q;
+            for (int k = 0; k < 4; k++) {
+                q.x[k] = a.cand_corners[src + 2 * k];
+                q.y[k] = a.cand_corners[src + 2 * k + 1];
+            }
+            const float module = quad_module_size(q, a.P.marker_size, a.P.marker_border_bits);
+            int win = __float2int_rn((float)a.P.rel_refine_win * module);
+            win = win < 1 ? 1 : win;
+            win = win < a.P.refine_win ? win : a.P.refine_win;
+            float patch[(2 * FID_SUBPIX_MAX_WIN + 3) * (2 * FID_SUBPIX_MAX_WIN + 3)];
+            corner_subpix(gray, a.W, a.H, (size_t)a.gray_pitch, &x, &y, win, a.subpix_masks + subpix_mask_offset(win), a.P.refine_max_iter,
+                          a.P.refine_min_acc * a.P.refine_min_acc, patch);
+        }
+        oc[(size_t)m * 8 + 2 * ci] = x;
+        oc[(size_t)m * 8 + 2 * ci + 1] = y;
+    }
+    for (int m = tid; m < n; m += FINISH_THREADS) a.out_ids[(size_t)f * a.max_markers + m] = a.cand_id[(size_t)f * a.max_sel + s_src[m]];
+    __syncthreads();
+    // pose, one thread per marker
+    if (a.do_pose) {
+        for (int m = tid; m < n; m += FINISH_THREADS) {
+            const int id = a.cand_id[(size_t)f * a.max_sel + s_src[m]];
+            double len = (double)(float)a.fiducial_len;  // estimatePoseSingleMarkers((float)fiducial_len, ...)  :425
+            for (int k = 0; k < a.n_override; k++)
+                if (a.override_ids[k] == id) len = a.override_lens[k];
+            PoseOut po;
+            solve_marker_pose(oc + (size_t)m * 8, a.cam, (float)len, a.fiducial_len, &po);
+            fid_transform t;
+            t.fiducial_id = id;
+            t.reserved = po.lm_iters;
+            for (int k = 0; k < 3; k++) {
+                t.translation[k] = po.tvec[k];
+                t.rvec[k] = po.rvec[k];
+            }
+            for (int k = 0; k < 4; k++) t.rotation[k] = po.quat[k];
+            t.image_error = po.image_error;
+            t.object_error = po.object_error;
+            t.fiducial_area = po.area;
+            a.out_tf[(size_t)f * a.max_markers + m] = t;
+        }
+    }
+}
+
+// Pose only (fid_pose): one thread per marker of a single list.
+struct PoseArgs {
+    int n;
+    const int32_t* ids;
+    const float* corners;
+    Camera cam;
+    double fiducial_len;
+    int n_override;
+    const int32_t* override_ids;
+    const double* override_lens;
+    fid_transform* out;
+};
+
+__global__ void __launch_bounds__(64) k_pose(const PoseArgs a) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= a.n) return;
+    const int id = a.ids[m];
+    double len = (double)(float)a.fiducial_len;
+    for (int k = 0; k < a.n_override; k++)
+        if (a.override_ids[k] == id) len = a.override_lens[k];
+    PoseOut po;
+    solve_marker_pose(a.corners + (size_t)m * 8, a.cam, (float)len, a.fiducial_len, &po);
+    fid_transform t;
+    t.fiducial_id = id;
+    t.reserved = po.lm_iters;
+    for (int k = 0; k < 3; k++) {
+        t.translation[k] = po.tvec[k];
+        t.rvec[k] = po.rvec[k];
+    }
+    for (int k = 0; k < 4; k++) t.rotation[k] = po.quat[k];
+    t.image_error = po.image_error;
+    t.object_error = po.object_error;
+    t.fiducial_area = po.area;
+    a.out[m] = t;
+}
+
+}  // namespace fid

@@ -39,8 +39,6 @@ inline void default_params(fid_params* p) {
     p->minGroupDistance = 0.21;
 }
 
-#define FID_MAX_WIN_RADIUS 31   // adaptive-threshold window <= 63
-#define FID_MAX_WARP_SIDE 64    // (markerSize + 2*border) * pixelPerCell <= 64
 
 // Returns FID_OK or an error status; fills dp.
 inline int make_dev_params(const fid_params& p, DevParams* dp) {
@@ -116,8 +114,5 @@ inline void subpix_mask(int win, float* mask /* (2win+1)^2 */) {
         }
     }
 }
-
-// Refinement window of one accepted marker: min(refine_win, max(1, cvRound(rel * moduleSize))).
-inline int dummy_unused() { return 0; }
 
 }  // namespace fid

