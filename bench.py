@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the aruco_detect hot path (detect + pose) on BASELINE.json's config C2.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA path through the C-ABI)
+  python bench.py --impl reference --gpus N --steps K ...   the reference's CPU path (cv2) on host cores
+
+A "step" is one pass of the hot path over one batch of synthetic 1920x1080 frames (16 markers of
+DICT_6X6_250 each): BGR8 frames -> ids, corners, rvec/tvec, quaternion, image/object error, area,
+followed by the per-camera fiducial_slam map update of those messages (and, for N > 1, one NCCL
+all-gather + deterministic merge of the per-rank map tables).  Frames shard one stream per GPU,
+weak scaling, no collective on the detect/pose path.
+
+  value  : frames/s, whole job, frames already resident in HBM when the timed region starts
+  e2e    : frames/s through the same C-ABI call with pinned HOST frames (H2D of every frame and D2H
+           of every result inside the timed region)
+  roofline: the threshold kernel (the HBM-bound stage BASELINE.json's metric names): algorithmic
+           bytes 3*W*H + n_scales*W*H/8 per frame / its CUDA-event time, vs the measured
+           copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline: the same frames through cv2's ArucoDetector + solvePnP + projectPoints (the OpenCV
+           calls of aruco_detect.cpp:350,247,210) on this box's host cores, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "C2"
+FIDUCIAL_LEN = 0.14
+FRAMES_PER_STEP = 32     # distinct frames per step; 32 x 6.2 MB = 199 MB > 126 MB L2
+SLOT_FRAMES = 16         # frames per in-flight chunk inside the library (two chunks pipeline)
+HBM_FALLBACK_GBS = 6650.0
+
+
+# ------------------------------------------------------------------------------------------------
+def rank_info():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                      stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=2)
+        except Exception:
+            self.p.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    except Exception:
+        return HBM_FALLBACK_GBS, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm (cv2): exactly the per-frame calls of the reference node
+# ------------------------------------------------------------------------------------------------
+_W = {}
+
+
+def _cpu_worker_init(nthreads, npy_path, dict_id, K, D):
+    """Worker of the throughput-mode CPU baseline (spawned, so OpenCV's thread pool is never forked)."""
+    sys.path.insert(0, ROOT)
+    import cv2
+
+    cv2.setNumThreads(nthreads)
+    _W["frames"] = np.load(npy_path, mmap_mode="r")
+    _W["cfg"] = (dict_id, K, D)
+
+
+def _cpu_worker_frame(i):
+    from oracle import aruco_oracle as ao
+
+    dict_id, K, D = _W["cfg"]
+    fr = _W["frames"]
+    ids, corners, rv, tv, fields = ao.detect_and_pose(np.ascontiguousarray(fr[i % len(fr)]), dict_id, K, D, FIDUCIAL_LEN)
+    return len(ids)
+
+
+def cpu_reference_fps(frames, dict_id, K, D, budget_s=12.0):
+    """Times the reference's CPU path on a bounded sample in both modes:
+    reference mode  = one process, OpenCV threads = all cores (what the single-threaded node does);
+    throughput mode = one single-threaded worker process per core, frames round-robin.
+    Returns dict(value=best fps, cores, sample)."""
+    import multiprocessing as mp
+    import tempfile
+
+    import cv2
+
+    from oracle import aruco_oracle as ao
+
+    ncores = os.cpu_count() or 1
+
+    def one(i):
+        return ao.detect_and_pose(frames[i % len(frames)], dict_id, K, D, FIDUCIAL_LEN)
+
+    # reference mode
+    cv2.setNumThreads(ncores)
+    one(0)
+    t0 = time.perf_counter()
+    n_ref = 0
+    while (time.perf_counter() - t0 < budget_s / 2 and n_ref < 4 * len(frames)) or n_ref < 3:
+        one(n_ref)
+        n_ref += 1
+    fps_ref = n_ref / (time.perf_counter() - t0)
+    # throughput mode
+    nproc = max(1, min(ncores, 64))
+    fps_thr, n_thr = 0.0, 0
+    tmp = tempfile.NamedTemporaryFile(suffix=".npy", delete=False)
+    try:
+        np.save(tmp, np.ascontiguousarray(frames))
+        tmp.close()
+        ctx = mp.get_context("spawn")
+        with ctx.Pool(nproc, initializer=_cpu_worker_init, initargs=(1, tmp.name, dict_id, K, D)) as pool:
+            pool.map(_cpu_worker_frame, range(nproc), chunksize=1)  # warm-up (imports, first-call setup)
+            t0 = time.perf_counter()
+            pool.map(_cpu_worker_frame, range(nproc), chunksize=1)
+            per_round = time.perf_counter() - t0
+            rounds = int(max(1, min(8, (budget_s / 2) / max(per_round, 1e-3))))
+            n_thr = nproc * rounds
+            t0 = time.perf_counter()
+            pool.map(_cpu_worker_frame, range(n_thr), chunksize=1)
+            fps_thr = n_thr / (time.perf_counter() - t0)
+    except Exception as e:  # pragma: no cover
+        print("throughput-mode CPU baseline failed: %r" % (e,), file=sys.stderr)
+    finally:
+        try:
+            os.unlink(tmp.name)
+        except OSError:
+            pass
+    best = max(fps_ref, fps_thr)
+    return {
+        "value": best,
+        "unit": "frames/s",
+        "cores": ncores if fps_ref >= fps_thr else nproc,
+        "kind": "reference",
+        "sample": "cv2 %s ArucoDetector(reference params)+solvePnP+projectPoints on %s frames: reference mode (1 proc, %d OpenCV threads) %d frames %.2f fps; "
+                  "throughput mode (%d procs x 1 thread) %d frames %.2f fps; value = better of the two; os.cpu_count=%d"
+                  % (cv2.__version__, WORKLOAD, ncores, n_ref, fps_ref, nproc, n_thr, fps_thr, ncores),
+    }
+
+
+def run_reference_arm(args):
+    rank, local_rank, world = rank_info()
+    if rank != 0:
+        return  # rank 0 alone runs and prints the CPU arm
+    from fiducials_b200 import synth
+
+    frames, truths, K, D, dict_id = synth.make_config_stream(WORKLOAD, 8, seed=0)
+    per_step = []
+    detail = None
+    budget = max(4.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        detail = cpu_reference_fps(frames, dict_id, K, D, budget_s=budget)
+        if i >= args.warmup:
+            per_step.append((detail["value"], time.perf_counter() - t0))
+    fps = float(np.median([p[0] for p in per_step]))
+    ms = float(np.mean([p[1] for p in per_step]) * 1e3)
+    detail["value"] = fps
+    out = {
+        "impl": "reference",
+        "metric": "frames/sec 1920x1080 (detect+pose)",
+        "value": fps,
+        "unit": "frames/s",
+        "n_gpus": args.gpus,
+        "steps": args.steps,
+        "warmup": args.warmup,
+        "ms_per_step": ms,
+        "higher_is_better": True,
+        "scaling": "weak",
+        "vs_baseline": None,
+        "dtype": "u8/f32/f64",
+        "data": "synthetic",
+        "config": {"workload": "C2: 1920x1080 BGR8 stream, 16 markers/frame, DICT_6X6_250, detect+pose; each step = bounded sample of the stream on host cores"},
+        "cpu_baseline": detail,
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+
+    rank, local_rank, world = rank_info()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the hot path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from fiducials_b200 import _lib, synth
+    from fiducials_b200.node import MAXM, Detector, FiducialSlam, default_params
+
+    lib = _lib.load()
+    W, H, n_markers, dict_id = synth.CONFIGS[WORKLOAD]
+    nf = FRAMES_PER_STEP
+    frames, truths, K, D, _ = synth.make_config_stream(WORKLOAD, nf, seed=rank)
+    det = Detector(default_params(dictionary=dict_id), local_rank, W, H, SLOT_FRAMES)
+    slam = FiducialSlam(device=local_rank, max_fiducials=512, n_instances=1)
+    ident = [0, 0, 0, 0, 0, 0, 1]
+
+    # pinned host copy + device-resident copy of the stream
+    hptr = C.c_void_p()
+    _lib.check(lib.fid_host_alloc(frames.nbytes, C.byref(hptr)))
+    pinned = np.ctypeslib.as_array(C.cast(hptr, C.POINTER(C.c_uint8)), shape=(frames.nbytes,)).reshape(frames.shape)
+    pinned[...] = frames
+    dptr = C.c_void_p()
+    _lib.check(lib.fid_device_alloc(det.h, frames.nbytes, C.byref(dptr)))
+    _lib.check(lib.fid_memcpy_h2d(det.h, dptr, hptr, frames.nbytes))
+
+    tables_gpu = None
+    if dist is not None:
+        table_bytes = slam.p.max_fiducials * C.sizeof(_lib.fid_map_record)
+        tables_gpu = [torch.empty(table_bytes, dtype=torch.uint8, device="cuda") for _ in range(world)]
+
+    launches = [0]
+
+    def step(on_device):
+        if on_device:
+            counts, ids, corners, tfs = det.detect_pose_batch(dptr.value, K, D, FIDUCIAL_LEN, on_device=True, n_frames=nf, width=W, height=H)
+        else:
+            counts, ids, corners, tfs = det.detect_pose_batch(pinned, K, D, FIDUCIAL_LEN)
+        launches[0] += det.last_counters()["kernel_launches"]
+        # fiducial_slam: the frames of this step are one camera stream -> one message per frame
+        msgs = [[tfs[f * MAXM + m] for m in range(int(counts[f]))] for f in range(nf)]
+        flat = [t for m in msgs for t in m]
+        offsets = np.zeros(nf + 1, np.int32)
+        offsets[1:] = np.cumsum(counts)
+        arr = (_lib.fid_transform * max(len(flat), 1))(*flat)
+        bc = _lib.fid_tf()
+        bc.q[3] = 1.0
+        _lib.check(lib.fid_map_update_sequence(slam.h, nf, offsets.ctypes.data_as(C.c_void_p), C.cast(arr, C.c_void_p), C.byref(bc), C.byref(bc), None))
+        launches[0] += 1
+        if dist is not None:
+            mine = torch.from_numpy(slam.export_table(0)).cuda()
+            dist.all_gather(tables_gpu, mine)
+            slam.merge_tables(torch.cat(tables_gpu).cpu().numpy(), world, instance=0)
+            launches[0] += 2
+        return counts
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(on_device, steps):
+        barrier()
+        launches[0] = 0
+        _lib.check(lib.fid_timer_start(det.h))
+        t0 = time.perf_counter()
+        total = 0
+        for _ in range(steps):
+            total += int(step(on_device).sum())
+        ms = C.c_float(0)
+        _lib.check(lib.fid_timer_stop(det.h, C.byref(ms)))
+        wall = time.perf_counter() - t0
+        barrier()
+        t = torch.tensor([ms.value / 1e3, wall], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), total, launches[0]
+
+    for _ in range(max(args.warmup, 3)):
+        step(True)
+    step(False)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    dev_s, dev_wall, n_markers_found, n_launch = timed(True, args.steps)
+    stage_ms = det.last_stage_ms()  # stages of the last batch call (nf frames)
+    counters = det.last_counters()
+    e2e_s, e2e_wall, _, _ = timed(False, args.steps)
+    clocks = sampler.stop()
+
+    frames_total = nf * args.steps * world
+    value = frames_total / dev_s
+    e2e_value = frames_total / e2e_s
+
+    if rank == 0:
+        n_scales = 13
+        algo_bytes = (3 * W * H + n_scales * W * H / 8.0) * nf  # per batch call, SURVEY 8d
+        thr_s = stage_ms["threshold"] / 1e3
+        peak, peak_src = measured_hbm_peak()
+        achieved = algo_bytes / thr_s / 1e9 if thr_s > 0 else 0.0
+        total_stage = sum(v for k, v in stage_ms.items() if k not in ("h2d", "d2h"))
+        roofline = {
+            "bound": "hbm",
+            "kernel": "k_threshold",
+            "achieved": achieved,
+            "peak": peak,
+            "unit": "GB/s",
+            "frac": achieved / peak,
+            "traffic": None,
+            "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": algo_bytes,
+            "launch_ms": stage_ms["threshold"],
+            "share_of_step": stage_ms["threshold"] / total_stage if total_stage else None,
+            "stage_ms_per_batch": stage_ms,
+            "work_per_batch": counters,
+        }
+        cpu = cpu_reference_fps(frames[:8], dict_id, K, D, budget_s=16.0)
+        d2h = nf * (4 + MAXM * 4 + MAXM * 32 + MAXM * C.sizeof(_lib.fid_transform))
+        out = {
+            "metric": "frames/sec 1920x1080 (detect+pose)",
+            "value": value,
+            "unit": "frames/s",
+            "n_gpus": world,
+            "steps": args.steps,
+            "warmup": max(args.warmup, 3),
+            "ms_per_step": dev_s * 1e3 / args.steps,
+            "higher_is_better": True,
+            "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "u8/i32 (threshold, contours), f32/f64 (sub-pixel, pose, map)",
+            "data": "synthetic",
+            "config": {
+                "workload": "C2: 1920x1080 BGR8 stream, 16 markers/frame, DICT_6X6_250, detect+pose+map update, %d distinct frames per step per GPU" % nf,
+                "frames_per_step_per_gpu": nf,
+                "l2": "inputs larger than L2 (%d MB of distinct frames per step vs 126 MB L2)" % (frames.nbytes // 2**20),
+                "parallelism": "one camera stream per GPU, no collective on detect/pose; map tables all-gathered (NCCL) and merged once per step" if world > 1 else "1 GPU",
+                "markers_found_per_step": n_markers_found // max(1, args.steps),
+            },
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(frames.nbytes), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3 / args.steps},
+            "gpu_launches": n_launch,
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "wallclock_s": {"device_resident": dev_wall, "e2e": e2e_wall},
+        }
+        print(json.dumps(out))
+    lib.fid_device_free(det.h, dptr)
+    lib.fid_host_free(hptr)
+    det.close()
+    slam.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

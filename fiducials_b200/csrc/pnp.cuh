@@ -19,6 +19,7 @@ template <int N>
 FID_HD void jacobi_eigen(double A[N][N], double w[N], double V[N][N]) {
     for (int i = 0; i < N; i++)
         for (int j = 0; j < N; j++) V[i][j] = i == j ? 1.0 : 0.0;
+#pragma unroll 1
     for (int sweep = 0; sweep < 60; sweep++) {
         double off = 0.0, diag = 0.0;
         for (int i = 0; i < N; i++) {
@@ -26,7 +27,12 @@ FID_HD void jacobi_eigen(double A[N][N], double w[N], double V[N][N]) {
             for (int j = i + 1; j < N; j++) off += A[i][j] * A[i][j];
         }
         if (off <= 1e-40 * diag || off == 0.0) break;
+        // NOTE: keep the rotation loops rolled.  nvcc 12.9 (-O1..-O3, sm_100a) miscompiles the fully
+        // unrolled N=6 instance (eigenvalues wrong, off-diagonal mass not reduced; host build of the
+        // same source is correct) -- found on B200 via tools/debug_pose.cu.
+#pragma unroll 1
         for (int p = 0; p < N - 1; p++)
+#pragma unroll 1
             for (int q = p + 1; q < N; q++) {
                 const double apq = A[p][q];
                 if (apq == 0.0) continue;
@@ -340,6 +346,10 @@ FID_HD void solve_marker_pose(const float corners[8], const Camera& cam, float m
     p[3] = t0[0];
     p[4] = t0[1];
     p[5] = t0[2];
+#ifdef FID_DEBUG_PNP
+    printf("H %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", Hm[0], Hm[1], Hm[2], Hm[3], Hm[4], Hm[5], Hm[6], Hm[7]);
+    printf("init %.17g %.17g %.17g %.17g %.17g %.17g\n", p[0], p[1], p[2], p[3], p[4], p[5]);
+#endif
     // 5. Levenberg-Marquardt (CvLevMarq schedule)
     double uv[8], J[8][6], err[8];
     project4(obj, p, cam, uv, J);
@@ -369,6 +379,15 @@ FID_HD void solve_marker_pose(const float corners[8], const Camera& cam, float m
             for (int a = 0; a < 6; a++)
                 for (int b = 0; b < 6; b++) A[a][b] = a == b ? JtJ[a][b] * scale : JtJ[a][b];
             solve_sym6(A, JtE, delta);
+#ifdef FID_DEBUG_PNP
+            if (iters == 0) {
+                printf("J0 %.17g %.17g %.17g %.17g %.17g %.17g\n", J[0][0], J[0][1], J[0][2], J[0][3], J[0][4], J[0][5]);
+                printf("J7 %.17g %.17g %.17g %.17g %.17g %.17g\n", J[7][0], J[7][1], J[7][2], J[7][3], J[7][4], J[7][5]);
+                printf("JtE %.17g %.17g %.17g %.17g %.17g %.17g\n", JtE[0], JtE[1], JtE[2], JtE[3], JtE[4], JtE[5]);
+                printf("Adiag %.17g %.17g %.17g %.17g %.17g %.17g scale %.17g\n", A[0][0], A[1][1], A[2][2], A[3][3], A[4][4], A[5][5], scale);
+                printf("delta %.17g %.17g %.17g %.17g %.17g %.17g\n", delta[0], delta[1], delta[2], delta[3], delta[4], delta[5]);
+            }
+#endif
             for (int a = 0; a < 6; a++) p[a] = prev[a] - delta[a];
             project4(obj, p, cam, uv, nullptr);
             double s = 0.0;
@@ -385,6 +404,9 @@ FID_HD void solve_marker_pose(const float corners[8], const Camera& cam, float m
         }
         lam = lam - 1 > -16 ? lam - 1 : -16;
         iters++;
+#ifdef FID_DEBUG_PNP
+        printf("it %d lam %d en %.17g prev %.17g p %.17g %.17g %.17g\n", iters, lam, en, prev_err, p[0], p[1], p[2]);
+#endif
         double dn = 0.0, pn = 0.0;
         for (int a = 0; a < 6; a++) {
             dn += (p[a] - prev[a]) * (p[a] - prev[a]);

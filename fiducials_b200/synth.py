@@ -93,8 +93,35 @@ def _blur(img: np.ndarray, sigma: float) -> np.ndarray:
     return out
 
 
-def make_frame(W: int, H: int, n_markers: int, dict_id: int, seed: int = 0, jitter: float = 0.08, first_id: int = 0, supersample: int = 2):
-    """Returns (bgr uint8[H,W,3], truth list of (id, float64[4,2] TL,TR,BR,BL image corners))."""
+def _rodrigues(rvec):
+    th = float(np.linalg.norm(rvec))
+    if th < 1e-12:
+        return np.eye(3)
+    k = np.asarray(rvec, np.float64) / th
+    Kx = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + math.sin(th) * Kx + (1 - math.cos(th)) * (Kx @ Kx)
+
+
+def project_points(obj, R, t, K, D):
+    """Pinhole + plumb_bob projection (numpy), obj [n,3] -> [n,2]."""
+    P = obj @ R.T + t
+    x, y = P[:, 0] / P[:, 2], P[:, 1] / P[:, 2]
+    k1, k2, p1, p2, k3 = [float(v) for v in D[:5]]
+    r2 = x * x + y * y
+    cd = 1 + k1 * r2 + k2 * r2 * r2 + k3 * r2 * r2 * r2
+    xd = x * cd + 2 * p1 * x * y + p2 * (r2 + 2 * x * x)
+    yd = y * cd + p1 * (r2 + 2 * y * y) + 2 * p2 * x * y
+    return np.stack([xd * K[0, 0] + K[0, 2], yd * K[1, 1] + K[1, 2]], 1)
+
+
+def make_frame(W: int, H: int, n_markers: int, dict_id: int, seed: int = 0, jitter: float = 0.08, first_id: int = 0, supersample: int = 2, marker_len: float = 0.14,
+               max_tilt_deg: float = 35.0, mode: str = "pose"):
+    """Returns (bgr uint8[H,W,3], truth list of (id, float64[4,2] TL,TR,BR,BL image corners)).
+
+    mode "pose": each marker is a square of side ``marker_len`` at a sampled 3-D pose (in-plane angle
+    U[0,2pi), tilt <= max_tilt_deg about a random in-plane axis, depth chosen so that it fills about
+    0.55 of its grid cell) projected with camera_for(W,H) incl. distortion.  mode "jitter": in-plane
+    rotation plus per-corner jitter (not a consistent perspective view)."""
     rng = np.random.default_rng(seed)
     ms, nmk, _, _ = dictionary_info(dict_id)
     cells = ms + 2
@@ -118,7 +145,22 @@ def make_frame(W: int, H: int, n_markers: int, dict_id: int, seed: int = 0, jitt
         ca, sa = math.cos(ang), math.sin(ang)
         base = np.array([[-0.5, -0.5], [0.5, -0.5], [0.5, 0.5], [-0.5, 0.5]]) * side
         quad = np.stack([cx + ca * base[:, 0] - sa * base[:, 1], cy + sa * base[:, 0] + ca * base[:, 1]], 1)
-        quad += rng.uniform(-jitter, jitter, (4, 2)) * side
+        jit = rng.uniform(-jitter, jitter, (4, 2)) * side
+        if mode == "pose":
+            Kc, Dc = camera_for(W, H)
+            f = Kc[0, 0]
+            z = f * marker_len / side
+            axis_ang = rng.uniform(0, 2 * math.pi)
+            tilt = math.radians(rng.uniform(0, max_tilt_deg))
+            R = _rodrigues(np.array([math.cos(axis_ang), math.sin(axis_ang), 0.0]) * tilt) @ _rodrigues(np.array([0.0, 0.0, ang]))
+            # marker frame: x right, y up, z out of the marker; camera looks along +z with y down
+            R = R @ np.diag([1.0, -1.0, -1.0])
+            t = np.array([(cx - Kc[0, 2]) * z / f, (cy - Kc[1, 2]) * z / f, z])
+            hl = marker_len / 2.0
+            obj = np.array([[-hl, hl, 0], [hl, hl, 0], [hl, -hl, 0], [-hl, -hl, 0]])
+            quad = project_points(obj, R, t, Kc, Dc)
+        else:
+            quad += jit
         truth.append((mid, quad.copy()))
         # marker plane coordinates: marker occupies [0,1]^2, quiet zone extends by q on every side
         q = 1.0 / 6.0
@@ -157,6 +199,26 @@ def make_frame(W: int, H: int, n_markers: int, dict_id: int, seed: int = 0, jitt
     img += rng.integers(-4, 5, img.shape).astype(np.float32)
     g = np.clip(np.rint(img), 0, 255).astype(np.uint8)
     return np.repeat(g[:, :, None], 3, axis=2), truth
+
+
+def make_config_stream(name: str, n_frames: int, seed: int = 0, realizations: int = 4):
+    """n distinct frames of a BASELINE config: ceil(n/realizations) marker layouts, each with
+    `realizations` independent noise draws (cheap to generate, distinct threshold planes)."""
+    W, H, n, d = CONFIGS[name]
+    out = np.empty((n_frames, H, W, 3), np.uint8)
+    truths = []
+    rng = np.random.default_rng(seed + 7919)
+    base = None
+    for i in range(n_frames):
+        if i % realizations == 0:
+            base, truth = make_frame(W, H, n, d, seed * 100003 + i, first_id=(i * 7) % 200)
+        g = base[:, :, 0].astype(np.int16)
+        if i % realizations:
+            g = g + rng.integers(-3, 4, g.shape, dtype=np.int16)
+        out[i] = np.clip(g, 0, 255).astype(np.uint8)[:, :, None]
+        truths.append(truth)
+    K, D = camera_for(W, H)
+    return out, truths, K, D, d
 
 
 def make_config_frame(name: str, seed: int = 0):

@@ -127,6 +127,11 @@ int fid_detect_pose_batch(fid_detector* h, int n_frames, const uint8_t* bgr, int
                           const fid_camera* cam, double fiducial_len, int n_override, const int32_t* override_ids, const double* override_lens,
                           int max_markers, int32_t* counts, int32_t* ids, float* corners, fid_transform* transforms);
 
+/* Device-side stopwatch for benchmarks: start records a CUDA event on the handle's compute stream,
+ * stop records a second one, waits for it and returns the elapsed milliseconds between the two. */
+int fid_timer_start(fid_detector* h);
+int fid_timer_stop(fid_detector* h, float* elapsed_ms);
+
 /* Pinned host memory helpers for callers that want the async copy path. */
 int fid_host_alloc(size_t bytes, void** out);
 int fid_host_free(void* p);
