@@ -164,7 +164,11 @@ FID_HD bool is_convex_int(const Pt16* q, int n) {
 }
 
 // The remaining filters of _findMarkerContours applied to a 4-vertex approximation.
-FID_HD bool quad_passes_filters(const Pt16* q, int n_contour, int W, int H, double min_corner_dist_rate, int min_dist_to_border) {
+// NOTE (found by black-box probing of cv2 4.13, DESIGN.md "border rule"): the minDistanceToBorder
+// test is NOT applied here.  In OpenCV 4.13 a quad touching the border still takes part in the
+// grouping step (it can become a group leader and un-select its neighbours) and only then is the
+// selected candidate discarded -- silently, together with its group.  See quad_near_border().
+FID_HD bool quad_passes_filters(const Pt16* q, int n_contour, int W, int H, double min_corner_dist_rate) {
     if (!is_convex_int(q, 4)) return false;
     const int mx = W > H ? W : H;
     double min_d = (double)mx * (double)mx;
@@ -175,10 +179,6 @@ FID_HD bool quad_passes_filters(const Pt16* q, int n_contour, int W, int H, doub
     }
     const double min_corner_px = (double)n_contour * min_corner_dist_rate;
     if (min_d < min_corner_px * min_corner_px) return false;
-    for (int j = 0; j < 4; j++) {
-        if (q[j].x < min_dist_to_border || q[j].y < min_dist_to_border || q[j].x > W - 1 - min_dist_to_border || q[j].y > H - 1 - min_dist_to_border)
-            return false;
-    }
     return true;
 }
 

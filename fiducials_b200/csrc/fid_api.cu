@@ -121,13 +121,13 @@ static FrameGeom make_geom(const fid_detector* h, int W, int H, size_t row_strid
     g.H = H;
     g.wpr = (W + 31) / 32;
     g.gray_pitch = g.wpr * 32;
-    g.mask_pitch = g.wpr * 32;
+    g.mask_tpr = mask_tiles_per_row(W);
     g.bgr_row_stride = row_stride;
     g.bgr_frame_stride = frame_stride;
     g.gray_frame_stride = (size_t)g.gray_pitch * H;
     g.bits_scale_stride = (size_t)g.wpr * H;
     g.bits_frame_stride = g.bits_scale_stride * h->P.n_scales;
-    g.mask_scale_stride = (size_t)g.mask_pitch * H;
+    g.mask_scale_stride = mask_plane_bytes(W, H);
     g.mask_frame_stride = g.mask_scale_stride * h->P.n_scales;
     return g;
 }
@@ -183,7 +183,7 @@ static int alloc_slot(fid_detector* h, Slot& s) {
     A(dalloc(&s.d_bgr, F * (size_t)W * H * 3));
     A(dalloc(&s.d_gray, F * pitch * H));
     A(dalloc(&s.d_bits, F * (size_t)S * wpr * H));
-    A(dalloc(&s.d_mask, F * (size_t)S * pitch * H));
+    A(dalloc(&s.d_mask, F * (size_t)S * mask_plane_bytes(W, H)));
     A(dalloc(&s.d_starts, (size_t)h->max_starts));
     A(dalloc(&s.d_chains, (size_t)h->max_chains));
     A(dalloc(&s.d_points, (size_t)h->max_points));
@@ -435,7 +435,6 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, int nf, const FrameGeom& g
         a.H = H;
         a.poly_accuracy_rate = P.poly_accuracy_rate;
         a.min_corner_dist_rate = P.min_corner_dist_rate;
-        a.min_dist_to_border = P.min_dist_to_border;
         k_approx<<<h->sm_count * 8, APPROX_THREADS, 0, st>>>(a);
         launches++;
     }
@@ -455,6 +454,9 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, int nf, const FrameGeom& g
         a.border_bits = P.marker_border_bits;
         a.min_marker_dist_rate = (float)P.min_marker_dist_rate;
         a.min_group_dist = (float)P.min_group_dist;
+        a.W = W;
+        a.H = H;
+        a.min_dist_to_border = P.min_dist_to_border;
         a.counters = s.d_counters;
         k_sort_group<<<nf, GROUP_THREADS, 0, st>>>(a);
         launches++;

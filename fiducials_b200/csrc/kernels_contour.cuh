@@ -42,7 +42,7 @@ struct FrameGeom {
     int W, H;
     int wpr;            // 32-bit words per bit-plane row
     int gray_pitch;     // bytes
-    int mask_pitch;     // bytes (== W rounded up to 32)
+    int mask_tpr;       // 16x8 mask tiles per tile row
     size_t bgr_row_stride, bgr_frame_stride;
     size_t gray_frame_stride;
     size_t bits_scale_stride, bits_frame_stride;  // in words
@@ -207,7 +207,8 @@ __global__ void __launch_bounds__(256) k_masks_starts(const MaskArgs a) {
         L = left_crack_starts(mid, nw);
         Rr = right_crack_starts(mid, nw);
         // 32 mask bytes -> 8 words
-        uint8_t* mrow = a.mask + (size_t)f * a.g.mask_frame_stride + (size_t)s * a.g.mask_scale_stride + (size_t)y * a.g.mask_pitch + 32 * w;
+        // tiled layout: this thread's 32 pixels are row (y & 7) of two adjacent 16x8 tiles
+        uint8_t* mrow = a.mask + (size_t)f * a.g.mask_frame_stride + (size_t)s * a.g.mask_scale_stride + (((size_t)(y >> 3) * a.g.mask_tpr + 2 * w) << 7) + ((y & 7) << 4);
         uint32_t out[8];
 #pragma unroll
         for (int q = 0; q < 8; q++) {
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(256) k_masks_starts(const MaskArgs a) {
         }
         uint4* dst = reinterpret_cast<uint4*>(mrow);
         dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
-        dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+        dst[8] = make_uint4(out[4], out[5], out[6], out[7]);  // next tile: +128 bytes
         (void)W;
     }
     // warp-aggregated append of the start cracks
@@ -274,9 +275,9 @@ __global__ void __launch_bounds__(256) k_walk(const WalkArgs a) {
         const StartRec st = a.starts[i];
         const int x = st.xy & 0xFFFF, y = st.xy >> 16;
         const int f = st.meta >> 8, s = (st.meta >> 1) & 0x7F, is_right = st.meta & 1;
-        const uint8_t* plane = a.mask + (size_t)f * a.g.mask_frame_stride + (size_t)s * a.g.mask_scale_stride;
+        const MaskView plane{a.mask + (size_t)f * a.g.mask_frame_stride + (size_t)s * a.g.mask_scale_stride, a.g.mask_tpr};
         int len = 0;
-        const int r = walk_reverse(plane, a.g.mask_pitch, x, y, is_right, a.max_len, &len);
+        const int r = walk_start(plane, x, y, is_right, a.max_len, &len);
         if (r == WALK_CANONICAL && len >= a.min_len && len <= a.max_len) {
             const unsigned int slot = atomicAdd(&a.counters->n_chains, 1u);
             const unsigned int off = atomicAdd(&a.counters->n_points, (unsigned int)len);
@@ -309,8 +310,8 @@ __global__ void __launch_bounds__(128) k_emit(const EmitArgs a) {
         const ChainRec c = a.chains[i];
         if (c.n == 0) continue;
         const int f = c.meta >> 8, s = (c.meta >> 1) & 0x7F, is_right = c.meta & 1;
-        const uint8_t* plane = a.mask + (size_t)f * a.g.mask_frame_stride + (size_t)s * a.g.mask_scale_stride;
-        trace_forward(plane, a.g.mask_pitch, c.xy & 0xFFFF, c.xy >> 16, is_right, (int)c.n, a.points + c.offset);
+        const MaskView plane{a.mask + (size_t)f * a.g.mask_frame_stride + (size_t)s * a.g.mask_scale_stride, a.g.mask_tpr};
+        trace_forward(plane, c.xy & 0xFFFF, c.xy >> 16, is_right, (int)c.n, a.points + c.offset);
     }
 }
 
@@ -400,7 +401,6 @@ struct ApproxArgs {
     int max_raw;
     int W, H;
     double poly_accuracy_rate, min_corner_dist_rate;
-    int min_dist_to_border;
 };
 
 __global__ void __launch_bounds__(APPROX_THREADS) k_approx(const ApproxArgs a) {
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(APPROX_THREADS) k_approx(const ApproxArgs a) {
         Pt16 q[FID_APPROX_MAX_V];
         const int nv = approx_poly_closed(red, p, (int)c.n, (double)c.n * a.poly_accuracy_rate, q);
         if (nv != 4) continue;
-        if (threadIdx.x == 0 && quad_passes_filters(q, (int)c.n, a.W, a.H, a.min_corner_dist_rate, a.min_dist_to_border)) {
+        if (threadIdx.x == 0 && quad_passes_filters(q, (int)c.n, a.W, a.H, a.min_corner_dist_rate)) {
             const int f = c.meta >> 8, s = (c.meta >> 1) & 0x7F, is_right = c.meta & 1;
             const unsigned int slot = atomicAdd(&a.n_raw[f], 1u);
             if (slot < (unsigned int)a.max_raw) {

@@ -50,6 +50,7 @@ struct GroupArgs {
     int max_raw, close_wpr, max_sel;
     int marker_size, border_bits;
     float min_marker_dist_rate, min_group_dist;
+    int W, H, min_dist_to_border;
     Counters* counters;
 };
 
@@ -119,12 +120,13 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_sort_group(const GroupArgs a)
     if (tid == 0) {
         const uint32_t* cbc = cb;
         const int cw = a.close_wpr;
-        auto close = [cbc, cw](int i, int j) -> bool { return (cbc[(size_t)i * cw + (j >> 5)] >> (j & 31)) & 1u; };
-        group_candidates(n, qs, a.marker_size, a.border_bits, a.min_group_dist, close, a.fs.selected + fo, a.fs.group_id + fo, a.fs.group_members + fo,
+        auto close_word = [cbc, cw](int i, int w) -> uint32_t { return cbc[(size_t)i * cw + w]; };
+        group_candidates(n, qs, a.marker_size, a.border_bits, a.min_group_dist, close_word, a.fs.selected + fo, a.fs.group_id + fo, a.fs.group_members + fo,
                          a.fs.next_in_group + fo, a.fs.group_head + fo, a.fs.group_tail + fo, a.fs.close_count + fo, a.fs.close_idx + fo, a.fs.close_off + fo);
         int ns = 0;
         for (int i = 0; i < n; i++) {
             if (!a.fs.selected[fo + i]) continue;
+            if (quad_near_border(qs[i], a.W, a.H, a.min_dist_to_border)) continue;  // dropped silently, with its group
             if (ns < a.max_sel) {
                 a.fs.sel_idx[fo + ns] = i;
                 ns++;

@@ -209,7 +209,46 @@ FID_HD void project4(const double obj[4][3], const double p[6], const Camera& ca
     }
 }
 
-// 4-point homography src(x,y) -> dst(x,y): normalised DLT, eigenvector of the smallest eigenvalue.
+// Gaussian elimination with partial pivoting, N x N, in place; returns false if singular.
+template <int N>
+FID_HD bool solve_linear(double A[N][N], double b[N]) {
+#pragma unroll 1
+    for (int i = 0; i < N; i++) {
+        int k = i;
+        for (int j = i + 1; j < N; j++)
+            if (fabs(A[j][i]) > fabs(A[k][i])) k = j;
+        if (fabs(A[k][i]) < 1e-300) return false;
+        if (k != i) {
+            for (int j = i; j < N; j++) {
+                const double t = A[i][j];
+                A[i][j] = A[k][j];
+                A[k][j] = t;
+            }
+            const double t = b[i];
+            b[i] = b[k];
+            b[k] = t;
+        }
+        const double d = 1.0 / A[i][i];
+        for (int j = i + 1; j < N; j++) {
+            const double alpha = A[j][i] * d;
+            for (int c = i + 1; c < N; c++) A[j][c] -= alpha * A[i][c];
+            b[j] -= alpha * b[i];
+        }
+    }
+#pragma unroll 1
+    for (int i = N - 1; i >= 0; i--) {
+        double s = b[i];
+        for (int c = i + 1; c < N; c++) s -= A[i][c] * b[c];
+        b[i] = s / A[i][i];
+    }
+    return true;
+}
+
+// 4-point homography src(x,y) -> dst(x,y).  OpenCV takes the eigenvector of the smallest eigenvalue
+// of the normalised 9x9 DLT matrix L^T L; for exactly 4 correspondences that null vector is the
+// exact solution of the 8 DLT equations, so it is obtained here by solving them directly (in the same
+// normalised coordinates, h22 = 1) -- identical up to rounding (~1e-14), far cheaper than a 9x9
+// Jacobi sweep.  If the normalised h22 vanishes (degenerate view) fall back to the eigenvector.
 FID_HD void homography4(const double src[4][2], const double dst[4][2], double Hm[9]) {
     double cm[2] = {0, 0}, cM[2] = {0, 0}, sm[2] = {0, 0}, sM[2] = {0, 0};
     for (int i = 0; i < 4; i++) {
@@ -232,24 +271,47 @@ FID_HD void homography4(const double src[4][2], const double dst[4][2], double H
         sm[k] = 4 / sm[k];
         sM[k] = 4 / sM[k];
     }
-    double LtL[9][9];
-    for (int i = 0; i < 9; i++)
-        for (int j = 0; j < 9; j++) LtL[i][j] = 0.0;
+    double H0[9];
+    double A[8][8], bb[8];
     for (int i = 0; i < 4; i++) {
         const double x = (dst[i][0] - cm[0]) * sm[0], y = (dst[i][1] - cm[1]) * sm[1];
         const double X = (src[i][0] - cM[0]) * sM[0], Y = (src[i][1] - cM[1]) * sM[1];
-        const double Lx[9] = {X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x};
-        const double Ly[9] = {0, 0, 0, X, Y, 1, -y * X, -y * Y, -y};
-        for (int j = 0; j < 9; j++)
-            for (int k = 0; k < 9; k++) LtL[j][k] += Lx[j] * Lx[k] + Ly[j] * Ly[k];
+        const double r0[8] = {X, Y, 1, 0, 0, 0, -x * X, -x * Y};
+        const double r1[8] = {0, 0, 0, X, Y, 1, -y * X, -y * Y};
+        for (int k = 0; k < 8; k++) {
+            A[2 * i][k] = r0[k];
+            A[2 * i + 1][k] = r1[k];
+        }
+        bb[2 * i] = x;
+        bb[2 * i + 1] = y;
     }
-    double w[9], V[9][9];
-    jacobi_eigen<9>(LtL, w, V);
-    int best = 0;
-    for (int i = 1; i < 9; i++)
-        if (w[i] < w[best]) best = i;
-    double H0[9];
-    for (int i = 0; i < 9; i++) H0[i] = V[i][best];
+    bool ok = solve_linear<8>(A, bb);
+    if (ok) {
+        for (int k = 0; k < 8; k++) {
+            H0[k] = bb[k];
+            if (!(fabs(bb[k]) < 1e12)) ok = false;
+        }
+        H0[8] = 1.0;
+    }
+    if (!ok) {
+        double LtL[9][9];
+        for (int i = 0; i < 9; i++)
+            for (int j = 0; j < 9; j++) LtL[i][j] = 0.0;
+        for (int i = 0; i < 4; i++) {
+            const double x = (dst[i][0] - cm[0]) * sm[0], y = (dst[i][1] - cm[1]) * sm[1];
+            const double X = (src[i][0] - cM[0]) * sM[0], Y = (src[i][1] - cM[1]) * sM[1];
+            const double Lx[9] = {X, Y, 1, 0, 0, 0, -x * X, -x * Y, -x};
+            const double Ly[9] = {0, 0, 0, X, Y, 1, -y * X, -y * Y, -y};
+            for (int j = 0; j < 9; j++)
+                for (int k = 0; k < 9; k++) LtL[j][k] += Lx[j] * Lx[k] + Ly[j] * Ly[k];
+        }
+        double w[9], V[9][9];
+        jacobi_eigen<9>(LtL, w, V);
+        int best = 0;
+        for (int i = 1; i < 9; i++)
+            if (w[i] < w[best]) best = i;
+        for (int i = 0; i < 9; i++) H0[i] = V[i][best];
+    }
     const double invHnorm[9] = {1.0 / sm[0], 0, cm[0], 0, 1.0 / sm[1], cm[1], 0, 0, 1};
     const double Hnorm2[9] = {sM[0], 0, -cM[0] * sM[0], 0, sM[1], -cM[1] * sM[1], 0, 0, 1};
     double T[9];
@@ -259,10 +321,26 @@ FID_HD void homography4(const double src[4][2], const double dst[4][2], double H
     for (int i = 0; i < 9; i++) Hm[i] *= inv;
 }
 
-// Solve (symmetric positive semi-definite) A x = b through its eigen-decomposition with the
-// singular-value cut-off of cv::solve(DECOMP_SVD).
+// Solve the LM normal equations A x = b (A symmetric; positive definite after the (1+lambda) diagonal
+// scaling).  OpenCV uses cv::solve(DECOMP_SVD); for a positive definite system the solutions agree
+// to rounding, so a pivoted elimination is used and the eigen-decomposition (with DECOMP_SVD's
+// singular-value cut-off) is kept only for the rank-deficient case.
 FID_HD void solve_sym6(const double Ain[6][6], const double b[6], double x[6]) {
-    double A[6][6], w[6], V[6][6];
+    double A[6][6];
+    for (int i = 0; i < 6; i++) {
+        x[i] = b[i];
+        for (int j = 0; j < 6; j++) A[i][j] = Ain[i][j];
+    }
+    // conditioning guard: smallest pivot relative to the largest diagonal entry
+    double dmax = 0.0;
+    for (int i = 0; i < 6; i++) dmax = fabs(Ain[i][i]) > dmax ? fabs(Ain[i][i]) : dmax;
+    bool ok = solve_linear<6>(A, x);
+    if (ok) {
+        for (int i = 0; i < 6; i++)
+            if (!(fabs(A[i][i]) > 1e-11 * dmax)) ok = false;  // A now holds U; tiny pivot => near singular
+    }
+    if (ok) return;
+    double w[6], V[6][6];
     for (int i = 0; i < 6; i++)
         for (int j = 0; j < 6; j++) A[i][j] = Ain[i][j];
     jacobi_eigen<6>(A, w, V);

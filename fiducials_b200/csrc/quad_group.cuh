@@ -64,6 +64,14 @@ FID_HD float quad_avg_distance(const QuadF& a, const QuadF& b) {
     return sqrtf(best);
 }
 
+// minDistanceToBorder rule, applied to SELECTED candidates after grouping (see approx_quad.cuh note).
+FID_HD bool quad_near_border(const QuadF& q, int W, int H, int min_dist_to_border) {
+    const float lo = (float)min_dist_to_border, hx = (float)(W - 1 - min_dist_to_border), hy = (float)(H - 1 - min_dist_to_border);
+    for (int j = 0; j < 4; j++)
+        if (q.x[j] < lo || q.y[j] < lo || q.x[j] > hx || q.y[j] > hy) return true;
+    return false;
+}
+
 // getAverageModuleSize
 FID_HD float quad_module_size(const QuadF& q, int marker_size, int border_bits) {
     float s = quad_perimeter(q);
@@ -72,13 +80,14 @@ FID_HD float quad_module_size(const QuadF& q, int marker_size, int border_bits) 
     return s;
 }
 
-// Serial grouping over candidates already sorted by descending perimeter (stable).  `close(i,j)` is
-// the pair predicate avgDist(i,j) < perimeter[j]*minMarkerDistanceRate evaluated by the caller (in
-// parallel on the GPU, as a bit matrix).  Outputs: selected[i] and, for group leaders, the list of
+// Serial grouping over candidates already sorted by descending perimeter (stable).  `close_word(i,w)`
+// returns bits [32w, 32w+32) of row i of the pair predicate avgDist(i,j) < perimeter[j] *
+// minMarkerDistanceRate (upper triangle, j > i), evaluated by the caller (in parallel on the GPU).
+// The matrix is sparse, so only set bits are visited -- in the same (i, j) order as OpenCV's loops.  Outputs: selected[i] and, for group leaders, the list of
 // close contours (indices) in close_idx[close_off[i] .. close_off[i+1]).
 // Scratch: group_id[n], group_of[..] arrays supplied by the caller.
-template <class ClosePred>
-FID_HD void group_candidates(int n, const QuadF* quads, int marker_size, int border_bits, float min_group_dist, const ClosePred& close, uint8_t* selected,
+template <class CloseWord>
+FID_HD void group_candidates(int n, const QuadF* quads, int marker_size, int border_bits, float min_group_dist, const CloseWord& close_word, uint8_t* selected,
                              int* group_id,        // [n]
                              int* group_members,   // [n]   members of all groups, appended per group via linked lists
                              int* next_in_group,   // [n]   linked list
@@ -95,9 +104,14 @@ FID_HD void group_candidates(int n, const QuadF* quads, int marker_size, int bor
         next_in_group[i] = -1;
         close_count[i] = 0;
     }
+    const int n_words = (n + 31) >> 5;
     for (int i = 0; i < n; i++) {
-        for (int j = i + 1; j < n; j++) {
-            if (!close(i, j)) continue;
+        for (int w = (i + 1) >> 5; w < n_words; w++) {
+          uint32_t bits = close_word(i, w);
+          while (bits) {
+            const int j = (w << 5) + fid_ctz(bits);
+            bits &= bits - 1;
+            if (j <= i || j >= n) continue;
             selected[i] = 0;
             selected[j] = 0;
             if (group_id[i] < 0 && group_id[j] < 0) {
@@ -117,6 +131,7 @@ FID_HD void group_candidates(int n, const QuadF* quads, int marker_size, int bor
                 next_in_group[group_tail[g]] = i;
                 group_tail[g] = i;
             }
+          }
         }
     }
     // per group: sort members ascending (largest perimeter first), keep the first, collect the

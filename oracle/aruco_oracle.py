@@ -221,8 +221,9 @@ def find_contours(plane: np.ndarray):
 
 
 def quad_candidates(g: np.ndarray, p=REFERENCE_PARAMS):
-    """_findMarkerContours over all scales: list of (scale, int32[4,2] quad in
-    approxPolyDP order, contour length n), concatenated scale-major, contour-list order."""
+    """_findMarkerContours over all scales *before* the border rule: list of (scale,
+    int32[4,2] quad in approxPolyDP order, contour length n), concatenated scale-major, contour-list
+    order."""
     H, W = g.shape
     out = []
     min_per = int(p["minMarkerPerimeterRate"] * max(W, H))
@@ -243,8 +244,8 @@ def quad_candidates(g: np.ndarray, p=REFERENCE_PARAMS):
                 min_d = min(min_d, d)
             if min_d < (n * p["minCornerDistanceRate"]) ** 2:
                 continue
-            b = p["minDistanceToBorder"]
-            if (pts[:, 0] < b).any() or (pts[:, 1] < b).any() or (pts[:, 0] > W - 1 - b).any() or (pts[:, 1] > H - 1 - b).any():
-                continue
+            # NB: no minDistanceToBorder test here.  Black-box probing of cv2 4.13 shows that quads
+            # touching the border still take part in the grouping step and are discarded only
+            # afterwards, with their whole group (tests/test_oracle_golden.py::test_border_rule_probe).
             out.append((s, ap.reshape(4, 2).astype(np.int32), n))
     return out

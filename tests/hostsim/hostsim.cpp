@@ -35,8 +35,16 @@ struct Start {
     int x, y, is_right;
 };
 
-static void masks_and_starts(const std::vector<uint32_t>& bits, int wpr, int W, int H, std::vector<uint8_t>& mask, std::vector<Start>& starts) {
-    mask.assign((size_t)W * H, 0);
+struct HostMask {
+    std::vector<uint8_t> bytes;
+    int tpr = 0;
+    MaskView view() const { return MaskView{bytes.data(), tpr}; }
+    uint8_t& ref(int x, int y) { return bytes[(((size_t)(y >> 3) * tpr + (x >> 4)) << 7) + ((y & 7) << 4) + (x & 15)]; }
+};
+
+static void masks_and_starts(const std::vector<uint32_t>& bits, int wpr, int W, int H, HostMask& mask, std::vector<Start>& starts) {
+    mask.tpr = mask_tiles_per_row(W);
+    mask.bytes.assign(mask_plane_bytes(W, H), 0);
     auto word = [&](int y, int w) -> uint32_t { return (y < 0 || y >= H || w < 0 || w >= wpr) ? 0u : bits[(size_t)y * wpr + w]; };
     for (int y = 0; y < H; y++)
         for (int w = 0; w < wpr; w++) {
@@ -45,7 +53,7 @@ static void masks_and_starts(const std::vector<uint32_t>& bits, int wpr, int W, 
                                     word(y + 1, w + 1));
             uint32_t L = left_crack_starts(mid, nw), R = right_crack_starts(mid, nw);
             for (int i = 0; i < 32 && 32 * w + i < W; i++) {
-                mask[(size_t)y * W + 32 * w + i] = mask_byte(nw, i);
+                mask.ref(32 * w + i, y) = mask_byte(nw, i);
                 if ((L >> i) & 1) starts.push_back({32 * w + i, y, 0});
                 if ((R >> i) & 1) starts.push_back({32 * w + i, y, 1});
             }
@@ -62,7 +70,7 @@ int hs_find_contours(const uint8_t* plane, int W, int H, int min_len, int max_le
     std::vector<uint32_t> bits;
     int wpr;
     pack_plane(plane, W, H, bits, wpr);
-    std::vector<uint8_t> mask;
+    HostMask mask;
     std::vector<Start> starts;
     masks_and_starts(bits, wpr, W, H, mask, starts);
     if (n_starts_out) *n_starts_out = (int64_t)starts.size();
@@ -73,13 +81,13 @@ int hs_find_contours(const uint8_t* plane, int W, int H, int min_len, int max_le
     std::vector<Chain> chains;
     for (const Start& s : starts) {
         int n = 0;
-        int st = walk_reverse(mask.data(), W, s.x, s.y, s.is_right, max_len, &n);
+        int st = walk_start(mask.view(), s.x, s.y, s.is_right, max_len, &n);
         if (st == WALK_CANONICAL && n >= min_len) chains.push_back({((int64_t)s.y * W + s.x) * 2 + s.is_right, s.x, s.y, s.is_right, n});
     }
     if (min_len <= 1) {  // isolated pixels are 1-point outer contours
         for (int y = 0; y < H; y++)
             for (int x = 0; x < W; x++)
-                if (plane[(size_t)y * W + x] && mask[(size_t)y * W + x] == 0) chains.push_back({((int64_t)y * W + x) * 2, x, y, 0, 1});
+                if (plane[(size_t)y * W + x] && mask.view().at(x, y) == 0) chains.push_back({((int64_t)y * W + x) * 2, x, y, 0, 1});
     }
     std::sort(chains.begin(), chains.end(), [](const Chain& a, const Chain& b) { return a.key > b.key; });  // reverse discovery order
     if ((int)chains.size() > max_contours) return -1;
@@ -87,11 +95,40 @@ int hs_find_contours(const uint8_t* plane, int W, int H, int min_len, int max_le
     for (size_t i = 0; i < chains.size(); i++) {
         const Chain& c = chains[i];
         if (off + c.n > max_pts) return -1;
-        trace_forward(mask.data(), W, c.x, c.y, c.is_right, c.n, reinterpret_cast<Pt16*>(out_pts) + off);
+        trace_forward(mask.view(), c.x, c.y, c.is_right, c.n, reinterpret_cast<Pt16*>(out_pts) + off);
         out_len[i] = c.n;
         off += c.n;
     }
     return (int)chains.size();
+}
+
+// Walk statistics of one plane: out[0] starts, [1] total reverse-walk steps, [2] walks > 64 steps,
+// [3] walks > 1024 steps, [4] walks that hit max_len, [5] canonical walks, [6] steps spent in
+// canonical walks, [7] steps spent in too-long walks.
+void hs_walk_stats(const uint8_t* plane, int W, int H, int max_len, int64_t* out) {
+    std::vector<uint32_t> bits;
+    int wpr;
+    pack_plane(plane, W, H, bits, wpr);
+    HostMask mask;
+    std::vector<Start> starts;
+    masks_and_starts(bits, wpr, W, H, mask, starts);
+    for (int i = 0; i < 8; i++) out[i] = 0;
+    out[0] = (int64_t)starts.size();
+    for (const Start& st : starts) {
+        int n = 0, steps = 0;
+        const int result = walk_start(mask.view(), st.x, st.y, st.is_right, max_len, &n, &steps);
+        out[1] += steps;
+        if (steps > 64) out[2]++;
+        if (steps > 1024) out[3]++;
+        if (result == WALK_TOO_LONG) {
+            out[4]++;
+            out[7] += steps;
+        }
+        if (result == WALK_CANONICAL) {
+            out[5]++;
+            out[6] += steps;
+        }
+    }
 }
 
 // approxPolyDP (closed) of one contour; returns vertex count (-1 = more than 8 before clean-up).
@@ -112,21 +149,21 @@ static void raw_candidates(const uint8_t* planes, int W, int H, const DevParams&
         std::vector<uint32_t> bits;
         int wpr;
         pack_plane(planes + (size_t)s * W * H, W, H, bits, wpr);
-        std::vector<uint8_t> mask;
+        HostMask mask;
         std::vector<Start> starts;
         masks_and_starts(bits, wpr, W, H, mask, starts);
         std::vector<RawQuad> found;
         std::vector<Pt16> pts;
         for (const Start& st : starts) {
             int n = 0;
-            if (walk_reverse(mask.data(), W, st.x, st.y, st.is_right, max_len, &n) != WALK_CANONICAL) continue;
+            if (walk_start(mask.view(), st.x, st.y, st.is_right, max_len, &n) != WALK_CANONICAL) continue;
             if (n < min_len || n > max_len) continue;
             pts.resize(n);
-            trace_forward(mask.data(), W, st.x, st.y, st.is_right, n, pts.data());
+            trace_forward(mask.view(), st.x, st.y, st.is_right, n, pts.data());
             Pt16 q[FID_APPROX_MAX_V];
             SerialReducer red;
             if (approx_poly_closed(red, pts.data(), n, (double)n * P.poly_accuracy_rate, q) != 4) continue;
-            if (!quad_passes_filters(q, n, W, H, P.min_corner_dist_rate, P.min_dist_to_border)) continue;
+            if (!quad_passes_filters(q, n, W, H, P.min_corner_dist_rate)) continue;
             RawQuad r;
             for (int k = 0; k < 4; k++) {
                 r.x[k] = q[k].x;
@@ -191,8 +228,15 @@ int hs_detect(const uint8_t* gray, const uint8_t* planes, int W, int H, int dict
     std::vector<uint8_t> selected(n);
     std::vector<int> gid(n), gmem(n), nxt(n), ghead(n), gtail(n), ccount(n), cidx(n), coff(n + 1);
     const float rate = (float)P.min_marker_dist_rate;
-    auto close = [&](int i, int j) { return quad_avg_distance(sq[i], sq[j]) < sper[j] * rate; };
-    group_candidates(n, sq.data(), P.marker_size, P.marker_border_bits, (float)P.min_group_dist, close, selected.data(), gid.data(), gmem.data(), nxt.data(),
+    auto close_word = [&](int i, int w) -> uint32_t {
+        uint32_t bits = 0;
+        for (int b = 0; b < 32; b++) {
+            const int j = 32 * w + b;
+            if (j > i && j < n && quad_avg_distance(sq[i], sq[j]) < sper[j] * rate) bits |= 1u << b;
+        }
+        return bits;
+    };
+    group_candidates(n, sq.data(), P.marker_size, P.marker_border_bits, (float)P.min_group_dist, close_word, selected.data(), gid.data(), gmem.data(), nxt.data(),
                      ghead.data(), gtail.data(), ccount.data(), cidx.data(), coff.data());
     std::vector<unsigned long long> dict;
     pack_dictionary(P, &dict);
@@ -204,6 +248,7 @@ int hs_detect(const uint8_t* gray, const uint8_t* planes, int W, int H, int dict
     std::vector<float> patch(13 * 13);
     for (int i = 0; i < n; i++) {
         if (!selected[i]) continue;
+        if (quad_near_border(sq[i], W, H, P.min_dist_to_border)) continue;
         n_sel++;
         QuadF use = sq[i];
         IdentifyResult r = identify_candidate(L, gray, W, H, (size_t)W, use, P, dict.data(), img.data(), hist);

@@ -222,6 +222,17 @@ def test_marker_near_border_and_partial(det_cache):
     _check_detect(det_cache(d, 550, 400), crop, d)
 
 
+def test_border_rule_sliding_marker(det_cache):
+    """A marker sliding out of the frame column by column (OpenCV 4.13 border rule)."""
+    bgr, truth, K, D, d = synth.make_config_frame("C1", 0)
+    right = np.array([q for _, q in truth])[:, :, 0].max()
+    det = det_cache(d, 640, 480)
+    for shift in range(int(640 - right) - 6, int(640 - right) + 8):
+        fr = np.roll(bgr, shift, axis=1)
+        fr[:, :shift] = 190
+        _check_detect(det, fr, d)
+
+
 def test_other_dictionaries(det_cache):
     for d in (4, 7, 8, 11):
         bgr, truth = synth.make_frame(640, 480, 4, d, seed=d)
@@ -262,14 +273,16 @@ def test_full_size_round_trip(det_cache, cfg):
     bgr, truth, K, D, d = synth.make_config_frame(cfg, 3)
     H, W = bgr.shape[:2]
     det = det_cache(d, W, H)
-    ids, corners = det.detect(bgr)
+    ids, corners = _check_detect(det, bgr, d)  # also identical to the oracle at full size
     tm = {m: q for m, q in truth}
     assert sorted(ids.tolist()) == sorted(tm)
-    for i, fid in enumerate(ids.tolist()):
-        assert np.abs(corners[i] - tm[fid]).max() < 1.5
+    err = np.array([np.abs(corners[i] - tm[fid]).max() for i, fid in enumerate(ids.tolist())])
+    assert np.median(err) < 1.0 and (err < 1.5).mean() >= 0.9  # a few rendered corners are ambiguous for cv2 too
     tfs = det.pose(ids, corners, K, D, 0.14)
     obj = ao.single_marker_object_points(0.14)
     for i, t in enumerate(tfs):
+        if err[i] >= 1.5:
+            continue
         proj, _ = cv2.projectPoints(obj, np.array(t.rvec), np.array(t.translation), K, D)
         assert np.abs(proj.reshape(4, 2) - corners[i]).max() < 1.0
         assert t.image_error < 1.0

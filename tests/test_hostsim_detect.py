@@ -46,6 +46,27 @@ def test_detect_matches_oracle_reference_frames(kat, name):
     assert np.abs(corners - kat[name + "_corners"]).max() <= 1e-3
 
 
+def test_border_rule_matches_cv2():
+    """Markers sliding out of the frame: OpenCV 4.13 discards a border-touching quad only AFTER the
+    grouping step (together with its group) -- found by black-box probing, see DESIGN.md.  A
+    candidate-level border test (OpenCV <= 4.6 behaviour) fails this test."""
+    bgr, truth, K, D, d = synth.make_config_frame("C1", 0)
+    quads = np.array([q for _, q in truth])
+    right = quads[:, :, 0].max()
+    n_cases = 0
+    for shift in range(int(640 - right) - 6, int(640 - right) + 8):
+        fr = np.roll(bgr, shift, axis=1)
+        fr[:, :shift] = 190
+        g = ao.gray(fr)
+        ids, corners, _ = hs.detect(g, ao.threshold_planes(g), d)
+        rids, rc = ao.detect(fr, d)
+        assert ids.tolist() == rids.tolist(), shift
+        if len(ids):
+            assert np.abs(corners - rc).max() <= 1e-3
+        n_cases += 1
+    assert n_cases >= 10
+
+
 def test_corner_subpix_bit_exact(kat):
     g = ao.gray(kat.frame("bag"))
     _, corners = ao.detect(kat.frame("bag"), 7, cornerRefinementMethod=cv2.aruco.CORNER_REFINE_NONE)
