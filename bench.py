@@ -337,7 +337,7 @@ def run_gpu_arm(args):
         thr_s = stage_ms["threshold"] / 1e3
         peak, peak_src = measured_hbm_peak()
         achieved = algo_bytes / thr_s / 1e9 if thr_s > 0 else 0.0
-        total_stage = sum(v for k, v in stage_ms.items() if k not in ("h2d", "d2h"))
+        total_stage = sum(v for k, v in stage_ms.items() if k not in ("h2d", "d2h") and not k.startswith("walk_r"))
         roofline = {
             "bound": "hbm",
             "kernel": "k_threshold",
@@ -353,7 +353,10 @@ def run_gpu_arm(args):
             "stage_ms_per_batch": stage_ms,
             "work_per_batch": counters,
         }
-        cpu = cpu_reference_fps(frames[:8], dict_id, K, D, budget_s=16.0)
+        if os.environ.get("FID_BENCH_SKIP_CPU"):  # profiling runs (ncu) only
+            cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "skipped (FID_BENCH_SKIP_CPU set)"}
+        else:
+            cpu = cpu_reference_fps(frames[:8], dict_id, K, D, budget_s=16.0)
         d2h = nf * (4 + MAXM * 4 + MAXM * 32 + MAXM * C.sizeof(_lib.fid_transform))
         out = {
             "metric": "frames/sec 1920x1080 (detect+pose)",

@@ -5,9 +5,10 @@
 // OpenCV's Suzuki-Abe scan is sequential (it marks visited pixels); here every border is found
 // independently:
 //
-//  * the plane is stored as one byte per pixel holding the 8-neighbour occupancy of that pixel
-//    (bit k set <=> neighbour in direction k is foreground; pixels outside the image are
-//    background, which is OpenCV 4.13's zero padding).  Direction codes (y down):
+//  * the walk reads the bit-packed threshold plane directly: per step the 3x3 neighbourhood of the
+//    current pixel is turned into an 8-bit occupancy mask (bit k set <=> neighbour in direction k
+//    is foreground; pixels outside the image are background, which is OpenCV 4.13's zero
+//    padding).  Direction codes (y down):
 //        0:(+1,0) 1:(+1,-1) 2:(0,-1) 3:(-1,-1) 4:(-1,0) 5:(-1,+1) 6:(0,+1) 7:(+1,+1)
 //  * a border is a cycle of states (pixel, dir to previous pixel a, dir to next pixel b) where b is
 //    the first foreground neighbour counter-clockwise after a.  The zero neighbours strictly
@@ -46,34 +47,80 @@ FID_HD int prev_cw(int m, int b) {
 
 enum { WALK_ABORT = 0, WALK_CANONICAL = 1, WALK_TOO_LONG = 2 };
 
-// Mask planes are stored in 16x8-pixel tiles of 128 bytes (one cache line, four 32-byte sectors of
-// 16x2 pixels): a border walk moves one pixel per step in any direction, so with row-major storage
-// every vertical step would touch a new line (an L2 round trip per step), whereas a tile keeps the
-// next ~10 steps in the line the walker already holds in L1.
-#define FID_MASK_TW 16
-#define FID_MASK_TH 8
-struct MaskView {
-    const uint8_t* base;
+// Threshold planes are bit-packed in 32x32-pixel tiles: a tile is 32 consecutive 32-bit words (one
+// 128-byte cache line), word r = row r of the tile, bit i = column i.  A border walk moves one pixel
+// per step in any direction; with this layout the 3x3 neighbourhood of a pixel is three words of the
+// line the walker already holds in L1 (30 steps out of 32 in either direction), and a whole 1080p
+// plane is 270 KB, so the 13 planes of many frames stay L2 resident.  (A first version stored one
+// neighbour-mask byte per pixel: 27 MB per 1080p frame -- every step of a long walk missed L2 and
+// the TLB, ~2300 cycles per step measured on B200.)
+struct BitView {
+    const uint32_t* base;
     int tiles_per_row;
-    FID_HD int at(int x, int y) const { return base[(((size_t)(y >> 3) * tiles_per_row + (x >> 4)) << 7) + ((y & 7) << 4) + (x & 15)]; }
+    int W, H;
+    // bits of pixels x-1, x, x+1 of row y in bits 0,1,2; 0 outside the image
+    FID_HD uint32_t row3(int x, int y) const {
+        if (y < 0 || y >= H) return 0u;
+        const int tx = x >> 5, xb = x & 31;
+        const uint32_t* t = base + ((size_t)(y >> 5) * tiles_per_row + tx) * 32 + (y & 31);
+        const uint32_t w = *t;
+        uint32_t r = (xb ? (w >> (xb - 1)) : (w << 1)) & 7u;
+        if (xb == 0 && tx > 0) r |= t[-32] >> 31;
+        if (xb == 31 && tx + 1 < tiles_per_row) r |= (t[32] & 1u) << 2;
+        return r;
+    }
+    // 8-neighbour occupancy mask of pixel (x,y)
+    FID_HD int at(int x, int y) const {
+        const int xb = x & 31, yb = y & 31;
+        uint32_t u, m, d;
+        if (xb >= 1 && xb <= 30 && yb >= 1 && yb <= 30) {
+            const uint32_t* t = base + ((size_t)(y >> 5) * tiles_per_row + (x >> 5)) * 32 + yb;
+            u = (t[-1] >> (xb - 1)) & 7u;
+            m = (t[0] >> (xb - 1)) & 7u;
+            d = (t[1] >> (xb - 1)) & 7u;
+        } else {
+            u = row3(x, y - 1);
+            m = row3(x, y);
+            d = row3(x, y + 1);
+        }
+        return (int)(((m >> 2) & 1u) | (((u >> 2) & 1u) << 1) | (((u >> 1) & 1u) << 2) | ((u & 1u) << 3) | ((m & 1u) << 4) | ((d & 1u) << 5) | (((d >> 1) & 1u) << 6) |
+                     (((d >> 2) & 1u) << 7));
+    }
+    // word holding pixels [32*tx, 32*tx+32) of row y; 0 outside
+    FID_HD uint32_t word(int tx, int y) const {
+        if (y < 0 || y >= H || tx < 0 || tx >= tiles_per_row) return 0u;
+        return base[((size_t)(y >> 5) * tiles_per_row + tx) * 32 + (y & 31)];
+    }
 };
-FID_HD size_t mask_plane_bytes(int W, int H) { return (size_t)((W + 31) / 32 * 2) * ((H + 7) / 8) * 128; }
-FID_HD int mask_tiles_per_row(int W) { return (W + 31) / 32 * 2; }
+typedef BitView MaskView;
+FID_HD int bit_tiles_per_row(int W) { return (W + 31) / 32; }
+FID_HD size_t bit_plane_words(int W, int H) { return (size_t)((W + 31) / 32) * ((H + 31) / 32) * 32; }
 
 // Walk the border owning the left (is_right=0) or right (is_right=1) crack of foreground pixel
-// (x0,y0) once around.  Returns WALK_CANONICAL with *n_out = contour point count if (x0,y0) is the
-// Suzuki start pixel of that border (outer border for a left crack, hole border for a right one),
-// WALK_ABORT as soon as a crack with a raster-smaller pixel proves it is not.
+// (x0,y0) once around.  WALK_CANONICAL with the contour point count n if (x0,y0) is the Suzuki start
+// pixel of that border (outer border for a left crack, hole border for a right one); WALK_ABORT as
+// soon as a crack with a raster-smaller pixel proves it is not.
 //
 // Direction matters for speed, not for the result: a left crack lies on a left-facing piece of
 // border, where walking BACKWARDS (clockwise search) heads up the image; a right crack lies on a
 // right-facing piece, where walking FORWARDS (counter-clockwise search) heads up.  Heading up
-// means the very next cracks are raster-smaller, so a non-canonical start dies within a few steps
-// (measured on 1080p marker scenes: 1.6 steps per start on average instead of 115 when every
-// start walks backwards).  *steps_out (optional) returns the number of steps taken.
-FID_HD int walk_start(const MaskView mask, int x0, int y0, int is_right, int max_len, int* n_out, int* steps_out = nullptr) {
-    int m = mask.at(x0, y0);
-    if (steps_out) *steps_out = 0;
+// means the very next cracks are raster-smaller, so a non-canonical start usually dies within a few
+// steps (1080p marker scenes: 12-21 steps per start on average instead of 115 when every start walks
+// backwards).
+//
+// The walk is resumable (WalkState + step budget) so that the GPU can run it in rounds of growing
+// budget: a warp then only ever holds walks of similar length (kernels_contour.cuh, k_walk_round).
+enum { WALK_CONTINUE = 3 };
+struct WalkState {
+    int x, y;  // current pixel
+    int dir;   // backwards walk: dir to the NEXT pixel's... see below; forwards: dir to next pixel
+    int n;     // steps taken
+    int a0, b0;
+};
+
+// Returns WALK_ABORT (isolated pixel / tie lost) or WALK_CONTINUE with the state initialised.
+FID_HD int walk_init(const MaskView mask, int x0, int y0, int is_right, WalkState* st) {
+    const int m = mask.at(x0, y0);
     if (m == 0) return WALK_ABORT;  // isolated pixel: 1-point contour, never long enough to matter
     const int crack = is_right ? 0 : 4;
     const int a0 = prev_cw(m, crack);
@@ -82,17 +129,30 @@ FID_HD int walk_start(const MaskView mask, int x0, int y0, int is_right, int max
         const int d = (b0 - a0 - 1) & 7;
         if (((4 - a0 - 1) & 7) < d) return WALK_ABORT;
     }
-    int x = x0, y = y0, n = 0;
-    int result;
+    st->x = x0;
+    st->y = y0;
+    st->n = 0;
+    st->a0 = a0;
+    st->b0 = b0;
+    st->dir = is_right ? b0 : a0;
+    return WALK_CONTINUE;
+}
+
+// Advance by at most `budget` steps.  Returns WALK_CANONICAL (st->n = contour length), WALK_ABORT,
+// WALK_TOO_LONG (more than max_len steps) or WALK_CONTINUE (budget exhausted, state updated).
+FID_HD int walk_resume(const MaskView mask, int x0, int y0, int is_right, int max_len, int budget, WalkState* st) {
+    int x = st->x, y = st->y, n = st->n, dir = st->dir;
+    const int a0 = st->a0, b0 = st->b0;
+    const int stop_at = n + budget;
+    int result = WALK_CONTINUE;
     if (!is_right) {
-        int a = a0;  // backwards: state = (pixel, dir to next); arrive from the next pixel
-        for (;;) {
+        int a = dir;  // backwards: `a` = direction from the current pixel to the previous one
+        while (n < stop_at) {
             x += dir_dx(a);
             y += dir_dy(a);
             n++;
             const int bq = (a + 4) & 7;
             if (x == x0 && y == y0 && bq == b0) {
-                *n_out = n;
                 result = WALK_CANONICAL;
                 break;
             }
@@ -100,7 +160,7 @@ FID_HD int walk_start(const MaskView mask, int x0, int y0, int is_right, int max
                 result = WALK_TOO_LONG;
                 break;
             }
-            m = mask.at(x, y);
+            const int m = mask.at(x, y);
             a = prev_cw(m, bq);
             const int d = (bq - a - 1) & 7;
             const bool exL = ((4 - a - 1) & 7) < d;
@@ -110,15 +170,15 @@ FID_HD int walk_start(const MaskView mask, int x0, int y0, int is_right, int max
                 break;
             }
         }
+        dir = a;
     } else {
-        int b = b0;  // forwards: state = (pixel, dir to previous); arrive from the previous pixel
-        for (;;) {
+        int b = dir;  // forwards: `b` = direction from the current pixel to the next one
+        while (n < stop_at) {
             x += dir_dx(b);
             y += dir_dy(b);
             n++;
             const int aq = (b + 4) & 7;
             if (x == x0 && y == y0 && aq == a0) {
-                *n_out = n;
                 result = WALK_CANONICAL;
                 break;
             }
@@ -126,21 +186,34 @@ FID_HD int walk_start(const MaskView mask, int x0, int y0, int is_right, int max
                 result = WALK_TOO_LONG;
                 break;
             }
-            m = mask.at(x, y);
+            const int m = mask.at(x, y);
             b = next_ccw(m, aq);
             const int d = (b - aq - 1) & 7;
             const bool exL = ((4 - aq - 1) & 7) < d;
             const bool exR = ((0 - aq - 1) & 7) < d;
-            if (exL || exR) {
-                if (y < y0 || (y == y0 && x < x0) || (exL && y == y0 && x == x0)) {
-                    result = WALK_ABORT;
-                    break;
-                }
+            if ((exL || exR) && (y < y0 || (y == y0 && x < x0) || (exL && y == y0 && x == x0))) {
+                result = WALK_ABORT;
+                break;
             }
         }
+        dir = b;
     }
-    if (steps_out) *steps_out = n;
+    st->x = x;
+    st->y = y;
+    st->n = n;
+    st->dir = dir;
     return result;
+}
+
+// One-shot walk (CPU harness, small inputs).  *steps_out (optional) returns the steps taken.
+FID_HD int walk_start(const MaskView mask, int x0, int y0, int is_right, int max_len, int* n_out, int* steps_out = nullptr) {
+    WalkState st;
+    if (steps_out) *steps_out = 0;
+    if (walk_init(mask, x0, y0, is_right, &st) == WALK_ABORT) return WALK_ABORT;
+    const int r = walk_resume(mask, x0, y0, is_right, max_len, 0x3fffffff, &st);
+    if (steps_out) *steps_out = st.n;
+    if (r == WALK_CANONICAL) *n_out = st.n;
+    return r;
 }
 
 // Emit the n contour points in OpenCV order (start pixel first, then Suzuki's direction).

@@ -25,14 +25,15 @@ using namespace fid;
     } while (0)
 
 enum { ST_H2D = 0, ST_THRESH, ST_MASKS, ST_WALK, ST_EMIT, ST_APPROX, ST_GROUP, ST_IDENT, ST_SUBPIX_POSE, ST_POSE_UNUSED, ST_D2H, ST_COUNT };
+enum { N_WALK_ROUNDS = 4 };
 
 struct Slot {
     uint8_t* d_bgr = nullptr;
     uint8_t* d_gray = nullptr;
     uint32_t* d_bits = nullptr;
-    uint8_t* d_mask = nullptr;
     StartRec* d_starts = nullptr;
     ChainRec* d_chains = nullptr;
+    WalkRec* d_queue[2] = {nullptr, nullptr};
     Pt16* d_points = nullptr;
     Counters* d_counters = nullptr;
     RawQuad* d_raw = nullptr;
@@ -55,6 +56,7 @@ struct Slot {
     int* h_nsel = nullptr;
     int* h_nrawc = nullptr;
     cudaEvent_t ev[ST_COUNT + 1]{};
+    cudaEvent_t ev_round[N_WALK_ROUNDS + 1]{};
     cudaEvent_t done = nullptr;
     cudaEvent_t copied = nullptr;
 };
@@ -66,7 +68,7 @@ struct fid_detector {
     DevParams P{};
     int max_w = 0, max_h = 0, max_batch = 0;
     int max_raw = 4096, close_wpr = 128, max_sel = 512, max_markers = FID_MAX_MARKERS;
-    unsigned int max_starts = 0, max_chains = 0, max_points = 0;
+    unsigned int max_starts = 0, max_chains = 0, max_points = 0, max_queue = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     Slot slot[2];
     float* d_subpix_masks = nullptr;
@@ -75,7 +77,7 @@ struct fid_detector {
     int32_t* d_pose_ids = nullptr;
     float* d_pose_corners = nullptr;
     fid_transform* d_pose_out = nullptr;
-    float stage_ms[ST_COUNT]{};
+    float stage_ms[ST_COUNT + N_WALK_ROUNDS]{};
     int64_t counters[8]{};
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     // last geometry (for debug calls)
@@ -121,14 +123,11 @@ static FrameGeom make_geom(const fid_detector* h, int W, int H, size_t row_strid
     g.H = H;
     g.wpr = (W + 31) / 32;
     g.gray_pitch = g.wpr * 32;
-    g.mask_tpr = mask_tiles_per_row(W);
     g.bgr_row_stride = row_stride;
     g.bgr_frame_stride = frame_stride;
     g.gray_frame_stride = (size_t)g.gray_pitch * H;
-    g.bits_scale_stride = (size_t)g.wpr * H;
+    g.bits_scale_stride = bit_plane_words(W, H);
     g.bits_frame_stride = g.bits_scale_stride * h->P.n_scales;
-    g.mask_scale_stride = mask_plane_bytes(W, H);
-    g.mask_frame_stride = g.mask_scale_stride * h->P.n_scales;
     return g;
 }
 
@@ -182,10 +181,11 @@ static int alloc_slot(fid_detector* h, Slot& s) {
     if ((rc = (expr)) != FID_OK) return rc;
     A(dalloc(&s.d_bgr, F * (size_t)W * H * 3));
     A(dalloc(&s.d_gray, F * pitch * H));
-    A(dalloc(&s.d_bits, F * (size_t)S * wpr * H));
-    A(dalloc(&s.d_mask, F * (size_t)S * mask_plane_bytes(W, H)));
+    A(dalloc(&s.d_bits, F * (size_t)S * bit_plane_words(W, H)));
     A(dalloc(&s.d_starts, (size_t)h->max_starts));
     A(dalloc(&s.d_chains, (size_t)h->max_chains));
+    A(dalloc(&s.d_queue[0], (size_t)h->max_queue));
+    A(dalloc(&s.d_queue[1], (size_t)h->max_queue));
     A(dalloc(&s.d_points, (size_t)h->max_points));
     A(dalloc(&s.d_counters, 1));
     const size_t R = F * h->max_raw;
@@ -224,13 +224,14 @@ static int alloc_slot(fid_detector* h, Slot& s) {
     A(halloc(&s.h_nrawc, F));
 #undef A
     for (int i = 0; i <= ST_COUNT; i++) CK(cudaEventCreate(&s.ev[i]));
+    for (int i = 0; i <= N_WALK_ROUNDS; i++) CK(cudaEventCreate(&s.ev_round[i]));
     CK(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&s.copied, cudaEventDisableTiming));
     return FID_OK;
 }
 
 static void free_slot(Slot& s) {
-    void* dptrs[] = {s.d_bgr,         s.d_gray,          s.d_bits,          s.d_mask,         s.d_starts,       s.d_chains,       s.d_points,      s.d_counters,
+    void* dptrs[] = {s.d_queue[0], s.d_queue[1], s.d_bgr,         s.d_gray,          s.d_bits,          s.d_starts,       s.d_chains,       s.d_points,      s.d_counters,
                      s.d_raw,         s.d_nraw,          s.fs.quads_tmp,    s.fs.per_tmp,     s.fs.quads,       s.fs.per,         s.fs.close_bits, s.fs.group_id,
                      s.fs.group_members, s.fs.next_in_group, s.fs.group_head, s.fs.group_tail, s.fs.close_count, s.fs.close_idx,   s.fs.close_off,  s.fs.selected,
                      s.fs.sel_idx,    s.d_nsel,          s.d_nrawc,         s.d_cand_id,      s.d_cand_corners, s.d_out_count,    s.d_out_ids,     s.d_out_corners,
@@ -242,6 +243,8 @@ static void free_slot(Slot& s) {
         if (p) cudaFreeHost(p);
     for (int i = 0; i <= ST_COUNT; i++)
         if (s.ev[i]) cudaEventDestroy(s.ev[i]);
+    for (int i = 0; i <= N_WALK_ROUNDS; i++)
+        if (s.ev_round[i]) cudaEventDestroy(s.ev_round[i]);
     if (s.done) cudaEventDestroy(s.done);
     if (s.copied) cudaEventDestroy(s.copied);
 }
@@ -274,6 +277,7 @@ extern "C" int fid_create(const fid_params* params, int device, int max_width, i
     h->max_starts = (unsigned int)std::min<size_t>(px * 6 + 65536, 0x7fffffffu);
     h->max_chains = (unsigned int)std::min<size_t>((size_t)max_batch * 65536, 0x7fffffffu);
     h->max_points = (unsigned int)std::min<size_t>(px * 4 + 65536, 0x7fffffffu);
+    h->max_queue = h->max_starts / 8 + 65536;  // walks that survive the first 32 steps: ~3 % of the start cracks
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     if ((rc = upload_constants()) != FID_OK || (rc = configure_kernels(h)) != FID_OK) {
@@ -379,7 +383,6 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, int nf, const FrameGeom& g
     {  // masks + starts
         MaskArgs a{};
         a.bits = s.d_bits;
-        a.mask = s.d_mask;
         a.starts = s.d_starts;
         a.counters = s.d_counters;
         a.max_starts = h->max_starts;
@@ -393,25 +396,42 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, int nf, const FrameGeom& g
     CK(cudaEventRecord(s.ev[ST_WALK], st));
     const int mx = W > H ? W : H;
     const int min_len = (int)(P.min_perimeter_rate * mx), max_len = (int)(P.max_perimeter_rate * mx);
-    {  // walk
+    {  // walk, in rounds of growing budget
         WalkArgs a{};
-        a.mask = s.d_mask;
+        a.bits = s.d_bits;
         a.starts = s.d_starts;
         a.chains = s.d_chains;
         a.counters = s.d_counters;
         a.max_starts = h->max_starts;
         a.max_chains = h->max_chains;
         a.max_points = h->max_points;
+        a.max_queue = h->max_queue;
         a.g = g;
         a.min_len = min_len;
         a.max_len = max_len;
-        k_walk<<<h->sm_count * 8, 256, 0, st>>>(a);
-        launches++;
+        static const int budgets[N_WALK_ROUNDS] = {1024, 0x3fffffff, 0, 0};
+        for (int r = 0; r < N_WALK_ROUNDS; r++) {
+            CK(cudaEventRecord(s.ev_round[r], st));
+            if (r >= 2) continue;
+            a.budget = budgets[r];
+            a.q_in = r > 0 ? s.d_queue[(r - 1) & 1] : nullptr;
+            a.q_out = s.d_queue[r & 1];
+            a.q_in_idx = r - 1;
+            a.q_out_idx = r;
+            a.chunk = r == 0 ? 256u : 32u;
+            unsigned int* work = &s.d_counters->work[r];
+            if (r == 0)
+                k_walk_persist<true><<<h->sm_count * 8, 256, 0, st>>>(a, work);
+            else
+                k_walk_persist<false><<<h->sm_count * 4, 128, 0, st>>>(a, work);
+            launches++;
+        }
+        CK(cudaEventRecord(s.ev_round[N_WALK_ROUNDS], st));
     }
     CK(cudaEventRecord(s.ev[ST_EMIT], st));
     {  // emit
         EmitArgs a{};
-        a.mask = s.d_mask;
+        a.bits = s.d_bits;
         a.chains = s.d_chains;
         a.points = s.d_points;
         a.counters = s.d_counters;
@@ -549,7 +569,7 @@ static int collect(fid_detector* h, Slot& s, int nf, int max_markers, int32_t* c
     float ms = 0;
     static const int order[] = {ST_THRESH, ST_MASKS, ST_WALK, ST_EMIT, ST_APPROX, ST_GROUP, ST_IDENT, ST_SUBPIX_POSE, ST_D2H, ST_COUNT};
     if (first_chunk) {
-        for (int i = 0; i < ST_COUNT; i++) h->stage_ms[i] = 0;
+        for (int i = 0; i < ST_COUNT + N_WALK_ROUNDS; i++) h->stage_ms[i] = 0;
         for (int i = 0; i < 6; i++) h->counters[i] = 0;
     }
     for (int i = 0; i + 1 < (int)(sizeof(order) / sizeof(order[0])); i++) {
@@ -559,6 +579,12 @@ static int collect(fid_detector* h, Slot& s, int nf, int max_markers, int32_t* c
         } else {
             cudaGetLastError();
         }
+    }
+    for (int r = 0; r < N_WALK_ROUNDS; r++) {
+        if (cudaEventElapsedTime(&ms, s.ev_round[r], s.ev_round[r + 1]) == cudaSuccess)
+            h->stage_ms[ST_COUNT + r] += ms;
+        else
+            cudaGetLastError();
     }
     h->counters[0] += s.h_counters->n_starts;
     h->counters[1] += s.h_counters->n_chains;
@@ -740,12 +766,13 @@ extern "C" int fid_debug_threshold(fid_detector* h, const uint8_t* bgr, int widt
     CK(cudaStreamSynchronize(h->stream));
     if (gray) CK(cudaMemcpy2D(gray, width, s.d_gray, g.gray_pitch, width, height, cudaMemcpyDeviceToHost));
     if (planes) {
-        std::vector<uint32_t> bits((size_t)h->P.n_scales * g.wpr * height);
+        std::vector<uint32_t> bits((size_t)h->P.n_scales * g.bits_scale_stride);
         CK(cudaMemcpy(bits.data(), s.d_bits, bits.size() * 4, cudaMemcpyDeviceToHost));
         for (int sc = 0; sc < h->P.n_scales; sc++)
             for (int y = 0; y < height; y++)
                 for (int x = 0; x < width; x++)
-                    planes[((size_t)sc * height + y) * width + x] = (bits[(size_t)sc * g.bits_scale_stride + (size_t)y * g.wpr + (x >> 5)] >> (x & 31)) & 1u;
+                    planes[((size_t)sc * height + y) * width + x] =
+                        (bits[(size_t)sc * g.bits_scale_stride + ((size_t)(y >> 5) * g.wpr + (x >> 5)) * 32 + (y & 31)] >> (x & 31)) & 1u;
     }
     if (n_scales) *n_scales = h->P.n_scales;
     return FID_OK;
@@ -778,9 +805,9 @@ extern "C" int fid_debug_candidates(fid_detector* h, int max_candidates, int* n,
 
 extern "C" int fid_last_stage_ms(fid_detector* h, float* ms, int max_stages, int* n_stages) {
     if (!h || !ms) return FID_ERR_INVALID_ARG;
-    const int n = std::min(max_stages, (int)ST_COUNT);
+    const int n = std::min(max_stages, (int)ST_COUNT + N_WALK_ROUNDS);
     for (int i = 0; i < n; i++) ms[i] = h->stage_ms[i];
-    if (n_stages) *n_stages = ST_COUNT;
+    if (n_stages) *n_stages = ST_COUNT + N_WALK_ROUNDS;
     return FID_OK;
 }
 

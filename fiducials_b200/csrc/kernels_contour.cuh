@@ -21,9 +21,17 @@ struct Counters {
     unsigned int n_starts;
     unsigned int n_chains;
     unsigned int n_points;
-    unsigned int overflow;  // bit0 starts, bit1 chains, bit2 points, bit3 raw quads, bit4 selected
-    unsigned int walk_steps_lo, walk_steps_hi;  // optional statistics
-    unsigned int pad[2];
+    unsigned int overflow;  // bit0 starts, bit1 chains, bit2 points, bit3 raw quads, bit4 selected, bit5 markers, bit6 walk queue
+    unsigned int n_q[3];    // walks suspended by rounds 0,1,2
+    unsigned int work[4];   // persistent-walker work counters, one per round
+    unsigned int pad;
+};
+
+struct WalkRec {       // a border walk suspended between rounds
+    uint32_t xy0;      // start pixel
+    uint32_t meta;     // frame << 8 | scale << 1 | is_right
+    uint32_t xy;       // current pixel
+    uint32_t state;    // dir | a0 << 3 | b0 << 6 | n << 9
 };
 
 struct StartRec {
@@ -40,13 +48,11 @@ struct ChainRec {
 
 struct FrameGeom {
     int W, H;
-    int wpr;            // 32-bit words per bit-plane row
+    int wpr;            // 32-pixel tiles per bit-plane tile row (== words per pixel row)
     int gray_pitch;     // bytes
-    int mask_tpr;       // 16x8 mask tiles per tile row
     size_t bgr_row_stride, bgr_frame_stride;
     size_t gray_frame_stride;
-    size_t bits_scale_stride, bits_frame_stride;  // in words
-    size_t mask_scale_stride, mask_frame_stride;  // in bytes
+    size_t bits_scale_stride, bits_frame_stride;  // in words (tiled 32x32, see BitView)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -165,17 +171,28 @@ __global__ void __launch_bounds__(THR_THREADS, 2) k_threshold(const ThreshArgs a
             const int S = (int)(bot[cx + r + 1] - bot[cx - r] - top[cx + r + 1] + top[cx - r]);
             const bool on = valid && (2 * S >= g2 * k * k);
             const uint32_t word = __ballot_sync(0xffffffffu, on);
-            if (lane == 0) bits[(size_t)s * a.g.bits_scale_stride + (size_t)y * a.g.wpr + (x >> 5)] = word;
+            if (lane == 0) bits[(size_t)s * a.g.bits_scale_stride + ((size_t)(y >> 5) * a.g.wpr + (x >> 5)) * 32 + (y & 31)] = word;
+        }
+    }
+    // rows of the last tile row that lie below the image must read as background
+    const int Hpad = (H + 31) & ~31;
+    if (ty0 + THR_TH >= H && Hpad > H) {
+        for (int u = tid; u < (Hpad - H) * (THR_TW / 32) * a.n_scales; u += THR_THREADS) {
+            const int s = u % a.n_scales;
+            const int t = u / a.n_scales;
+            const int seg = t % (THR_TW / 32), y = H + t / (THR_TW / 32);
+            const int x = tx0 + seg * 32;
+            if (x < W) bits[(size_t)s * a.g.bits_scale_stride + ((size_t)(y >> 5) * a.g.wpr + (x >> 5)) * 32 + (y & 31)] = 0u;
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// k_masks_starts: one thread per (frame, scale, row, word).
+// k_starts: one thread per (frame, scale, row, 32-pixel word): start cracks (exact local prune) ->
+// queue.  Pure bit-plane work: 9 words in, two bit masks out.
 // ---------------------------------------------------------------------------------------------------
 struct MaskArgs {
     const uint32_t* bits;
-    uint8_t* mask;
     StartRec* starts;
     Counters* counters;
     unsigned int max_starts;
@@ -199,28 +216,14 @@ __global__ void __launch_bounds__(256) k_masks_starts(const MaskArgs a) {
         t /= H;
         s = (int)(t % a.n_scales);
         f = (int)(t / a.n_scales);
-        const uint32_t* plane = a.bits + (size_t)f * a.g.bits_frame_stride + (size_t)s * a.g.bits_scale_stride;
-        auto word = [&](int yy, int ww) -> uint32_t { return (yy < 0 || yy >= H || ww < 0 || ww >= wpr) ? 0u : __ldg(plane + (size_t)yy * wpr + ww); };
-        const uint32_t mid = word(y, w);
-        const NbrWords nw = nbr_words(word(y - 1, w - 1), word(y - 1, w), word(y - 1, w + 1), word(y, w - 1), mid, word(y, w + 1), word(y + 1, w - 1),
-                                      word(y + 1, w), word(y + 1, w + 1));
-        L = left_crack_starts(mid, nw);
-        Rr = right_crack_starts(mid, nw);
-        // 32 mask bytes -> 8 words
-        // tiled layout: this thread's 32 pixels are row (y & 7) of two adjacent 16x8 tiles
-        uint8_t* mrow = a.mask + (size_t)f * a.g.mask_frame_stride + (size_t)s * a.g.mask_scale_stride + (((size_t)(y >> 3) * a.g.mask_tpr + 2 * w) << 7) + ((y & 7) << 4);
-        uint32_t out[8];
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            uint32_t v = 0;
-#pragma unroll
-            for (int b = 0; b < 4; b++) v |= (uint32_t)mask_byte(nw, 4 * q + b) << (8 * b);
-            out[q] = v;
+        const BitView plane{a.bits + (size_t)f * a.g.bits_frame_stride + (size_t)s * a.g.bits_scale_stride, wpr, W, H};
+        const uint32_t mid = plane.word(w, y);
+        if (mid) {
+            const NbrWords nw = nbr_words(plane.word(w - 1, y - 1), plane.word(w, y - 1), plane.word(w + 1, y - 1), plane.word(w - 1, y), mid, plane.word(w + 1, y),
+                                          plane.word(w - 1, y + 1), plane.word(w, y + 1), plane.word(w + 1, y + 1));
+            L = left_crack_starts(mid, nw);
+            Rr = right_crack_starts(mid, nw);
         }
-        uint4* dst = reinterpret_cast<uint4*>(mrow);
-        dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
-        dst[8] = make_uint4(out[4], out[5], out[6], out[7]);  // next tile: +128 bytes
-        (void)W;
     }
     // warp-aggregated append of the start cracks
     const int cnt = __popc(L) + __popc(Rr);
@@ -256,36 +259,119 @@ __global__ void __launch_bounds__(256) k_masks_starts(const MaskArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------------
-// k_walk: grid-stride over the start queue.
+// Border walk in rounds of growing step budget (32, 256, 2048, rest).  Walk lengths are heavy
+// tailed (most start cracks die within a few steps, a few percent walk hundreds, the canonical
+// starts of marker outlines walk thousands), and a warp is as slow as its longest lane -- run in one
+// go, E[max over 32 lanes] was ~400 steps although the mean is ~15.  Each round walks every lane by
+// at most its budget and re-queues the undecided walks, so lanes of a warp stay within one budget.
+// k_walk_first: one thread per start crack.  k_walk_round: one thread per suspended walk.
 // ---------------------------------------------------------------------------------------------------
 struct WalkArgs {
-    const uint8_t* mask;
+    const uint32_t* bits;
     const StartRec* starts;
+    const WalkRec* q_in;
+    WalkRec* q_out;
     ChainRec* chains;
     Counters* counters;
-    unsigned int max_starts, max_chains, max_points;
+    unsigned int max_starts, max_chains, max_points, max_queue;
+    int q_in_idx, q_out_idx;  // indices into Counters::n_q (-1 = none)
     FrameGeom g;
-    int min_len, max_len;
+    int min_len, max_len, budget;
+    unsigned int chunk;  // queue items a warp takes per atomic
 };
 
-__global__ void __launch_bounds__(256) k_walk(const WalkArgs a) {
-    unsigned int n = a.counters->n_starts;
-    n = n < a.max_starts ? n : a.max_starts;
-    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const StartRec st = a.starts[i];
-        const int x = st.xy & 0xFFFF, y = st.xy >> 16;
-        const int f = st.meta >> 8, s = (st.meta >> 1) & 0x7F, is_right = st.meta & 1;
-        const MaskView plane{a.mask + (size_t)f * a.g.mask_frame_stride + (size_t)s * a.g.mask_scale_stride, a.g.mask_tpr};
-        int len = 0;
-        const int r = walk_start(plane, x, y, is_right, a.max_len, &len);
-        if (r == WALK_CANONICAL && len >= a.min_len && len <= a.max_len) {
-            const unsigned int slot = atomicAdd(&a.counters->n_chains, 1u);
-            const unsigned int off = atomicAdd(&a.counters->n_points, (unsigned int)len);
-            if (slot < a.max_chains && off + (unsigned int)len <= a.max_points) {
-                a.chains[slot] = ChainRec{st.xy, st.meta, (uint32_t)len, off};
-            } else {
-                if (slot < a.max_chains) a.chains[slot] = ChainRec{st.xy, st.meta, 0u, 0u};
-                atomicOr(&a.counters->overflow, slot >= a.max_chains ? 2u : 4u);
+// Persistent-lane walker: every lane always holds a live walk.  A lane whose walk ends (abort,
+// canonical, suspended) immediately pulls the next queue item instead of idling until the slowest
+// lane of its warp is done; items are handed out in order from warp-private chunks of the queue
+// (one global atomic per `chunk` items: large for the start-crack round, 32 for the long-walk round).  FIRST = items are start cracks, else suspended walks.
+#define WALK_STEPS_PER_POLL 8
+
+template <bool FIRST>
+__global__ void __launch_bounds__(256) k_walk_persist(const WalkArgs a, unsigned int* work_counter) {
+    unsigned int n = FIRST ? a.counters->n_starts : a.counters->n_q[a.q_in_idx];
+    n = n < (FIRST ? a.max_starts : a.max_queue) ? n : (FIRST ? a.max_starts : a.max_queue);
+    const unsigned int lane = threadIdx.x & 31;
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    unsigned int next = 0, hi = 0;  // warp-uniform: current chunk [next, hi)
+    bool exhausted = false;         // warp-uniform: the queue has no more chunks
+    bool active = false;
+    WalkState st{};
+    uint32_t xy0 = 0, meta = 0;
+    int x0 = 0, y0 = 0, is_right = 0, budget_end = 0;
+    BitView plane{nullptr, 0, 0, 0};
+    for (;;) {
+        // ---- refill idle lanes
+        const uint32_t need = __ballot_sync(0xffffffffu, !active);
+        if (need) {
+            if (!exhausted && next >= hi) {  // warp-uniform: take a fresh chunk of the queue
+                unsigned int lo = 0;
+                if (lane == 0) lo = atomicAdd(work_counter, a.chunk);
+                lo = __shfl_sync(0xffffffffu, lo, 0);
+                next = lo;
+                hi = lo + a.chunk < n ? lo + a.chunk : n;
+                if (lo >= n) exhausted = true;
+            }
+            if (!exhausted) {
+                const unsigned int want = (unsigned int)__popc(need);
+                const unsigned int avail = hi - next;
+                const unsigned int give = want < avail ? want : avail;
+                const unsigned int rank = (unsigned int)__popc(need & lt_mask);
+                if (!active && rank < give) {
+                    const unsigned int idx = next + rank;
+                    if (FIRST) {
+                        const StartRec sr = a.starts[idx];
+                        xy0 = sr.xy;
+                        meta = sr.meta;
+                    } else {
+                        const WalkRec wr = a.q_in[idx];
+                        xy0 = wr.xy0;
+                        meta = wr.meta;
+                        st.x = wr.xy & 0xFFFF;
+                        st.y = wr.xy >> 16;
+                        st.dir = wr.state & 7;
+                        st.a0 = (wr.state >> 3) & 7;
+                        st.b0 = (wr.state >> 6) & 7;
+                        st.n = wr.state >> 9;
+                    }
+                    x0 = xy0 & 0xFFFF;
+                    y0 = xy0 >> 16;
+                    is_right = meta & 1;
+                    const int f = meta >> 8, s = (meta >> 1) & 0x7F;
+                    plane = BitView{a.bits + (size_t)f * a.g.bits_frame_stride + (size_t)s * a.g.bits_scale_stride, a.g.wpr, a.g.W, a.g.H};
+                    const int r = FIRST ? walk_init(plane, x0, y0, is_right, &st) : WALK_CONTINUE;
+                    active = r == WALK_CONTINUE;
+                    budget_end = st.n + a.budget;
+                }
+                next += give;
+            }
+            if (exhausted && !__any_sync(0xffffffffu, active)) break;
+        }
+        // ---- a few steps for every live lane
+        if (active) {
+            const int left = budget_end - st.n;
+            const int r = walk_resume(plane, x0, y0, is_right, a.max_len, left < WALK_STEPS_PER_POLL ? left : WALK_STEPS_PER_POLL, &st);
+            int result = r;
+            if (r == WALK_CONTINUE && st.n < budget_end) result = -1;  // keep walking
+            if (result >= 0) {
+                active = false;
+                if (result == WALK_CANONICAL && st.n >= a.min_len && st.n <= a.max_len) {
+                    const unsigned int slot = atomicAdd(&a.counters->n_chains, 1u);
+                    const unsigned int off = atomicAdd(&a.counters->n_points, (unsigned int)st.n);
+                    if (slot < a.max_chains && off + (unsigned int)st.n <= a.max_points) {
+                        a.chains[slot] = ChainRec{xy0, meta, (uint32_t)st.n, off};
+                    } else {
+                        if (slot < a.max_chains) a.chains[slot] = ChainRec{xy0, meta, 0u, 0u};
+                        atomicOr(&a.counters->overflow, slot >= a.max_chains ? 2u : 4u);
+                    }
+                } else if (result == WALK_CONTINUE) {
+                    const unsigned int pos = atomicAdd(&a.counters->n_q[a.q_out_idx], 1u);
+                    if (pos < a.max_queue) {
+                        a.q_out[pos] = WalkRec{xy0, meta, (uint32_t)st.x | ((uint32_t)st.y << 16),
+                                               (uint32_t)st.dir | ((uint32_t)st.a0 << 3) | ((uint32_t)st.b0 << 6) | ((uint32_t)st.n << 9)};
+                    } else {
+                        atomicOr(&a.counters->overflow, 64u);
+                    }
+                }
             }
         }
     }
@@ -295,7 +381,7 @@ __global__ void __launch_bounds__(256) k_walk(const WalkArgs a) {
 // k_emit: one thread per surviving border writes its ordered points.
 // ---------------------------------------------------------------------------------------------------
 struct EmitArgs {
-    const uint8_t* mask;
+    const uint32_t* bits;
     const ChainRec* chains;
     Pt16* points;
     const Counters* counters;
@@ -310,7 +396,7 @@ __global__ void __launch_bounds__(128) k_emit(const EmitArgs a) {
         const ChainRec c = a.chains[i];
         if (c.n == 0) continue;
         const int f = c.meta >> 8, s = (c.meta >> 1) & 0x7F, is_right = c.meta & 1;
-        const MaskView plane{a.mask + (size_t)f * a.g.mask_frame_stride + (size_t)s * a.g.mask_scale_stride, a.g.mask_tpr};
+        const BitView plane{a.bits + (size_t)f * a.g.bits_frame_stride + (size_t)s * a.g.bits_scale_stride, a.g.wpr, a.g.W, a.g.H};
         trace_forward(plane, c.xy & 0xFFFF, c.xy >> 16, is_right, (int)c.n, a.points + c.offset);
     }
 }

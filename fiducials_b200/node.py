@@ -133,7 +133,7 @@ class Detector:
                                                  clen.ctypes.data_as(C.c_void_p)))
         return quads[: n.value].reshape(-1, 4, 2), scale[: n.value], clen[: n.value]
 
-    STAGES = ["h2d", "threshold", "masks_starts", "walk", "emit", "approx", "group", "identify", "subpix_pose", "_", "d2h"]
+    STAGES = ["h2d", "threshold", "masks_starts", "walk", "emit", "approx", "group", "identify", "subpix_pose", "_", "d2h", "walk_r0", "walk_r1", "walk_r2", "walk_r3"]
 
     def last_stage_ms(self):
         ms = np.zeros(16, np.float32)

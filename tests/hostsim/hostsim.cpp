@@ -23,39 +23,40 @@
 
 using namespace fid;
 
-static void pack_plane(const uint8_t* plane, int W, int H, std::vector<uint32_t>& bits, int& wpr) {
-    wpr = (W + 31) / 32;
-    bits.assign((size_t)wpr * H, 0u);
+// Tiled bit plane exactly as the CUDA threshold kernel writes it (BitView layout).
+struct HostPlane {
+    std::vector<uint32_t> words;
+    int tpr = 0, W = 0, H = 0;
+    BitView view() const { return BitView{words.data(), tpr, W, H}; }
+};
+
+static void pack_plane(const uint8_t* plane, int W, int H, HostPlane& hp) {
+    hp.tpr = bit_tiles_per_row(W);
+    hp.W = W;
+    hp.H = H;
+    hp.words.assign(bit_plane_words(W, H), 0u);
     for (int y = 0; y < H; y++)
         for (int x = 0; x < W; x++)
-            if (plane[(size_t)y * W + x]) bits[(size_t)y * wpr + (x >> 5)] |= 1u << (x & 31);
+            if (plane[(size_t)y * W + x]) hp.words[((size_t)(y >> 5) * hp.tpr + (x >> 5)) * 32 + (y & 31)] |= 1u << (x & 31);
 }
 
 struct Start {
     int x, y, is_right;
 };
 
-struct HostMask {
-    std::vector<uint8_t> bytes;
-    int tpr = 0;
-    MaskView view() const { return MaskView{bytes.data(), tpr}; }
-    uint8_t& ref(int x, int y) { return bytes[(((size_t)(y >> 3) * tpr + (x >> 4)) << 7) + ((y & 7) << 4) + (x & 15)]; }
-};
-
-static void masks_and_starts(const std::vector<uint32_t>& bits, int wpr, int W, int H, HostMask& mask, std::vector<Start>& starts) {
-    mask.tpr = mask_tiles_per_row(W);
-    mask.bytes.assign(mask_plane_bytes(W, H), 0);
-    auto word = [&](int y, int w) -> uint32_t { return (y < 0 || y >= H || w < 0 || w >= wpr) ? 0u : bits[(size_t)y * wpr + w]; };
-    for (int y = 0; y < H; y++)
-        for (int w = 0; w < wpr; w++) {
-            const uint32_t mid = word(y, w);
-            NbrWords nw = nbr_words(word(y - 1, w - 1), word(y - 1, w), word(y - 1, w + 1), word(y, w - 1), mid, word(y, w + 1), word(y + 1, w - 1), word(y + 1, w),
-                                    word(y + 1, w + 1));
+static void find_starts(const HostPlane& hp, std::vector<Start>& starts) {
+    const BitView v = hp.view();
+    for (int y = 0; y < hp.H; y++)
+        for (int w = 0; w < hp.tpr; w++) {
+            const uint32_t mid = v.word(w, y);
+            NbrWords nw = nbr_words(v.word(w - 1, y - 1), v.word(w, y - 1), v.word(w + 1, y - 1), v.word(w - 1, y), mid, v.word(w + 1, y), v.word(w - 1, y + 1), v.word(w, y + 1),
+                                    v.word(w + 1, y + 1));
             uint32_t L = left_crack_starts(mid, nw), R = right_crack_starts(mid, nw);
-            for (int i = 0; i < 32 && 32 * w + i < W; i++) {
-                mask.ref(32 * w + i, y) = mask_byte(nw, i);
+            for (int i = 0; i < 32 && 32 * w + i < hp.W; i++) {
                 if ((L >> i) & 1) starts.push_back({32 * w + i, y, 0});
                 if ((R >> i) & 1) starts.push_back({32 * w + i, y, 1});
+                // the per-pixel neighbour mask must agree with the word-level construction
+                if (((mid >> i) & 1) && v.at(32 * w + i, y) != mask_byte(nw, i)) abort();
             }
         }
 }
@@ -67,12 +68,10 @@ extern "C" {
 // -1 if a buffer is too small.  *n_walk_steps returns the total number of reverse-walk steps taken.
 int hs_find_contours(const uint8_t* plane, int W, int H, int min_len, int max_len, int16_t* out_pts, int64_t max_pts, int32_t* out_len, int max_contours,
                      int64_t* n_starts_out) {
-    std::vector<uint32_t> bits;
-    int wpr;
-    pack_plane(plane, W, H, bits, wpr);
-    HostMask mask;
+    HostPlane mask;
+    pack_plane(plane, W, H, mask);
     std::vector<Start> starts;
-    masks_and_starts(bits, wpr, W, H, mask, starts);
+    find_starts(mask, starts);
     if (n_starts_out) *n_starts_out = (int64_t)starts.size();
     struct Chain {
         int64_t key;
@@ -106,12 +105,10 @@ int hs_find_contours(const uint8_t* plane, int W, int H, int min_len, int max_le
 // [3] walks > 1024 steps, [4] walks that hit max_len, [5] canonical walks, [6] steps spent in
 // canonical walks, [7] steps spent in too-long walks.
 void hs_walk_stats(const uint8_t* plane, int W, int H, int max_len, int64_t* out) {
-    std::vector<uint32_t> bits;
-    int wpr;
-    pack_plane(plane, W, H, bits, wpr);
-    HostMask mask;
+    HostPlane mask;
+    pack_plane(plane, W, H, mask);
     std::vector<Start> starts;
-    masks_and_starts(bits, wpr, W, H, mask, starts);
+    find_starts(mask, starts);
     for (int i = 0; i < 8; i++) out[i] = 0;
     out[0] = (int64_t)starts.size();
     for (const Start& st : starts) {
@@ -146,12 +143,10 @@ static void raw_candidates(const uint8_t* planes, int W, int H, const DevParams&
     const int mx = W > H ? W : H;
     const int min_len = (int)(P.min_perimeter_rate * mx), max_len = (int)(P.max_perimeter_rate * mx);
     for (int s = 0; s < P.n_scales; s++) {
-        std::vector<uint32_t> bits;
-        int wpr;
-        pack_plane(planes + (size_t)s * W * H, W, H, bits, wpr);
-        HostMask mask;
+        HostPlane mask;
+        pack_plane(planes + (size_t)s * W * H, W, H, mask);
         std::vector<Start> starts;
-        masks_and_starts(bits, wpr, W, H, mask, starts);
+        find_starts(mask, starts);
         std::vector<RawQuad> found;
         std::vector<Pt16> pts;
         for (const Start& st : starts) {
