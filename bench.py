@@ -37,8 +37,8 @@ sys.path.insert(0, ROOT)
 
 WORKLOAD = "C2"
 FIDUCIAL_LEN = 0.14
-FRAMES_PER_STEP = 32     # distinct frames per step; 32 x 6.2 MB = 199 MB > 126 MB L2
-SLOT_FRAMES = 16         # frames per in-flight chunk inside the library (two chunks pipeline)
+FRAMES_PER_STEP = int(os.environ.get("FID_BENCH_FRAMES", "128"))  # distinct frames per step; 128 x 6.2 MB = 796 MB >> 126 MB L2
+SLOT_FRAMES = int(os.environ.get("FID_BENCH_SLOT", "64"))     # frames per in-flight chunk inside the library (two chunks pipeline)
 HBM_FALLBACK_GBS = 6650.0
 
 
@@ -249,7 +249,7 @@ def run_gpu_arm(args):
     lib = _lib.load()
     W, H, n_markers, dict_id = synth.CONFIGS[WORKLOAD]
     nf = FRAMES_PER_STEP
-    frames, truths, K, D, _ = synth.make_config_stream(WORKLOAD, nf, seed=rank)
+    frames, truths, K, D, _ = synth.make_config_stream(WORKLOAD, nf, seed=rank, realizations=8)
     det = Detector(default_params(dictionary=dict_id), local_rank, W, H, SLOT_FRAMES)
     slam = FiducialSlam(device=local_rank, max_fiducials=512, n_instances=1)
     ident = [0, 0, 0, 0, 0, 0, 1]

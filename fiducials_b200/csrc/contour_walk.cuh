@@ -92,9 +92,75 @@ struct BitView {
         return base[((size_t)(y >> 5) * tiles_per_row + tx) * 32 + (y & 31)];
     }
 };
-typedef BitView MaskView;
 FID_HD int bit_tiles_per_row(int W) { return (W + 31) / 32; }
 FID_HD size_t bit_plane_words(int W, int H) { return (size_t)((W + 31) / 32) * ((H + 31) / 32) * 32; }
+
+// ---- walking representation: halo tiles + step tables -----------------------------------------------
+// For walking, every plane is re-tiled into 30x30-pixel tiles stored with a 1-pixel halo as 32 words
+// of 32 bits (128 bytes, one cache line): word r of tile (ty,tx) holds image row 30*ty-1+r, bit i
+// holds image column 30*tx-1+i, background outside the image.  The 3x3 neighbourhood of any pixel
+// then lies in ONE tile -- three loads from the line the walker already holds, no edge cases -- and
+// the nine bits index a 4 KB table that returns the next direction and the examined-crack flags.
+#define FID_HALO_T 30
+FID_HD int div30(int v) { return (int)(((unsigned)v * 34953u) >> 20); }  // exact for 0 <= v < 2^15
+FID_HD int halo_tiles_x(int W) { return (W + FID_HALO_T - 1) / FID_HALO_T; }
+FID_HD size_t halo_plane_words(int W, int H) { return (size_t)halo_tiles_x(W) * ((H + FID_HALO_T - 1) / FID_HALO_T) * 32; }
+
+struct HaloView {
+    const uint32_t* base;
+    int tiles_per_row;
+    // 9 neighbourhood bits: bits 0-2 row y-1 (x-1,x,x+1), bits 3-5 row y, bits 6-8 row y+1
+    FID_HD uint32_t idx9(int x, int y) const {
+        const int qx = div30(x), qy = div30(y);
+        const int i = x - FID_HALO_T * qx, r = y - FID_HALO_T * qy;
+        const uint32_t* t = base + ((size_t)qy * tiles_per_row + qx) * 32 + r;
+        return ((t[0] >> i) & 7u) | (((t[1] >> i) & 7u) << 3) | (((t[2] >> i) & 7u) << 6);
+    }
+};
+
+FID_HD int mask_from_idx9(uint32_t v) {
+    const uint32_t u = v & 7u, m = (v >> 3) & 7u, d = (v >> 6) & 7u;
+    return (int)(((m >> 2) & 1u) | (((u >> 2) & 1u) << 1) | (((u >> 1) & 1u) << 2) | ((u & 1u) << 3) | ((m & 1u) << 4) | ((d & 1u) << 5) | (((d >> 1) & 1u) << 6) |
+                 (((d >> 2) & 1u) << 7));
+}
+
+// Step tables, 512 neighbourhoods x 8 incoming directions, one byte each:
+//   prev[idx9*8 + b] : a = first foreground neighbour clockwise from b      (backwards step)
+//   next[idx9*8 + a] : b = first foreground neighbour counter-clockwise from a (forwards step)
+// bits 0-2 = the direction found, bit 3 = left crack examined, bit 4 = right crack examined.
+#define FID_LUT_SIZE 4096
+inline void build_step_tables(uint8_t* prev, uint8_t* next) {
+    for (int v = 0; v < 512; v++) {
+        const int m = mask_from_idx9((uint32_t)v);
+        for (int dir = 0; dir < 8; dir++) {
+            uint8_t ep = 0, en = 0;
+            if (m != 0) {
+                const int a = prev_cw(m, dir);  // backwards: arrive with dir-to-next = dir
+                int d = (dir - a - 1) & 7;
+                ep = (uint8_t)(a | ((((4 - a - 1) & 7) < d) ? 8 : 0) | ((((0 - a - 1) & 7) < d) ? 16 : 0));
+                const int b = next_ccw(m, dir);  // forwards: arrive with dir-to-previous = dir
+                d = (b - dir - 1) & 7;
+                en = (uint8_t)(b | ((((4 - dir - 1) & 7) < d) ? 8 : 0) | ((((0 - dir - 1) & 7) < d) ? 16 : 0));
+            }
+            prev[v * 8 + dir] = ep;
+            next[v * 8 + dir] = en;
+        }
+    }
+}
+
+struct WalkCtx {
+    HaloView plane;
+    const uint8_t* lut_prev;
+    const uint8_t* lut_next;
+};
+
+FID_HD uint8_t lut_load(const uint8_t* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
 
 // Walk the border owning the left (is_right=0) or right (is_right=1) crack of foreground pixel
 // (x0,y0) once around.  WALK_CANONICAL with the contour point count n if (x0,y0) is the Suzuki start
@@ -109,22 +175,22 @@ FID_HD size_t bit_plane_words(int W, int H) { return (size_t)((W + 31) / 32) * (
 // backwards).
 //
 // The walk is resumable (WalkState + step budget) so that the GPU can run it in rounds of growing
-// budget: a warp then only ever holds walks of similar length (kernels_contour.cuh, k_walk_round).
+// budget: a warp then only ever holds walks of similar length (kernels_contour.cuh).
 enum { WALK_CONTINUE = 3 };
 struct WalkState {
     int x, y;  // current pixel
-    int dir;   // backwards walk: dir to the NEXT pixel's... see below; forwards: dir to next pixel
+    int dir;   // backwards walk: direction to the previous pixel; forwards: direction to the next pixel
     int n;     // steps taken
     int a0, b0;
 };
 
 // Returns WALK_ABORT (isolated pixel / tie lost) or WALK_CONTINUE with the state initialised.
-FID_HD int walk_init(const MaskView mask, int x0, int y0, int is_right, WalkState* st) {
-    const int m = mask.at(x0, y0);
-    if (m == 0) return WALK_ABORT;  // isolated pixel: 1-point contour, never long enough to matter
+FID_HD int walk_init(const WalkCtx& c, int x0, int y0, int is_right, WalkState* st) {
+    const uint32_t v = c.plane.idx9(x0, y0);
+    if ((v & ~0x10u) == 0u) return WALK_ABORT;  // isolated pixel: 1-point contour, never long enough to matter
     const int crack = is_right ? 0 : 4;
-    const int a0 = prev_cw(m, crack);
-    const int b0 = next_ccw(m, crack);
+    const int a0 = lut_load(c.lut_prev + v * 8 + crack) & 7;
+    const int b0 = lut_load(c.lut_next + v * 8 + crack) & 7;
     if (is_right) {  // the same state also owns the left crack -> the left-crack walker wins the tie
         const int d = (b0 - a0 - 1) & 7;
         if (((4 - a0 - 1) & 7) < d) return WALK_ABORT;
@@ -140,63 +206,34 @@ FID_HD int walk_init(const MaskView mask, int x0, int y0, int is_right, WalkStat
 
 // Advance by at most `budget` steps.  Returns WALK_CANONICAL (st->n = contour length), WALK_ABORT,
 // WALK_TOO_LONG (more than max_len steps) or WALK_CONTINUE (budget exhausted, state updated).
-FID_HD int walk_resume(const MaskView mask, int x0, int y0, int is_right, int max_len, int budget, WalkState* st) {
+template <bool IS_RIGHT>
+FID_HD int walk_resume_dir(const WalkCtx& c, int x0, int y0, int max_len, int budget, WalkState* st) {
     int x = st->x, y = st->y, n = st->n, dir = st->dir;
-    const int a0 = st->a0, b0 = st->b0;
+    const int ref = IS_RIGHT ? st->a0 : st->b0;  // closing condition: arrive at the start with this direction
+    const uint8_t* lut = IS_RIGHT ? c.lut_next : c.lut_prev;
     const int stop_at = n + budget;
     int result = WALK_CONTINUE;
-    if (!is_right) {
-        int a = dir;  // backwards: `a` = direction from the current pixel to the previous one
-        while (n < stop_at) {
-            x += dir_dx(a);
-            y += dir_dy(a);
-            n++;
-            const int bq = (a + 4) & 7;
-            if (x == x0 && y == y0 && bq == b0) {
-                result = WALK_CANONICAL;
-                break;
-            }
-            if (n > max_len) {
-                result = WALK_TOO_LONG;
-                break;
-            }
-            const int m = mask.at(x, y);
-            a = prev_cw(m, bq);
-            const int d = (bq - a - 1) & 7;
-            const bool exL = ((4 - a - 1) & 7) < d;
-            const bool exR = ((0 - a - 1) & 7) < d;
-            if ((exL || exR) && (y < y0 || (y == y0 && x < x0))) {
+    while (n < stop_at) {
+        x += dir_dx(dir);
+        y += dir_dy(dir);
+        n++;
+        const int back = (dir + 4) & 7;
+        if (x == x0 && y == y0 && back == ref) {
+            result = WALK_CANONICAL;
+            break;
+        }
+        if (n > max_len) {
+            result = WALK_TOO_LONG;
+            break;
+        }
+        const int e = lut_load(lut + c.plane.idx9(x, y) * 8 + back);
+        dir = e & 7;
+        if (e & 0x18) {
+            if (y < y0 || (y == y0 && x < x0) || (IS_RIGHT && (e & 8) && y == y0 && x == x0)) {
                 result = WALK_ABORT;
                 break;
             }
         }
-        dir = a;
-    } else {
-        int b = dir;  // forwards: `b` = direction from the current pixel to the next one
-        while (n < stop_at) {
-            x += dir_dx(b);
-            y += dir_dy(b);
-            n++;
-            const int aq = (b + 4) & 7;
-            if (x == x0 && y == y0 && aq == a0) {
-                result = WALK_CANONICAL;
-                break;
-            }
-            if (n > max_len) {
-                result = WALK_TOO_LONG;
-                break;
-            }
-            const int m = mask.at(x, y);
-            b = next_ccw(m, aq);
-            const int d = (b - aq - 1) & 7;
-            const bool exL = ((4 - aq - 1) & 7) < d;
-            const bool exR = ((0 - aq - 1) & 7) < d;
-            if ((exL || exR) && (y < y0 || (y == y0 && x < x0) || (exL && y == y0 && x == x0))) {
-                result = WALK_ABORT;
-                break;
-            }
-        }
-        dir = b;
     }
     st->x = x;
     st->y = y;
@@ -205,35 +242,40 @@ FID_HD int walk_resume(const MaskView mask, int x0, int y0, int is_right, int ma
     return result;
 }
 
+FID_HD int walk_resume(const WalkCtx& c, int x0, int y0, int is_right, int max_len, int budget, WalkState* st) {
+    return is_right ? walk_resume_dir<true>(c, x0, y0, max_len, budget, st) : walk_resume_dir<false>(c, x0, y0, max_len, budget, st);
+}
+
 // One-shot walk (CPU harness, small inputs).  *steps_out (optional) returns the steps taken.
-FID_HD int walk_start(const MaskView mask, int x0, int y0, int is_right, int max_len, int* n_out, int* steps_out = nullptr) {
+FID_HD int walk_start(const WalkCtx& c, int x0, int y0, int is_right, int max_len, int* n_out, int* steps_out = nullptr) {
     WalkState st;
     if (steps_out) *steps_out = 0;
-    if (walk_init(mask, x0, y0, is_right, &st) == WALK_ABORT) return WALK_ABORT;
-    const int r = walk_resume(mask, x0, y0, is_right, max_len, 0x3fffffff, &st);
+    if (walk_init(c, x0, y0, is_right, &st) == WALK_ABORT) return WALK_ABORT;
+    const int r = walk_resume(c, x0, y0, is_right, max_len, 0x3fffffff, &st);
     if (steps_out) *steps_out = st.n;
     if (r == WALK_CANONICAL) *n_out = st.n;
     return r;
 }
 
 // Emit the n contour points in OpenCV order (start pixel first, then Suzuki's direction).
-FID_HD void trace_forward(const MaskView mask, int x0, int y0, int is_right, int n, Pt16* out) {
-    int m = mask.at(x0, y0);
+FID_HD void trace_forward(const WalkCtx& c, int x0, int y0, int is_right, int n, Pt16* out) {
+    const uint32_t v = c.plane.idx9(x0, y0);
     int x = x0, y = y0;
-    if (m == 0) {
+    if ((v & ~0x10u) == 0u) {
         out[0].x = (int16_t)x;
         out[0].y = (int16_t)y;
         return;
     }
-    int a = prev_cw(m, is_right ? 0 : 4);
+    int a = lut_load(c.lut_prev + v * 8 + (is_right ? 0 : 4)) & 7;
+    uint32_t cur = v;
     for (int i = 0; i < n; i++) {
         out[i].x = (int16_t)x;
         out[i].y = (int16_t)y;
-        const int b = next_ccw(m, a);
+        const int b = lut_load(c.lut_next + cur * 8 + a) & 7;
         x += dir_dx(b);
         y += dir_dy(b);
         a = (b + 4) & 7;
-        m = mask.at(x, y);
+        cur = c.plane.idx9(x, y);
     }
 }
 

@@ -25,12 +25,13 @@ using namespace fid;
     } while (0)
 
 enum { ST_H2D = 0, ST_THRESH, ST_MASKS, ST_WALK, ST_EMIT, ST_APPROX, ST_GROUP, ST_IDENT, ST_SUBPIX_POSE, ST_POSE_UNUSED, ST_D2H, ST_COUNT };
-enum { N_WALK_ROUNDS = 4 };
+enum { N_WALK_ROUNDS = FID_WALK_MAX_ROUNDS };
 
 struct Slot {
     uint8_t* d_bgr = nullptr;
     uint8_t* d_gray = nullptr;
     uint32_t* d_bits = nullptr;
+    uint32_t* d_halo = nullptr;
     StartRec* d_starts = nullptr;
     ChainRec* d_chains = nullptr;
     WalkRec* d_queue[2] = {nullptr, nullptr};
@@ -72,6 +73,11 @@ struct fid_detector {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     Slot slot[2];
     float* d_subpix_masks = nullptr;
+    uint8_t* d_lut_prev = nullptr;
+    uint8_t* d_lut_next = nullptr;
+    int walk_rounds = 0;
+    int walk_budget[FID_WALK_MAX_ROUNDS]{};
+    int walk_persist[FID_WALK_MAX_ROUNDS]{};
     int32_t* d_override_ids = nullptr;
     double* d_override_lens = nullptr;
     int32_t* d_pose_ids = nullptr;
@@ -128,6 +134,9 @@ static FrameGeom make_geom(const fid_detector* h, int W, int H, size_t row_strid
     g.gray_frame_stride = (size_t)g.gray_pitch * H;
     g.bits_scale_stride = bit_plane_words(W, H);
     g.bits_frame_stride = g.bits_scale_stride * h->P.n_scales;
+    g.halo_tpr = halo_tiles_x(W);
+    g.halo_scale_stride = halo_plane_words(W, H);
+    g.halo_frame_stride = g.halo_scale_stride * h->P.n_scales;
     return g;
 }
 
@@ -182,6 +191,7 @@ static int alloc_slot(fid_detector* h, Slot& s) {
     A(dalloc(&s.d_bgr, F * (size_t)W * H * 3));
     A(dalloc(&s.d_gray, F * pitch * H));
     A(dalloc(&s.d_bits, F * (size_t)S * bit_plane_words(W, H)));
+    A(dalloc(&s.d_halo, F * (size_t)S * halo_plane_words(W, H)));
     A(dalloc(&s.d_starts, (size_t)h->max_starts));
     A(dalloc(&s.d_chains, (size_t)h->max_chains));
     A(dalloc(&s.d_queue[0], (size_t)h->max_queue));
@@ -231,7 +241,7 @@ static int alloc_slot(fid_detector* h, Slot& s) {
 }
 
 static void free_slot(Slot& s) {
-    void* dptrs[] = {s.d_queue[0], s.d_queue[1], s.d_bgr,         s.d_gray,          s.d_bits,          s.d_starts,       s.d_chains,       s.d_points,      s.d_counters,
+    void* dptrs[] = {s.d_halo, s.d_queue[0], s.d_queue[1], s.d_bgr,         s.d_gray,          s.d_bits,          s.d_starts,       s.d_chains,       s.d_points,      s.d_counters,
                      s.d_raw,         s.d_nraw,          s.fs.quads_tmp,    s.fs.per_tmp,     s.fs.quads,       s.fs.per,         s.fs.close_bits, s.fs.group_id,
                      s.fs.group_members, s.fs.next_in_group, s.fs.group_head, s.fs.group_tail, s.fs.close_count, s.fs.close_idx,   s.fs.close_off,  s.fs.selected,
                      s.fs.sel_idx,    s.d_nsel,          s.d_nrawc,         s.d_cand_id,      s.d_cand_corners, s.d_out_count,    s.d_out_ids,     s.d_out_corners,
@@ -303,6 +313,43 @@ extern "C" int fid_create(const fid_params* params, int device, int max_width, i
         }
         CK(cudaMemcpy(h->d_subpix_masks, masks.data(), masks.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
+    {   // step tables of the border walk
+        std::vector<uint8_t> lp(FID_LUT_SIZE), ln(FID_LUT_SIZE);
+        build_step_tables(lp.data(), ln.data());
+        if ((rc = dalloc(&h->d_lut_prev, (size_t)FID_LUT_SIZE)) != FID_OK || (rc = dalloc(&h->d_lut_next, (size_t)FID_LUT_SIZE)) != FID_OK) {
+            fid_destroy(h);
+            return rc;
+        }
+        CK(cudaMemcpy(h->d_lut_prev, lp.data(), FID_LUT_SIZE, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->d_lut_next, ln.data(), FID_LUT_SIZE, cudaMemcpyHostToDevice));
+    }
+    {   // walk plan: budgets per round, 'p' prefix = persistent lanes, 0 = unbounded (must be last)
+        const char* plan = getenv("FID_WALK_PLAN");
+        if (!plan || !*plan) plan = "8,64,512,0";
+        h->walk_rounds = 0;
+        const char* c = plan;
+        while (*c && h->walk_rounds < FID_WALK_MAX_ROUNDS) {
+            int persist = 0;
+            if (*c == 'p') {
+                persist = 1;
+                c++;
+            }
+            char* end = nullptr;
+            long v = strtol(c, &end, 10);
+            if (end == c) break;
+            h->walk_budget[h->walk_rounds] = v <= 0 ? 0x3fffffff : (int)v;
+            h->walk_persist[h->walk_rounds] = persist;
+            h->walk_rounds++;
+            c = end;
+            if (*c == ',') c++;
+        }
+        if (h->walk_rounds == 0 || h->walk_budget[h->walk_rounds - 1] != 0x3fffffff) {
+            if (h->walk_rounds == FID_WALK_MAX_ROUNDS) h->walk_rounds--;
+            h->walk_budget[h->walk_rounds] = 0x3fffffff;
+            h->walk_persist[h->walk_rounds] = 1;
+            h->walk_rounds++;
+        }
+    }
     if ((rc = dalloc(&h->d_override_ids, 1024)) != FID_OK || (rc = dalloc(&h->d_override_lens, 1024)) != FID_OK || (rc = dalloc(&h->d_pose_ids, 4096)) != FID_OK ||
         (rc = dalloc(&h->d_pose_corners, 4096 * 8)) != FID_OK || (rc = dalloc(&h->d_pose_out, 4096)) != FID_OK) {
         fid_destroy(h);
@@ -317,7 +364,7 @@ extern "C" int fid_destroy(fid_detector* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (int i = 0; i < 2; i++) free_slot(h->slot[i]);
-    void* ptrs[] = {h->d_subpix_masks, h->d_override_ids, h->d_override_lens, h->d_pose_ids, h->d_pose_corners, h->d_pose_out};
+    void* ptrs[] = {h->d_lut_prev, h->d_lut_next, h->d_subpix_masks, h->d_override_ids, h->d_override_lens, h->d_pose_ids, h->d_pose_corners, h->d_pose_out};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (h->t0) cudaEventDestroy(h->t0);
@@ -392,13 +439,24 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, int nf, const FrameGeom& g
         const long long total = (long long)nf * P.n_scales * H * g.wpr;
         k_masks_starts<<<(unsigned int)((total + 255) / 256), 256, 0, st>>>(a);
         launches++;
+        RetileArgs r{};
+        r.bits = s.d_bits;
+        r.halo = s.d_halo;
+        r.g = g;
+        r.n_scales = P.n_scales;
+        r.n_frames = nf;
+        const long long rt = (long long)nf * P.n_scales * (long long)g.halo_scale_stride;
+        k_retile<<<(unsigned int)((rt + 255) / 256), 256, 0, st>>>(r);
+        launches++;
     }
     CK(cudaEventRecord(s.ev[ST_WALK], st));
     const int mx = W > H ? W : H;
     const int min_len = (int)(P.min_perimeter_rate * mx), max_len = (int)(P.max_perimeter_rate * mx);
     {  // walk, in rounds of growing budget
         WalkArgs a{};
-        a.bits = s.d_bits;
+        a.halo = s.d_halo;
+        a.lut_prev = h->d_lut_prev;
+        a.lut_next = h->d_lut_next;
         a.starts = s.d_starts;
         a.chains = s.d_chains;
         a.counters = s.d_counters;
@@ -409,21 +467,17 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, int nf, const FrameGeom& g
         a.g = g;
         a.min_len = min_len;
         a.max_len = max_len;
-        static const int budgets[N_WALK_ROUNDS] = {1024, 0x3fffffff, 0, 0};
         for (int r = 0; r < N_WALK_ROUNDS; r++) {
             CK(cudaEventRecord(s.ev_round[r], st));
-            if (r >= 2) continue;
-            a.budget = budgets[r];
+            if (r >= h->walk_rounds) continue;
+            a.round = r;
+            a.budget = h->walk_budget[r];
+            a.persistent = h->walk_persist[r];
             a.q_in = r > 0 ? s.d_queue[(r - 1) & 1] : nullptr;
             a.q_out = s.d_queue[r & 1];
-            a.q_in_idx = r - 1;
-            a.q_out_idx = r;
             a.chunk = r == 0 ? 256u : 32u;
-            unsigned int* work = &s.d_counters->work[r];
-            if (r == 0)
-                k_walk_persist<true><<<h->sm_count * 8, 256, 0, st>>>(a, work);
-            else
-                k_walk_persist<false><<<h->sm_count * 4, 128, 0, st>>>(a, work);
+            const int blocks = r == 0 ? h->sm_count * 8 : (r == 1 ? h->sm_count * 8 : h->sm_count * 4);
+            k_walk<<<blocks, 256, 0, st>>>(a);
             launches++;
         }
         CK(cudaEventRecord(s.ev_round[N_WALK_ROUNDS], st));
@@ -431,7 +485,9 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, int nf, const FrameGeom& g
     CK(cudaEventRecord(s.ev[ST_EMIT], st));
     {  // emit
         EmitArgs a{};
-        a.bits = s.d_bits;
+        a.halo = s.d_halo;
+        a.lut_prev = h->d_lut_prev;
+        a.lut_next = h->d_lut_next;
         a.chains = s.d_chains;
         a.points = s.d_points;
         a.counters = s.d_counters;
@@ -586,7 +642,7 @@ static int collect(fid_detector* h, Slot& s, int nf, int max_markers, int32_t* c
         else
             cudaGetLastError();
     }
-    h->counters[0] += s.h_counters->n_starts;
+    h->counters[0] += (int64_t)s.h_counters->n_starts[0] + s.h_counters->n_starts[1];
     h->counters[1] += s.h_counters->n_chains;
     h->counters[2] += s.h_counters->n_points;
     for (int f = 0; f < nf; f++) {

@@ -17,14 +17,15 @@
 namespace fid {
 
 // ---- batch-wide work queues ------------------------------------------------------------------------
+#define FID_WALK_MAX_ROUNDS 8
 struct Counters {
-    unsigned int n_starts;
+    unsigned int n_starts[2];  // left-crack / right-crack start queues
     unsigned int n_chains;
     unsigned int n_points;
     unsigned int overflow;  // bit0 starts, bit1 chains, bit2 points, bit3 raw quads, bit4 selected, bit5 markers, bit6 walk queue
-    unsigned int n_q[3];    // walks suspended by rounds 0,1,2
-    unsigned int work[4];   // persistent-walker work counters, one per round
-    unsigned int pad;
+    unsigned int n_q[FID_WALK_MAX_ROUNDS][2];  // walks suspended by each round, per direction
+    unsigned int work[FID_WALK_MAX_ROUNDS][2]; // persistent-walker work counters, per direction
+    unsigned int pad[3];
 };
 
 struct WalkRec {       // a border walk suspended between rounds
@@ -53,6 +54,8 @@ struct FrameGeom {
     size_t bgr_row_stride, bgr_frame_stride;
     size_t gray_frame_stride;
     size_t bits_scale_stride, bits_frame_stride;  // in words (tiled 32x32, see BitView)
+    int halo_tpr;       // 30x30(+halo) walk tiles per tile row
+    size_t halo_scale_stride, halo_frame_stride;  // in words (see HaloView)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -225,87 +228,186 @@ __global__ void __launch_bounds__(256) k_masks_starts(const MaskArgs a) {
             Rr = right_crack_starts(mid, nw);
         }
     }
-    // warp-aggregated append of the start cracks
-    const int cnt = __popc(L) + __popc(Rr);
-    int incl = cnt;
+    // warp-aggregated append: left cracks grow from the front of the buffer, right cracks from the
+    // back, so that every warp of the walk kernels sees a single direction
+    const uint32_t meta_base = ((uint32_t)f << 8) | ((uint32_t)s << 1);
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-    }
-    const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
-    unsigned int base = 0;
-    if (warp_total > 0) {
-        if (lane == 31) base = atomicAdd(&a.counters->n_starts, (unsigned int)warp_total);
+    for (int side = 0; side < 2; side++) {
+        uint32_t bitsv = side ? Rr : L;
+        const int cnt = __popc(bitsv);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
+        if (warp_total == 0) continue;
+        unsigned int base = 0;
+        if (lane == 31) base = atomicAdd(&a.counters->n_starts[side], (unsigned int)warp_total);
         base = __shfl_sync(0xffffffffu, base, 31);
-    }
-    if (cnt > 0) {
         unsigned int pos = base + (unsigned int)(incl - cnt);
-        const uint32_t meta_base = ((uint32_t)f << 8) | ((uint32_t)s << 1);
-        while (L) {
-            const int i = __ffs(L) - 1;
-            L &= L - 1;
-            if (pos < a.max_starts) a.starts[pos] = StartRec{(uint32_t)(32 * w + i) | ((uint32_t)y << 16), meta_base};
+        while (bitsv) {
+            const int i = __ffs(bitsv) - 1;
+            bitsv &= bitsv - 1;
+            if (pos < a.max_starts / 2) {
+                const unsigned int slot = side ? a.max_starts - 1 - pos : pos;
+                a.starts[slot] = StartRec{(uint32_t)(32 * w + i) | ((uint32_t)y << 16), meta_base | (uint32_t)side};
+            } else {
+                atomicOr(&a.counters->overflow, 1u);
+            }
             pos++;
         }
-        while (Rr) {
-            const int i = __ffs(Rr) - 1;
-            Rr &= Rr - 1;
-            if (pos < a.max_starts) a.starts[pos] = StartRec{(uint32_t)(32 * w + i) | ((uint32_t)y << 16), meta_base | 1u};
-            pos++;
-        }
-        if (pos > a.max_starts) atomicOr(&a.counters->overflow, 1u);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Border walk in rounds of growing step budget (32, 256, 2048, rest).  Walk lengths are heavy
-// tailed (most start cracks die within a few steps, a few percent walk hundreds, the canonical
-// starts of marker outlines walk thousands), and a warp is as slow as its longest lane -- run in one
-// go, E[max over 32 lanes] was ~400 steps although the mean is ~15.  Each round walks every lane by
-// at most its budget and re-queues the undecided walks, so lanes of a warp stay within one budget.
-// k_walk_first: one thread per start crack.  k_walk_round: one thread per suspended walk.
+// k_retile: aligned bit planes -> 30x30(+1 halo) walk tiles (HaloView).  One thread per tile word.
+// ---------------------------------------------------------------------------------------------------
+struct RetileArgs {
+    const uint32_t* bits;
+    uint32_t* halo;
+    FrameGeom g;
+    int n_scales, n_frames;
+};
+
+__global__ void __launch_bounds__(256) k_retile(const RetileArgs a) {
+    const int W = a.g.W, H = a.g.H;
+    const int tpr = a.g.halo_tpr;
+    const size_t words_per_plane = a.g.halo_scale_stride;
+    const long long total = (long long)a.n_frames * a.n_scales * (long long)words_per_plane;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const long long plane_id = gid / (long long)words_per_plane;
+    const int wi = (int)(gid - plane_id * (long long)words_per_plane);
+    const int f = (int)(plane_id / a.n_scales), s = (int)(plane_id - (long long)f * a.n_scales);
+    const int tile = wi >> 5, r = wi & 31;
+    const int ty = tile / tpr, tx = tile - ty * tpr;
+    const int Y = FID_HALO_T * ty - 1 + r, X0 = FID_HALO_T * tx - 1;
+    uint32_t out = 0;
+    if (Y >= 0 && Y < H) {
+        const BitView plane{a.bits + (size_t)f * a.g.bits_frame_stride + (size_t)s * a.g.bits_scale_stride, a.g.wpr, W, H};
+        const int w0 = X0 >> 5, sh = X0 & 31;  // arithmetic shift: X0 = -1 -> w0 = -1, sh = 31
+        const uint32_t lo = plane.word(w0, Y), hi = plane.word(w0 + 1, Y);
+        out = sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
+    }
+    a.halo[(size_t)f * a.g.halo_frame_stride + (size_t)s * a.g.halo_scale_stride + wi] = out;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Border walk in rounds of growing step budget.  Walk lengths are heavy tailed (most start cracks
+// die within a few steps, a few percent walk hundreds, the canonical starts of marker outlines walk
+// thousands) and the walk is issue bound, so idle lanes are the cost: each round walks every lane by
+// at most its budget and re-queues the undecided walks, which keeps the lanes of a warp within one
+// budget of each other; the last, long rounds run "persistent" (a lane that finishes pulls the next
+// queue item when at least half the warp is idle).  Left-crack (backwards) and right-crack
+// (forwards) walks live in separate queue regions, so a warp executes a single direction.
 // ---------------------------------------------------------------------------------------------------
 struct WalkArgs {
-    const uint32_t* bits;
-    const StartRec* starts;
-    const WalkRec* q_in;
+    const uint32_t* halo;
+    const uint8_t* lut_prev;
+    const uint8_t* lut_next;
+    const StartRec* starts;   // round 0 input: left items at [0, nL), right items at [max_starts-1 ...]
+    const WalkRec* q_in;      // later rounds: left items at [0, nL), right items at [max_queue-1 ...]
     WalkRec* q_out;
     ChainRec* chains;
     Counters* counters;
     unsigned int max_starts, max_chains, max_points, max_queue;
-    int q_in_idx, q_out_idx;  // indices into Counters::n_q (-1 = none)
+    int round;                // 0 = items are start cracks
     FrameGeom g;
     int min_len, max_len, budget;
-    unsigned int chunk;  // queue items a warp takes per atomic
+    int persistent;
+    unsigned int chunk;       // persistent mode: queue items a warp takes per atomic
 };
 
-// Persistent-lane walker: every lane always holds a live walk.  A lane whose walk ends (abort,
-// canonical, suspended) immediately pulls the next queue item instead of idling until the slowest
-// lane of its warp is done; items are handed out in order from warp-private chunks of the queue
-// (one global atomic per `chunk` items: large for the start-crack round, 32 for the long-walk round).  FIRST = items are start cracks, else suspended walks.
-#define WALK_STEPS_PER_POLL 8
+struct WalkItem {
+    uint32_t xy0, meta;
+    WalkState st;
+    int x0, y0;
+    WalkCtx ctx;
+};
 
-template <bool FIRST>
-__global__ void __launch_bounds__(256) k_walk_persist(const WalkArgs a, unsigned int* work_counter) {
-    unsigned int n = FIRST ? a.counters->n_starts : a.counters->n_q[a.q_in_idx];
-    n = n < (FIRST ? a.max_starts : a.max_queue) ? n : (FIRST ? a.max_starts : a.max_queue);
+template <bool IS_RIGHT>
+__device__ __forceinline__ bool walk_load_item(const WalkArgs& a, unsigned int idx, WalkItem& it) {
+    // returns true if the item is live after initialisation
+    if (a.round == 0) {
+        const StartRec sr = a.starts[IS_RIGHT ? a.max_starts - 1 - idx : idx];
+        it.xy0 = sr.xy;
+        it.meta = sr.meta;
+    } else {
+        const WalkRec wr = a.q_in[IS_RIGHT ? a.max_queue - 1 - idx : idx];
+        it.xy0 = wr.xy0;
+        it.meta = wr.meta;
+        it.st.x = wr.xy & 0xFFFF;
+        it.st.y = wr.xy >> 16;
+        it.st.dir = wr.state & 7;
+        it.st.a0 = (wr.state >> 3) & 7;
+        it.st.b0 = (wr.state >> 6) & 7;
+        it.st.n = wr.state >> 9;
+    }
+    it.x0 = it.xy0 & 0xFFFF;
+    it.y0 = it.xy0 >> 16;
+    const int f = it.meta >> 8, s = (it.meta >> 1) & 0x7F;
+    it.ctx.plane = HaloView{a.halo + (size_t)f * a.g.halo_frame_stride + (size_t)s * a.g.halo_scale_stride, a.g.halo_tpr};
+    it.ctx.lut_prev = a.lut_prev;
+    it.ctx.lut_next = a.lut_next;
+    if (a.round == 0) return walk_init(it.ctx, it.x0, it.y0, IS_RIGHT ? 1 : 0, &it.st) == WALK_CONTINUE;
+    return true;
+}
+
+template <bool IS_RIGHT>
+__device__ __forceinline__ void walk_retire(const WalkArgs& a, int result, const WalkItem& it) {
+    if (result == WALK_CANONICAL && it.st.n >= a.min_len && it.st.n <= a.max_len) {
+        const unsigned int slot = atomicAdd(&a.counters->n_chains, 1u);
+        const unsigned int off = atomicAdd(&a.counters->n_points, (unsigned int)it.st.n);
+        if (slot < a.max_chains && off + (unsigned int)it.st.n <= a.max_points) {
+            a.chains[slot] = ChainRec{it.xy0, it.meta, (uint32_t)it.st.n, off};
+        } else {
+            if (slot < a.max_chains) a.chains[slot] = ChainRec{it.xy0, it.meta, 0u, 0u};
+            atomicOr(&a.counters->overflow, slot >= a.max_chains ? 2u : 4u);
+        }
+    } else if (result == WALK_CONTINUE) {
+        const unsigned int pos = atomicAdd(&a.counters->n_q[a.round][IS_RIGHT ? 1 : 0], 1u);
+        if (pos < a.max_queue / 2) {
+            a.q_out[IS_RIGHT ? a.max_queue - 1 - pos : pos] =
+                WalkRec{it.xy0, it.meta, (uint32_t)it.st.x | ((uint32_t)it.st.y << 16),
+                        (uint32_t)it.st.dir | ((uint32_t)it.st.a0 << 3) | ((uint32_t)it.st.b0 << 6) | ((uint32_t)it.st.n << 9)};
+        } else {
+            atomicOr(&a.counters->overflow, 64u);
+        }
+    }
+}
+
+template <bool IS_RIGHT>
+__device__ __forceinline__ void walk_side(const WalkArgs& a, unsigned int n, unsigned int first_warp, unsigned int n_warps) {
+    // `n` items of one direction, processed by warps first_warp .. first_warp+n_warps-1 of the grid
     const unsigned int lane = threadIdx.x & 31;
+    const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (warp < first_warp || warp >= first_warp + n_warps) return;
+    const unsigned int my = warp - first_warp;
+    if (!a.persistent) {
+        for (unsigned int base = my * 32; base < n; base += n_warps * 32) {
+            const unsigned int idx = base + lane;
+            if (idx >= n) continue;
+            WalkItem it;
+            if (!walk_load_item<IS_RIGHT>(a, idx, it)) continue;
+            const int r = walk_resume_dir<IS_RIGHT>(it.ctx, it.x0, it.y0, a.max_len, a.budget, &it.st);
+            walk_retire<IS_RIGHT>(a, r, it);
+        }
+        return;
+    }
+    // persistent lanes
     const unsigned int lt_mask = (1u << lane) - 1u;
-    unsigned int next = 0, hi = 0;  // warp-uniform: current chunk [next, hi)
-    bool exhausted = false;         // warp-uniform: the queue has no more chunks
-    bool active = false;
-    WalkState st{};
-    uint32_t xy0 = 0, meta = 0;
-    int x0 = 0, y0 = 0, is_right = 0, budget_end = 0;
-    BitView plane{nullptr, 0, 0, 0};
+    unsigned int next = 0, hi = 0;
+    bool exhausted = false, active = false;
+    int budget_end = 0;
+    WalkItem it;
     for (;;) {
-        // ---- refill idle lanes
         const uint32_t need = __ballot_sync(0xffffffffu, !active);
-        if (need) {
-            if (!exhausted && next >= hi) {  // warp-uniform: take a fresh chunk of the queue
+        if (__popc(need) >= 16) {  // refill only when at least half the warp is idle
+            if (!exhausted && next >= hi) {
                 unsigned int lo = 0;
-                if (lane == 0) lo = atomicAdd(work_counter, a.chunk);
+                if (lane == 0) lo = atomicAdd(&a.counters->work[a.round][IS_RIGHT ? 1 : 0], a.chunk);
                 lo = __shfl_sync(0xffffffffu, lo, 0);
                 next = lo;
                 hi = lo + a.chunk < n ? lo + a.chunk : n;
@@ -317,71 +419,56 @@ __global__ void __launch_bounds__(256) k_walk_persist(const WalkArgs a, unsigned
                 const unsigned int give = want < avail ? want : avail;
                 const unsigned int rank = (unsigned int)__popc(need & lt_mask);
                 if (!active && rank < give) {
-                    const unsigned int idx = next + rank;
-                    if (FIRST) {
-                        const StartRec sr = a.starts[idx];
-                        xy0 = sr.xy;
-                        meta = sr.meta;
-                    } else {
-                        const WalkRec wr = a.q_in[idx];
-                        xy0 = wr.xy0;
-                        meta = wr.meta;
-                        st.x = wr.xy & 0xFFFF;
-                        st.y = wr.xy >> 16;
-                        st.dir = wr.state & 7;
-                        st.a0 = (wr.state >> 3) & 7;
-                        st.b0 = (wr.state >> 6) & 7;
-                        st.n = wr.state >> 9;
-                    }
-                    x0 = xy0 & 0xFFFF;
-                    y0 = xy0 >> 16;
-                    is_right = meta & 1;
-                    const int f = meta >> 8, s = (meta >> 1) & 0x7F;
-                    plane = BitView{a.bits + (size_t)f * a.g.bits_frame_stride + (size_t)s * a.g.bits_scale_stride, a.g.wpr, a.g.W, a.g.H};
-                    const int r = FIRST ? walk_init(plane, x0, y0, is_right, &st) : WALK_CONTINUE;
-                    active = r == WALK_CONTINUE;
-                    budget_end = st.n + a.budget;
+                    active = walk_load_item<IS_RIGHT>(a, next + rank, it);
+                    budget_end = it.st.n + a.budget;
                 }
                 next += give;
             }
             if (exhausted && !__any_sync(0xffffffffu, active)) break;
         }
-        // ---- a few steps for every live lane
         if (active) {
-            const int left = budget_end - st.n;
-            const int r = walk_resume(plane, x0, y0, is_right, a.max_len, left < WALK_STEPS_PER_POLL ? left : WALK_STEPS_PER_POLL, &st);
-            int result = r;
-            if (r == WALK_CONTINUE && st.n < budget_end) result = -1;  // keep walking
-            if (result >= 0) {
+            const int left = budget_end - it.st.n;
+            const int r = walk_resume_dir<IS_RIGHT>(it.ctx, it.x0, it.y0, a.max_len, left < 16 ? left : 16, &it.st);
+            if (!(r == WALK_CONTINUE && it.st.n < budget_end)) {
                 active = false;
-                if (result == WALK_CANONICAL && st.n >= a.min_len && st.n <= a.max_len) {
-                    const unsigned int slot = atomicAdd(&a.counters->n_chains, 1u);
-                    const unsigned int off = atomicAdd(&a.counters->n_points, (unsigned int)st.n);
-                    if (slot < a.max_chains && off + (unsigned int)st.n <= a.max_points) {
-                        a.chains[slot] = ChainRec{xy0, meta, (uint32_t)st.n, off};
-                    } else {
-                        if (slot < a.max_chains) a.chains[slot] = ChainRec{xy0, meta, 0u, 0u};
-                        atomicOr(&a.counters->overflow, slot >= a.max_chains ? 2u : 4u);
-                    }
-                } else if (result == WALK_CONTINUE) {
-                    const unsigned int pos = atomicAdd(&a.counters->n_q[a.q_out_idx], 1u);
-                    if (pos < a.max_queue) {
-                        a.q_out[pos] = WalkRec{xy0, meta, (uint32_t)st.x | ((uint32_t)st.y << 16),
-                                               (uint32_t)st.dir | ((uint32_t)st.a0 << 3) | ((uint32_t)st.b0 << 6) | ((uint32_t)st.n << 9)};
-                    } else {
-                        atomicOr(&a.counters->overflow, 64u);
-                    }
-                }
+                walk_retire<IS_RIGHT>(a, r, it);
             }
         }
     }
+}
+
+__global__ void __launch_bounds__(256) k_walk(const WalkArgs a) {
+    unsigned int nL, nR;
+    if (a.round == 0) {
+        nL = a.counters->n_starts[0];
+        nR = a.counters->n_starts[1];
+        const unsigned int cap = a.max_starts / 2;
+        nL = nL < cap ? nL : cap;
+        nR = nR < cap ? nR : cap;
+    } else {
+        nL = a.counters->n_q[a.round - 1][0];
+        nR = a.counters->n_q[a.round - 1][1];
+        const unsigned int cap = a.max_queue / 2;
+        nL = nL < cap ? nL : cap;
+        nR = nR < cap ? nR : cap;
+    }
+    // split the grid's warps between the two directions in proportion to their queue lengths
+    const unsigned int total_warps = (gridDim.x * blockDim.x) >> 5;
+    unsigned int wL = (unsigned int)(((unsigned long long)total_warps * nL) / ((unsigned long long)nL + nR + 1));
+    if (nL && wL == 0) wL = 1;
+    if (nR && wL >= total_warps) wL = total_warps - 1;
+    if (!nR) wL = total_warps;
+    if (nL) walk_side<false>(a, nL, 0, wL);
+    if (nR) walk_side<true>(a, nR, wL, total_warps - wL);
 }
 
 // ---------------------------------------------------------------------------------------------------
 // k_emit: one thread per surviving border writes its ordered points.
 // ---------------------------------------------------------------------------------------------------
 struct EmitArgs {
-    const uint32_t* bits;
+    const uint32_t* halo;
+    const uint8_t* lut_prev;
+    const uint8_t* lut_next;
     const ChainRec* chains;
     Pt16* points;
     const Counters* counters;
@@ -396,8 +483,8 @@ __global__ void __launch_bounds__(128) k_emit(const EmitArgs a) {
         const ChainRec c = a.chains[i];
         if (c.n == 0) continue;
         const int f = c.meta >> 8, s = (c.meta >> 1) & 0x7F, is_right = c.meta & 1;
-        const BitView plane{a.bits + (size_t)f * a.g.bits_frame_stride + (size_t)s * a.g.bits_scale_stride, a.g.wpr, a.g.W, a.g.H};
-        trace_forward(plane, c.xy & 0xFFFF, c.xy >> 16, is_right, (int)c.n, a.points + c.offset);
+        const WalkCtx ctx{HaloView{a.halo + (size_t)f * a.g.halo_frame_stride + (size_t)s * a.g.halo_scale_stride, a.g.halo_tpr}, a.lut_prev, a.lut_next};
+        trace_forward(ctx, c.xy & 0xFFFF, c.xy >> 16, is_right, (int)c.n, a.points + c.offset);
     }
 }
 

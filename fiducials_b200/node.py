@@ -133,12 +133,12 @@ class Detector:
                                                  clen.ctypes.data_as(C.c_void_p)))
         return quads[: n.value].reshape(-1, 4, 2), scale[: n.value], clen[: n.value]
 
-    STAGES = ["h2d", "threshold", "masks_starts", "walk", "emit", "approx", "group", "identify", "subpix_pose", "_", "d2h", "walk_r0", "walk_r1", "walk_r2", "walk_r3"]
+    STAGES = ["h2d", "threshold", "masks_starts", "walk", "emit", "approx", "group", "identify", "subpix_pose", "_", "d2h", "walk_r0", "walk_r1", "walk_r2", "walk_r3", "walk_r4", "walk_r5", "walk_r6", "walk_r7"]
 
     def last_stage_ms(self):
-        ms = np.zeros(16, np.float32)
+        ms = np.zeros(32, np.float32)
         n = C.c_int(0)
-        _lib.check(self.lib.fid_last_stage_ms(self.h, ms.ctypes.data_as(C.c_void_p), 16, C.byref(n)))
+        _lib.check(self.lib.fid_last_stage_ms(self.h, ms.ctypes.data_as(C.c_void_p), 32, C.byref(n)))
         return {k: float(ms[i]) for i, k in enumerate(self.STAGES) if k != "_"}
 
     COUNTERS = ["start_cracks", "contours_in_range", "contour_points", "quad_candidates", "selected", "markers", "kernel_launches"]

@@ -151,8 +151,8 @@ int fid_debug_candidates(fid_detector* h, int max_candidates, int* n, int32_t* q
 
 /* Per-stage device times (milliseconds, CUDA events) of the last batch call:
  * [0] h2d copy, [1] threshold, [2] masks+starts, [3] border walk, [4] chain emit, [5] polygon+filters,
- * [6] group, [7] identify, [8] subpix+pose, [9] unused, [10] d2h, [11..14] the four border-walk
- * rounds (budgets 32, 256, 2048, rest); n_stages returns 15. */
+ * [6] group, [7] identify, [8] subpix+pose, [9] unused, [10] d2h, [11..18] the border-walk rounds
+ * (unused rounds read 0); n_stages returns 19. */
 int fid_last_stage_ms(fid_detector* h, float* ms, int max_stages, int* n_stages);
 /* Work counters of the last batch call: [0] start cracks, [1] walk survivors (contours in range),
  * [2] contour points emitted, [3] quad candidates, [4] candidates selected, [5] markers,

@@ -44,6 +44,49 @@ struct Start {
     int x, y, is_right;
 };
 
+// Walk representation exactly as k_retile builds it + the step tables.
+struct HostWalk {
+    std::vector<uint32_t> halo;
+    int tpr = 0;
+    static const uint8_t* lut_prev() {
+        static std::vector<uint8_t> p, n;
+        if (p.empty()) {
+            p.resize(FID_LUT_SIZE);
+            n.resize(FID_LUT_SIZE);
+            build_step_tables(p.data(), n.data());
+            next_store() = n;
+        }
+        return p.data();
+    }
+    static std::vector<uint8_t>& next_store() {
+        static std::vector<uint8_t> n;
+        return n;
+    }
+    static const uint8_t* lut_next() {
+        lut_prev();
+        return next_store().data();
+    }
+    void build(const HostPlane& hp) {
+        tpr = halo_tiles_x(hp.W);
+        halo.assign(halo_plane_words(hp.W, hp.H), 0u);
+        const BitView v = hp.view();
+        const int tiles_y = (hp.H + FID_HALO_T - 1) / FID_HALO_T;
+        for (int ty = 0; ty < tiles_y; ty++)
+            for (int tx = 0; tx < tpr; tx++)
+                for (int r = 0; r < 32; r++) {
+                    const int Y = FID_HALO_T * ty - 1 + r, X0 = FID_HALO_T * tx - 1;
+                    uint32_t out = 0;
+                    if (Y >= 0 && Y < hp.H) {
+                        const int w0 = X0 >> 5, sh = X0 & 31;
+                        const uint32_t lo = v.word(w0, Y), hi = v.word(w0 + 1, Y);
+                        out = sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
+                    }
+                    halo[((size_t)ty * tpr + tx) * 32 + r] = out;
+                }
+    }
+    WalkCtx ctx() const { return WalkCtx{HaloView{halo.data(), tpr}, lut_prev(), lut_next()}; }
+};
+
 static void find_starts(const HostPlane& hp, std::vector<Start>& starts) {
     const BitView v = hp.view();
     for (int y = 0; y < hp.H; y++)
@@ -72,6 +115,8 @@ int hs_find_contours(const uint8_t* plane, int W, int H, int min_len, int max_le
     pack_plane(plane, W, H, mask);
     std::vector<Start> starts;
     find_starts(mask, starts);
+    HostWalk hw;
+    hw.build(mask);
     if (n_starts_out) *n_starts_out = (int64_t)starts.size();
     struct Chain {
         int64_t key;
@@ -80,7 +125,7 @@ int hs_find_contours(const uint8_t* plane, int W, int H, int min_len, int max_le
     std::vector<Chain> chains;
     for (const Start& s : starts) {
         int n = 0;
-        int st = walk_start(mask.view(), s.x, s.y, s.is_right, max_len, &n);
+        int st = walk_start(hw.ctx(), s.x, s.y, s.is_right, max_len, &n);
         if (st == WALK_CANONICAL && n >= min_len) chains.push_back({((int64_t)s.y * W + s.x) * 2 + s.is_right, s.x, s.y, s.is_right, n});
     }
     if (min_len <= 1) {  // isolated pixels are 1-point outer contours
@@ -94,7 +139,7 @@ int hs_find_contours(const uint8_t* plane, int W, int H, int min_len, int max_le
     for (size_t i = 0; i < chains.size(); i++) {
         const Chain& c = chains[i];
         if (off + c.n > max_pts) return -1;
-        trace_forward(mask.view(), c.x, c.y, c.is_right, c.n, reinterpret_cast<Pt16*>(out_pts) + off);
+        trace_forward(hw.ctx(), c.x, c.y, c.is_right, c.n, reinterpret_cast<Pt16*>(out_pts) + off);
         out_len[i] = c.n;
         off += c.n;
     }
@@ -109,11 +154,13 @@ void hs_walk_stats(const uint8_t* plane, int W, int H, int max_len, int64_t* out
     pack_plane(plane, W, H, mask);
     std::vector<Start> starts;
     find_starts(mask, starts);
+    HostWalk hw;
+    hw.build(mask);
     for (int i = 0; i < 8; i++) out[i] = 0;
     out[0] = (int64_t)starts.size();
     for (const Start& st : starts) {
         int n = 0, steps = 0;
-        const int result = walk_start(mask.view(), st.x, st.y, st.is_right, max_len, &n, &steps);
+        const int result = walk_start(hw.ctx(), st.x, st.y, st.is_right, max_len, &n, &steps);
         out[1] += steps;
         if (steps > 64) out[2]++;
         if (steps > 1024) out[3]++;
@@ -126,6 +173,27 @@ void hs_walk_stats(const uint8_t* plane, int W, int H, int max_len, int64_t* out
             out[6] += steps;
         }
     }
+}
+
+// Detailed walk log of one plane: for every start with more than min_steps steps:
+// rows of (x, y, is_right, result, steps).  Returns the number of rows.
+int hs_walk_log(const uint8_t* plane, int W, int H, int max_len, int min_steps, int32_t* out, int max_rows) {
+    HostPlane mask;
+    pack_plane(plane, W, H, mask);
+    std::vector<Start> starts;
+    find_starts(mask, starts);
+    HostWalk hw;
+    hw.build(mask);
+    int rows = 0;
+    for (const Start& st : starts) {
+        int n = 0, steps = 0;
+        const int result = walk_start(hw.ctx(), st.x, st.y, st.is_right, max_len, &n, &steps);
+        if (steps > min_steps && rows < max_rows) {
+            int32_t* o = out + 5 * rows++;
+            o[0] = st.x; o[1] = st.y; o[2] = st.is_right; o[3] = result; o[4] = steps;
+        }
+    }
+    return rows;
 }
 
 // approxPolyDP (closed) of one contour; returns vertex count (-1 = more than 8 before clean-up).
@@ -147,14 +215,16 @@ static void raw_candidates(const uint8_t* planes, int W, int H, const DevParams&
         pack_plane(planes + (size_t)s * W * H, W, H, mask);
         std::vector<Start> starts;
         find_starts(mask, starts);
+        HostWalk hw;
+        hw.build(mask);
         std::vector<RawQuad> found;
         std::vector<Pt16> pts;
         for (const Start& st : starts) {
             int n = 0;
-            if (walk_start(mask.view(), st.x, st.y, st.is_right, max_len, &n) != WALK_CANONICAL) continue;
+            if (walk_start(hw.ctx(), st.x, st.y, st.is_right, max_len, &n) != WALK_CANONICAL) continue;
             if (n < min_len || n > max_len) continue;
             pts.resize(n);
-            trace_forward(mask.view(), st.x, st.y, st.is_right, n, pts.data());
+            trace_forward(hw.ctx(), st.x, st.y, st.is_right, n, pts.data());
             Pt16 q[FID_APPROX_MAX_V];
             SerialReducer red;
             if (approx_poly_closed(red, pts.data(), n, (double)n * P.poly_accuracy_rate, q) != 4) continue;
