@@ -244,6 +244,7 @@ def run_gpu_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from fiducials_b200 import _lib, synth
+    from fiducials_b200.multigpu import allgather_tables
     from fiducials_b200.node import MAXM, Detector, FiducialSlam, default_params
 
     lib = _lib.load()
@@ -263,11 +264,6 @@ def run_gpu_arm(args):
     _lib.check(lib.fid_device_alloc(det.h, frames.nbytes, C.byref(dptr)))
     _lib.check(lib.fid_memcpy_h2d(det.h, dptr, hptr, frames.nbytes))
 
-    tables_gpu = None
-    if dist is not None:
-        table_bytes = slam.p.max_fiducials * C.sizeof(_lib.fid_map_record)
-        tables_gpu = [torch.empty(table_bytes, dtype=torch.uint8, device="cuda") for _ in range(world)]
-
     launches = [0]
 
     def step(on_device):
@@ -286,10 +282,9 @@ def run_gpu_arm(args):
         bc.q[3] = 1.0
         _lib.check(lib.fid_map_update_sequence(slam.h, nf, offsets.ctypes.data_as(C.c_void_p), C.cast(arr, C.c_void_p), C.byref(bc), C.byref(bc), None))
         launches[0] += 1
-        if dist is not None:
-            mine = torch.from_numpy(slam.export_table(0)).cuda()
-            dist.all_gather(tables_gpu, mine)
-            slam.merge_tables(torch.cat(tables_gpu).cpu().numpy(), world, instance=0)
+        if dist is not None:  # one NCCL all-gather of the per-rank map tables, same deterministic merge on every rank
+            tables = allgather_tables(slam.export_table(0), dist, device="cuda")
+            slam.merge_tables(tables.reshape(-1), world, instance=0)
             launches[0] += 2
         return counts
 

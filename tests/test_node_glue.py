@@ -1,0 +1,58 @@
+"""The C++ node glue (fiducials_b200/csrc/node_glue.hpp): builds and links on the GPU-less box; on a
+GPU box it runs a frame through imageCallback / poseEstimateCallback / transformCallback and the
+printed messages are compared with the oracle."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "hostsim", "node_glue_main")
+
+
+def _build():
+    import __graft_entry__ as g
+    from fiducials_b200 import _lib
+
+    if not os.path.exists(_lib.LIB_PATH):
+        g.build()
+    libdir = os.path.join(ROOT, "fiducials_b200")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", EXE, os.path.join(ROOT, "tests", "node_glue_main.cpp"), "-L" + libdir, "-lfiducials_b200",
+                           "-Wl,-rpath," + libdir, "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64", "-lcudart"])
+
+
+def test_node_glue_builds_and_fails_loudly_without_gpu(tmp_path):
+    import torch
+
+    _build()
+    if torch.cuda.is_available():
+        pytest.skip("GPU present; see the gpu test")
+    raw = tmp_path / "f.bgr"
+    raw.write_bytes(bytes(64 * 64 * 3))
+    r = subprocess.run([EXE, str(raw), "64", "64", "6", "0.14"], capture_output=True, text=True)
+    assert r.returncode == 1 and "no usable CUDA device" in r.stderr
+
+
+@pytest.mark.gpu
+def test_node_glue_messages_match_oracle(tmp_path):
+    from fiducials_b200 import synth
+    from oracle import aruco_oracle as ao
+
+    _build()
+    bgr, truth, K, D, d = synth.make_config_frame("C1", 0)
+    raw = tmp_path / "f.bgr"
+    raw.write_bytes(bgr.tobytes())
+    args = [EXE, str(raw), "640", "480", str(d), "0.14"] + [repr(float(v)) for v in (K[0, 0], K[1, 1], K[0, 2], K[1, 2])] + [repr(float(v)) for v in D[:5]]
+    r = subprocess.run(args, capture_output=True, text=True, check=True)
+    ids, corners, rv, tv, fields = ao.detect_and_pose(bgr, d, K, D, 0.14)
+    V = [l.split() for l in r.stdout.splitlines() if l.startswith("V ")]
+    T = [l.split() for l in r.stdout.splitlines() if l.startswith("T ")]
+    M = [l.split() for l in r.stdout.splitlines() if l.startswith("M ")]
+    assert [int(v[1]) for v in V] == ids.tolist()
+    for i, v in enumerate(V):
+        assert np.abs(np.array(v[2:], float) - corners[i].reshape(-1)).max() < 1e-3
+    for i, t in enumerate(T):
+        vals = np.array(t[2:], float)
+        assert np.abs(vals[:3] - fields[i]["translation"]).max() < 1e-3 and np.abs(vals[3:7] - fields[i]["rotation"]).max() < 1e-3
+    assert sorted(int(m[1]) for m in M) == sorted(ids.tolist())
