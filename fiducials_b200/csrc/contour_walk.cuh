@@ -5,10 +5,10 @@
 // OpenCV's Suzuki-Abe scan is sequential (it marks visited pixels); here every border is found
 // independently:
 //
-//  * the walk reads the bit-packed threshold plane directly: per step the 3x3 neighbourhood of the
-//    current pixel is turned into an 8-bit occupancy mask (bit k set <=> neighbour in direction k
-//    is foreground; pixels outside the image are background, which is OpenCV 4.13's zero
-//    padding).  Direction codes (y down):
+//  * the walk reads the bit-packed threshold plane directly (halo tiles, below): per step the 3x3
+//    neighbourhood of the current pixel indexes a table; conceptually it is an 8-bit occupancy mask
+//    (bit k set <=> neighbour in direction k is foreground; pixels outside the image are
+//    background, which is OpenCV 4.13's zero padding).  Direction codes (y down):
 //        0:(+1,0) 1:(+1,-1) 2:(0,-1) 3:(-1,-1) 4:(-1,0) 5:(-1,+1) 6:(0,+1) 7:(+1,+1)
 //  * a border is a cycle of states (pixel, dir to previous pixel a, dir to next pixel b) where b is
 //    the first foreground neighbour counter-clockwise after a.  The zero neighbours strictly
@@ -46,54 +46,6 @@ FID_HD int prev_cw(int m, int b) {
 }
 
 enum { WALK_ABORT = 0, WALK_CANONICAL = 1, WALK_TOO_LONG = 2 };
-
-// Threshold planes are bit-packed in 32x32-pixel tiles: a tile is 32 consecutive 32-bit words (one
-// 128-byte cache line), word r = row r of the tile, bit i = column i.  A border walk moves one pixel
-// per step in any direction; with this layout the 3x3 neighbourhood of a pixel is three words of the
-// line the walker already holds in L1 (30 steps out of 32 in either direction), and a whole 1080p
-// plane is 270 KB, so the 13 planes of many frames stay L2 resident.  (A first version stored one
-// neighbour-mask byte per pixel: 27 MB per 1080p frame -- every step of a long walk missed L2 and
-// the TLB, ~2300 cycles per step measured on B200.)
-struct BitView {
-    const uint32_t* base;
-    int tiles_per_row;
-    int W, H;
-    // bits of pixels x-1, x, x+1 of row y in bits 0,1,2; 0 outside the image
-    FID_HD uint32_t row3(int x, int y) const {
-        if (y < 0 || y >= H) return 0u;
-        const int tx = x >> 5, xb = x & 31;
-        const uint32_t* t = base + ((size_t)(y >> 5) * tiles_per_row + tx) * 32 + (y & 31);
-        const uint32_t w = *t;
-        uint32_t r = (xb ? (w >> (xb - 1)) : (w << 1)) & 7u;
-        if (xb == 0 && tx > 0) r |= t[-32] >> 31;
-        if (xb == 31 && tx + 1 < tiles_per_row) r |= (t[32] & 1u) << 2;
-        return r;
-    }
-    // 8-neighbour occupancy mask of pixel (x,y)
-    FID_HD int at(int x, int y) const {
-        const int xb = x & 31, yb = y & 31;
-        uint32_t u, m, d;
-        if (xb >= 1 && xb <= 30 && yb >= 1 && yb <= 30) {
-            const uint32_t* t = base + ((size_t)(y >> 5) * tiles_per_row + (x >> 5)) * 32 + yb;
-            u = (t[-1] >> (xb - 1)) & 7u;
-            m = (t[0] >> (xb - 1)) & 7u;
-            d = (t[1] >> (xb - 1)) & 7u;
-        } else {
-            u = row3(x, y - 1);
-            m = row3(x, y);
-            d = row3(x, y + 1);
-        }
-        return (int)(((m >> 2) & 1u) | (((u >> 2) & 1u) << 1) | (((u >> 1) & 1u) << 2) | ((u & 1u) << 3) | ((m & 1u) << 4) | ((d & 1u) << 5) | (((d >> 1) & 1u) << 6) |
-                     (((d >> 2) & 1u) << 7));
-    }
-    // word holding pixels [32*tx, 32*tx+32) of row y; 0 outside
-    FID_HD uint32_t word(int tx, int y) const {
-        if (y < 0 || y >= H || tx < 0 || tx >= tiles_per_row) return 0u;
-        return base[((size_t)(y >> 5) * tiles_per_row + tx) * 32 + (y & 31)];
-    }
-};
-FID_HD int bit_tiles_per_row(int W) { return (W + 31) / 32; }
-FID_HD size_t bit_plane_words(int W, int H) { return (size_t)((W + 31) / 32) * ((H + 31) / 32) * 32; }
 
 // ---- walking representation: halo tiles + step tables -----------------------------------------------
 // For walking, every plane is re-tiled into 30x30-pixel tiles stored with a 1-pixel halo as 32 words
@@ -206,8 +158,14 @@ FID_HD int walk_init(const WalkCtx& c, int x0, int y0, int is_right, WalkState* 
 
 // Advance by at most `budget` steps.  Returns WALK_CANONICAL (st->n = contour length), WALK_ABORT,
 // WALK_TOO_LONG (more than max_len steps) or WALK_CONTINUE (budget exhausted, state updated).
-template <bool IS_RIGHT>
-FID_HD int walk_resume_dir(const WalkCtx& c, int x0, int y0, int max_len, int budget, WalkState* st) {
+struct NoVisit {
+    FID_HD void operator()(int, int, bool, bool) const {}
+};
+
+// `visit(x, y, exL, exR)` is called for every state that owns a left/right crack whose pixel is raster
+// larger than the start (i.e. a crack this walk has just proven non-canonical).
+template <bool IS_RIGHT, class Visit = NoVisit>
+FID_HD int walk_resume_dir(const WalkCtx& c, int x0, int y0, int max_len, int budget, WalkState* st, const Visit& visit = Visit()) {
     int x = st->x, y = st->y, n = st->n, dir = st->dir;
     const int ref = IS_RIGHT ? st->a0 : st->b0;  // closing condition: arrive at the start with this direction
     const uint8_t* lut = IS_RIGHT ? c.lut_next : c.lut_prev;
@@ -233,6 +191,7 @@ FID_HD int walk_resume_dir(const WalkCtx& c, int x0, int y0, int max_len, int bu
                 result = WALK_ABORT;
                 break;
             }
+            visit(x, y, (e & 8) != 0, (e & 16) != 0);
         }
     }
     st->x = x;
@@ -257,7 +216,9 @@ FID_HD int walk_start(const WalkCtx& c, int x0, int y0, int is_right, int max_le
     return r;
 }
 
-// Emit the n contour points in OpenCV order (start pixel first, then Suzuki's direction).
+// Emit the n contour points in OpenCV order (start pixel first, then Suzuki's direction).  Points are
+// written four at a time (16-byte stores); `out` must be 16-byte aligned and have room for n rounded
+// up to a multiple of 4.
 FID_HD void trace_forward(const WalkCtx& c, int x0, int y0, int is_right, int n, Pt16* out) {
     const uint32_t v = c.plane.idx9(x0, y0);
     int x = x0, y = y0;
@@ -268,53 +229,34 @@ FID_HD void trace_forward(const WalkCtx& c, int x0, int y0, int is_right, int n,
     }
     int a = lut_load(c.lut_prev + v * 8 + (is_right ? 0 : 4)) & 7;
     uint32_t cur = v;
+    uint32_t buf[4];
+    uint32_t* out32 = reinterpret_cast<uint32_t*>(out);
     for (int i = 0; i < n; i++) {
-        out[i].x = (int16_t)x;
-        out[i].y = (int16_t)y;
+        buf[i & 3] = (uint32_t)(uint16_t)x | ((uint32_t)(uint16_t)y << 16);
+        if ((i & 3) == 3) {
+#if defined(__CUDA_ARCH__)
+            *reinterpret_cast<uint4*>(out32 + i - 3) = make_uint4(buf[0], buf[1], buf[2], buf[3]);
+#else
+            for (int k = 0; k < 4; k++) out32[i - 3 + k] = buf[k];
+#endif
+        }
         const int b = lut_load(c.lut_next + cur * 8 + a) & 7;
         x += dir_dx(b);
         y += dir_dy(b);
         a = (b + 4) & 7;
         cur = c.plane.idx9(x, y);
     }
+    for (int k = 0; k < (n & 3); k++) out32[(n & ~3) + k] = buf[k];
 }
 
-// ---- neighbour masks and start cracks from bit-packed planes ------------------------------------
-// A threshold plane is bit-packed 32 pixels per word, LSB = lowest x.  For the word holding pixels
-// [32w, 32w+32) of row y, up/mid/down are the words of rows y-1,y,y+1 (0 outside the image) and
-// *_l / *_r the neighbouring words to the left / right (0 outside).
-struct NbrWords {
-    uint32_t d[8];  // d[k] bit i set <=> neighbour k of pixel i is foreground
-};
-
-FID_HD uint32_t shl_in(uint32_t w, uint32_t left) { return (w << 1) | (left >> 31); }   // value at x-1
-FID_HD uint32_t shr_in(uint32_t w, uint32_t right) { return (w >> 1) | (right << 31); }  // value at x+1
-
-FID_HD NbrWords nbr_words(uint32_t up_l, uint32_t up, uint32_t up_r, uint32_t mid_l, uint32_t mid, uint32_t mid_r, uint32_t dn_l, uint32_t dn,
-                          uint32_t dn_r) {
-    NbrWords n;
-    n.d[0] = shr_in(mid, mid_r);
-    n.d[1] = shr_in(up, up_r);
-    n.d[2] = up;
-    n.d[3] = shl_in(up, up_l);
-    n.d[4] = shl_in(mid, mid_l);
-    n.d[5] = shl_in(dn, dn_l);
-    n.d[6] = dn;
-    n.d[7] = shr_in(dn, dn_r);
-    return n;
-}
-
-// Start cracks that survive the exact local prune: a left crack of (x,y) is dominated when (x,y-1)
-// is foreground with a zero left neighbour (that crack lies on the same border and is raster
-// smaller); same for right cracks.
-FID_HD uint32_t left_crack_starts(uint32_t mid, const NbrWords& n) { return mid & ~n.d[4] & ~(n.d[2] & ~n.d[3]); }
-FID_HD uint32_t right_crack_starts(uint32_t mid, const NbrWords& n) { return mid & ~n.d[0] & ~(n.d[2] & ~n.d[1]); }
-
-FID_HD uint8_t mask_byte(const NbrWords& n, int i) {
-    uint32_t v = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) v |= ((n.d[k] >> i) & 1u) << k;
-    return (uint8_t)v;
+// ---- start cracks of one halo-tile row -----------------------------------------------------------------
+// up / mid = words r-1 / r of a tile (r = 1..30).  A left crack of a pixel is a candidate start unless
+// the pixel above is foreground with a zero left neighbour (that crack lies on the same border and
+// is raster smaller, so it dominates); same for right cracks.  Only interior bits 1..30 are reported.
+FID_HD void halo_row_starts(uint32_t up, uint32_t mid, uint32_t* L, uint32_t* R) {
+    const uint32_t interior = 0x7FFFFFFEu;
+    *L = mid & ~(mid << 1) & ~(up & ~(up << 1)) & interior;
+    *R = mid & ~(mid >> 1) & ~(up & ~(up >> 1)) & interior;
 }
 
 }  // namespace fid

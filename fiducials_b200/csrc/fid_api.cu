@@ -10,6 +10,7 @@
 
 #include "../../include/fiducials_b200.h"
 #include "kernels_contour.cuh"
+#include "kernels_threshold.cuh"
 #include "kernels_marker.cuh"
 #include "params_host.h"
 
@@ -30,7 +31,6 @@ enum { N_WALK_ROUNDS = FID_WALK_MAX_ROUNDS };
 struct Slot {
     uint8_t* d_bgr = nullptr;
     uint8_t* d_gray = nullptr;
-    uint32_t* d_bits = nullptr;
     uint32_t* d_halo = nullptr;
     StartRec* d_starts = nullptr;
     ChainRec* d_chains = nullptr;
@@ -76,6 +76,7 @@ struct fid_detector {
     uint8_t* d_lut_prev = nullptr;
     uint8_t* d_lut_next = nullptr;
     int walk_rounds = 0;
+    int emit_blocks_per_sm = 2;
     int walk_budget[FID_WALK_MAX_ROUNDS]{};
     int walk_persist[FID_WALK_MAX_ROUNDS]{};
     int32_t* d_override_ids = nullptr;
@@ -127,14 +128,12 @@ static FrameGeom make_geom(const fid_detector* h, int W, int H, size_t row_strid
     FrameGeom g;
     g.W = W;
     g.H = H;
-    g.wpr = (W + 31) / 32;
-    g.gray_pitch = g.wpr * 32;
+    g.gray_pitch = (W + 31) / 32 * 32;
     g.bgr_row_stride = row_stride;
     g.bgr_frame_stride = frame_stride;
     g.gray_frame_stride = (size_t)g.gray_pitch * H;
-    g.bits_scale_stride = bit_plane_words(W, H);
-    g.bits_frame_stride = g.bits_scale_stride * h->P.n_scales;
     g.halo_tpr = halo_tiles_x(W);
+    g.halo_tiles_y = (H + FID_HALO_T - 1) / FID_HALO_T;
     g.halo_scale_stride = halo_plane_words(W, H);
     g.halo_frame_stride = g.halo_scale_stride * h->P.n_scales;
     return g;
@@ -162,10 +161,6 @@ static int upload_constants() {
     return FID_OK;
 }
 
-static size_t thresh_smem(int r_max) {
-    const int RW = THR_TW + 2 * r_max, RH = THR_TH + 2 * r_max;
-    return (size_t)(RH + 1) * (RW + 1) * 4 + THR_TW * THR_TH;
-}
 static size_t ident_smem(const DevParams& P) { return (size_t)P.n_markers * 4 * 8 + IDENT_WARPS * 256 * 4 + IDENT_WARPS * FID_MAX_WARP_SIDE_SQ; }
 
 static int r_max_of(const DevParams& P) {
@@ -175,7 +170,8 @@ static int r_max_of(const DevParams& P) {
 }
 
 static int configure_kernels(fid_detector* h) {
-    CK(cudaFuncSetAttribute(k_threshold, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thresh_smem(FID_MAX_WIN_RADIUS)));
+    CK(cudaFuncSetAttribute(k_threshold<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thresh_smem_bytes(THR_FAST_R)));
+    CK(cudaFuncSetAttribute(k_threshold<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thresh_smem_bytes(FID_MAX_WIN_RADIUS)));
     CK(cudaFuncSetAttribute(k_identify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1000 * 4 * 8 + IDENT_WARPS * 256 * 4 + IDENT_WARPS * FID_MAX_WARP_SIDE_SQ)));
     return FID_OK;
 }
@@ -190,7 +186,6 @@ static int alloc_slot(fid_detector* h, Slot& s) {
     if ((rc = (expr)) != FID_OK) return rc;
     A(dalloc(&s.d_bgr, F * (size_t)W * H * 3));
     A(dalloc(&s.d_gray, F * pitch * H));
-    A(dalloc(&s.d_bits, F * (size_t)S * bit_plane_words(W, H)));
     A(dalloc(&s.d_halo, F * (size_t)S * halo_plane_words(W, H)));
     A(dalloc(&s.d_starts, (size_t)h->max_starts));
     A(dalloc(&s.d_chains, (size_t)h->max_chains));
@@ -241,7 +236,7 @@ static int alloc_slot(fid_detector* h, Slot& s) {
 }
 
 static void free_slot(Slot& s) {
-    void* dptrs[] = {s.d_halo, s.d_queue[0], s.d_queue[1], s.d_bgr,         s.d_gray,          s.d_bits,          s.d_starts,       s.d_chains,       s.d_points,      s.d_counters,
+    void* dptrs[] = {s.d_halo, s.d_queue[0], s.d_queue[1], s.d_bgr,         s.d_gray,          s.d_starts,       s.d_chains,       s.d_points,      s.d_counters,
                      s.d_raw,         s.d_nraw,          s.fs.quads_tmp,    s.fs.per_tmp,     s.fs.quads,       s.fs.per,         s.fs.close_bits, s.fs.group_id,
                      s.fs.group_members, s.fs.next_in_group, s.fs.group_head, s.fs.group_tail, s.fs.close_count, s.fs.close_idx,   s.fs.close_off,  s.fs.selected,
                      s.fs.sel_idx,    s.d_nsel,          s.d_nrawc,         s.d_cand_id,      s.d_cand_corners, s.d_out_count,    s.d_out_ids,     s.d_out_corners,
@@ -324,8 +319,9 @@ extern "C" int fid_create(const fid_params* params, int device, int max_width, i
         CK(cudaMemcpy(h->d_lut_next, ln.data(), FID_LUT_SIZE, cudaMemcpyHostToDevice));
     }
     {   // walk plan: budgets per round, 'p' prefix = persistent lanes, 0 = unbounded (must be last)
+        if (const char* e = getenv("FID_EMIT_BLOCKS")) h->emit_blocks_per_sm = std::max(1, atoi(e));
         const char* plan = getenv("FID_WALK_PLAN");
-        if (!plan || !*plan) plan = "8,64,512,0";
+        if (!plan || !*plan) plan = "8,64,512,p0";
         h->walk_rounds = 0;
         const char* c = plan;
         while (*c && h->walk_rounds < FID_WALK_MAX_ROUNDS) {
@@ -411,42 +407,63 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, int nf, const FrameGeom& g
     CK(cudaMemsetAsync(s.d_counters, 0, sizeof(Counters), st));
     CK(cudaMemsetAsync(s.d_nraw, 0, sizeof(unsigned int) * nf, st));
     CK(cudaEventRecord(s.ev[ST_THRESH], st));
-    {  // threshold
+    {  // gray + threshold (halo tiles)
+        GrayArgs ga{};
+        ga.bgr = d_bgr;
+        ga.gray = s.d_gray;
+        ga.W = W;
+        ga.H = H;
+        ga.n_frames = nf;
+        ga.bgr_row_stride = g.bgr_row_stride;
+        ga.bgr_frame_stride = g.bgr_frame_stride;
+        ga.gray_pitch = g.gray_pitch;
+        ga.gray_frame_stride = g.gray_frame_stride;
+        const long long gq = (long long)nf * H * ((W + 3) / 4);
+        k_gray<<<(unsigned int)((gq + 255) / 256), 256, 0, st>>>(ga);
+        launches++;
         ThreshArgs a{};
-        a.bgr = d_bgr;
         a.gray = s.d_gray;
-        a.bits = s.d_bits;
-        a.g = g;
+        a.halo = s.d_halo;
+        a.W = W;
+        a.H = H;
+        a.n_frames = nf;
+        a.gray_pitch = g.gray_pitch;
+        a.gray_frame_stride = g.gray_frame_stride;
+        a.halo_tpr = g.halo_tpr;
+        a.halo_tiles_y = g.halo_tiles_y;
+        a.halo_scale_stride = g.halo_scale_stride;
+        a.halo_frame_stride = g.halo_frame_stride;
         a.n_scales = P.n_scales;
         a.r_max = r_max_of(P);
         a.thresh_c = P.thresh_c;
-        for (int i = 0; i < P.n_scales; i++) a.win[i] = P.win[i];
-        dim3 grid((W + THR_TW - 1) / THR_TW, (H + THR_TH - 1) / THR_TH, nf);
-        k_threshold<<<grid, THR_THREADS, thresh_smem(a.r_max), st>>>(a);
+        bool fast = P.n_scales == 13;
+        for (int i = 0; i < P.n_scales; i++) {
+            a.win[i] = P.win[i];
+            fast = fast && P.win[i] == 3 + 4 * i;
+        }
+        dim3 grid((g.halo_tpr + THR_TILES_X - 1) / THR_TILES_X, (g.halo_tiles_y + THR_TILES_Y - 1) / THR_TILES_Y, nf);
+        if (fast)
+            k_threshold<true><<<grid, THR_THREADS, thresh_smem_bytes(THR_FAST_R), st>>>(a);
+        else
+            k_threshold<false><<<grid, THR_THREADS, thresh_smem_bytes(a.r_max), st>>>(a);
         launches++;
     }
     CK(cudaEventRecord(s.ev[ST_MASKS], st));
     if (stop_after == ST_THRESH) return FID_OK;
-    {  // masks + starts
-        MaskArgs a{};
-        a.bits = s.d_bits;
+    {  // start cracks
+        StartsArgs a{};
+        a.halo = s.d_halo;
         a.starts = s.d_starts;
         a.counters = s.d_counters;
         a.max_starts = h->max_starts;
-        a.g = g;
+        a.halo_tpr = g.halo_tpr;
+        a.halo_tiles_y = g.halo_tiles_y;
+        a.halo_scale_stride = g.halo_scale_stride;
+        a.halo_frame_stride = g.halo_frame_stride;
         a.n_scales = P.n_scales;
         a.n_frames = nf;
-        const long long total = (long long)nf * P.n_scales * H * g.wpr;
-        k_masks_starts<<<(unsigned int)((total + 255) / 256), 256, 0, st>>>(a);
-        launches++;
-        RetileArgs r{};
-        r.bits = s.d_bits;
-        r.halo = s.d_halo;
-        r.g = g;
-        r.n_scales = P.n_scales;
-        r.n_frames = nf;
-        const long long rt = (long long)nf * P.n_scales * (long long)g.halo_scale_stride;
-        k_retile<<<(unsigned int)((rt + 255) / 256), 256, 0, st>>>(r);
+        const long long total = (long long)nf * P.n_scales * (long long)g.halo_scale_stride;
+        k_starts<<<(unsigned int)((total + 255) / 256), 256, 0, st>>>(a);
         launches++;
     }
     CK(cudaEventRecord(s.ev[ST_WALK], st));
@@ -491,9 +508,10 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, int nf, const FrameGeom& g
         a.chains = s.d_chains;
         a.points = s.d_points;
         a.counters = s.d_counters;
+        a.work_counter = &s.d_counters->emit_work;
         a.max_chains = h->max_chains;
         a.g = g;
-        k_emit<<<h->sm_count * 4, 128, 0, st>>>(a);
+        k_emit<<<h->sm_count * h->emit_blocks_per_sm, 64, 0, st>>>(a);
         launches++;
     }
     CK(cudaEventRecord(s.ev[ST_APPROX], st));
@@ -822,13 +840,15 @@ extern "C" int fid_debug_threshold(fid_detector* h, const uint8_t* bgr, int widt
     CK(cudaStreamSynchronize(h->stream));
     if (gray) CK(cudaMemcpy2D(gray, width, s.d_gray, g.gray_pitch, width, height, cudaMemcpyDeviceToHost));
     if (planes) {
-        std::vector<uint32_t> bits((size_t)h->P.n_scales * g.bits_scale_stride);
-        CK(cudaMemcpy(bits.data(), s.d_bits, bits.size() * 4, cudaMemcpyDeviceToHost));
+        std::vector<uint32_t> bits((size_t)h->P.n_scales * g.halo_scale_stride);
+        CK(cudaMemcpy(bits.data(), s.d_halo, bits.size() * 4, cudaMemcpyDeviceToHost));
         for (int sc = 0; sc < h->P.n_scales; sc++)
             for (int y = 0; y < height; y++)
-                for (int x = 0; x < width; x++)
-                    planes[((size_t)sc * height + y) * width + x] =
-                        (bits[(size_t)sc * g.bits_scale_stride + ((size_t)(y >> 5) * g.wpr + (x >> 5)) * 32 + (y & 31)] >> (x & 31)) & 1u;
+                for (int x = 0; x < width; x++) {
+                    const int tx = x / FID_HALO_T, ty = y / FID_HALO_T;
+                    const uint32_t wv = bits[(size_t)sc * g.halo_scale_stride + ((size_t)ty * g.halo_tpr + tx) * 32 + (y - FID_HALO_T * ty + 1)];
+                    planes[((size_t)sc * height + y) * width + x] = (wv >> (x - FID_HALO_T * tx + 1)) & 1u;
+                }
     }
     if (n_scales) *n_scales = h->P.n_scales;
     return FID_OK;

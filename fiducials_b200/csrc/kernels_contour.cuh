@@ -1,7 +1,6 @@
-// CUDA kernels, front half of the per-frame pipeline (sm_100a):
-//   k_threshold     BGR8 -> gray + n_scales bit-packed adaptive-threshold planes   
-//   k_masks_starts  bit planes -> 8-neighbour mask bytes + start-crack queue       (A.3b)
-//   k_walk          one thread per start crack: backwards border walk, canonical test, length
+// CUDA kernels, contour half of the per-frame pipeline (sm_100a); the threshold stage that feeds it
+// is in kernels_threshold.cuh:
+//   k_walk          one thread per start crack / suspended walk: border walk, canonical test, length (A.3b)
 //   k_emit          one thread per surviving border: ordered contour points
 //   k_approx        one block per contour: approxPolyDP + quad filters             (A.4)
 // All kernels take a batch of frames (blockIdx.z / queue entries carry the frame index) so that a
@@ -25,7 +24,8 @@ struct Counters {
     unsigned int overflow;  // bit0 starts, bit1 chains, bit2 points, bit3 raw quads, bit4 selected, bit5 markers, bit6 walk queue
     unsigned int n_q[FID_WALK_MAX_ROUNDS][2];  // walks suspended by each round, per direction
     unsigned int work[FID_WALK_MAX_ROUNDS][2]; // persistent-walker work counters, per direction
-    unsigned int pad[3];
+    unsigned int emit_work;
+    unsigned int pad[2];
 };
 
 struct WalkRec {       // a border walk suspended between rounds
@@ -49,250 +49,12 @@ struct ChainRec {
 
 struct FrameGeom {
     int W, H;
-    int wpr;            // 32-pixel tiles per bit-plane tile row (== words per pixel row)
     int gray_pitch;     // bytes
     size_t bgr_row_stride, bgr_frame_stride;
     size_t gray_frame_stride;
-    size_t bits_scale_stride, bits_frame_stride;  // in words (tiled 32x32, see BitView)
-    int halo_tpr;       // 30x30(+halo) walk tiles per tile row
+    int halo_tpr, halo_tiles_y;  // 30x30(+halo) tiles per tile row / tile rows
     size_t halo_scale_stride, halo_frame_stride;  // in words (see HaloView)
 };
-
-// ---------------------------------------------------------------------------------------------------
-// k_threshold: one CTA per 128x64 output tile.  The tile plus a halo of r_max pixels is converted to
-// gray once (15-bit fixed point, cv::cvtColor BGR2GRAY), a summed-area table of the region is built
-// in shared memory, and every scale's box sum is 4 table look-ups.  BINARY_INV with the mean
-// rounded half-to-even and no ties for odd windows reduces to the integer test
-//     2*S >= (2*g + 2*C - 1) * k^2          
-// A warp covers 32 consecutive pixels, so __ballot_sync yields the packed plane word directly.
-// Algorithmic HBM traffic per frame: 3*W*H read + W*H (gray) + n_scales*W*H/8 written.
-// ---------------------------------------------------------------------------------------------------
-#define THR_TW 128
-#define THR_TH 64
-#define THR_THREADS 256
-
-struct ThreshArgs {
-    const uint8_t* bgr;
-    uint8_t* gray;
-    uint32_t* bits;
-    FrameGeom g;
-    int n_scales;
-    int r_max;
-    int thresh_c;
-    int win[FID_MAX_SCALES];
-};
-
-__global__ void __launch_bounds__(THR_THREADS, 2) k_threshold(const ThreshArgs a) {
-    extern __shared__ uint32_t smem_u32[];
-    const int R = a.r_max;
-    const int RW = THR_TW + 2 * R, RH = THR_TH + 2 * R;
-    const int SP = RW + 1;                                // SAT pitch (with a zero first row/column)
-    uint32_t* sat = smem_u32;                             // (RH+1) x SP
-    uint8_t* tile_gray = (uint8_t*)(sat + (RH + 1) * SP);  // THR_TH x THR_TW
-
-    const int f = blockIdx.z;
-    const int tx0 = blockIdx.x * THR_TW, ty0 = blockIdx.y * THR_TH;
-    const int W = a.g.W, H = a.g.H;
-    const uint8_t* bgr = a.bgr + (size_t)f * a.g.bgr_frame_stride;
-    const int tid = threadIdx.x;
-
-    // zero first row / column
-    for (int i = tid; i < SP; i += THR_THREADS) sat[i] = 0;
-    for (int i = tid; i <= RH; i += THR_THREADS) sat[i * SP] = 0;
-    // A. gray of the region (replicate border)
-    for (int p = tid; p < RW * RH; p += THR_THREADS) {
-        const int ry = p / RW, rx = p - ry * RW;
-        int x = tx0 - R + rx, y = ty0 - R + ry;
-        x = x < 0 ? 0 : (x > W - 1 ? W - 1 : x);
-        y = y < 0 ? 0 : (y > H - 1 ? H - 1 : y);
-        const uint8_t* px = bgr + (size_t)y * a.g.bgr_row_stride + 3 * x;
-        const uint32_t gv = (3735u * px[0] + 19235u * px[1] + 9798u * px[2] + 16384u) >> 15;
-        sat[(ry + 1) * SP + rx + 1] = gv;
-        const int ix = rx - R, iy = ry - R;
-        if (ix >= 0 && ix < THR_TW && iy >= 0 && iy < THR_TH) tile_gray[iy * THR_TW + ix] = (uint8_t)gv;
-    }
-    __syncthreads();
-    // gray plane out (coalesced 4-byte stores)
-    {
-        uint8_t* gout = a.gray + (size_t)f * a.g.gray_frame_stride;
-        for (int p = tid; p < THR_TW * THR_TH / 4; p += THR_THREADS) {
-            const int iy = p / (THR_TW / 4), ix = (p - iy * (THR_TW / 4)) * 4;
-            const int x = tx0 + ix, y = ty0 + iy;
-            if (y < H && x < W) {
-                if (x + 3 < W && (a.g.gray_pitch & 3) == 0) {
-                    *reinterpret_cast<uint32_t*>(gout + (size_t)y * a.g.gray_pitch + x) = *reinterpret_cast<const uint32_t*>(tile_gray + iy * THR_TW + ix);
-                } else {
-                    for (int k = 0; k < 4 && x + k < W; k++) gout[(size_t)y * a.g.gray_pitch + x + k] = tile_gray[iy * THR_TW + ix + k];
-                }
-            }
-        }
-    }
-    // B. row prefix sums: one warp per row, 32-wide shuffle scans with carry
-    const int warp = tid >> 5, lane = tid & 31;
-    for (int ry = warp; ry < RH; ry += THR_THREADS / 32) {
-        uint32_t* row = sat + (ry + 1) * SP + 1;
-        uint32_t carry = 0;
-        for (int c0 = 0; c0 < RW; c0 += 32) {
-            const int c = c0 + lane;
-            uint32_t v = c < RW ? row[c] : 0u;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
-                if (lane >= d) v += t;
-            }
-            v += carry;
-            if (c < RW) row[c] = v;
-            carry = __shfl_sync(0xffffffffu, v, 31);
-        }
-    }
-    __syncthreads();
-    // C. column prefix sums: one thread per column
-    for (int c = tid; c < RW; c += THR_THREADS) {
-        uint32_t acc = 0;
-        uint32_t* col = sat + SP + 1 + c;
-        for (int ry = 0; ry < RH; ry++) {
-            acc += col[ry * SP];
-            col[ry * SP] = acc;
-        }
-    }
-    __syncthreads();
-    // D. thresholds: unit = (row, 32-pixel segment)
-    uint32_t* bits = a.bits + (size_t)f * a.g.bits_frame_stride;
-    const int twoC = 2 * a.thresh_c - 1;
-    for (int u = warp; u < THR_TH * (THR_TW / 32); u += THR_THREADS / 32) {
-        const int iy = u / (THR_TW / 32), seg = u - iy * (THR_TW / 32);
-        const int ix = seg * 32 + lane;
-        const int x = tx0 + ix, y = ty0 + iy;
-        if (y >= H || tx0 + seg * 32 >= W) continue;  // warp-uniform
-        const bool valid = x < W;
-        const int g2 = 2 * (int)tile_gray[iy * THR_TW + ix] + twoC;
-        const int cx = ix + R, cy = iy + R;  // region coordinates of the pixel
-        for (int s = 0; s < a.n_scales; s++) {
-            const int k = a.win[s], r = k >> 1;
-            const uint32_t* top = sat + (cy - r) * SP;
-            const uint32_t* bot = sat + (cy + r + 1) * SP;
-            const int S = (int)(bot[cx + r + 1] - bot[cx - r] - top[cx + r + 1] + top[cx - r]);
-            const bool on = valid && (2 * S >= g2 * k * k);
-            const uint32_t word = __ballot_sync(0xffffffffu, on);
-            if (lane == 0) bits[(size_t)s * a.g.bits_scale_stride + ((size_t)(y >> 5) * a.g.wpr + (x >> 5)) * 32 + (y & 31)] = word;
-        }
-    }
-    // rows of the last tile row that lie below the image must read as background
-    const int Hpad = (H + 31) & ~31;
-    if (ty0 + THR_TH >= H && Hpad > H) {
-        for (int u = tid; u < (Hpad - H) * (THR_TW / 32) * a.n_scales; u += THR_THREADS) {
-            const int s = u % a.n_scales;
-            const int t = u / a.n_scales;
-            const int seg = t % (THR_TW / 32), y = H + t / (THR_TW / 32);
-            const int x = tx0 + seg * 32;
-            if (x < W) bits[(size_t)s * a.g.bits_scale_stride + ((size_t)(y >> 5) * a.g.wpr + (x >> 5)) * 32 + (y & 31)] = 0u;
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// k_starts: one thread per (frame, scale, row, 32-pixel word): start cracks (exact local prune) ->
-// queue.  Pure bit-plane work: 9 words in, two bit masks out.
-// ---------------------------------------------------------------------------------------------------
-struct MaskArgs {
-    const uint32_t* bits;
-    StartRec* starts;
-    Counters* counters;
-    unsigned int max_starts;
-    FrameGeom g;
-    int n_scales;
-    int n_frames;
-};
-
-__global__ void __launch_bounds__(256) k_masks_starts(const MaskArgs a) {
-    const int wpr = a.g.wpr, H = a.g.H, W = a.g.W;
-    const long long total = (long long)a.n_frames * a.n_scales * H * wpr;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    uint32_t L = 0, Rr = 0;
-    int f = 0, s = 0, y = 0, w = 0;
-    if (gid < total) {
-        long long t = gid;
-        w = (int)(t % wpr);
-        t /= wpr;
-        y = (int)(t % H);
-        t /= H;
-        s = (int)(t % a.n_scales);
-        f = (int)(t / a.n_scales);
-        const BitView plane{a.bits + (size_t)f * a.g.bits_frame_stride + (size_t)s * a.g.bits_scale_stride, wpr, W, H};
-        const uint32_t mid = plane.word(w, y);
-        if (mid) {
-            const NbrWords nw = nbr_words(plane.word(w - 1, y - 1), plane.word(w, y - 1), plane.word(w + 1, y - 1), plane.word(w - 1, y), mid, plane.word(w + 1, y),
-                                          plane.word(w - 1, y + 1), plane.word(w, y + 1), plane.word(w + 1, y + 1));
-            L = left_crack_starts(mid, nw);
-            Rr = right_crack_starts(mid, nw);
-        }
-    }
-    // warp-aggregated append: left cracks grow from the front of the buffer, right cracks from the
-    // back, so that every warp of the walk kernels sees a single direction
-    const uint32_t meta_base = ((uint32_t)f << 8) | ((uint32_t)s << 1);
-#pragma unroll
-    for (int side = 0; side < 2; side++) {
-        uint32_t bitsv = side ? Rr : L;
-        const int cnt = __popc(bitsv);
-        int incl = cnt;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
-        }
-        const int warp_total = __shfl_sync(0xffffffffu, incl, 31);
-        if (warp_total == 0) continue;
-        unsigned int base = 0;
-        if (lane == 31) base = atomicAdd(&a.counters->n_starts[side], (unsigned int)warp_total);
-        base = __shfl_sync(0xffffffffu, base, 31);
-        unsigned int pos = base + (unsigned int)(incl - cnt);
-        while (bitsv) {
-            const int i = __ffs(bitsv) - 1;
-            bitsv &= bitsv - 1;
-            if (pos < a.max_starts / 2) {
-                const unsigned int slot = side ? a.max_starts - 1 - pos : pos;
-                a.starts[slot] = StartRec{(uint32_t)(32 * w + i) | ((uint32_t)y << 16), meta_base | (uint32_t)side};
-            } else {
-                atomicOr(&a.counters->overflow, 1u);
-            }
-            pos++;
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// k_retile: aligned bit planes -> 30x30(+1 halo) walk tiles (HaloView).  One thread per tile word.
-// ---------------------------------------------------------------------------------------------------
-struct RetileArgs {
-    const uint32_t* bits;
-    uint32_t* halo;
-    FrameGeom g;
-    int n_scales, n_frames;
-};
-
-__global__ void __launch_bounds__(256) k_retile(const RetileArgs a) {
-    const int W = a.g.W, H = a.g.H;
-    const int tpr = a.g.halo_tpr;
-    const size_t words_per_plane = a.g.halo_scale_stride;
-    const long long total = (long long)a.n_frames * a.n_scales * (long long)words_per_plane;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= total) return;
-    const long long plane_id = gid / (long long)words_per_plane;
-    const int wi = (int)(gid - plane_id * (long long)words_per_plane);
-    const int f = (int)(plane_id / a.n_scales), s = (int)(plane_id - (long long)f * a.n_scales);
-    const int tile = wi >> 5, r = wi & 31;
-    const int ty = tile / tpr, tx = tile - ty * tpr;
-    const int Y = FID_HALO_T * ty - 1 + r, X0 = FID_HALO_T * tx - 1;
-    uint32_t out = 0;
-    if (Y >= 0 && Y < H) {
-        const BitView plane{a.bits + (size_t)f * a.g.bits_frame_stride + (size_t)s * a.g.bits_scale_stride, a.g.wpr, W, H};
-        const int w0 = X0 >> 5, sh = X0 & 31;  // arithmetic shift: X0 = -1 -> w0 = -1, sh = 31
-        const uint32_t lo = plane.word(w0, Y), hi = plane.word(w0 + 1, Y);
-        out = sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
-    }
-    a.halo[(size_t)f * a.g.halo_frame_stride + (size_t)s * a.g.halo_scale_stride + wi] = out;
-}
 
 // ---------------------------------------------------------------------------------------------------
 // Border walk in rounds of growing step budget.  Walk lengths are heavy tailed (most start cracks
@@ -359,7 +121,7 @@ template <bool IS_RIGHT>
 __device__ __forceinline__ void walk_retire(const WalkArgs& a, int result, const WalkItem& it) {
     if (result == WALK_CANONICAL && it.st.n >= a.min_len && it.st.n <= a.max_len) {
         const unsigned int slot = atomicAdd(&a.counters->n_chains, 1u);
-        const unsigned int off = atomicAdd(&a.counters->n_points, (unsigned int)it.st.n);
+        const unsigned int off = atomicAdd(&a.counters->n_points, ((unsigned int)it.st.n + 3u) & ~3u);  // 16-byte aligned chains
         if (slot < a.max_chains && off + (unsigned int)it.st.n <= a.max_points) {
             a.chains[slot] = ChainRec{it.xy0, it.meta, (uint32_t)it.st.n, off};
         } else {
@@ -472,19 +234,33 @@ struct EmitArgs {
     const ChainRec* chains;
     Pt16* points;
     const Counters* counters;
+    unsigned int* work_counter;
     unsigned int max_chains;
     FrameGeom g;
 };
 
-__global__ void __launch_bounds__(128) k_emit(const EmitArgs a) {
+__global__ void __launch_bounds__(64) k_emit(const EmitArgs a) {
+    // Chains are appended by the walk rounds in order of growing length, so they are handed out from
+    // the END of the list (longest first), 32 at a time per warp through one atomic: long chains start
+    // immediately and the short ones fill the tail of the kernel.
     unsigned int n = a.counters->n_chains;
     n = n < a.max_chains ? n : a.max_chains;
-    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const ChainRec c = a.chains[i];
-        if (c.n == 0) continue;
-        const int f = c.meta >> 8, s = (c.meta >> 1) & 0x7F, is_right = c.meta & 1;
-        const WalkCtx ctx{HaloView{a.halo + (size_t)f * a.g.halo_frame_stride + (size_t)s * a.g.halo_scale_stride, a.g.halo_tpr}, a.lut_prev, a.lut_next};
-        trace_forward(ctx, c.xy & 0xFFFF, c.xy >> 16, is_right, (int)c.n, a.points + c.offset);
+    const unsigned int lane = threadIdx.x & 31;
+    for (;;) {
+        unsigned int base = 0;
+        if (lane == 0) base = atomicAdd(a.work_counter, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= n) break;
+        const unsigned int k = base + lane;
+        if (k < n) {
+            const ChainRec c = a.chains[n - 1 - k];
+            if (c.n != 0) {
+                const int f = c.meta >> 8, s = (c.meta >> 1) & 0x7F, is_right = c.meta & 1;
+                const WalkCtx ctx{HaloView{a.halo + (size_t)f * a.g.halo_frame_stride + (size_t)s * a.g.halo_scale_stride, a.g.halo_tpr}, a.lut_prev, a.lut_next};
+                trace_forward(ctx, c.xy & 0xFFFF, c.xy >> 16, is_right, (int)c.n, a.points + c.offset);
+            }
+        }
+        __syncwarp();
     }
 }
 

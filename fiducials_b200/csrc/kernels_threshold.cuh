@@ -1,0 +1,262 @@
+// CUDA kernels, threshold stage (sm_100a):
+//   k_gray       BGR8 -> gray (cv::cvtColor BGR2GRAY, 15-bit fixed point); 4 pixels per
+//                thread, 12-byte vector loads / 4-byte store
+//   k_threshold  gray -> n_scales adaptive-threshold planes, written directly as the
+//                bit-packed halo tiles the border walk reads (contour_walk.cuh, HaloView)
+//   k_starts     halo tiles -> start-crack queues (exact local prune), three words per thread
+//
+// k_threshold: one CTA per 120x60 output pixels = 4x2 halo tiles.  The CTA loads the gray region it
+// needs (output + 1 halo pixel + r_max on every side, replicate border) into shared memory, turns
+// it into a summed-area table, and every scale's box sum is 4 look-ups.  BINARY_INV with the mean
+// rounded half-to-even (no ties for odd windows) reduces to the integer test
+//     2*S >= (2*g + 2*C - 1) * k^2
+// A warp covers the 32 bit positions of one tile word, so __ballot_sync IS the word.  With the
+// reference's windows 3,7,...,51 the scale loop is unrolled at compile time and every table offset
+// is an immediate.
+// Algorithmic HBM bytes per frame: 3*W*H in + n_scales*W*H/8 out (+ W*H gray out/in).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+#include "contour_walk.cuh"
+
+namespace fid {
+
+struct GrayArgs {
+    const uint8_t* bgr;
+    uint8_t* gray;
+    int W, H, n_frames;
+    size_t bgr_row_stride, bgr_frame_stride;
+    int gray_pitch;
+    size_t gray_frame_stride;
+};
+
+__device__ __forceinline__ uint32_t gray_of(uint32_t b, uint32_t g, uint32_t r) { return (3735u * b + 19235u * g + 9798u * r + 16384u) >> 15; }
+
+__global__ void __launch_bounds__(256) k_gray(const GrayArgs a) {
+    const int quads = (a.W + 3) >> 2;
+    const long long total = (long long)a.n_frames * a.H * quads;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= total) return;
+    const int q = (int)(gid % quads);
+    const long long t = gid / quads;
+    const int y = (int)(t % a.H), f = (int)(t / a.H);
+    const int x = q * 4;
+    const uint8_t* src = a.bgr + (size_t)f * a.bgr_frame_stride + (size_t)y * a.bgr_row_stride + 3 * (size_t)x;
+    uint8_t* dst = a.gray + (size_t)f * a.gray_frame_stride + (size_t)y * a.gray_pitch + x;
+    if (x + 3 < a.W && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
+        const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(src));      // B0 G0 R0 B1
+        const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t*>(src) + 1);  // G1 R1 B2 G2
+        const uint32_t w2 = __ldg(reinterpret_cast<const uint32_t*>(src) + 2);  // R2 B3 G3 R3
+        const uint32_t g0 = gray_of(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u);
+        const uint32_t g1 = gray_of(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u);
+        const uint32_t g2 = gray_of((w1 >> 16) & 255u, w1 >> 24, w2 & 255u);
+        const uint32_t g3 = gray_of((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24);
+        *reinterpret_cast<uint32_t*>(dst) = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);  // gray_pitch and x are multiples of 4
+    } else {
+        for (int k = 0; k < 4 && x + k < a.W; k++) dst[k] = (uint8_t)gray_of(src[3 * k], src[3 * k + 1], src[3 * k + 2]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+#define THR_TILES_X 4
+#define THR_TILES_Y 2
+#define THR_OW (THR_TILES_X * FID_HALO_T)  // 120 output columns per CTA
+#define THR_OH (THR_TILES_Y * FID_HALO_T)  // 60 output rows per CTA
+#define THR_THREADS 256
+#define THR_FAST_R 25                      // r_max of the reference's window set
+
+struct ThreshArgs {
+    const uint8_t* gray;
+    uint32_t* halo;
+    int W, H, n_frames;
+    int gray_pitch;
+    size_t gray_frame_stride;
+    int halo_tpr, halo_tiles_y;
+    size_t halo_scale_stride, halo_frame_stride;
+    int n_scales;
+    int r_max;
+    int thresh_c;
+    int win[FID_MAX_SCALES];
+};
+
+__host__ __device__ inline size_t thresh_smem_bytes(int r_max) {
+    const int RW = THR_OW + 2 + 2 * r_max, RH = THR_OH + 2 + 2 * r_max;
+    return (size_t)(RH + 1) * (RW + 1) * 4;
+}
+
+// FAST: windows 3 + 4*s (s = 0..12), r_max = 25 -> everything below is compile-time.
+template <bool FAST>
+__global__ void __launch_bounds__(THR_THREADS, 2) k_threshold(const ThreshArgs a) {
+    extern __shared__ uint32_t sat[];
+    const int R = FAST ? THR_FAST_R : a.r_max;
+    const int RW = THR_OW + 2 + 2 * R, RH = THR_OH + 2 + 2 * R;
+    const int SP = RW + 1;  // table pitch; row 0 / column 0 are zero
+    const int f = blockIdx.z;
+    const int X0 = blockIdx.x * THR_OW, Y0 = blockIdx.y * THR_OH;  // first output pixel of the CTA
+    const int W = a.W, H = a.H;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint8_t* gray = a.gray + (size_t)f * a.gray_frame_stride;
+
+    for (int i = tid; i < SP; i += THR_THREADS) sat[i] = 0;
+    for (int i = tid; i <= RH; i += THR_THREADS) sat[i * SP] = 0;
+    // A. gray region (replicate border): region (0,0) = image (X0-1-R, Y0-1-R)
+    for (int ry = warp; ry < RH; ry += THR_THREADS / 32) {
+        int y = Y0 - 1 - R + ry;
+        y = y < 0 ? 0 : (y > H - 1 ? H - 1 : y);
+        const uint8_t* grow = gray + (size_t)y * a.gray_pitch;
+        uint32_t* srow = sat + (ry + 1) * SP + 1;
+        for (int rx = lane; rx < RW; rx += 32) {
+            int x = X0 - 1 - R + rx;
+            x = x < 0 ? 0 : (x > W - 1 ? W - 1 : x);
+            srow[rx] = __ldg(grow + x);
+        }
+    }
+    __syncthreads();
+    // B. row prefix sums: one warp per row, 32-wide shuffle scans with carry
+    for (int ry = warp; ry < RH; ry += THR_THREADS / 32) {
+        uint32_t* row = sat + (ry + 1) * SP + 1;
+        uint32_t carry = 0;
+        for (int c0 = 0; c0 < RW; c0 += 32) {
+            const int c = c0 + lane;
+            uint32_t v = c < RW ? row[c] : 0u;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+                if (lane >= d) v += t;
+            }
+            v += carry;
+            if (c < RW) row[c] = v;
+            carry = __shfl_sync(0xffffffffu, v, 31);
+        }
+    }
+    __syncthreads();
+    // C. column prefix sums: one thread per column
+    for (int c = tid; c < RW; c += THR_THREADS) {
+        uint32_t acc = 0;
+        uint32_t* col = sat + SP + 1 + c;
+        for (int ry = 0; ry < RH; ry++) {
+            acc += col[ry * SP];
+            col[ry * SP] = acc;
+        }
+    }
+    __syncthreads();
+    // D. one warp-iteration per tile word: unit = (tile row tyl, word r, tile column txl)
+    const int twoC = 2 * a.thresh_c - 1;
+    for (int u = warp; u < THR_TILES_Y * 32 * THR_TILES_X; u += THR_THREADS / 32) {
+        const int txl = u % THR_TILES_X, r = (u / THR_TILES_X) & 31, tyl = u / (THR_TILES_X * 32);
+        const int tx = blockIdx.x * THR_TILES_X + txl, ty = blockIdx.y * THR_TILES_Y + tyl;
+        if (tx >= a.halo_tpr || ty >= a.halo_tiles_y) continue;  // warp-uniform
+        const int X = X0 + FID_HALO_T * txl - 1 + lane, Y = Y0 + FID_HALO_T * tyl - 1 + r;
+        const bool valid = X >= 0 && X < W && Y >= 0 && Y < H;
+        const int cx = FID_HALO_T * txl + lane + R, cy = FID_HALO_T * tyl + r + R;  // region coordinates
+        const uint32_t* p = sat + cy * SP + cx;  // table entry "above-left" of the pixel
+        const int g = (int)(p[SP + 1] - p[1] - p[SP] + p[0]);
+        const int g2 = 2 * g + twoC;
+        uint32_t* out = a.halo + (size_t)f * a.halo_frame_stride + ((size_t)ty * a.halo_tpr + tx) * 32 + r;
+        if (FAST) {
+#pragma unroll
+            for (int s = 0; s < 13; s++) {
+                const int rr = 1 + 2 * s, k = 2 * rr + 1;
+                const int S = (int)(p[(rr + 1) * SP + rr + 1] - p[(rr + 1) * SP - rr] - p[-rr * SP + rr + 1] + p[-rr * SP - rr]);
+                const uint32_t word = __ballot_sync(0xffffffffu, valid && (2 * S >= g2 * (k * k)));
+                if (lane == 0) out[(size_t)s * a.halo_scale_stride] = word;
+            }
+        } else {
+            for (int s = 0; s < a.n_scales; s++) {
+                const int k = a.win[s], rr = k >> 1;
+                const int S = (int)(p[(rr + 1) * SP + rr + 1] - p[(rr + 1) * SP - rr] - p[-rr * SP + rr + 1] + p[-rr * SP - rr]);
+                const uint32_t word = __ballot_sync(0xffffffffu, valid && (2 * S >= g2 * (k * k)));
+                if (lane == 0) out[(size_t)s * a.halo_scale_stride] = word;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// k_starts: one thread per interior word (tile, r = 1..30) of every plane.  A left crack of (x,y) is
+// dominated when (x,y-1) is foreground with a zero left neighbour (that crack lies on the same
+// border and is raster smaller); same for right cracks -- exact prune, pure bit-ops.
+// ---------------------------------------------------------------------------------------------------
+struct StartsArgs {
+    const uint32_t* halo;
+    StartRec* starts;
+    Counters* counters;
+    unsigned int max_starts;
+    int halo_tpr, halo_tiles_y;
+    size_t halo_scale_stride, halo_frame_stride;
+    int n_scales, n_frames;
+};
+
+__global__ void __launch_bounds__(256) k_starts(const StartsArgs a) {
+    const long long words_per_plane = (long long)a.halo_tpr * a.halo_tiles_y * 32;
+    const long long total = (long long)a.n_frames * a.n_scales * words_per_plane;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    uint32_t L = 0, Rr = 0;
+    int f = 0, s = 0, tile = 0, r = 0;
+    if (gid < total) {
+        const long long plane_id = gid / words_per_plane;
+        const int wi = (int)(gid - plane_id * words_per_plane);
+        f = (int)(plane_id / a.n_scales);
+        s = (int)(plane_id - (long long)f * a.n_scales);
+        tile = wi >> 5;
+        r = wi & 31;
+        if (r >= 1 && r <= FID_HALO_T) {
+            const uint32_t* t = a.halo + (size_t)f * a.halo_frame_stride + (size_t)s * a.halo_scale_stride + (size_t)wi;
+            const uint32_t mid = __ldg(t);
+            if (mid) halo_row_starts(__ldg(t - 1), mid, &L, &Rr);
+        }
+    }
+    // block-aggregated append (one atomic per block and side -- a per-warp atomic on two hot counters
+    // serialised in L2 and cost 4 ms per 128 frames): left cracks grow from the front of the buffer,
+    // right cracks from the back, so that every warp of the walk kernels sees a single direction
+    __shared__ unsigned int warp_tot[2][8];
+    __shared__ unsigned int block_base[2];
+    const int ty = tile / a.halo_tpr, tx = tile - ty * a.halo_tpr;
+    const uint32_t y = (uint32_t)(FID_HALO_T * ty - 1 + r);
+    const uint32_t meta_base = ((uint32_t)f << 8) | ((uint32_t)s << 1);
+    const int warp = threadIdx.x >> 5;
+    int excl[2];
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const int cnt = __popc(side ? Rr : L);
+        int incl = cnt;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        excl[side] = incl - cnt;
+        if (lane == 31) warp_tot[side][warp] = (unsigned int)incl;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        unsigned int tot = 0;
+        for (int w = 0; w < 8; w++) {
+            const unsigned int t = warp_tot[threadIdx.x][w];
+            warp_tot[threadIdx.x][w] = tot;
+            tot += t;
+        }
+        block_base[threadIdx.x] = tot ? atomicAdd(&a.counters->n_starts[threadIdx.x], tot) : 0u;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        uint32_t bitsv = side ? Rr : L;
+        unsigned int pos = block_base[side] + warp_tot[side][warp] + (unsigned int)excl[side];
+        while (bitsv) {
+            const int i = __ffs(bitsv) - 1;
+            bitsv &= bitsv - 1;
+            if (pos < a.max_starts / 2) {
+                const unsigned int slot = side ? a.max_starts - 1 - pos : pos;
+                a.starts[slot] = StartRec{(uint32_t)(FID_HALO_T * tx - 1 + i) | (y << 16), meta_base | (uint32_t)side};
+            } else {
+                atomicOr(&a.counters->overflow, 1u);
+            }
+            pos++;
+        }
+    }
+}
+
+}  // namespace fid

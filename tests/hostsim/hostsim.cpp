@@ -23,86 +23,66 @@
 
 using namespace fid;
 
-// Tiled bit plane exactly as the CUDA threshold kernel writes it (BitView layout).
-struct HostPlane {
-    std::vector<uint32_t> words;
-    int tpr = 0, W = 0, H = 0;
-    BitView view() const { return BitView{words.data(), tpr, W, H}; }
-};
-
-static void pack_plane(const uint8_t* plane, int W, int H, HostPlane& hp) {
-    hp.tpr = bit_tiles_per_row(W);
-    hp.W = W;
-    hp.H = H;
-    hp.words.assign(bit_plane_words(W, H), 0u);
-    for (int y = 0; y < H; y++)
-        for (int x = 0; x < W; x++)
-            if (plane[(size_t)y * W + x]) hp.words[((size_t)(y >> 5) * hp.tpr + (x >> 5)) * 32 + (y & 31)] |= 1u << (x & 31);
-}
-
+// Walk representation exactly as k_threshold writes it (HaloView layout) + the step tables.
 struct Start {
     int x, y, is_right;
 };
 
-// Walk representation exactly as k_retile builds it + the step tables.
-struct HostWalk {
+struct HostPlane {
     std::vector<uint32_t> halo;
-    int tpr = 0;
-    static const uint8_t* lut_prev() {
+    int tpr = 0, tiles_y = 0, W = 0, H = 0;
+    static std::vector<uint8_t>& lut(int which) {
         static std::vector<uint8_t> p, n;
         if (p.empty()) {
             p.resize(FID_LUT_SIZE);
             n.resize(FID_LUT_SIZE);
             build_step_tables(p.data(), n.data());
-            next_store() = n;
         }
-        return p.data();
+        return which ? n : p;
     }
-    static std::vector<uint8_t>& next_store() {
-        static std::vector<uint8_t> n;
-        return n;
-    }
-    static const uint8_t* lut_next() {
-        lut_prev();
-        return next_store().data();
-    }
-    void build(const HostPlane& hp) {
-        tpr = halo_tiles_x(hp.W);
-        halo.assign(halo_plane_words(hp.W, hp.H), 0u);
-        const BitView v = hp.view();
-        const int tiles_y = (hp.H + FID_HALO_T - 1) / FID_HALO_T;
-        for (int ty = 0; ty < tiles_y; ty++)
-            for (int tx = 0; tx < tpr; tx++)
-                for (int r = 0; r < 32; r++) {
-                    const int Y = FID_HALO_T * ty - 1 + r, X0 = FID_HALO_T * tx - 1;
-                    uint32_t out = 0;
-                    if (Y >= 0 && Y < hp.H) {
-                        const int w0 = X0 >> 5, sh = X0 & 31;
-                        const uint32_t lo = v.word(w0, Y), hi = v.word(w0 + 1, Y);
-                        out = sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
-                    }
-                    halo[((size_t)ty * tpr + tx) * 32 + r] = out;
-                }
-    }
-    WalkCtx ctx() const { return WalkCtx{HaloView{halo.data(), tpr}, lut_prev(), lut_next()}; }
+    WalkCtx ctx() const { return WalkCtx{HaloView{halo.data(), tpr}, lut(0).data(), lut(1).data()}; }
 };
 
-static void find_starts(const HostPlane& hp, std::vector<Start>& starts) {
-    const BitView v = hp.view();
-    for (int y = 0; y < hp.H; y++)
-        for (int w = 0; w < hp.tpr; w++) {
-            const uint32_t mid = v.word(w, y);
-            NbrWords nw = nbr_words(v.word(w - 1, y - 1), v.word(w, y - 1), v.word(w + 1, y - 1), v.word(w - 1, y), mid, v.word(w + 1, y), v.word(w - 1, y + 1), v.word(w, y + 1),
-                                    v.word(w + 1, y + 1));
-            uint32_t L = left_crack_starts(mid, nw), R = right_crack_starts(mid, nw);
-            for (int i = 0; i < 32 && 32 * w + i < hp.W; i++) {
-                if ((L >> i) & 1) starts.push_back({32 * w + i, y, 0});
-                if ((R >> i) & 1) starts.push_back({32 * w + i, y, 1});
-                // the per-pixel neighbour mask must agree with the word-level construction
-                if (((mid >> i) & 1) && v.at(32 * w + i, y) != mask_byte(nw, i)) abort();
+static void pack_plane(const uint8_t* plane, int W, int H, HostPlane& hp) {
+    hp.W = W;
+    hp.H = H;
+    hp.tpr = halo_tiles_x(W);
+    hp.tiles_y = (H + FID_HALO_T - 1) / FID_HALO_T;
+    hp.halo.assign(halo_plane_words(W, H), 0u);
+    for (int ty = 0; ty < hp.tiles_y; ty++)
+        for (int tx = 0; tx < hp.tpr; tx++)
+            for (int r = 0; r < 32; r++) {
+                const int Y = FID_HALO_T * ty - 1 + r;
+                if (Y < 0 || Y >= H) continue;
+                uint32_t w = 0;
+                for (int i = 0; i < 32; i++) {
+                    const int X = FID_HALO_T * tx - 1 + i;
+                    if (X >= 0 && X < W && plane[(size_t)Y * W + X]) w |= 1u << i;
+                }
+                hp.halo[((size_t)ty * hp.tpr + tx) * 32 + r] = w;
             }
-        }
 }
+
+static void find_starts(const HostPlane& hp, std::vector<Start>& starts) {
+    for (int ty = 0; ty < hp.tiles_y; ty++)
+        for (int r = 1; r <= FID_HALO_T; r++)
+            for (int tx = 0; tx < hp.tpr; tx++) {
+                const uint32_t* t = hp.halo.data() + ((size_t)ty * hp.tpr + tx) * 32 + r;
+                uint32_t L = 0, R = 0;
+                if (t[0]) halo_row_starts(t[-1], t[0], &L, &R);
+                const int y = FID_HALO_T * ty - 1 + r;
+                for (int i = 1; i <= FID_HALO_T; i++) {
+                    if ((L >> i) & 1) starts.push_back({FID_HALO_T * tx - 1 + i, y, 0});
+                    if ((R >> i) & 1) starts.push_back({FID_HALO_T * tx - 1 + i, y, 1});
+                }
+            }
+}
+
+struct HostWalk {  // thin adapter kept for the harness below
+    const HostPlane* hp = nullptr;
+    void build(const HostPlane& p) { hp = &p; }
+    WalkCtx ctx() const { return hp->ctx(); }
+};
 
 extern "C" {
 
@@ -131,7 +111,7 @@ int hs_find_contours(const uint8_t* plane, int W, int H, int min_len, int max_le
     if (min_len <= 1) {  // isolated pixels are 1-point outer contours
         for (int y = 0; y < H; y++)
             for (int x = 0; x < W; x++)
-                if (plane[(size_t)y * W + x] && mask.view().at(x, y) == 0) chains.push_back({((int64_t)y * W + x) * 2, x, y, 0, 1});
+                if (plane[(size_t)y * W + x] && (mask.ctx().plane.idx9(x, y) & ~0x10u) == 0u) chains.push_back({((int64_t)y * W + x) * 2, x, y, 0, 1});
     }
     std::sort(chains.begin(), chains.end(), [](const Chain& a, const Chain& b) { return a.key > b.key; });  // reverse discovery order
     if ((int)chains.size() > max_contours) return -1;
@@ -139,7 +119,9 @@ int hs_find_contours(const uint8_t* plane, int W, int H, int min_len, int max_le
     for (size_t i = 0; i < chains.size(); i++) {
         const Chain& c = chains[i];
         if (off + c.n > max_pts) return -1;
-        trace_forward(hw.ctx(), c.x, c.y, c.is_right, c.n, reinterpret_cast<Pt16*>(out_pts) + off);
+        std::vector<Pt16> tmp((size_t)c.n + 4);
+        trace_forward(hw.ctx(), c.x, c.y, c.is_right, c.n, tmp.data());
+        memcpy(reinterpret_cast<Pt16*>(out_pts) + off, tmp.data(), sizeof(Pt16) * c.n);
         out_len[i] = c.n;
         off += c.n;
     }
@@ -196,6 +178,51 @@ int hs_walk_log(const uint8_t* plane, int W, int H, int max_len, int min_steps, 
     return rows;
 }
 
+// Simulation of the round-based walk with optional kill marks: a walk that passes the crack of
+// another (raster-larger) start clears that start's alive bit; dead starts are dropped when their
+// next round begins.  out[r] = steps taken in round r, out[8+r] = walks entering round r.
+void hs_walk_sim(const uint8_t* plane, int W, int H, int max_len, const int* budgets, int n_rounds, int use_kills, int64_t* out) {
+    HostPlane mask;
+    pack_plane(plane, W, H, mask);
+    std::vector<Start> starts;
+    find_starts(mask, starts);
+    HostWalk hw;
+    hw.build(mask);
+    std::vector<uint8_t> aliveL((size_t)W * H, 0), aliveR((size_t)W * H, 0);
+    for (const Start& s : starts) (s.is_right ? aliveR : aliveL)[(size_t)s.y * W + s.x] = 1;
+    struct Live { Start s; WalkState st; };
+    std::vector<Live> cur, nxt;
+    for (int i = 0; i < 16; i++) out[i] = 0;
+    const WalkCtx ctx = hw.ctx();
+    for (const Start& s : starts) {
+        Live l;
+        l.s = s;
+        if (walk_init(ctx, s.x, s.y, s.is_right, &l.st) == WALK_CONTINUE) cur.push_back(l);
+    }
+    for (int r = 0; r < n_rounds; r++) {
+        out[8 + r] = (int64_t)cur.size();
+        nxt.clear();
+        for (Live& l : cur) {
+            if (use_kills && !(l.s.is_right ? aliveR : aliveL)[(size_t)l.s.y * W + l.s.x]) continue;
+            const int before = l.st.n;
+            const int x0 = l.s.x, y0 = l.s.y, isr = l.s.is_right;
+            auto visit = [&](int x, int y, bool exL, bool exR) {
+                if (!use_kills) return;
+                if (exL && !(x == x0 && y == y0 && !isr)) aliveL[(size_t)y * W + x] = 0;
+                if (exR && !(x == x0 && y == y0 && isr)) aliveR[(size_t)y * W + x] = 0;
+            };
+            int res;
+            if (l.s.is_right)
+                res = walk_resume_dir<true>(ctx, x0, y0, max_len, budgets[r], &l.st, visit);
+            else
+                res = walk_resume_dir<false>(ctx, x0, y0, max_len, budgets[r], &l.st, visit);
+            out[r] += l.st.n - before;
+            if (res == WALK_CONTINUE) nxt.push_back(l);
+        }
+        cur.swap(nxt);
+    }
+}
+
 // approxPolyDP (closed) of one contour; returns vertex count (-1 = more than 8 before clean-up).
 int hs_approx_poly(const int16_t* pts, int n, double eps, int16_t* out) {
     SerialReducer red;
@@ -223,7 +250,7 @@ static void raw_candidates(const uint8_t* planes, int W, int H, const DevParams&
             int n = 0;
             if (walk_start(hw.ctx(), st.x, st.y, st.is_right, max_len, &n) != WALK_CANONICAL) continue;
             if (n < min_len || n > max_len) continue;
-            pts.resize(n);
+            pts.resize((size_t)n + 4);
             trace_forward(hw.ctx(), st.x, st.y, st.is_right, n, pts.data());
             Pt16 q[FID_APPROX_MAX_V];
             SerialReducer red;
