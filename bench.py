@@ -273,14 +273,9 @@ def run_gpu_arm(args):
             counts, ids, corners, tfs = det.detect_pose_batch(pinned, K, D, FIDUCIAL_LEN)
         launches[0] += det.last_counters()["kernel_launches"]
         # fiducial_slam: the frames of this step are one camera stream -> one message per frame
-        msgs = [[tfs[f * MAXM + m] for m in range(int(counts[f]))] for f in range(nf)]
-        flat = [t for m in msgs for t in m]
-        offsets = np.zeros(nf + 1, np.int32)
-        offsets[1:] = np.cumsum(counts)
-        arr = (_lib.fid_transform * max(len(flat), 1))(*flat)
-        bc = _lib.fid_tf()
-        bc.q[3] = 1.0
-        _lib.check(lib.fid_map_update_sequence(slam.h, nf, offsets.ctypes.data_as(C.c_void_p), C.cast(arr, C.c_void_p), C.byref(bc), C.byref(bc), None))
+        # (enqueued asynchronously: the sequential fold of this step overlaps the detection of the next one;
+        #  the timed region ends with slam.sync())
+        slam.update_frames(counts, tfs, ident, ident, asynchronous=dist is None)
         launches[0] += 1
         if dist is not None:  # one NCCL all-gather of the per-rank map tables, same deterministic merge on every rank
             tables = allgather_tables(slam.export_table(0), dist, device="cuda")
@@ -301,6 +296,7 @@ def run_gpu_arm(args):
         total = 0
         for _ in range(steps):
             total += int(step(on_device).sum())
+        slam.sync()
         ms = C.c_float(0)
         _lib.check(lib.fid_timer_stop(det.h, C.byref(ms)))
         wall = time.perf_counter() - t0

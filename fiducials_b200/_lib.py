@@ -105,7 +105,7 @@ EXPORTS = [
     "fid_strerror", "fid_version", "fid_default_params", "fid_create", "fid_destroy", "fid_set_params", "fid_detect", "fid_pose",
     "fid_detect_pose_batch", "fid_timer_start", "fid_timer_stop", "fid_host_alloc", "fid_host_free", "fid_device_alloc", "fid_device_free", "fid_memcpy_h2d", "fid_debug_threshold",
     "fid_debug_candidates", "fid_last_stage_ms", "fid_last_counters", "fid_map_default_params", "fid_map_create", "fid_map_destroy", "fid_map_clear",
-    "fid_map_load", "fid_map_update", "fid_map_update_sequence", "fid_map_entries", "fid_map_export", "fid_map_merge", "fid_map_export_device",
+    "fid_map_load", "fid_map_update", "fid_map_update_sequence", "fid_map_update_frames", "fid_map_update_frames_async", "fid_map_sync", "fid_map_entries", "fid_map_export", "fid_map_merge", "fid_map_export_device",
     "fid_map_merge_device",
 ]
 
@@ -149,6 +149,9 @@ def load():
     lib.fid_map_load.argtypes = [vp, i32, i32, vp]
     lib.fid_map_update.argtypes = [vp, i32, i32, vp, C.POINTER(fid_tf), C.POINTER(fid_tf), C.POINTER(fid_robot_pose)]
     lib.fid_map_update_sequence.argtypes = [vp, i32, vp, vp, C.POINTER(fid_tf), C.POINTER(fid_tf), vp]
+    lib.fid_map_update_frames.argtypes = [vp, i32, i32, vp, vp, i32, C.POINTER(fid_tf), C.POINTER(fid_tf), C.POINTER(fid_robot_pose)]
+    lib.fid_map_update_frames_async.argtypes = [vp, i32, i32, vp, vp, i32, C.POINTER(fid_tf), C.POINTER(fid_tf)]
+    lib.fid_map_sync.argtypes = [vp]
     lib.fid_map_entries.argtypes = [vp, i32, i32, C.POINTER(i32), vp]
     lib.fid_map_export.argtypes = [vp, i32, vp]
     lib.fid_map_merge.argtypes = [vp, i32, i32, vp]

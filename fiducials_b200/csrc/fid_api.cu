@@ -71,6 +71,7 @@ struct fid_detector {
     int max_raw = 4096, close_wpr = 128, max_sel = 512, max_markers = FID_MAX_MARKERS;
     unsigned int max_starts = 0, max_chains = 0, max_points = 0, max_queue = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t slot_stream[2] = {nullptr, nullptr};  // one compute stream per slot: latency-bound stages of one chunk overlap the other chunk
     Slot slot[2];
     float* d_subpix_masks = nullptr;
     uint8_t* d_lut_prev = nullptr;
@@ -285,6 +286,8 @@ extern "C" int fid_create(const fid_params* params, int device, int max_width, i
     h->max_queue = h->max_starts / 8 + 65536;  // walks that survive the first 32 steps: ~3 % of the start cracks
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->slot_stream[0], cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&h->slot_stream[1], cudaStreamNonBlocking));
     if ((rc = upload_constants()) != FID_OK || (rc = configure_kernels(h)) != FID_OK) {
         fid_destroy(h);
         return rc;
@@ -367,6 +370,8 @@ extern "C" int fid_destroy(fid_detector* h) {
     if (h->t1) cudaEventDestroy(h->t1);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (int i = 0; i < 2; i++)
+        if (h->slot_stream[i]) cudaStreamDestroy(h->slot_stream[i]);
     delete h;
     return FID_OK;
 }
@@ -397,10 +402,9 @@ static Camera make_camera(const fid_camera* c) {
     return cam;
 }
 
-// Enqueue the whole pipeline for `nf` frames resident in s.d_bgr (geometry g) on h->stream.
-static int enqueue_pipeline(fid_detector* h, Slot& s, int nf, const FrameGeom& g, const uint8_t* d_bgr, const fid_camera* cam, double fiducial_len, int n_override,
-                            int stop_after /* -1 = all */) {
-    cudaStream_t st = h->stream;
+// Enqueue the whole pipeline for `nf` frames resident in d_bgr (geometry g) on stream `st`.
+static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, const FrameGeom& g, const uint8_t* d_bgr, const fid_camera* cam, double fiducial_len,
+                            int n_override, int stop_after /* -1 = all */) {
     const DevParams& P = h->P;
     const int W = g.W, H = g.H;
     int launches = 0;
@@ -609,8 +613,7 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, int nf, const FrameGeom& g
     return FID_OK;
 }
 
-static int enqueue_d2h(fid_detector* h, Slot& s, int nf, bool with_pose) {
-    cudaStream_t st = h->stream;
+static int enqueue_d2h(fid_detector* h, Slot& s, cudaStream_t st, int nf, bool with_pose) {
     const size_t M = (size_t)nf * h->max_markers;
     CK(cudaMemcpyAsync(s.h_out_count, s.d_out_count, sizeof(int32_t) * nf, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(s.h_out_ids, s.d_out_ids, sizeof(int32_t) * M, cudaMemcpyDeviceToHost, st));
@@ -676,6 +679,7 @@ static int upload_overrides(fid_detector* h, int n_override, const int32_t* ids,
     if (n_override > 0) {
         CK(cudaMemcpyAsync(h->d_override_ids, ids, sizeof(int32_t) * n_override, cudaMemcpyHostToDevice, h->stream));
         CK(cudaMemcpyAsync(h->d_override_lens, lens, sizeof(double) * n_override, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaStreamSynchronize(h->stream));  // the slot streams read them
     }
     return FID_OK;
 }
@@ -717,13 +721,13 @@ extern "C" int fid_detect_pose_batch(fid_detector* h, int n_frames, const uint8_
                                              cudaMemcpyHostToDevice, h->copy_stream));
                 }
                 CK(cudaEventRecord(s.copied, h->copy_stream));
-                CK(cudaStreamWaitEvent(h->stream, s.copied, 0));
+                CK(cudaStreamWaitEvent(h->slot_stream[c & 1], s.copied, 0));
                 d_in = s.d_bgr;
                 g = make_geom(h, width, height, (size_t)width * 3, (size_t)width * 3 * height);
             }
-            rc = enqueue_pipeline(h, s, nf, g, d_in, cam, fiducial_len, n_override, -1);
+            rc = enqueue_pipeline(h, s, h->slot_stream[c & 1], nf, g, d_in, cam, fiducial_len, n_override, -1);
             if (rc != FID_OK) return rc;
-            rc = enqueue_d2h(h, s, nf, cam != nullptr);
+            rc = enqueue_d2h(h, s, h->slot_stream[c & 1], nf, cam != nullptr);
             if (rc != FID_OK) return rc;
             h->last_frames = nf;
         }
@@ -781,6 +785,8 @@ extern "C" int fid_timer_start(fid_detector* h) {
         CK(cudaEventCreate(&h->t1));
     }
     CK(cudaStreamSynchronize(h->copy_stream));
+    CK(cudaStreamSynchronize(h->slot_stream[0]));
+    CK(cudaStreamSynchronize(h->slot_stream[1]));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaEventRecord(h->t0, h->stream));
     return FID_OK;
@@ -789,6 +795,8 @@ extern "C" int fid_timer_stop(fid_detector* h, float* elapsed_ms) {
     if (!h || !elapsed_ms || !h->t0) return FID_ERR_INVALID_ARG;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->copy_stream));
+    CK(cudaStreamSynchronize(h->slot_stream[0]));
+    CK(cudaStreamSynchronize(h->slot_stream[1]));
     CK(cudaEventRecord(h->t1, h->stream));
     CK(cudaEventSynchronize(h->t1));
     CK(cudaEventElapsedTime(elapsed_ms, h->t0, h->t1));
@@ -835,7 +843,7 @@ extern "C" int fid_debug_threshold(fid_detector* h, const uint8_t* bgr, int widt
     Slot& s = h->slot[0];
     CK(cudaMemcpy2DAsync(s.d_bgr, (size_t)width * 3, bgr, stride, (size_t)width * 3, height, cudaMemcpyHostToDevice, h->stream));
     const FrameGeom g = make_geom(h, width, height, (size_t)width * 3, (size_t)width * 3 * height);
-    const int rc = enqueue_pipeline(h, s, 1, g, s.d_bgr, nullptr, 0.0, 0, ST_THRESH);
+    const int rc = enqueue_pipeline(h, s, h->stream, 1, g, s.d_bgr, nullptr, 0.0, 0, ST_THRESH);
     if (rc != FID_OK) return rc;
     CK(cudaStreamSynchronize(h->stream));
     if (gray) CK(cudaMemcpy2D(gray, width, s.d_gray, g.gray_pitch, width, height, cudaMemcpyDeviceToHost));

@@ -211,6 +211,7 @@ extern "C" int fid_map_destroy(fid_map* m) {
 extern "C" int fid_map_clear(fid_map* m, int instance) {
     if (!m || instance < 0 || instance >= m->p.n_instances) return FID_ERR_INVALID_ARG;
     CK(cudaSetDevice(m->device));
+    CK(cudaStreamSynchronize(m->stream));
     // clearCallback (map.cpp:809-817): fiducials.clear(); initialFrameNum = frameNum; originFid = -1
     MapState st;
     CK(cudaMemcpy(&st, m->d_state + instance, sizeof(st), cudaMemcpyDeviceToHost));
@@ -234,6 +235,7 @@ static void tf_to_twv(const fid_tf& t, Twv* o) {
 extern "C" int fid_map_load(fid_map* m, int instance, int n, const fid_map_file_entry* entries) {
     if (!m || instance < 0 || instance >= m->p.n_instances || n < 0 || (n > 0 && !entries)) return FID_ERR_INVALID_ARG;
     CK(cudaSetDevice(m->device));
+    CK(cudaStreamSynchronize(m->stream));
     MapState st;
     CK(cudaMemcpy(&st, m->d_state + instance, sizeof(st), cudaMemcpyDeviceToHost));
     std::vector<MapEntry> e(st.capacity);
@@ -280,8 +282,9 @@ static int ensure(T** p, size_t* cap, size_t need) {
 }
 
 static int run_sequence(fid_map* m, int inst_lo, int n_inst, int n_msgs, const int32_t* offsets, const fid_transform* obs, const fid_tf* T_baseCam,
-                        const fid_tf* T_camBase, fid_robot_pose* robot) {
+                        const fid_tf* T_camBase, fid_robot_pose* robot, bool async = false) {
     CK(cudaSetDevice(m->device));
+    CK(cudaStreamSynchronize(m->stream));  // a pending asynchronous update still owns the staging buffers
     const size_t n_off = (size_t)n_inst * (n_msgs + 1);
     size_t total_obs = 0;
     for (size_t i = 0; i < n_off; i++) total_obs = std::max<size_t>(total_obs, (size_t)offsets[i]);
@@ -298,6 +301,7 @@ static int run_sequence(fid_map* m, int inst_lo, int n_inst, int n_msgs, const i
         ho[i].object_error = obs[i].object_error;
         ho[i].area = obs[i].fiducial_area;
     }
+    // (pageable sources: the runtime stages these copies before returning, so the host vectors may die)
     if (total_obs) CK(cudaMemcpyAsync(m->d_obs, ho.data(), sizeof(Obs) * total_obs, cudaMemcpyHostToDevice, m->stream));
     CK(cudaMemcpyAsync(m->d_offsets, offsets, sizeof(int32_t) * n_off, cudaMemcpyHostToDevice, m->stream));
     Twv tf[2];
@@ -325,6 +329,7 @@ static int run_sequence(fid_map* m, int inst_lo, int n_inst, int n_msgs, const i
     a.robot = m->d_robot;
     k_map_sequence<<<(n_inst + 31) / 32, 32, 0, m->stream>>>(a);
     CK(cudaGetLastError());
+    if (async) return FID_OK;
     std::vector<RobotPose> hr((size_t)n_inst * n_msgs);
     CK(cudaMemcpyAsync(hr.data(), m->d_robot, sizeof(RobotPose) * hr.size(), cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
@@ -357,9 +362,43 @@ extern "C" int fid_map_update_sequence(fid_map* m, int n_msgs, const int32_t* of
     return run_sequence(m, 0, m->p.n_instances, n_msgs, offsets, obs, T_baseCam, T_camBase, robot);
 }
 
+static int update_frames_impl(fid_map* m, int instance, int n_frames, const int32_t* counts, const fid_transform* transforms, int max_markers, const fid_tf* T_baseCam,
+                              const fid_tf* T_camBase, fid_robot_pose* last_robot, bool async) {
+    if (!m || instance < 0 || instance >= m->p.n_instances || n_frames < 1 || !counts || !transforms || max_markers < 1) return FID_ERR_INVALID_ARG;
+    std::vector<int32_t> off((size_t)n_frames + 1, 0);
+    std::vector<fid_transform> flat;
+    for (int f = 0; f < n_frames; f++) {
+        const int c = std::min(std::max(counts[f], 0), std::min(max_markers, (int)FID_MAX_OBS));
+        off[f] = (int32_t)flat.size();
+        flat.insert(flat.end(), transforms + (size_t)f * max_markers, transforms + (size_t)f * max_markers + c);
+    }
+    off[n_frames] = (int32_t)flat.size();
+    std::vector<fid_robot_pose> robots((size_t)n_frames);
+    fid_transform dummy{};
+    const int rc = run_sequence(m, instance, 1, n_frames, off.data(), flat.empty() ? &dummy : flat.data(), T_baseCam, T_camBase, async ? nullptr : robots.data(), async);
+    if (rc == FID_OK && last_robot && !async) *last_robot = robots[(size_t)n_frames - 1];
+    return rc;
+}
+
+extern "C" int fid_map_update_frames(fid_map* m, int instance, int n_frames, const int32_t* counts, const fid_transform* transforms, int max_markers, const fid_tf* T_baseCam,
+                                     const fid_tf* T_camBase, fid_robot_pose* last_robot) {
+    return update_frames_impl(m, instance, n_frames, counts, transforms, max_markers, T_baseCam, T_camBase, last_robot, false);
+}
+extern "C" int fid_map_update_frames_async(fid_map* m, int instance, int n_frames, const int32_t* counts, const fid_transform* transforms, int max_markers,
+                                           const fid_tf* T_baseCam, const fid_tf* T_camBase) {
+    return update_frames_impl(m, instance, n_frames, counts, transforms, max_markers, T_baseCam, T_camBase, nullptr, true);
+}
+extern "C" int fid_map_sync(fid_map* m) {
+    if (!m) return FID_ERR_INVALID_ARG;
+    CK(cudaSetDevice(m->device));
+    CK(cudaStreamSynchronize(m->stream));
+    return FID_OK;
+}
+
 extern "C" int fid_map_entries(fid_map* m, int instance, int max_entries, int* n, fid_map_entry* entries) {
     if (!m || instance < 0 || instance >= m->p.n_instances || !n) return FID_ERR_INVALID_ARG;
     CK(cudaSetDevice(m->device));
+    CK(cudaStreamSynchronize(m->stream));
     MapState st;
     CK(cudaMemcpy(&st, m->d_state + instance, sizeof(st), cudaMemcpyDeviceToHost));
     std::vector<MapEntry> e(st.n);

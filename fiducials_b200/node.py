@@ -101,11 +101,13 @@ class Detector:
             frames = np.ascontiguousarray(frames, np.uint8)
             n, H, W = frames.shape[:3]
             ptr = frames.ctypes.data_as(C.c_void_p)
-        counts = np.zeros(n, np.int32)
-        ids = np.zeros((n, MAXM), np.int32)
-        corners = np.zeros((n, MAXM, 8), np.float32)
         cam = _camera(K, D) if K is not None else None
-        tfs = (_lib.fid_transform * (n * MAXM))() if cam is not None else None
+        key = (n, cam is not None)
+        if getattr(self, "_out_key", None) != key:  # output buffers are reused between calls of the same shape
+            self._out = (np.zeros(n, np.int32), np.zeros((n, MAXM), np.int32), np.zeros((n, MAXM, 8), np.float32),
+                         (_lib.fid_transform * (n * MAXM))() if cam is not None else None)
+            self._out_key = key
+        counts, ids, corners, tfs = self._out
         oi, ol, no = _overrides(overrides)
         st = self.lib.fid_detect_pose_batch(self.h, n, ptr, 1 if on_device else 0, W, H, W * 3, W * 3 * H, C.byref(cam) if cam is not None else None, float(fiducial_len), no,
                                             oi.ctypes.data_as(C.c_void_p), ol.ctypes.data_as(C.c_void_p), MAXM, counts.ctypes.data_as(C.c_void_p),
@@ -340,6 +342,23 @@ class FiducialSlam:
         _lib.check(self.lib.fid_map_update_sequence(self.h, n_msgs, offsets.ctypes.data_as(C.c_void_p), C.cast(arr, C.c_void_p), C.byref(bc) if bc is not None else None,
                                                     C.byref(cb) if cb is not None else None, C.cast(robots, C.c_void_p)), "fid_map_update_sequence")
         return robots
+
+    def update_frames(self, counts, tfs, T_baseCam=None, T_camBase=None, instance=0, asynchronous=False):
+        """One message per frame straight from Detector.detect_pose_batch's dense output.  With
+        asynchronous=True the fold is only enqueued (it overlaps the next detection); sync() waits."""
+        counts = np.ascontiguousarray(counts, np.int32)
+        bc, cb = _tf(T_baseCam), _tf(T_camBase)
+        if asynchronous:
+            _lib.check(self.lib.fid_map_update_frames_async(self.h, instance, len(counts), counts.ctypes.data_as(C.c_void_p), C.cast(tfs, C.c_void_p), MAXM,
+                                                            C.byref(bc) if bc is not None else None, C.byref(cb) if cb is not None else None), "fid_map_update_frames_async")
+            return None
+        robot = _lib.fid_robot_pose()
+        _lib.check(self.lib.fid_map_update_frames(self.h, instance, len(counts), counts.ctypes.data_as(C.c_void_p), C.cast(tfs, C.c_void_p), MAXM,
+                                                  C.byref(bc) if bc is not None else None, C.byref(cb) if cb is not None else None, C.byref(robot)), "fid_map_update_frames")
+        return robot
+
+    def sync(self):
+        _lib.check(self.lib.fid_map_sync(self.h))
 
     def entries(self, instance=0):
         cap = self.p.max_fiducials

@@ -222,6 +222,18 @@ int fid_map_update(fid_map* m, int instance, int n_obs, const fid_transform* obs
 int fid_map_update_sequence(fid_map* m, int n_msgs, const int32_t* offsets, const fid_transform* obs, const fid_tf* T_baseCam, const fid_tf* T_camBase,
                             fid_robot_pose* robot);
 
+/* Same, fed straight from the dense output of fid_detect_pose_batch: frame f contributes
+ * counts[f] transforms starting at transforms[f * max_markers]; one message per frame, in order, into
+ * one instance (one camera stream). */
+int fid_map_update_frames(fid_map* m, int instance, int n_frames, const int32_t* counts, const fid_transform* transforms, int max_markers, const fid_tf* T_baseCam,
+                          const fid_tf* T_camBase, fid_robot_pose* last_robot);
+/* Asynchronous form: the observations are copied and the update is enqueued on the map's stream; the
+ * call returns at once so that the (sequential, latency-bound) fold overlaps the detection of the next
+ * frames.  Every other fid_map_* call, and fid_map_sync, waits for pending updates first. */
+int fid_map_update_frames_async(fid_map* m, int instance, int n_frames, const int32_t* counts, const fid_transform* transforms, int max_markers, const fid_tf* T_baseCam,
+                                const fid_tf* T_camBase);
+int fid_map_sync(fid_map* m);
+
 /* publishMap (map.cpp:629-654): entries in ascending fiducial id. */
 int fid_map_entries(fid_map* m, int instance, int max_entries, int* n, fid_map_entry* entries);
 

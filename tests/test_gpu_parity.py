@@ -177,6 +177,7 @@ def test_batch_equals_single_and_device_input(det_cache):
     det1 = det_cache(d, 640, 480)
     detb = det_cache(d, 640, 480, 2)  # 5 frames through 2-frame slots: 3 chunks, exercises the pipeline
     counts, ids, corners, tfs = detb.detect_pose_batch(frames, K, D, 0.14)
+    counts, ids, corners = counts.copy(), ids.copy(), corners.copy()  # the wrapper reuses its output buffers
     for f in range(5):
         sid, sc = det1.detect(frames[f])
         n = int(counts[f])
