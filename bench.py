@@ -151,7 +151,7 @@ def cpu_reference_fps(frames, dict_id, K, D, budget_s=12.0):
         n_ref += 1
     fps_ref = n_ref / (time.perf_counter() - t0)
     # throughput mode
-    nproc = max(1, min(ncores, 64))
+    nproc = max(1, ncores)
     fps_thr, n_thr = 0.0, 0
     tmp = tempfile.NamedTemporaryFile(suffix=".npy", delete=False)
     try:
@@ -270,6 +270,7 @@ def run_gpu_arm(args):
         if on_device:
             counts, ids, corners, tfs = det.detect_pose_batch(dptr.value, K, D, FIDUCIAL_LEN, on_device=True, n_frames=nf, width=W, height=H)
         else:
+            lib.fid_hint_next(det.h, hptr)  # streaming: the next step's first chunk uploads while this step computes
             counts, ids, corners, tfs = det.detect_pose_batch(pinned, K, D, FIDUCIAL_LEN)
         launches[0] += det.last_counters()["kernel_launches"]
         # fiducial_slam: the frames of this step are one camera stream -> one message per frame

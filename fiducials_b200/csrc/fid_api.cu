@@ -73,6 +73,12 @@ struct fid_detector {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaStream_t slot_stream[2] = {nullptr, nullptr};  // one compute stream per slot: latency-bound stages of one chunk overlap the other chunk
     Slot slot[2];
+    // streaming prefetch (fid_hint_next): first chunk of the next call, ping-pong
+    uint8_t* d_pf[2] = {nullptr, nullptr};
+    cudaEvent_t pf_done[2] = {nullptr, nullptr};
+    const uint8_t* pf_host = nullptr;
+    const uint8_t* hint_next = nullptr;
+    int pf_idx = 0, pf_frames = 0, pf_w = 0, pf_h = 0;
     float* d_subpix_masks = nullptr;
     uint8_t* d_lut_prev = nullptr;
     uint8_t* d_lut_next = nullptr;
@@ -349,6 +355,13 @@ extern "C" int fid_create(const fid_params* params, int device, int max_width, i
             h->walk_rounds++;
         }
     }
+    for (int i = 0; i < 2; i++) {
+        if ((rc = dalloc(&h->d_pf[i], (size_t)max_batch * max_width * max_height * 3)) != FID_OK) {
+            fid_destroy(h);
+            return rc;
+        }
+        CK(cudaEventCreateWithFlags(&h->pf_done[i], cudaEventDisableTiming));
+    }
     if ((rc = dalloc(&h->d_override_ids, 1024)) != FID_OK || (rc = dalloc(&h->d_override_lens, 1024)) != FID_OK || (rc = dalloc(&h->d_pose_ids, 4096)) != FID_OK ||
         (rc = dalloc(&h->d_pose_corners, 4096 * 8)) != FID_OK || (rc = dalloc(&h->d_pose_out, 4096)) != FID_OK) {
         fid_destroy(h);
@@ -363,9 +376,11 @@ extern "C" int fid_destroy(fid_detector* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (int i = 0; i < 2; i++) free_slot(h->slot[i]);
-    void* ptrs[] = {h->d_lut_prev, h->d_lut_next, h->d_subpix_masks, h->d_override_ids, h->d_override_lens, h->d_pose_ids, h->d_pose_corners, h->d_pose_out};
+    void* ptrs[] = {h->d_pf[0], h->d_pf[1], h->d_lut_prev, h->d_lut_next, h->d_subpix_masks, h->d_override_ids, h->d_override_lens, h->d_pose_ids, h->d_pose_corners, h->d_pose_out};
     for (void* p : ptrs)
         if (p) cudaFree(p);
+    for (int i = 0; i < 2; i++)
+        if (h->pf_done[i]) cudaEventDestroy(h->pf_done[i]);
     if (h->t0) cudaEventDestroy(h->t0);
     if (h->t1) cudaEventDestroy(h->t1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -708,9 +723,16 @@ extern "C" int fid_detect_pose_batch(fid_detector* h, int n_frames, const uint8_
             const uint8_t* src = bgr + (size_t)c * B * frame_stride;
             const uint8_t* d_in;
             FrameGeom g;
+            const bool contiguous = row_stride == (size_t)width * 3 && frame_stride == row_stride * height;
             if (bgr_on_device) {
                 d_in = src;
                 g = make_geom(h, width, height, row_stride, frame_stride);
+            } else if (c == 0 && h->pf_host == bgr && h->pf_frames == nf && h->pf_w == width && h->pf_h == height && contiguous) {
+                // first chunk was uploaded in the background during the previous call (fid_hint_next)
+                CK(cudaStreamWaitEvent(h->slot_stream[0], h->pf_done[h->pf_idx], 0));
+                d_in = h->d_pf[h->pf_idx];
+                g = make_geom(h, width, height, (size_t)width * 3, (size_t)width * 3 * height);
+                h->pf_host = nullptr;
             } else {
                 // slot reuse: its previous results must have been collected (done below) before overwrite
                 if (row_stride == (size_t)width * 3 && frame_stride == row_stride * height) {
@@ -724,6 +746,19 @@ extern "C" int fid_detect_pose_batch(fid_detector* h, int n_frames, const uint8_
                 CK(cudaStreamWaitEvent(h->slot_stream[c & 1], s.copied, 0));
                 d_in = s.d_bgr;
                 g = make_geom(h, width, height, (size_t)width * 3, (size_t)width * 3 * height);
+            }
+            if (c == n_chunks - 1 && h->hint_next && !bgr_on_device && contiguous) {
+                // all uploads of this call are queued: start on the first chunk of the next call
+                const int nf0 = std::min(B, n_frames);
+                const int idx = h->pf_idx ^ 1;
+                CK(cudaMemcpyAsync(h->d_pf[idx], h->hint_next, (size_t)nf0 * frame_stride, cudaMemcpyHostToDevice, h->copy_stream));
+                CK(cudaEventRecord(h->pf_done[idx], h->copy_stream));
+                h->pf_idx = idx;
+                h->pf_host = h->hint_next;
+                h->pf_frames = nf0;
+                h->pf_w = width;
+                h->pf_h = height;
+                h->hint_next = nullptr;
             }
             rc = enqueue_pipeline(h, s, h->slot_stream[c & 1], nf, g, d_in, cam, fiducial_len, n_override, -1);
             if (rc != FID_OK) return rc;
@@ -774,6 +809,12 @@ extern "C" int fid_pose(fid_detector* h, int n, const int32_t* ids, const float*
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, h->d_pose_out, sizeof(fid_transform) * n, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    return FID_OK;
+}
+
+extern "C" int fid_hint_next(fid_detector* h, const uint8_t* next_bgr) {
+    if (!h) return FID_ERR_INVALID_ARG;
+    h->hint_next = next_bgr;
     return FID_OK;
 }
 

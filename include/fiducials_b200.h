@@ -127,6 +127,13 @@ int fid_detect_pose_batch(fid_detector* h, int n_frames, const uint8_t* bgr, int
                           const fid_camera* cam, double fiducial_len, int n_override, const int32_t* override_ids, const double* override_lens,
                           int max_markers, int32_t* counts, int32_t* ids, float* corners, fid_transform* transforms);
 
+/* Streaming hint: `next_bgr` (pinned host memory, same frame count and geometry as the call that
+ * follows this hint) will be the `bgr` argument of the call after that one.  The library then
+ * uploads its first chunk in the background once the uploads of the call in progress are queued, so
+ * the next call does not start with an exposed H2D copy.  The frames must not change between the
+ * hinted call and their own call.  Passing NULL clears the hint. */
+int fid_hint_next(fid_detector* h, const uint8_t* next_bgr);
+
 /* Device-side stopwatch for benchmarks: start records a CUDA event on the handle's compute stream,
  * stop records a second one, waits for it and returns the elapsed milliseconds between the two. */
 int fid_timer_start(fid_detector* h);

@@ -195,6 +195,27 @@ def test_batch_equals_single_and_device_input(det_cache):
     lib.fid_device_free(detb.h, dptr)
 
 
+def test_streaming_hint_prefetch(det_cache):
+    """fid_hint_next: the next call's first chunk is uploaded during the current call; results must
+    not depend on whether a call's first chunk came from the prefetch buffer."""
+    frames_a = np.stack([synth.make_config_frame("C1", s)[0] for s in range(5)])
+    frames_b = np.stack([synth.make_config_frame("C1", 10 + s)[0] for s in range(5)])
+    _, _, K, D, d = synth.make_config_frame("C1", 0)
+    det = det_cache(d, 640, 480, 2)
+    ref_a = [x.copy() for x in det.detect_pose_batch(frames_a, K, D, 0.14)[:3]]
+    ref_b = [x.copy() for x in det.detect_pose_batch(frames_b, K, D, 0.14)[:3]]
+    lib = det.lib
+    lib.fid_hint_next(det.h, frames_b.ctypes.data_as(C.c_void_p))  # b follows a
+    got_a = [x.copy() for x in det.detect_pose_batch(frames_a, K, D, 0.14)[:3]]
+    lib.fid_hint_next(det.h, frames_a.ctypes.data_as(C.c_void_p))  # a follows b
+    got_b = [x.copy() for x in det.detect_pose_batch(frames_b, K, D, 0.14)[:3]]  # first chunk from the prefetch buffer
+    got_a2 = [x.copy() for x in det.detect_pose_batch(frames_a, K, D, 0.14)[:3]]  # prefetched again
+    other = [x.copy() for x in det.detect_pose_batch(frames_b, K, D, 0.14)[:3]]  # no hint pending: plain path
+    for got, ref in ((got_a, ref_a), (got_b, ref_b), (got_a2, ref_a), (other, ref_b)):
+        for g, r in zip(got, ref):
+            assert np.array_equal(g, r)
+
+
 @pytest.mark.parametrize("kind", ["black", "white", "noise", "stripes"])
 def test_frames_without_markers(det_cache, kind):
     rng = np.random.default_rng(5)
