@@ -273,15 +273,17 @@ def run_gpu_arm(args):
             lib.fid_hint_next(det.h, hptr)  # streaming: the next step's first chunk uploads while this step computes
             counts, ids, corners, tfs = det.detect_pose_batch(pinned, K, D, FIDUCIAL_LEN)
         launches[0] += det.last_counters()["kernel_launches"]
-        # fiducial_slam: the frames of this step are one camera stream -> one message per frame
-        # (enqueued asynchronously: the sequential fold of this step overlaps the detection of the next one;
-        #  the timed region ends with slam.sync())
-        slam.update_frames(counts, tfs, ident, ident, asynchronous=dist is None)
-        launches[0] += 1
-        if dist is not None:  # one NCCL all-gather of the per-rank map tables, same deterministic merge on every rank
+        # fiducial_slam: the frames of this step are one camera stream -> one message per frame.  The
+        # sequential fold is enqueued asynchronously so that it overlaps the detection of the next step
+        # (the timed region ends with slam.sync()).  With N > 1 the per-rank map tables (as of the
+        # previous step's fold, which finished long ago) are first exchanged with ONE NCCL all-gather and
+        # merged identically on every rank.
+        if dist is not None:
             tables = allgather_tables(slam.export_table(0), dist, device="cuda")
             slam.merge_tables(tables.reshape(-1), world, instance=0)
             launches[0] += 2
+        slam.update_frames(counts, tfs, ident, ident, asynchronous=True)
+        launches[0] += 1
         return counts
 
     def barrier():

@@ -30,6 +30,8 @@ struct fid_map {
     MapState* d_state = nullptr;      // [n_instances]
     MapEntry* d_entries = nullptr;    // [n_instances][cap]
     uint32_t* d_links = nullptr;      // [n_instances][cap][ceil(cap/32)]
+    int32_t* d_hash = nullptr;        // [n_instances][2][hash_size]  id -> slot
+    int hash_size = 0;
     fid_map_record* d_export = nullptr;  // [n_instances][cap]
     Obs* d_obs = nullptr;
     size_t obs_cap = 0;
@@ -47,6 +49,8 @@ struct SeqArgs {
     MapEntry* entries;
     uint32_t* links;
     int cap, links_wpr;
+    int32_t* hash;
+    int hash_size;
     int n_instances, n_msgs;
     const int32_t* offsets;  // [n_instances][n_msgs+1]
     const Obs* obs;
@@ -64,10 +68,11 @@ __global__ void k_map_sequence(const SeqArgs a) {
     MapEntry* e = a.entries + (size_t)inst * a.cap;
     uint32_t* links = a.links ? a.links + (size_t)inst * a.cap * a.links_wpr : nullptr;
     const int32_t* off = a.offsets + (size_t)inst * (a.n_msgs + 1);
+    MapHash hash{a.hash + (size_t)inst * 2 * a.hash_size, a.hash + (size_t)inst * 2 * a.hash_size + a.hash_size, a.hash_size};
     for (int k = 0; k < a.n_msgs; k++) {
         RobotPose rp;
         map_update(st, e, links, a.obs + off[k], off[k + 1] - off[k], a.have_base_cam ? &a.tf[0] : nullptr, a.have_cam_base ? &a.tf[1] : nullptr, a.weighting_scale,
-                   a.use_area, a.systematic_error, &rp);
+                   a.use_area, a.systematic_error, &rp, &hash);
         if (a.robot) a.robot[(size_t)inst * a.n_msgs + k] = rp;
     }
     a.state[inst] = st;
@@ -107,6 +112,7 @@ __global__ void k_map_merge(MapState* state, MapEntry* entries, int cap, int ins
     MapState st = state[inst];
     MapEntry* e = entries + (size_t)inst * cap;
     st.n = 0;
+    st.hash_valid = 0;
     for (int t = 0; t < n_tables; t++) {
         const fid_map_record* tab = tables + (size_t)t * cap;
         for (int i = 0; i < cap; i++) {  // exported tables are id-ascending
@@ -160,6 +166,8 @@ static int reset_state(fid_map* m, int inst_lo, int inst_hi) {
         s.capacity = m->p.max_fiducials;
         s.origin_fid = -1;
         s.read_only = m->p.read_only_map;
+        s.hash_size = m->hash_size;
+        s.hash_valid = 0;
     }
     CK(cudaMemcpy(m->d_state + inst_lo, st.data(), sizeof(MapState) * st.size(), cudaMemcpyHostToDevice));
     const size_t wpr = (m->p.max_fiducials + 31) / 32;
@@ -180,8 +188,11 @@ extern "C" int fid_map_create(const fid_map_params* p, int device, fid_map** out
     m->device = device;
     m->p = *p;
     const size_t cap = p->max_fiducials, ni = p->n_instances, wpr = (cap + 31) / 32;
+    m->hash_size = 16;
+    while ((size_t)m->hash_size < 2 * cap) m->hash_size *= 2;
     if (cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking) != cudaSuccess || cudaMalloc((void**)&m->d_state, sizeof(MapState) * ni) != cudaSuccess ||
         cudaMalloc((void**)&m->d_entries, sizeof(MapEntry) * ni * cap) != cudaSuccess || cudaMalloc((void**)&m->d_links, sizeof(uint32_t) * ni * cap * wpr) != cudaSuccess ||
+        cudaMalloc((void**)&m->d_hash, sizeof(int32_t) * ni * 2 * (size_t)m->hash_size) != cudaSuccess ||
         cudaMalloc((void**)&m->d_export, sizeof(fid_map_record) * ni * cap) != cudaSuccess || cudaMalloc((void**)&m->d_tf, sizeof(Twv) * 2) != cudaSuccess) {
         cudaGetLastError();
         fid_map_destroy(m);
@@ -200,7 +211,7 @@ extern "C" int fid_map_destroy(fid_map* m) {
     if (!m) return FID_ERR_INVALID_ARG;
     cudaSetDevice(m->device);
     cudaDeviceSynchronize();
-    void* ptrs[] = {m->d_state, m->d_entries, m->d_links, m->d_export, m->d_obs, m->d_offsets, m->d_robot, m->d_tf, m->d_merge_in};
+    void* ptrs[] = {m->d_hash, m->d_state, m->d_entries, m->d_links, m->d_export, m->d_obs, m->d_offsets, m->d_robot, m->d_tf, m->d_merge_in};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (m->stream) cudaStreamDestroy(m->stream);
@@ -220,6 +231,7 @@ extern "C" int fid_map_clear(fid_map* m, int instance) {
     st.origin_fid = -1;
     st.initializing = 0;
     st.overflow = 0;
+    st.hash_valid = 0;
     CK(cudaMemcpy(m->d_state + instance, &st, sizeof(st), cudaMemcpyHostToDevice));
     return FID_OK;
 }
@@ -261,6 +273,7 @@ extern "C" int fid_map_load(fid_map* m, int instance, int n, const fid_map_file_
         e[slot].pose.t[2] = entries[i].z;
         e[slot].pose.var = entries[i].variance;
     }
+    st.hash_valid = 0;
     if (st.n) CK(cudaMemcpy(m->d_entries + (size_t)instance * st.capacity, e.data(), sizeof(MapEntry) * st.n, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(m->d_state + instance, &st, sizeof(st), cudaMemcpyHostToDevice));
     return FID_OK;
@@ -316,6 +329,8 @@ static int run_sequence(fid_map* m, int inst_lo, int n_inst, int n_msgs, const i
     a.links_wpr = (cap + 31) / 32;
     a.links = m->d_links + (size_t)inst_lo * cap * a.links_wpr;
     a.cap = cap;
+    a.hash = m->d_hash + (size_t)inst_lo * 2 * m->hash_size;
+    a.hash_size = m->hash_size;
     a.n_instances = n_inst;
     a.n_msgs = n_msgs;
     a.offsets = m->d_offsets;

@@ -164,7 +164,27 @@ struct MapState {  // Map members map.h:118-134 that carry arithmetic state
     int32_t initializing;
     int32_t read_only;
     int32_t overflow;    // set if an insertion did not fit
+    int32_t hash_size;   // power of two >= 2*capacity; 0 = no hash table (linear search)
+    int32_t hash_valid;  // 0 = rebuild the id -> slot table from the entries before the next update
 };
+
+// id -> slot open-addressing table (linear probing); key = id + 1 (0 = empty), value = slot.
+struct MapHash {
+    int32_t* keys;
+    int32_t* vals;
+    int32_t size;
+};
+
+FID_HD uint32_t map_hash_of(int id) { return (uint32_t)id * 2654435761u; }
+
+FID_HD void map_hash_insert(const MapHash& h, int id, int slot) {
+    uint32_t p = map_hash_of(id) & (uint32_t)(h.size - 1);
+    while (h.keys[p] != 0 && h.keys[p] != id + 1) p = (p + 1) & (uint32_t)(h.size - 1);
+    h.keys[p] = id + 1;
+    h.vals[p] = slot;
+}
+
+FID_HD void map_hash_rebuild(const MapHash& h, const struct MapEntry* e, int n);
 
 struct Obs {  // one FiducialTransform as consumed by transformCallback
     int32_t id;
@@ -185,7 +205,20 @@ struct RobotPose {  // T_mapBase after updatePose
 
 #define FID_MAX_OBS 64
 
-FID_HD int map_find(const MapState& st, const MapEntry* e, int id) {
+FID_HD void map_hash_rebuild(const MapHash& h, const MapEntry* e, int n) {
+    for (int i = 0; i < h.size; i++) h.keys[i] = 0;
+    for (int i = 0; i < n; i++) map_hash_insert(h, e[i].id, i);
+}
+
+FID_HD int map_find(const MapState& st, const MapEntry* e, int id, const MapHash* h = nullptr) {
+    if (h && h->size > 0) {
+        uint32_t p = map_hash_of(id) & (uint32_t)(h->size - 1);
+        while (h->keys[p] != 0) {
+            if (h->keys[p] == id + 1) return h->vals[p];
+            p = (p + 1) & (uint32_t)(h->size - 1);
+        }
+        return -1;
+    }
     for (int i = 0; i < st.n; i++)
         if (e[i].id == id) return i;
     return -1;
@@ -195,7 +228,12 @@ FID_HD bool isnan3(const double t[3]) { return t[0] != t[0] || t[1] != t[1] || t
 
 // links: capacity x capacity bit matrix (row = slot, bit = other slot), may be null.
 FID_HD void map_update(MapState& st, MapEntry* e, uint32_t* links, const Obs* obs_in, int n_obs, const Twv* T_baseCam /*null = lookup failed*/,
-                       const Twv* T_camBase /*null = lookup failed*/, double weighting_scale, int use_area, double systematic_error, RobotPose* robot) {
+                       const Twv* T_camBase /*null = lookup failed*/, double weighting_scale, int use_area, double systematic_error, RobotPose* robot,
+                       const MapHash* hash = nullptr) {
+    if (hash && hash->size > 0 && !st.hash_valid) {
+        map_hash_rebuild(*hash, e, st.n);
+        st.hash_valid = 1;
+    }
     robot->valid = 0;
     robot->n_estimates = 0;
     if (n_obs > FID_MAX_OBS) n_obs = FID_MAX_OBS;
@@ -233,6 +271,7 @@ FID_HD void map_update(MapState& st, MapEntry* e, uint32_t* links, const Obs* ob
                 e[0].num_obs = 0;
                 e[0].pose = T;
                 st.n = 1;
+                if (hash && hash->size > 0) map_hash_insert(*hash, obs_in[idx].id, 0);
             } else if (idx >= 0) {
                 st.overflow = 1;
             }
@@ -244,7 +283,7 @@ FID_HD void map_update(MapState& st, MapEntry* e, uint32_t* links, const Obs* ob
                         T = twv_mul(*T_baseCam, camFid[i]);
                         T.var = camFid[i].var;
                     }
-                    const int slot = map_find(st, e, st.origin_fid);
+                    const int slot = map_find(st, e, st.origin_fid, hash);
                     if (slot >= 0) {
                         twv_update(e[slot].pose, T);
                         e[slot].num_obs++;
@@ -255,7 +294,7 @@ FID_HD void map_update(MapState& st, MapEntry* e, uint32_t* links, const Obs* ob
         }
         if (st.frame_num - st.initial_frame_num > 10 && st.origin_fid != -1) {
             st.initializing = 0;
-            const int slot = map_find(st, e, st.origin_fid);
+            const int slot = map_find(st, e, st.origin_fid, hash);
             if (slot >= 0) e[slot].pose.var = 0.0;
         }
         return;
@@ -276,7 +315,7 @@ FID_HD void map_update(MapState& st, MapEntry* e, uint32_t* links, const Obs* ob
     int n_est = 0;
     Twv mapBase;
     for (int i = 0; i < n_obs; i++) {
-        const int slot = map_find(st, e, obs_in[i].id);
+        const int slot = map_find(st, e, obs_in[i].id, hash);
         if (slot < 0) continue;
         Twv fidCam = twv_inverse(camFid[i]);
         Twv p = twv_mul(e[slot].pose, fidCam);
@@ -314,7 +353,7 @@ FID_HD void map_update(MapState& st, MapEntry* e, uint32_t* links, const Obs* ob
         for (int i = 0; i < n_obs; i++) {
             const Twv mapFid = twv_mul(mapCam, camFid[i]);
             if (isnan3(mapFid.t)) continue;
-            int slot = map_find(st, e, obs_in[i].id);
+            int slot = map_find(st, e, obs_in[i].id, hash);
             if (slot < 0) {
                 if (st.n >= st.capacity) {
                     st.overflow = 1;
@@ -324,6 +363,7 @@ FID_HD void map_update(MapState& st, MapEntry* e, uint32_t* links, const Obs* ob
                 e[slot].id = obs_in[i].id;
                 e[slot].num_obs = 0;
                 e[slot].pose = mapFid;
+                if (hash && hash->size > 0) map_hash_insert(*hash, obs_in[i].id, slot);
             }
             if (e[slot].pose.var != 0) {
                 twv_update(e[slot].pose, mapFid);
@@ -333,13 +373,13 @@ FID_HD void map_update(MapState& st, MapEntry* e, uint32_t* links, const Obs* ob
         // links (map.cpp:217-222): every fiducial seen in this frame links to every other one
         if (links) {
             const int wpr = (st.capacity + 31) / 32;
+            int slots[FID_MAX_OBS];
+            for (int i = 0; i < n_obs; i++) slots[i] = map_find(st, e, obs_in[i].id, hash);
             for (int i = 0; i < n_obs; i++) {
-                const int slot = map_find(st, e, obs_in[i].id);
-                if (slot < 0) continue;
+                if (slots[i] < 0) continue;
                 for (int j = 0; j < n_obs; j++) {
-                    if (obs_in[j].id == obs_in[i].id) continue;
-                    const int other = map_find(st, e, obs_in[j].id);
-                    if (other >= 0) links[(size_t)slot * wpr + (other >> 5)] |= 1u << (other & 31);
+                    if (obs_in[j].id == obs_in[i].id || slots[j] < 0) continue;
+                    links[(size_t)slots[i] * wpr + (slots[j] >> 5)] |= 1u << (slots[j] & 31);
                 }
             }
         }

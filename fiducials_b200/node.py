@@ -360,6 +360,18 @@ class FiducialSlam:
     def sync(self):
         _lib.check(self.lib.fid_map_sync(self.h))
 
+    TRANSFORM_DTYPE = np.dtype([("fiducial_id", "<i4"), ("reserved", "<i4"), ("translation", "<f8", 3), ("rotation", "<f8", 4), ("image_error", "<f8"),
+                                ("object_error", "<f8"), ("fiducial_area", "<f8"), ("rvec", "<f8", 3)])
+
+    def replay_raw(self, offsets: np.ndarray, obs: np.ndarray, T_baseCam=None, T_camBase=None):
+        """offsets int32 [n_instances, n_msgs+1] into obs (TRANSFORM_DTYPE records); one launch."""
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        obs = np.ascontiguousarray(obs)
+        assert obs.dtype == self.TRANSFORM_DTYPE and offsets.shape[0] == self.p.n_instances
+        bc, cb = _tf(T_baseCam), _tf(T_camBase)
+        _lib.check(self.lib.fid_map_update_sequence(self.h, offsets.shape[1] - 1, offsets.ctypes.data_as(C.c_void_p), obs.ctypes.data_as(C.c_void_p),
+                                                    C.byref(bc) if bc is not None else None, C.byref(cb) if cb is not None else None, None), "fid_map_update_sequence")
+
     def entries(self, instance=0):
         cap = self.p.max_fiducials
         arr = (_lib.fid_map_entry * cap)()

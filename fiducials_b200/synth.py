@@ -221,6 +221,59 @@ def make_config_stream(name: str, n_frames: int, seed: int = 0, realizations: in
     return out, truths, K, D, d
 
 
+def _q_from_rpy(roll, pitch, yaw):
+    hy, hp, hr = yaw * 0.5, pitch * 0.5, roll * 0.5
+    cy, sy, cp, sp, cr, sr = math.cos(hy), math.sin(hy), math.cos(hp), math.sin(hp), math.cos(hr), math.sin(hr)
+    return np.array([sr * cp * cy - cr * sp * sy, cr * sp * cy + sr * cp * sy, cr * cp * sy - sr * sp * cy, cr * cp * cy + sr * sp * sy])
+
+
+def _q_to_R(q):
+    x, y, z, w = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)], [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def _R_to_q(R):
+    w = math.sqrt(max(0.0, 1 + R[0, 0] + R[1, 1] + R[2, 2])) / 2
+    x = math.copysign(math.sqrt(max(0.0, 1 + R[0, 0] - R[1, 1] - R[2, 2])) / 2, R[2, 1] - R[1, 2])
+    y = math.copysign(math.sqrt(max(0.0, 1 - R[0, 0] + R[1, 1] - R[2, 2])) / 2, R[0, 2] - R[2, 0])
+    z = math.copysign(math.sqrt(max(0.0, 1 - R[0, 0] - R[1, 1] + R[2, 2])) / 2, R[1, 0] - R[0, 1])
+    return np.array([x, y, z, w])
+
+
+def make_c5_sequence(n_frames: int = 1000, seed: int = 0, cols: int = 25, rows: int = 20, visible: int = 10):
+    """BASELINE.json config C5: 500 fiducials on a 25x20 ceiling grid (1 m pitch,
+    z = 2.5 m, rpy = (180,0,180) deg like fiducial_slam/scripts/init_map.py:30), a camera on a
+    lawn-mower path below, `visible` nearest fiducials per frame with noise sigma_t = 5 mm,
+    sigma_R = 0.5 deg and object_error ~ U[1e-4, 1e-2].  Returns (messages, seed_entry) where
+    messages[k] is a list of FiducialTransform-like dicts and seed_entry the map-file row that pins
+    fiducial 0 (variance 0).  The camera is the base frame (identity T_baseCam)."""
+    rng = np.random.default_rng(seed)
+    pos = np.array([[float(i % cols), float(i // cols), 2.5] for i in range(cols * rows)])
+    q_fid = _q_from_rpy(math.pi, 0.0, math.pi)
+    R_fid = _q_to_R(q_fid)
+    msgs = []
+    for k in range(n_frames):
+        s = k / max(1, n_frames - 1) * rows  # lawn mower: sweep x back and forth while y advances
+        row = min(int(s), rows - 1)
+        fx = s - row
+        cam = np.array([fx * (cols - 1) if row % 2 == 0 else (1 - fx) * (cols - 1), row + 0.0, 0.0])
+        yaw = 0.3 * math.sin(0.05 * k)
+        R_cam = _q_to_R(_q_from_rpy(0.0, 0.0, yaw))
+        d = np.linalg.norm(pos[:, :2] - cam[:2], axis=1)
+        vis = np.argsort(d, kind="stable")[:visible]
+        order = rng.permutation(vis)
+        m = []
+        for i in order:
+            t = R_cam.T @ (pos[i] - cam) + rng.normal(0, 0.005, 3)
+            dR = _q_to_R(_q_from_rpy(*rng.normal(0, math.radians(0.5), 3)))
+            q = _R_to_q(R_cam.T @ R_fid @ dR)
+            m.append(dict(fiducial_id=int(i), translation=t, rotation=q, image_error=0.1, object_error=float(rng.uniform(1e-4, 1e-2)), fiducial_area=1500.0))
+        msgs.append(m)
+    seed_entry = [0, pos[0][0], pos[0][1], pos[0][2], 180.0, 0.0, 180.0, 0.0, 0]
+    return msgs, seed_entry
+
+
 def make_config_frame(name: str, seed: int = 0):
     W, H, n, d = CONFIGS[name]
     bgr, truth = make_frame(W, H, n, d, seed)

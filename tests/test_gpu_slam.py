@@ -161,3 +161,33 @@ def test_merge_matches_oracle_merge():
         assert np.abs(np.array([e.x, e.y, e.z]) - np.array(pose.t)).max() < 1e-9
         assert np.abs(np.array([e.rx, e.ry, e.rz]) - np.array(rr)).max() < 1e-9
         assert e.num_obs == n
+
+
+def test_c5_pose_graph_sequence():
+    """BASELINE.json config C5 (500 fiducials, ~10 observations per frame): the device fold equals the
+    numpy restatement of Map::update over a 250-frame prefix, and the full 1000-frame sequence runs
+    in one launch for several map instances at once."""
+    from fiducials_b200 import synth
+    from fiducials_b200.node import FiducialSlam
+
+    msgs, seed_entry = synth.make_c5_sequence(1000, seed=0)
+    ident = so.TWV.identity()
+    ref = so.Map()
+    ref.load_entry(*seed_entry)
+    for m in msgs[:250]:
+        ref.update(so.observations_from_transforms(m), ident, ident)
+    slam = FiducialSlam(max_fiducials=512, n_instances=1)
+    slam.loadMap([seed_entry])
+    slam.replay([msgs[:250]], _tf7(ident), _tf7(ident))
+    _cmp_entries(slam.entries(0), ref.entries(), 1e-4)  # BASELINE tolerance: 1e-4 m / 1e-4 rad
+    _cmp_entries(slam.entries(0), ref.entries(), 1e-8)
+    many = FiducialSlam(max_fiducials=512, n_instances=4)
+    for i in range(4):
+        many.loadMap([seed_entry], instance=i)
+    many.replay([msgs] * 4, _tf7(ident), _tf7(ident))
+    e0 = many.entries(0)
+    assert len(e0) > 300  # the lawn-mower path has seen most of the ceiling
+    for i in range(1, 4):
+        ei = many.entries(i)
+        assert [a.fiducial_id for a in ei] == [a.fiducial_id for a in e0]
+        assert all(a.x == b.x and a.rz == b.rz for a, b in zip(ei, e0))  # deterministic across instances

@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""BASELINE.json config C5: 500-fiducial / 10k-observation map update.  Reports map updates/s of
+(a) the reference algorithm on one CPU core (oracle/_ref/libslam_oracle.so, the C++ restatement --
+the reference is strictly sequential, so one core is what it can use per map), and
+(b) the CUDA fold for 1, 64 and 1024 independent map instances replayed in one launch.
+The reference node itself is capped at 20 updates/s by design (fiducial_slam.cpp:116,138-143)."""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from fiducials_b200 import synth  # noqa: E402
+from fiducials_b200.node import FiducialSlam  # noqa: E402
+
+
+def cpu_replay(msgs, seed_entry, reps=5):
+    lib = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libslam_oracle.so"))
+    flat = np.array([[m["fiducial_id"], *m["translation"], *m["rotation"], m["object_error"], m["fiducial_area"]] for msg in msgs for m in msg], np.float64)
+    off = np.zeros(len(msgs) + 1, np.int32)
+    off[1:] = np.cumsum([len(m) for m in msgs])
+    q = synth._q_from_rpy(np.radians(seed_entry[4]), np.radians(seed_entry[5]), np.radians(seed_entry[6]))
+    seed = np.array([[seed_entry[0], seed_entry[1], seed_entry[2], seed_entry[3], *q, seed_entry[7]]], np.float64)
+    ident = np.array([0, 0, 0, 0, 0, 0, 1], np.float64)
+    out = np.zeros((512, 14))
+    best = 1e9
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        n = lib.slam_c_replay(512, 1, seed.ctypes.data_as(C.c_void_p), len(msgs), off.ctypes.data_as(C.c_void_p), flat.ctypes.data_as(C.c_void_p),
+                              ident.ctypes.data_as(C.c_void_p), ident.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), None)
+        best = min(best, time.perf_counter() - t0)
+    return best, n
+
+
+def main():
+    msgs, seed_entry = synth.make_c5_sequence(1000, seed=0)
+    n_obs = sum(len(m) for m in msgs)
+    res = {"config": "C5: 500 fiducials, %d frames, %d observations" % (len(msgs), n_obs)}
+    t, n = cpu_replay(msgs, seed_entry)
+    res["cpu_1core"] = {"seconds": t, "updates_per_s": len(msgs) / t, "observations_per_s": n_obs / t, "map_entries": n}
+    ident = [0, 0, 0, 0, 0, 0, 1]
+    one = np.zeros(n_obs, FiducialSlam.TRANSFORM_DTYPE)
+    k = 0
+    for msg in msgs:
+        for m in msg:
+            one[k]["fiducial_id"] = m["fiducial_id"]
+            one[k]["translation"] = m["translation"]
+            one[k]["rotation"] = m["rotation"]
+            one[k]["image_error"], one[k]["object_error"], one[k]["fiducial_area"] = m["image_error"], m["object_error"], m["fiducial_area"]
+            k += 1
+    off1 = np.zeros(len(msgs) + 1, np.int64)
+    off1[1:] = np.cumsum([len(m) for m in msgs])
+    for ni in (1, 64, 1024, 8192):
+        slam = FiducialSlam(max_fiducials=512, n_instances=ni)
+        obs = np.tile(one, ni)
+        offsets = (off1[None, :] + (np.arange(ni) * n_obs)[:, None]).astype(np.int32)
+        best = 1e9
+        for rep in range(3):
+            for i in range(ni):
+                slam.clear(i)
+            slam.loadMap([seed_entry], instance=0)
+            if ni > 1:  # load the seed into every instance through one export/merge-free path: replicate by loadMap
+                for i in range(1, ni):
+                    slam.loadMap([seed_entry], instance=i)
+            t0 = time.perf_counter()
+            slam.replay_raw(offsets, obs, ident, ident)
+            best = min(best, time.perf_counter() - t0)
+        res["gpu_%d_instances" % ni] = {"seconds": best, "updates_per_s": ni * len(msgs) / best, "observations_per_s": ni * n_obs / best, "map_entries": len(slam.entries(0))}
+        slam.close()
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
