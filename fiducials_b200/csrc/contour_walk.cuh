@@ -250,13 +250,27 @@ FID_HD void trace_forward(const WalkCtx& c, int x0, int y0, int is_right, int n,
 }
 
 // ---- start cracks of one halo-tile row -----------------------------------------------------------------
-// up / mid = words r-1 / r of a tile (r = 1..30).  A left crack of a pixel is a candidate start unless
-// the pixel above is foreground with a zero left neighbour (that crack lies on the same border and
-// is raster smaller, so it dominates); same for right cracks.  Only interior bits 1..30 are reported.
+// up / mid = words r-1 / r of a tile (r = 1..30); only interior bits 1..30 are reported.  Every
+// left/right crack is a potential Suzuki start; the ones that a walk would discard within its first
+// step are removed here with bit operations (all rules are exact -- they only drop cracks whose
+// walk provably aborts, so the set of canonical starts is unchanged):
+//   L0  pixel above is foreground with a zero left neighbour        -> that crack dominates
+//   L1  up, up-left zero and up-right foreground                     -> first backward step lands on
+//       (x+1,y-1), whose left neighbour (x,y-1) is an examined zero: raster-smaller left crack
+//   L2  up-left foreground, (x-2,y) and (x-2,y-1) zero               -> first backward step lands on
+//       (x-1,y-1) which owns a left crack
+// and the mirror images R0..R2 for right cracks (forward walk).
 FID_HD void halo_row_starts(uint32_t up, uint32_t mid, uint32_t* L, uint32_t* R) {
     const uint32_t interior = 0x7FFFFFFEu;
-    *L = mid & ~(mid << 1) & ~(up & ~(up << 1)) & interior;
-    *R = mid & ~(mid >> 1) & ~(up & ~(up >> 1)) & interior;
+    const uint32_t up_l = up << 1, up_r = up >> 1, mid_l = mid << 1, mid_r = mid >> 1;
+    uint32_t l = mid & ~mid_l & ~(up & ~up_l);
+    l &= ~(~up & ~up_l & up_r);
+    l &= ~(up_l & ~(mid << 2) & ~(up << 2) & 0xFFFFFFFCu);
+    uint32_t r = mid & ~mid_r & ~(up & ~up_r);
+    r &= ~(~up & ~up_r & up_l);
+    r &= ~(up_r & ~(mid >> 2) & ~(up >> 2) & 0x3FFFFFFFu);
+    *L = l & interior;
+    *R = r & interior;
 }
 
 }  // namespace fid
