@@ -7,7 +7,7 @@ using namespace fid;
 __global__ void k(const float* c, Camera cam, PoseOut* out) { solve_marker_pose(c, cam, 0.14f, 0.14, out); }
 int main() {
     // C1 seed 0 marker 0 corners (from the oracle) and camera
-    float c[8] = {CORNERS};
+    float c[8] = {174.0747f, 105.04338f, 129.32097f, 208.1023f, 13.963207f, 167.47575f, 67.718f, 60.5f};  // any 4 marker corners
     Camera cam = {0.73 * 640, 0.73 * 640, 320, 240, 0.1349735087283542, -0.2335869827451621, 0.0006697030315075139, 0.004846737465872353, 0.0};
     PoseOut h;
     printf("--- host\n");
