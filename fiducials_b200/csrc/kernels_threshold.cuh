@@ -113,21 +113,24 @@ __global__ void __launch_bounds__(THR_THREADS, 2) k_threshold(const ThreshArgs a
         }
     }
     __syncthreads();
-    // B. row prefix sums: one warp per row, 32-wide shuffle scans with carry
-    for (int ry = warp; ry < RH; ry += THR_THREADS / 32) {
+    // B. row prefix sums: one thread per row, serial (conflict-free: the pitch is odd); the two CTAs
+    //    resident on an SM hide each other's dependent-add chains, and the shuffle-scan alternative
+    //    costs ~4x the instructions
+    for (int ry = tid; ry < RH; ry += THR_THREADS) {
         uint32_t* row = sat + (ry + 1) * SP + 1;
-        uint32_t carry = 0;
-        for (int c0 = 0; c0 < RW; c0 += 32) {
-            const int c = c0 + lane;
-            uint32_t v = c < RW ? row[c] : 0u;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
-                if (lane >= d) v += t;
-            }
-            v += carry;
-            if (c < RW) row[c] = v;
-            carry = __shfl_sync(0xffffffffu, v, 31);
+        uint32_t acc = 0;
+        int c = 0;
+        for (; c + 4 <= RW; c += 4) {
+            const uint32_t v0 = row[c], v1 = row[c + 1], v2 = row[c + 2], v3 = row[c + 3];
+            row[c] = acc + v0;
+            row[c + 1] = acc + v0 + v1;
+            row[c + 2] = acc + v0 + v1 + v2;
+            acc += v0 + v1 + v2 + v3;
+            row[c + 3] = acc;
+        }
+        for (; c < RW; c++) {
+            acc += row[c];
+            row[c] = acc;
         }
     }
     __syncthreads();
