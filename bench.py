@@ -332,14 +332,19 @@ def run_gpu_arm(args):
         peak, peak_src = measured_hbm_peak()
         achieved = algo_bytes / thr_s / 1e9 if thr_s > 0 else 0.0
         total_stage = sum(v for k, v in stage_ms.items() if k not in ("h2d", "d2h") and not k.startswith("walk_r"))
+        traffic = None
+        try:  # DRAM bytes of the stage from the committed ncu --set full capture (per frame, scaled to this launch)
+            traffic = float(json.load(open(os.path.join(ROOT, "profiles", "r01_threshold_traffic.json")))["dram_bytes_per_frame"]) * nf
+        except Exception:
+            pass
         roofline = {
             "bound": "hbm",
-            "kernel": "k_threshold",
+            "kernel": "k_gray + k_threshold (threshold stage)",
             "achieved": achieved,
             "peak": peak,
             "unit": "GB/s",
             "frac": achieved / peak,
-            "traffic": None,
+            "traffic": traffic,
             "peak_source": peak_src,
             "algorithmic_bytes_per_launch": algo_bytes,
             "launch_ms": stage_ms["threshold"],
