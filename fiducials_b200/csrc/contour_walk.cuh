@@ -201,6 +201,92 @@ FID_HD int walk_resume_dir(const WalkCtx& c, int x0, int y0, int max_len, int bu
     return result;
 }
 
+// ---- bidirectional walk -------------------------------------------------------------------------------
+// A start that survives the first few steps in its "uphill" direction is typically a local peak of a
+// ragged border: the raster-smaller crack that disproves it may be a few steps away in EITHER
+// direction, and in the wrong direction it is a whole lap away.  So from the second round on a walk
+// runs a forward and a backward walker in lock step (two independent dependency chains per thread)
+// and gives up as soon as either meets a raster-smaller crack: 2*min(d_fwd, d_bwd) steps instead of
+// d_chosen.  The canonical start is recognised when the two walkers meet (same cycle state); the sum
+// of their step counts is then the contour length.
+struct WalkState2 {
+    int xf, yf, df;  // forward walker: pixel, direction to the next pixel
+    int xb, yb, db;  // backward walker: pixel, direction to the previous pixel
+    int n;           // steps taken by both walkers together
+    int nf;          // steps taken by the forward walker
+};
+
+// Continue a one-directional WalkState (walk_init / walk_resume_dir) as a bidirectional one.
+template <bool IS_RIGHT>
+FID_HD void walk_split(int x0, int y0, const WalkState& st, WalkState2* s2) {
+    if (IS_RIGHT) {  // the forward walker has moved, the backward one still sits on the start state
+        s2->xf = st.x; s2->yf = st.y; s2->df = st.dir;
+        s2->xb = x0; s2->yb = y0; s2->db = st.a0;
+        s2->nf = st.n;
+    } else {
+        s2->xb = st.x; s2->yb = st.y; s2->db = st.dir;
+        s2->xf = x0; s2->yf = y0; s2->df = st.b0;
+        s2->nf = 0;
+    }
+    s2->n = st.n;
+}
+
+// Advance both walkers by at most `budget` steps in total (budget even).  Same results as
+// walk_resume_dir.
+template <bool IS_RIGHT>
+FID_HD int walk_resume_bidir(const WalkCtx& c, int x0, int y0, int max_len, int budget, WalkState2* st) {
+    int xf = st->xf, yf = st->yf, df = st->df, xb = st->xb, yb = st->yb, db = st->db, n = st->n, nf = st->nf;
+    const int stop_at = n + budget;
+    int result = WALK_CONTINUE;
+    while (n < stop_at) {
+        // forward step
+        xf += dir_dx(df);
+        yf += dir_dy(df);
+        n++;
+        nf++;
+        const int back_f = (df + 4) & 7;
+        if (xf == xb && yf == yb && back_f == db) {
+            result = WALK_CANONICAL;
+            break;
+        }
+        if (n > max_len) {
+            result = WALK_TOO_LONG;
+            break;
+        }
+        // backward step (independent of the forward one: the two table look-ups overlap)
+        const int xb1 = xb + dir_dx(db), yb1 = yb + dir_dy(db);
+        const int back_b = (db + 4) & 7;
+        const int ef = lut_load(c.lut_next + c.plane.idx9(xf, yf) * 8 + back_f);
+        const int eb = lut_load(c.lut_prev + c.plane.idx9(xb1, yb1) * 8 + back_b);
+        df = ef & 7;
+        if ((ef & 0x18) && (yf < y0 || (yf == y0 && xf < x0) || (IS_RIGHT && (ef & 8) && yf == y0 && xf == x0))) {
+            result = WALK_ABORT;
+            break;
+        }
+        xb = xb1;
+        yb = yb1;
+        n++;
+        if (xb == xf && yb == yf && back_b == df) {
+            result = WALK_CANONICAL;
+            break;
+        }
+        if (n > max_len) {
+            result = WALK_TOO_LONG;
+            break;
+        }
+        db = eb & 7;
+        if ((eb & 0x18) && (yb < y0 || (yb == y0 && xb < x0) || (IS_RIGHT && (eb & 8) && yb == y0 && xb == x0))) {
+            result = WALK_ABORT;
+            break;
+        }
+    }
+    st->xf = xf; st->yf = yf; st->df = df;
+    st->xb = xb; st->yb = yb; st->db = db;
+    st->n = n;
+    st->nf = nf;
+    return result;
+}
+
 FID_HD int walk_resume(const WalkCtx& c, int x0, int y0, int is_right, int max_len, int budget, WalkState* st) {
     return is_right ? walk_resume_dir<true>(c, x0, y0, max_len, budget, st) : walk_resume_dir<false>(c, x0, y0, max_len, budget, st);
 }
@@ -247,6 +333,110 @@ FID_HD void trace_forward(const WalkCtx& c, int x0, int y0, int is_right, int n,
         cur = c.plane.idx9(x, y);
     }
     for (int k = 0; k < (n & 3); k++) out32[(n & ~3) + k] = buf[k];
+}
+
+// ---- contour emission in segments ------------------------------------------------------------------
+// A contour found by the bidirectional walk (length n, the forward walker took nf of the steps) is
+// written by several independent threads: the points 0 .. nf-1 forwards from the start state, the
+// points n-1 .. nf backwards from it, and -- for long contours -- each half again cut at the
+// checkpoints the walkers dropped every FID_CKPT_STEP steps.  A segment is (state, count, index of
+// the state's own point); the order of the points is cv2.findContours' (start pixel first, Suzuki's
+// direction).
+#define FID_CKPT_STEP 256
+#define FID_CKPT_MAX 16
+struct SegRec {
+    uint32_t xy;    // pixel of the state
+    uint32_t meta;  // frame << 8 | scale << 1 | backward
+    uint32_t dn;    // dir | count << 3: forward segment -> dir to the next pixel, backward -> dir to the previous one
+    uint32_t off;   // index of the state's own point in the point buffer
+};
+struct WalkCkpt {
+    // side 0: forward walker, side 1: backward walker; dn = dir | (steps that walker had taken) << 3
+    uint32_t xy[2][FID_CKPT_MAX];
+    uint32_t dn[2][FID_CKPT_MAX];
+    int count[2];
+};
+
+// forward: points[off + t] = pixel after t steps, t = 0 .. count-1
+// backward: points[off - t] = pixel after t steps, t = 1 .. count
+FID_HD void trace_segment(const WalkCtx& c, const SegRec& s, uint32_t* points) {
+    int x = (int)(s.xy & 0xFFFF), y = (int)(s.xy >> 16), dir = (int)(s.dn & 7);
+    const int count = (int)(s.dn >> 3);
+    if (s.meta & 1u) {
+        uint32_t* out = points + s.off;
+        for (int t = 1; t <= count; t++) {
+            x += dir_dx(dir);
+            y += dir_dy(dir);
+            out[-t] = (uint32_t)x | ((uint32_t)y << 16);
+            dir = lut_load(c.lut_prev + c.plane.idx9(x, y) * 8 + ((dir + 4) & 7)) & 7;
+        }
+    } else {
+        uint32_t* out = points + s.off;
+        for (int t = 0; t < count; t++) {
+            out[t] = (uint32_t)x | ((uint32_t)y << 16);
+            x += dir_dx(dir);
+            y += dir_dy(dir);
+            dir = lut_load(c.lut_next + c.plane.idx9(x, y) * 8 + ((dir + 4) & 7)) & 7;
+        }
+    }
+}
+
+// Number of segments of a contour, and the segments themselves (sink(k, SegRec) for k = 0 .. count-1).
+FID_HD int segment_count(const WalkCkpt* ck) { return 2 + (ck ? ck->count[0] + ck->count[1] : 0); }
+template <class Sink>
+FID_HD void make_segments(const WalkCtx& c, int x0, int y0, int is_right, int n, int nf, const WalkCkpt* ck, uint32_t meta_fs, uint32_t chain_off, const Sink& sink) {
+    const uint32_t v = c.plane.idx9(x0, y0);
+    const int crack = is_right ? 0 : 4;
+    const int a0 = lut_load(c.lut_prev + v * 8 + crack) & 7, b0 = lut_load(c.lut_next + v * 8 + crack) & 7;
+    const uint32_t xy0 = (uint32_t)x0 | ((uint32_t)y0 << 16);
+    const uint32_t meta = meta_fs & ~1u;
+    int k = 0;
+    {  // forward half: points 0 .. nf-1
+        uint32_t xy = xy0;
+        int dir = b0, at = 0;
+        const int m = ck ? ck->count[0] : 0;
+        for (int i = 0; i <= m; i++) {
+            const int next_at = i < m ? (int)(ck->dn[0][i] >> 3) : nf;
+            sink(k++, SegRec{xy, meta, (uint32_t)dir | ((uint32_t)(next_at - at) << 3), chain_off + (uint32_t)at});
+            if (i < m) {
+                xy = ck->xy[0][i];
+                dir = (int)(ck->dn[0][i] & 7);
+                at = next_at;
+            }
+        }
+    }
+    {  // backward half: points n-1 .. nf
+        uint32_t xy = xy0;
+        int dir = a0, at = 0;  // at = steps the backward walker had taken
+        const int nb = n - nf;
+        const int m = ck ? ck->count[1] : 0;
+        for (int i = 0; i <= m; i++) {
+            const int next_at = i < m ? (int)(ck->dn[1][i] >> 3) : nb;
+            sink(k++, SegRec{xy, meta | 1u, (uint32_t)dir | ((uint32_t)(next_at - at) << 3), chain_off + (uint32_t)(n - at)});
+            if (i < m) {
+                xy = ck->xy[1][i];
+                dir = (int)(ck->dn[1][i] & 7);
+                at = next_at;
+            }
+        }
+    }
+}
+
+// Drop checkpoints of both walkers when they have moved FID_CKPT_STEP steps since their last one.
+FID_HD void walk_checkpoint(const WalkState2& st, WalkCkpt* ck, int* last_f, int* last_b, int step = FID_CKPT_STEP) {
+    const int nb = st.n - st.nf;
+    if (st.nf - *last_f >= step && ck->count[0] < FID_CKPT_MAX) {
+        const int i = ck->count[0]++;
+        ck->xy[0][i] = (uint32_t)st.xf | ((uint32_t)st.yf << 16);
+        ck->dn[0][i] = (uint32_t)st.df | ((uint32_t)st.nf << 3);
+        *last_f = st.nf;
+    }
+    if (nb - *last_b >= step && ck->count[1] < FID_CKPT_MAX) {
+        const int i = ck->count[1]++;
+        ck->xy[1][i] = (uint32_t)st.xb | ((uint32_t)st.yb << 16);
+        ck->dn[1][i] = (uint32_t)st.db | ((uint32_t)nb << 3);
+        *last_b = nb;
+    }
 }
 
 // ---- start cracks of one halo-tile row -----------------------------------------------------------------

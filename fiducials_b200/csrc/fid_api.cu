@@ -27,6 +27,7 @@ using namespace fid;
 
 enum { ST_H2D = 0, ST_THRESH, ST_MASKS, ST_WALK, ST_EMIT, ST_APPROX, ST_GROUP, ST_IDENT, ST_SUBPIX_POSE, ST_POSE_UNUSED, ST_D2H, ST_COUNT };
 enum { N_WALK_ROUNDS = FID_WALK_MAX_ROUNDS };
+enum { MAX_SLOTS = 4 };
 
 struct Slot {
     uint8_t* d_bgr = nullptr;
@@ -34,6 +35,7 @@ struct Slot {
     uint32_t* d_halo = nullptr;
     StartRec* d_starts = nullptr;
     ChainRec* d_chains = nullptr;
+    SegRec* d_segs = nullptr;
     WalkRec* d_queue[2] = {nullptr, nullptr};
     Pt16* d_points = nullptr;
     Counters* d_counters = nullptr;
@@ -69,10 +71,13 @@ struct fid_detector {
     DevParams P{};
     int max_w = 0, max_h = 0, max_batch = 0;
     int max_raw = 4096, close_wpr = 128, max_sel = 512, max_markers = FID_MAX_MARKERS;
-    unsigned int max_starts = 0, max_chains = 0, max_points = 0, max_queue = 0;
+    unsigned int max_starts = 0, max_chains = 0, max_points = 0, max_queue = 0, max_segs = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaStream_t slot_stream[2] = {nullptr, nullptr};  // one compute stream per slot: latency-bound stages of one chunk overlap the other chunk
-    Slot slot[2];
+    // one compute stream per slot (chunk in flight): the latency-bound stages of one chunk overlap the
+    // issue-bound stages of the others.  FID_SLOTS (2..4, default 2)
+    int n_slots = 2;
+    cudaStream_t slot_stream[MAX_SLOTS] = {};
+    Slot slot[MAX_SLOTS];
     // streaming prefetch (fid_hint_next): first chunk of the next call, ping-pong
     uint8_t* d_pf[2] = {nullptr, nullptr};
     cudaEvent_t pf_done[2] = {nullptr, nullptr};
@@ -83,7 +88,7 @@ struct fid_detector {
     uint8_t* d_lut_prev = nullptr;
     uint8_t* d_lut_next = nullptr;
     int walk_rounds = 0;
-    int emit_blocks_per_sm = 2;
+    int emit_blocks_per_sm = 8;
     int walk_budget[FID_WALK_MAX_ROUNDS]{};
     int walk_persist[FID_WALK_MAX_ROUNDS]{};
     int32_t* d_override_ids = nullptr;
@@ -196,6 +201,7 @@ static int alloc_slot(fid_detector* h, Slot& s) {
     A(dalloc(&s.d_halo, F * (size_t)S * halo_plane_words(W, H)));
     A(dalloc(&s.d_starts, (size_t)h->max_starts));
     A(dalloc(&s.d_chains, (size_t)h->max_chains));
+    A(dalloc(&s.d_segs, (size_t)h->max_segs));
     A(dalloc(&s.d_queue[0], (size_t)h->max_queue));
     A(dalloc(&s.d_queue[1], (size_t)h->max_queue));
     A(dalloc(&s.d_points, (size_t)h->max_points));
@@ -243,7 +249,7 @@ static int alloc_slot(fid_detector* h, Slot& s) {
 }
 
 static void free_slot(Slot& s) {
-    void* dptrs[] = {s.d_halo, s.d_queue[0], s.d_queue[1], s.d_bgr,         s.d_gray,          s.d_starts,       s.d_chains,       s.d_points,      s.d_counters,
+    void* dptrs[] = {s.d_segs, s.d_halo, s.d_queue[0], s.d_queue[1], s.d_bgr,         s.d_gray,          s.d_starts,       s.d_chains,       s.d_points,      s.d_counters,
                      s.d_raw,         s.d_nraw,          s.fs.quads_tmp,    s.fs.per_tmp,     s.fs.quads,       s.fs.per,         s.fs.close_bits, s.fs.group_id,
                      s.fs.group_members, s.fs.next_in_group, s.fs.group_head, s.fs.group_tail, s.fs.close_count, s.fs.close_idx,   s.fs.close_off,  s.fs.selected,
                      s.fs.sel_idx,    s.d_nsel,          s.d_nrawc,         s.d_cand_id,      s.d_cand_corners, s.d_out_count,    s.d_out_ids,     s.d_out_corners,
@@ -289,16 +295,17 @@ extern "C" int fid_create(const fid_params* params, int device, int max_width, i
     h->max_starts = (unsigned int)std::min<size_t>(px * 6 + 65536, 0x7fffffffu);
     h->max_chains = (unsigned int)std::min<size_t>((size_t)max_batch * 65536, 0x7fffffffu);
     h->max_points = (unsigned int)std::min<size_t>(px * 4 + 65536, 0x7fffffffu);
+    h->max_segs = h->max_chains * 4;  // two per contour + checkpoints of the long ones
     h->max_queue = h->max_starts / 8 + 65536;  // walks that survive the first 32 steps: ~3 % of the start cracks
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&h->slot_stream[0], cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&h->slot_stream[1], cudaStreamNonBlocking));
+    if (const char* e = getenv("FID_SLOTS")) h->n_slots = std::max(2, std::min((int)MAX_SLOTS, atoi(e)));
+    for (int i = 0; i < h->n_slots; i++) CK(cudaStreamCreateWithFlags(&h->slot_stream[i], cudaStreamNonBlocking));
     if ((rc = upload_constants()) != FID_OK || (rc = configure_kernels(h)) != FID_OK) {
         fid_destroy(h);
         return rc;
     }
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < h->n_slots; i++)
         if ((rc = alloc_slot(h, h->slot[i])) != FID_OK) {
             fid_destroy(h);
             return rc;
@@ -375,7 +382,7 @@ extern "C" int fid_destroy(fid_detector* h) {
     if (!h) return FID_ERR_INVALID_ARG;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < 2; i++) free_slot(h->slot[i]);
+    for (int i = 0; i < MAX_SLOTS; i++) free_slot(h->slot[i]);
     void* ptrs[] = {h->d_pf[0], h->d_pf[1], h->d_lut_prev, h->d_lut_next, h->d_subpix_masks, h->d_override_ids, h->d_override_lens, h->d_pose_ids, h->d_pose_corners, h->d_pose_out};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -385,7 +392,7 @@ extern "C" int fid_destroy(fid_detector* h) {
     if (h->t1) cudaEventDestroy(h->t1);
     if (h->stream) cudaStreamDestroy(h->stream);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
-    for (int i = 0; i < 2; i++)
+    for (int i = 0; i < MAX_SLOTS; i++)
         if (h->slot_stream[i]) cudaStreamDestroy(h->slot_stream[i]);
     delete h;
     return FID_OK;
@@ -495,6 +502,8 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
         a.lut_next = h->d_lut_next;
         a.starts = s.d_starts;
         a.chains = s.d_chains;
+        a.segs = s.d_segs;
+        a.max_segs = h->max_segs;
         a.counters = s.d_counters;
         a.max_starts = h->max_starts;
         a.max_chains = h->max_chains;
@@ -524,11 +533,11 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
         a.halo = s.d_halo;
         a.lut_prev = h->d_lut_prev;
         a.lut_next = h->d_lut_next;
-        a.chains = s.d_chains;
+        a.segs = s.d_segs;
         a.points = s.d_points;
         a.counters = s.d_counters;
         a.work_counter = &s.d_counters->emit_work;
-        a.max_chains = h->max_chains;
+        a.max_segs = h->max_segs;
         a.g = g;
         k_emit<<<h->sm_count * h->emit_blocks_per_sm, 64, 0, st>>>(a);
         launches++;
@@ -715,10 +724,13 @@ extern "C" int fid_detect_pose_batch(fid_detector* h, int n_frames, const uint8_
     const int n_chunks = (n_frames + B - 1) / B;
     h->counters[6] = 0;
     h->stage_ms[ST_H2D] = 0;
-    // software pipeline over chunks: copy(c+1) overlaps compute(c); two slots
-    for (int c = 0; c <= n_chunks; c++) {
+    // software pipeline over chunks: up to n_slots chunks in flight, each on its own stream; results of
+    // chunk c are collected n_slots-1 chunks later
+    const int NS = h->n_slots;
+    for (int c = 0; c < n_chunks + NS - 1; c++) {
         if (c < n_chunks) {
-            Slot& s = h->slot[c & 1];
+            Slot& s = h->slot[c % NS];
+            cudaStream_t cst = h->slot_stream[c % NS];
             const int nf = std::min(B, n_frames - c * B);
             const uint8_t* src = bgr + (size_t)c * B * frame_stride;
             const uint8_t* d_in;
@@ -743,7 +755,7 @@ extern "C" int fid_detect_pose_batch(fid_detector* h, int n_frames, const uint8_
                                              cudaMemcpyHostToDevice, h->copy_stream));
                 }
                 CK(cudaEventRecord(s.copied, h->copy_stream));
-                CK(cudaStreamWaitEvent(h->slot_stream[c & 1], s.copied, 0));
+                CK(cudaStreamWaitEvent(cst, s.copied, 0));
                 d_in = s.d_bgr;
                 g = make_geom(h, width, height, (size_t)width * 3, (size_t)width * 3 * height);
             }
@@ -760,15 +772,15 @@ extern "C" int fid_detect_pose_batch(fid_detector* h, int n_frames, const uint8_
                 h->pf_h = height;
                 h->hint_next = nullptr;
             }
-            rc = enqueue_pipeline(h, s, h->slot_stream[c & 1], nf, g, d_in, cam, fiducial_len, n_override, -1);
+            rc = enqueue_pipeline(h, s, cst, nf, g, d_in, cam, fiducial_len, n_override, -1);
             if (rc != FID_OK) return rc;
-            rc = enqueue_d2h(h, s, h->slot_stream[c & 1], nf, cam != nullptr);
+            rc = enqueue_d2h(h, s, cst, nf, cam != nullptr);
             if (rc != FID_OK) return rc;
             h->last_frames = nf;
         }
-        if (c > 0) {
-            const int pc = c - 1;
-            Slot& s = h->slot[pc & 1];
+        if (c >= NS - 1) {
+            const int pc = c - (NS - 1);
+            Slot& s = h->slot[pc % NS];
             const int nf = std::min(B, n_frames - pc * B);
             rc = collect(h, s, nf, max_markers, counts + (size_t)pc * B, ids ? ids + (size_t)pc * B * max_markers : nullptr,
                          corners ? corners + (size_t)pc * B * max_markers * 8 : nullptr, (transforms && cam) ? transforms + (size_t)pc * B * max_markers : nullptr, pc == 0);
@@ -826,8 +838,7 @@ extern "C" int fid_timer_start(fid_detector* h) {
         CK(cudaEventCreate(&h->t1));
     }
     CK(cudaStreamSynchronize(h->copy_stream));
-    CK(cudaStreamSynchronize(h->slot_stream[0]));
-    CK(cudaStreamSynchronize(h->slot_stream[1]));
+    for (int i = 0; i < h->n_slots; i++) CK(cudaStreamSynchronize(h->slot_stream[i]));
     CK(cudaStreamSynchronize(h->stream));
     CK(cudaEventRecord(h->t0, h->stream));
     return FID_OK;
@@ -836,8 +847,7 @@ extern "C" int fid_timer_stop(fid_detector* h, float* elapsed_ms) {
     if (!h || !elapsed_ms || !h->t0) return FID_ERR_INVALID_ARG;
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->copy_stream));
-    CK(cudaStreamSynchronize(h->slot_stream[0]));
-    CK(cudaStreamSynchronize(h->slot_stream[1]));
+    for (int i = 0; i < h->n_slots; i++) CK(cudaStreamSynchronize(h->slot_stream[i]));
     CK(cudaEventRecord(h->t1, h->stream));
     CK(cudaEventSynchronize(h->t1));
     CK(cudaEventElapsedTime(elapsed_ms, h->t0, h->t1));

@@ -25,14 +25,17 @@ struct Counters {
     unsigned int n_q[FID_WALK_MAX_ROUNDS][2];  // walks suspended by each round, per direction
     unsigned int work[FID_WALK_MAX_ROUNDS][2]; // persistent-walker work counters, per direction
     unsigned int emit_work;
-    unsigned int pad[2];
+    unsigned int n_segs;       // contour segments queued for k_emit
+    unsigned int pad[1];
 };
 
-struct WalkRec {       // a border walk suspended between rounds
+struct WalkRec {       // a bidirectional border walk suspended between rounds (contour_walk.cuh, WalkState2)
     uint32_t xy0;      // start pixel
     uint32_t meta;     // frame << 8 | scale << 1 | is_right
-    uint32_t xy;       // current pixel
-    uint32_t state;    // dir | a0 << 3 | b0 << 6 | n << 9
+    uint32_t xyf;      // forward walker's pixel
+    uint32_t xyb;      // backward walker's pixel
+    uint32_t state;    // df | db << 3 | n << 6
+    uint32_t nf;       // steps of the forward walker
 };
 
 struct StartRec {
@@ -73,8 +76,9 @@ struct WalkArgs {
     const WalkRec* q_in;      // later rounds: left items at [0, nL), right items at [max_queue-1 ...]
     WalkRec* q_out;
     ChainRec* chains;
+    SegRec* segs;
     Counters* counters;
-    unsigned int max_starts, max_chains, max_points, max_queue;
+    unsigned int max_starts, max_chains, max_points, max_queue, max_segs;
     int round;                // 0 = items are start cracks
     FrameGeom g;
     int min_len, max_len, budget;
@@ -84,56 +88,67 @@ struct WalkArgs {
 
 struct WalkItem {
     uint32_t xy0, meta;
-    WalkState st;
+    WalkState2 st;
     int x0, y0;
     WalkCtx ctx;
 };
 
-template <bool IS_RIGHT>
-__device__ __forceinline__ bool walk_load_item(const WalkArgs& a, unsigned int idx, WalkItem& it) {
-    // returns true if the item is live after initialisation
-    if (a.round == 0) {
-        const StartRec sr = a.starts[IS_RIGHT ? a.max_starts - 1 - idx : idx];
-        it.xy0 = sr.xy;
-        it.meta = sr.meta;
-    } else {
-        const WalkRec wr = a.q_in[IS_RIGHT ? a.max_queue - 1 - idx : idx];
-        it.xy0 = wr.xy0;
-        it.meta = wr.meta;
-        it.st.x = wr.xy & 0xFFFF;
-        it.st.y = wr.xy >> 16;
-        it.st.dir = wr.state & 7;
-        it.st.a0 = (wr.state >> 3) & 7;
-        it.st.b0 = (wr.state >> 6) & 7;
-        it.st.n = wr.state >> 9;
-    }
-    it.x0 = it.xy0 & 0xFFFF;
-    it.y0 = it.xy0 >> 16;
-    const int f = it.meta >> 8, s = (it.meta >> 1) & 0x7F;
-    it.ctx.plane = HaloView{a.halo + (size_t)f * a.g.halo_frame_stride + (size_t)s * a.g.halo_scale_stride, a.g.halo_tpr};
-    it.ctx.lut_prev = a.lut_prev;
-    it.ctx.lut_next = a.lut_next;
-    if (a.round == 0) return walk_init(it.ctx, it.x0, it.y0, IS_RIGHT ? 1 : 0, &it.st) == WALK_CONTINUE;
-    return true;
+__device__ __forceinline__ WalkCtx walk_ctx_of(const WalkArgs& a, uint32_t meta) {
+    const int f = meta >> 8, s = (meta >> 1) & 0x7F;
+    WalkCtx ctx;
+    ctx.plane = HaloView{a.halo + (size_t)f * a.g.halo_frame_stride + (size_t)s * a.g.halo_scale_stride, a.g.halo_tpr};
+    ctx.lut_prev = a.lut_prev;
+    ctx.lut_next = a.lut_next;
+    return ctx;
 }
 
 template <bool IS_RIGHT>
-__device__ __forceinline__ void walk_retire(const WalkArgs& a, int result, const WalkItem& it) {
-    if (result == WALK_CANONICAL && it.st.n >= a.min_len && it.st.n <= a.max_len) {
+__device__ __forceinline__ void walk_load_item(const WalkArgs& a, unsigned int idx, WalkItem& it) {
+    const uint2* q = reinterpret_cast<const uint2*>(a.q_in + (IS_RIGHT ? a.max_queue - 1 - idx : idx));
+    const uint2 w0 = q[0], w1 = q[1], w2 = q[2];
+    it.xy0 = w0.x;
+    it.meta = w0.y;
+    it.st.xf = w1.x & 0xFFFF;
+    it.st.yf = w1.x >> 16;
+    it.st.xb = w1.y & 0xFFFF;
+    it.st.yb = w1.y >> 16;
+    it.st.df = w2.x & 7;
+    it.st.db = (w2.x >> 3) & 7;
+    it.st.n = w2.x >> 6;
+    it.st.nf = w2.y;
+    it.x0 = it.xy0 & 0xFFFF;
+    it.y0 = it.xy0 >> 16;
+    it.ctx = walk_ctx_of(a, it.meta);
+}
+
+template <bool IS_RIGHT>
+__device__ __forceinline__ void walk_retire(const WalkArgs& a, int result, uint32_t xy0, uint32_t meta, const WalkState2& st, const WalkCtx& ctx, const WalkCkpt* ck) {
+    if (result == WALK_CANONICAL && st.n >= a.min_len && st.n <= a.max_len) {
         const unsigned int slot = atomicAdd(&a.counters->n_chains, 1u);
-        const unsigned int off = atomicAdd(&a.counters->n_points, ((unsigned int)it.st.n + 3u) & ~3u);  // 16-byte aligned chains
-        if (slot < a.max_chains && off + (unsigned int)it.st.n <= a.max_points) {
-            a.chains[slot] = ChainRec{it.xy0, it.meta, (uint32_t)it.st.n, off};
+        const unsigned int off = atomicAdd(&a.counters->n_points, ((unsigned int)st.n + 3u) & ~3u);  // 16-byte aligned chains
+        if (slot < a.max_chains && off + (unsigned int)st.n <= a.max_points) {
+            a.chains[slot] = ChainRec{xy0, meta, (uint32_t)st.n, off};
+            const unsigned int nseg = (unsigned int)segment_count(ck);
+            const unsigned int sbase = atomicAdd(&a.counters->n_segs, nseg);
+            if (sbase + nseg <= a.max_segs) {
+                SegRec* out = a.segs + sbase;
+                make_segments(ctx, (int)(xy0 & 0xFFFF), (int)(xy0 >> 16), IS_RIGHT ? 1 : 0, st.n, st.nf, ck, meta, off,
+                              [out](int k, const SegRec& sr) { *reinterpret_cast<uint4*>(out + k) = make_uint4(sr.xy, sr.meta, sr.dn, sr.off); });
+            } else {
+                a.chains[slot].n = 0;
+                atomicOr(&a.counters->overflow, 2u);
+            }
         } else {
-            if (slot < a.max_chains) a.chains[slot] = ChainRec{it.xy0, it.meta, 0u, 0u};
+            if (slot < a.max_chains) a.chains[slot] = ChainRec{xy0, meta, 0u, 0u};
             atomicOr(&a.counters->overflow, slot >= a.max_chains ? 2u : 4u);
         }
     } else if (result == WALK_CONTINUE) {
         const unsigned int pos = atomicAdd(&a.counters->n_q[a.round][IS_RIGHT ? 1 : 0], 1u);
         if (pos < a.max_queue / 2) {
-            a.q_out[IS_RIGHT ? a.max_queue - 1 - pos : pos] =
-                WalkRec{it.xy0, it.meta, (uint32_t)it.st.x | ((uint32_t)it.st.y << 16),
-                        (uint32_t)it.st.dir | ((uint32_t)it.st.a0 << 3) | ((uint32_t)it.st.b0 << 6) | ((uint32_t)it.st.n << 9)};
+            uint2* q = reinterpret_cast<uint2*>(a.q_out + (IS_RIGHT ? a.max_queue - 1 - pos : pos));
+            q[0] = make_uint2(xy0, meta);
+            q[1] = make_uint2((uint32_t)st.xf | ((uint32_t)st.yf << 16), (uint32_t)st.xb | ((uint32_t)st.yb << 16));
+            q[2] = make_uint2((uint32_t)st.df | ((uint32_t)st.db << 3) | ((uint32_t)st.n << 6), (uint32_t)st.nf);
         } else {
             atomicOr(&a.counters->overflow, 64u);
         }
@@ -147,14 +162,32 @@ __device__ __forceinline__ void walk_side(const WalkArgs& a, unsigned int n, uns
     const unsigned int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (warp < first_warp || warp >= first_warp + n_warps) return;
     const unsigned int my = warp - first_warp;
+    if (a.round == 0) {
+        // start cracks: one-directional walk "uphill" (left cracks backwards, right cracks forwards), which
+        // disproves nine starts out of ten within the first few steps; survivors continue bidirectionally
+        for (unsigned int base = my * 32; base < n; base += n_warps * 32) {
+            const unsigned int idx = base + lane;
+            if (idx >= n) continue;
+            const StartRec sr = a.starts[IS_RIGHT ? a.max_starts - 1 - idx : idx];
+            const WalkCtx ctx = walk_ctx_of(a, sr.meta);
+            const int x0 = sr.xy & 0xFFFF, y0 = sr.xy >> 16;
+            WalkState st;
+            if (walk_init(ctx, x0, y0, IS_RIGHT ? 1 : 0, &st) != WALK_CONTINUE) continue;
+            const int r = walk_resume_dir<IS_RIGHT>(ctx, x0, y0, a.max_len, a.budget, &st);
+            WalkState2 s2;
+            walk_split<IS_RIGHT>(x0, y0, st, &s2);
+            walk_retire<IS_RIGHT>(a, r, sr.xy, sr.meta, s2, ctx, nullptr);
+        }
+        return;
+    }
     if (!a.persistent) {
         for (unsigned int base = my * 32; base < n; base += n_warps * 32) {
             const unsigned int idx = base + lane;
             if (idx >= n) continue;
             WalkItem it;
-            if (!walk_load_item<IS_RIGHT>(a, idx, it)) continue;
-            const int r = walk_resume_dir<IS_RIGHT>(it.ctx, it.x0, it.y0, a.max_len, a.budget, &it.st);
-            walk_retire<IS_RIGHT>(a, r, it);
+            walk_load_item<IS_RIGHT>(a, idx, it);
+            const int r = walk_resume_bidir<IS_RIGHT>(it.ctx, it.x0, it.y0, a.max_len, a.budget, &it.st);
+            walk_retire<IS_RIGHT>(a, r, it.xy0, it.meta, it.st, it.ctx, nullptr);
         }
         return;
     }
@@ -162,8 +195,10 @@ __device__ __forceinline__ void walk_side(const WalkArgs& a, unsigned int n, uns
     const unsigned int lt_mask = (1u << lane) - 1u;
     unsigned int next = 0, hi = 0;
     bool exhausted = false, active = false;
-    int budget_end = 0;
+    int budget_end = 0, last_f = 0, last_b = 0;
     WalkItem it;
+    WalkCkpt ck;  // checkpoints of the current walk (local memory; touched once per FID_CKPT_STEP steps)
+    ck.count[0] = ck.count[1] = 0;
     for (;;) {
         const uint32_t need = __ballot_sync(0xffffffffu, !active);
         if (__popc(need) >= 16) {  // refill only when at least half the warp is idle
@@ -181,8 +216,11 @@ __device__ __forceinline__ void walk_side(const WalkArgs& a, unsigned int n, uns
                 const unsigned int give = want < avail ? want : avail;
                 const unsigned int rank = (unsigned int)__popc(need & lt_mask);
                 if (!active && rank < give) {
-                    active = walk_load_item<IS_RIGHT>(a, next + rank, it);
+                    walk_load_item<IS_RIGHT>(a, next + rank, it);
+                    active = true;
                     budget_end = it.st.n + a.budget;
+                    ck.count[0] = ck.count[1] = 0;
+                    last_f = last_b = 0;
                 }
                 next += give;
             }
@@ -190,10 +228,12 @@ __device__ __forceinline__ void walk_side(const WalkArgs& a, unsigned int n, uns
         }
         if (active) {
             const int left = budget_end - it.st.n;
-            const int r = walk_resume_dir<IS_RIGHT>(it.ctx, it.x0, it.y0, a.max_len, left < 16 ? left : 16, &it.st);
-            if (!(r == WALK_CONTINUE && it.st.n < budget_end)) {
+            const int r = walk_resume_bidir<IS_RIGHT>(it.ctx, it.x0, it.y0, a.max_len, left < 16 ? left : 16, &it.st);
+            if (r == WALK_CONTINUE && it.st.n < budget_end) {
+                walk_checkpoint(it.st, &ck, &last_f, &last_b);
+            } else {
                 active = false;
-                walk_retire<IS_RIGHT>(a, r, it);
+                walk_retire<IS_RIGHT>(a, r, it.xy0, it.meta, it.st, it.ctx, &ck);
             }
         }
     }
@@ -231,20 +271,20 @@ struct EmitArgs {
     const uint32_t* halo;
     const uint8_t* lut_prev;
     const uint8_t* lut_next;
-    const ChainRec* chains;
+    const SegRec* segs;
     Pt16* points;
     const Counters* counters;
     unsigned int* work_counter;
-    unsigned int max_chains;
+    unsigned int max_segs;
     FrameGeom g;
 };
 
 __global__ void __launch_bounds__(64) k_emit(const EmitArgs a) {
-    // Chains are appended by the walk rounds in order of growing length, so they are handed out from
-    // the END of the list (longest first), 32 at a time per warp through one atomic: long chains start
-    // immediately and the short ones fill the tail of the kernel.
-    unsigned int n = a.counters->n_chains;
-    n = n < a.max_chains ? n : a.max_chains;
+    // One thread per contour segment (contour_walk.cuh): at most ~FID_CKPT_STEP + one walk pass dependent
+    // steps each.  Segments are handed out 32 at a time per warp through one atomic, from the END of
+    // the list: the long-contour segments of the last walk round start first.
+    unsigned int n = a.counters->n_segs;
+    n = n < a.max_segs ? n : a.max_segs;
     const unsigned int lane = threadIdx.x & 31;
     for (;;) {
         unsigned int base = 0;
@@ -253,12 +293,11 @@ __global__ void __launch_bounds__(64) k_emit(const EmitArgs a) {
         if (base >= n) break;
         const unsigned int k = base + lane;
         if (k < n) {
-            const ChainRec c = a.chains[n - 1 - k];
-            if (c.n != 0) {
-                const int f = c.meta >> 8, s = (c.meta >> 1) & 0x7F, is_right = c.meta & 1;
-                const WalkCtx ctx{HaloView{a.halo + (size_t)f * a.g.halo_frame_stride + (size_t)s * a.g.halo_scale_stride, a.g.halo_tpr}, a.lut_prev, a.lut_next};
-                trace_forward(ctx, c.xy & 0xFFFF, c.xy >> 16, is_right, (int)c.n, a.points + c.offset);
-            }
+            const uint4 w = *reinterpret_cast<const uint4*>(a.segs + (n - 1 - k));
+            const SegRec sr{w.x, w.y, w.z, w.w};
+            const int f = sr.meta >> 8, s = (sr.meta >> 1) & 0x7F;
+            const WalkCtx ctx{HaloView{a.halo + (size_t)f * a.g.halo_frame_stride + (size_t)s * a.g.halo_scale_stride, a.g.halo_tpr}, a.lut_prev, a.lut_next};
+            trace_segment(ctx, sr, reinterpret_cast<uint32_t*>(a.points));
         }
         __syncwarp();
     }

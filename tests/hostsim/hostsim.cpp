@@ -86,11 +86,39 @@ struct HostWalk {  // thin adapter kept for the harness below
 
 extern "C" {
 
+// Walk + emission exactly as the GPU does them: `uni` one-directional steps (round 0), then the
+// bidirectional walk in passes of `pass` steps with checkpoints every `ck_step` steps, then one
+// trace_segment per segment.  Returns WALK_* and fills pts (n points) for a canonical start.
+static int walk_and_emit(const WalkCtx& ctx, const Start& s, int max_len, int uni, int pass, int ck_step, std::vector<uint32_t>& pts, int* n_out) {
+    WalkState st;
+    if (walk_init(ctx, s.x, s.y, s.is_right, &st) != WALK_CONTINUE) return WALK_ABORT;
+    int r = uni > 0 ? walk_resume(ctx, s.x, s.y, s.is_right, max_len, uni, &st) : WALK_CONTINUE;
+    WalkState2 s2;
+    if (s.is_right) walk_split<true>(s.x, s.y, st, &s2); else walk_split<false>(s.x, s.y, st, &s2);
+    WalkCkpt ck;
+    ck.count[0] = ck.count[1] = 0;
+    int last_f = 0, last_b = 0;
+    while (r == WALK_CONTINUE) {
+        r = s.is_right ? walk_resume_bidir<true>(ctx, s.x, s.y, max_len, pass, &s2) : walk_resume_bidir<false>(ctx, s.x, s.y, max_len, pass, &s2);
+        if (r == WALK_CONTINUE && ck_step > 0) walk_checkpoint(s2, &ck, &last_f, &last_b, ck_step);
+    }
+    if (r != WALK_CANONICAL) return r;
+    const int n = s2.n;
+    *n_out = n;
+    pts.assign((size_t)n, 0xFFFFFFFFu);
+    std::vector<SegRec> segs((size_t)segment_count(&ck));
+    make_segments(ctx, s.x, s.y, s.is_right, n, s2.nf, &ck, 0u, 0u, [&](int k, const SegRec& sr) { segs[(size_t)k] = sr; });
+    for (const SegRec& sr : segs) trace_segment(ctx, sr, pts.data());
+    return r;
+}
+
 // All contours of a {0,!=0} plane with min_len <= n <= max_len, in cv2.findContours list order.
 // out_pts: (x,y) int16 pairs, out_len: per-contour lengths.  Returns the number of contours, or
-// -1 if a buffer is too small.  *n_walk_steps returns the total number of reverse-walk steps taken.
-int hs_find_contours(const uint8_t* plane, int W, int H, int min_len, int max_len, int16_t* out_pts, int64_t max_pts, int32_t* out_len, int max_contours,
-                     int64_t* n_starts_out) {
+// -1 if a buffer is too small.  mode 0: one-directional walk + trace_forward; mode 1: the GPU's
+// round structure (8 one-directional steps, bidirectional passes of 16, checkpoints, segments);
+// mode 2: same with tiny passes/checkpoint spacing to exercise every code path on small planes.
+int hs_find_contours_mode(const uint8_t* plane, int W, int H, int min_len, int max_len, int16_t* out_pts, int64_t max_pts, int32_t* out_len, int max_contours,
+                          int64_t* n_starts_out, int mode) {
     HostPlane mask;
     pack_plane(plane, W, H, mask);
     std::vector<Start> starts;
@@ -101,17 +129,24 @@ int hs_find_contours(const uint8_t* plane, int W, int H, int min_len, int max_le
     struct Chain {
         int64_t key;
         int x, y, is_right, n;
+        std::vector<uint32_t> pts;
     };
     std::vector<Chain> chains;
     for (const Start& s : starts) {
         int n = 0;
-        int st = walk_start(hw.ctx(), s.x, s.y, s.is_right, max_len, &n);
-        if (st == WALK_CANONICAL && n >= min_len) chains.push_back({((int64_t)s.y * W + s.x) * 2 + s.is_right, s.x, s.y, s.is_right, n});
+        std::vector<uint32_t> pts;
+        int st;
+        if (mode == 0)
+            st = walk_start(hw.ctx(), s.x, s.y, s.is_right, max_len, &n);
+        else
+            st = walk_and_emit(hw.ctx(), s, max_len, mode == 1 ? 8 : 1, mode == 1 ? 16 : 2, mode == 1 ? FID_CKPT_STEP : 3, pts, &n);
+        if (st == WALK_CANONICAL && n >= min_len) chains.push_back({((int64_t)s.y * W + s.x) * 2 + s.is_right, s.x, s.y, s.is_right, n, std::move(pts)});
     }
     if (min_len <= 1) {  // isolated pixels are 1-point outer contours
         for (int y = 0; y < H; y++)
             for (int x = 0; x < W; x++)
-                if (plane[(size_t)y * W + x] && (mask.ctx().plane.idx9(x, y) & ~0x10u) == 0u) chains.push_back({((int64_t)y * W + x) * 2, x, y, 0, 1});
+                if (plane[(size_t)y * W + x] && (mask.ctx().plane.idx9(x, y) & ~0x10u) == 0u)
+                    chains.push_back({((int64_t)y * W + x) * 2, x, y, 0, 1, std::vector<uint32_t>{(uint32_t)x | ((uint32_t)y << 16)}});
     }
     std::sort(chains.begin(), chains.end(), [](const Chain& a, const Chain& b) { return a.key > b.key; });  // reverse discovery order
     if ((int)chains.size() > max_contours) return -1;
@@ -119,13 +154,22 @@ int hs_find_contours(const uint8_t* plane, int W, int H, int min_len, int max_le
     for (size_t i = 0; i < chains.size(); i++) {
         const Chain& c = chains[i];
         if (off + c.n > max_pts) return -1;
-        std::vector<Pt16> tmp((size_t)c.n + 4);
-        trace_forward(hw.ctx(), c.x, c.y, c.is_right, c.n, tmp.data());
-        memcpy(reinterpret_cast<Pt16*>(out_pts) + off, tmp.data(), sizeof(Pt16) * c.n);
+        if (mode == 0 && c.n > 1) {
+            std::vector<Pt16> tmp((size_t)c.n + 4);
+            trace_forward(hw.ctx(), c.x, c.y, c.is_right, c.n, tmp.data());
+            memcpy(reinterpret_cast<Pt16*>(out_pts) + off, tmp.data(), sizeof(Pt16) * c.n);
+        } else {
+            memcpy(reinterpret_cast<Pt16*>(out_pts) + off, c.pts.data(), sizeof(Pt16) * c.n);
+        }
         out_len[i] = c.n;
         off += c.n;
     }
     return (int)chains.size();
+}
+
+int hs_find_contours(const uint8_t* plane, int W, int H, int min_len, int max_len, int16_t* out_pts, int64_t max_pts, int32_t* out_len, int max_contours,
+                     int64_t* n_starts_out) {
+    return hs_find_contours_mode(plane, W, H, min_len, max_len, out_pts, max_pts, out_len, max_contours, n_starts_out, 1);
 }
 
 // Walk statistics of one plane: out[0] starts, [1] total reverse-walk steps, [2] walks > 64 steps,
@@ -221,6 +265,92 @@ void hs_walk_sim(const uint8_t* plane, int W, int H, int max_len, const int* bud
         }
         cur.swap(nxt);
     }
+}
+
+// Round-based walk with bidirectional walkers from round `bidir_from` on (contour_walk.cuh,
+// walk_resume_bidir).  out[r] = steps in round r, out[8+r] = walks entering round r, out[16] = canonical
+// walks found, out[17] = sum of their lengths, out[18] = too-long walks.
+void hs_walk_sim2(const uint8_t* plane, int W, int H, int max_len, const int* budgets, int n_rounds, int bidir_from, int64_t* out) {
+    HostPlane mask;
+    pack_plane(plane, W, H, mask);
+    std::vector<Start> starts;
+    find_starts(mask, starts);
+    HostWalk hw;
+    hw.build(mask);
+    struct Live { Start s; WalkState st; WalkState2 s2; bool split; };
+    std::vector<Live> cur, nxt;
+    for (int i = 0; i < 24; i++) out[i] = 0;
+    const WalkCtx ctx = hw.ctx();
+    for (const Start& s : starts) {
+        Live l;
+        l.s = s;
+        l.split = false;
+        if (walk_init(ctx, s.x, s.y, s.is_right, &l.st) == WALK_CONTINUE) cur.push_back(l);
+    }
+    for (int r = 0; r < n_rounds; r++) {
+        out[8 + r] = (int64_t)cur.size();
+        nxt.clear();
+        for (Live& l : cur) {
+            const int x0 = l.s.x, y0 = l.s.y;
+            int res, before, after;
+            if (r >= bidir_from) {
+                if (!l.split) {
+                    if (l.s.is_right) walk_split<true>(x0, y0, l.st, &l.s2); else walk_split<false>(x0, y0, l.st, &l.s2);
+                    l.split = true;
+                }
+                before = l.s2.n;
+                res = l.s.is_right ? walk_resume_bidir<true>(ctx, x0, y0, max_len, budgets[r], &l.s2) : walk_resume_bidir<false>(ctx, x0, y0, max_len, budgets[r], &l.s2);
+                after = l.s2.n;
+            } else {
+                before = l.st.n;
+                res = l.s.is_right ? walk_resume_dir<true>(ctx, x0, y0, max_len, budgets[r], &l.st) : walk_resume_dir<false>(ctx, x0, y0, max_len, budgets[r], &l.st);
+                after = l.st.n;
+            }
+            out[r] += after - before;
+            if (res == WALK_CONTINUE) nxt.push_back(l);
+            if (res == WALK_CANONICAL) { out[16]++; out[17] += after; }
+            if (res == WALK_TOO_LONG) out[18]++;
+        }
+        cur.swap(nxt);
+    }
+}
+
+// Every start crack of the plane walked one-directionally and bidirectionally (after `uni_steps` steps of
+// the one-directional walk, as the GPU does between round 0 and round 1): number of starts whose
+// (result, contour length) differ.  out[0] = starts, out[1] = canonical.
+int hs_walk_bidir_check(const uint8_t* plane, int W, int H, int max_len, int uni_steps, int chunk, int64_t* out) {
+    HostPlane mask;
+    pack_plane(plane, W, H, mask);
+    std::vector<Start> starts;
+    find_starts(mask, starts);
+    HostWalk hw;
+    hw.build(mask);
+    const WalkCtx ctx = hw.ctx();
+    int bad = 0;
+    out[0] = (int64_t)starts.size();
+    out[1] = 0;
+    for (const Start& s : starts) {
+        int n1 = 0;
+        const int r1 = walk_start(ctx, s.x, s.y, s.is_right, max_len, &n1);
+        WalkState st;
+        int r2 = walk_init(ctx, s.x, s.y, s.is_right, &st), n2 = 0;
+        if (r2 == WALK_CONTINUE) {
+            r2 = uni_steps > 0 ? walk_resume(ctx, s.x, s.y, s.is_right, max_len, uni_steps, &st) : WALK_CONTINUE;
+            n2 = st.n;
+            if (r2 == WALK_CONTINUE) {
+                WalkState2 s2;
+                if (s.is_right) walk_split<true>(s.x, s.y, st, &s2); else walk_split<false>(s.x, s.y, st, &s2);
+                do {
+                    r2 = s.is_right ? walk_resume_bidir<true>(ctx, s.x, s.y, max_len, chunk, &s2) : walk_resume_bidir<false>(ctx, s.x, s.y, max_len, chunk, &s2);
+                } while (r2 == WALK_CONTINUE);
+                n2 = s2.n;
+            }
+        }
+        if (r1 == WALK_CANONICAL) out[1]++;
+        // ABORT and TOO_LONG both mean "no contour": which one is hit first depends on the direction walked
+        if ((r1 == WALK_CANONICAL) != (r2 == WALK_CANONICAL) || (r1 == WALK_CANONICAL && n1 != n2)) bad++;
+    }
+    return bad;
 }
 
 // approxPolyDP (closed) of one contour; returns vertex count (-1 = more than 8 before clean-up).

@@ -22,7 +22,7 @@ def load():
     return _lib
 
 
-def find_contours(plane, min_len=1, max_len=1 << 30):
+def find_contours(plane, min_len=1, max_len=1 << 30, mode=1):
     lib = load()
     plane = np.ascontiguousarray(plane, np.uint8)
     H, W = plane.shape
@@ -30,8 +30,8 @@ def find_contours(plane, min_len=1, max_len=1 << 30):
     pts = np.zeros((max_pts, 2), np.int16)
     lens = np.zeros(plane.size + 16, np.int32)
     nstarts = C.c_int64(0)
-    n = lib.hs_find_contours(plane.ctypes.data_as(C.c_void_p), W, H, min_len, min(max_len, 1 << 30), pts.ctypes.data_as(C.c_void_p), C.c_int64(max_pts),
-                             lens.ctypes.data_as(C.c_void_p), len(lens), C.byref(nstarts))
+    n = lib.hs_find_contours_mode(plane.ctypes.data_as(C.c_void_p), W, H, min_len, min(max_len, 1 << 30), pts.ctypes.data_as(C.c_void_p), C.c_int64(max_pts),
+                                  lens.ctypes.data_as(C.c_void_p), len(lens), C.byref(nstarts), mode)
     assert n >= 0
     out = []
     off = 0

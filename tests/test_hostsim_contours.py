@@ -14,14 +14,18 @@ def _same(a, b):
     return len(a) == len(b) and all(x.shape == y.shape and np.array_equal(x, y) for x, y in zip(a, b))
 
 
+MODES = (0, 1, 2)  # one-directional walk; the GPU's rounds + segments; the same with tiny passes/checkpoints
+
+
 @pytest.mark.parametrize("density", [0.2, 0.4, 0.5, 0.6, 0.8])
 def test_find_contours_noise(density):
     rng = np.random.default_rng(int(density * 100))
     for shape in [(37, 53), (64, 64), (120, 161)]:
         plane = (rng.random(shape) < density).astype(np.uint8)
-        ours, _ = hs.find_contours(plane)
         ref = ao.find_contours(plane)
-        assert _same(ours, ref)
+        for mode in MODES:
+            ours, _ = hs.find_contours(plane, mode=mode)
+            assert _same(ours, ref)
 
 
 def test_find_contours_blobs_and_edges():
@@ -36,14 +40,16 @@ def test_find_contours_blobs_and_edges():
         cv2.line(img, p0, p1, int(rng.integers(0, 2)), int(rng.integers(1, 4)))
     img[0, :] = 1  # touches the frame
     img[:, -1] = 1
-    ours, _ = hs.find_contours(img)
-    assert _same(ours, ao.find_contours(img))
+    for mode in MODES:
+        ours, _ = hs.find_contours(img, mode=mode)
+        assert _same(ours, ao.find_contours(img))
 
 
 def test_find_contours_degenerate():
     for plane in [np.zeros((5, 7), np.uint8), np.ones((5, 7), np.uint8), np.eye(9, dtype=np.uint8), np.ones((1, 40), np.uint8), np.ones((33, 1), np.uint8)]:
-        ours, _ = hs.find_contours(plane)
-        assert _same(ours, ao.find_contours(plane))
+        for mode in MODES:
+            ours, _ = hs.find_contours(plane, mode=mode)
+            assert _same(ours, ao.find_contours(plane))
 
 
 @pytest.mark.parametrize("cfg,seed", [("C1", 0), ("C1", 1), ("C3", 2)])
@@ -52,9 +58,44 @@ def test_find_contours_threshold_planes(cfg, seed):
     g = ao.gray(bgr)
     planes = ao.threshold_planes(g)
     for s in (0, 3, 12):
-        ours, nstarts = hs.find_contours(planes[s])
         ref = ao.find_contours(planes[s])
-        assert _same(ours, ref)
+        for mode in MODES:
+            ours, nstarts = hs.find_contours(planes[s], mode=mode)
+            assert _same(ours, ref)
+
+
+def _bidir_mismatches(plane, max_len, uni_steps, chunk):
+    import ctypes as C
+    lib = hs.load()
+    lib.hs_walk_bidir_check.restype = C.c_int
+    lib.hs_walk_bidir_check.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    plane = np.ascontiguousarray(plane, np.uint8)
+    out = np.zeros(2, np.int64)
+    bad = lib.hs_walk_bidir_check(plane.ctypes.data, plane.shape[1], plane.shape[0], max_len, uni_steps, chunk, out.ctypes.data)
+    return bad, int(out[0]), int(out[1])
+
+
+def test_bidirectional_walk_equals_one_directional():
+    """walk_resume_bidir (rounds >= 1 of k_walk) decides every start crack exactly like the one-directional
+    walk that is pinned to cv2.findContours above: same verdict, same contour length."""
+    rng = np.random.default_rng(11)
+    planes = [(rng.random((90, 131)) < d).astype(np.uint8) for d in (0.3, 0.5, 0.62, 0.8)]
+    img = np.zeros((200, 260), np.uint8)
+    for _ in range(40):
+        cv2.circle(img, (int(rng.integers(0, 260)), int(rng.integers(0, 200))), int(rng.integers(2, 30)), 1, int(rng.choice([-1, 1, 2, 3])))
+    img[0, :] = 1
+    img[:, -1] = 1
+    planes += [img, np.eye(9, dtype=np.uint8), np.ones((5, 7), np.uint8), np.ones((1, 40), np.uint8), np.ones((33, 1), np.uint8)]
+    bgr, *_ = synth.make_config_frame("C1", 3)
+    tp = ao.threshold_planes(ao.gray(bgr))
+    planes += [tp[1], tp[12]]
+    total = 0
+    for plane in planes:
+        for max_len, uni, chunk in [(1 << 20, 0, 2), (1 << 20, 8, 64), (1 << 20, 3, 16), (40, 8, 6), (41, 0, 1 << 20)]:
+            bad, n_starts, n_canon = _bidir_mismatches(plane, max_len, uni, chunk)
+            assert bad == 0
+            total += n_canon
+    assert total > 1000
 
 
 def test_length_filter_matches(kat):

@@ -20,3 +20,5 @@ for it in range(4):
     t2 = time.perf_counter()
     st = det.last_stage_ms()
     print("iter", it, "detect %.1f ms  map %.1f ms  stage sum %.1f  entries %d markers %d" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3, sum(v for k, v in st.items() if not k.startswith("walk_r")), len(slam.entries()), int(counts.sum())))
+print({k: round(v, 3) for k, v in det.last_stage_ms().items() if v > 0.002})
+print("counters", det.last_counters() if hasattr(det, "last_counters") else None)
