@@ -76,23 +76,25 @@ FID_HD int mask_from_idx9(uint32_t v) {
                  (((d >> 2) & 1u) << 7));
 }
 
-// Step tables, 512 neighbourhoods x 8 incoming directions, one byte each:
+// Step tables, 512 neighbourhoods x 8 incoming directions, one 32-bit word each:
 //   prev[idx9*8 + b] : a = first foreground neighbour clockwise from b      (backwards step)
 //   next[idx9*8 + a] : b = first foreground neighbour counter-clockwise from a (forwards step)
-// bits 0-2 = the direction found, bit 3 = left crack examined, bit 4 = right crack examined.
+// bits 0-2 = the direction found, bit 3 = left crack examined, bit 4 = right crack examined,
+// bits 5.. = the move in that direction on a packed pixel (y << 16 | x): (dy << 16) + dx + 65537.
 #define FID_LUT_SIZE 4096
-inline void build_step_tables(uint8_t* prev, uint8_t* next) {
+FID_HD uint32_t pack_move(int dir) { return (uint32_t)(dir_dy(dir) * 65536 + dir_dx(dir) + 65537); }
+inline void build_step_tables(uint32_t* prev, uint32_t* next) {
     for (int v = 0; v < 512; v++) {
         const int m = mask_from_idx9((uint32_t)v);
         for (int dir = 0; dir < 8; dir++) {
-            uint8_t ep = 0, en = 0;
+            uint32_t ep = 0, en = 0;
             if (m != 0) {
                 const int a = prev_cw(m, dir);  // backwards: arrive with dir-to-next = dir
                 int d = (dir - a - 1) & 7;
-                ep = (uint8_t)(a | ((((4 - a - 1) & 7) < d) ? 8 : 0) | ((((0 - a - 1) & 7) < d) ? 16 : 0));
+                ep = (uint32_t)(a | ((((4 - a - 1) & 7) < d) ? 8 : 0) | ((((0 - a - 1) & 7) < d) ? 16 : 0)) | (pack_move(a) << 5);
                 const int b = next_ccw(m, dir);  // forwards: arrive with dir-to-previous = dir
                 d = (b - dir - 1) & 7;
-                en = (uint8_t)(b | ((((4 - dir - 1) & 7) < d) ? 8 : 0) | ((((0 - dir - 1) & 7) < d) ? 16 : 0));
+                en = (uint32_t)(b | ((((4 - dir - 1) & 7) < d) ? 8 : 0) | ((((0 - dir - 1) & 7) < d) ? 16 : 0)) | (pack_move(b) << 5);
             }
             prev[v * 8 + dir] = ep;
             next[v * 8 + dir] = en;
@@ -102,11 +104,11 @@ inline void build_step_tables(uint8_t* prev, uint8_t* next) {
 
 struct WalkCtx {
     HaloView plane;
-    const uint8_t* lut_prev;
-    const uint8_t* lut_next;
+    const uint32_t* lut_prev;
+    const uint32_t* lut_next;
 };
 
-FID_HD uint8_t lut_load(const uint8_t* p) {
+FID_HD uint32_t lut_load(const uint32_t* p) {
 #if defined(__CUDA_ARCH__)
     return __ldg(p);
 #else
@@ -168,7 +170,7 @@ template <bool IS_RIGHT, class Visit = NoVisit>
 FID_HD int walk_resume_dir(const WalkCtx& c, int x0, int y0, int max_len, int budget, WalkState* st, const Visit& visit = Visit()) {
     int x = st->x, y = st->y, n = st->n, dir = st->dir;
     const int ref = IS_RIGHT ? st->a0 : st->b0;  // closing condition: arrive at the start with this direction
-    const uint8_t* lut = IS_RIGHT ? c.lut_next : c.lut_prev;
+    const uint32_t* lut = IS_RIGHT ? c.lut_next : c.lut_prev;
     const int stop_at = n + budget;
     int result = WALK_CONTINUE;
     while (n < stop_at) {
@@ -287,6 +289,111 @@ FID_HD int walk_resume_bidir(const WalkCtx& c, int x0, int y0, int max_len, int 
     return result;
 }
 
+// ---- hot-loop versions ----------------------------------------------------------------------------------
+// Same walks on packed pixels (y << 16 | x: raster order is unsigned integer order, a move is one add of
+// the table's packed delta) with 32-bit index arithmetic and the per-step max_len test hoisted out of the
+// loop.  A warp executes its instruction stream in order, so the length of the longest walk of a launch
+// times the instructions per step IS the tail latency of the launch: these loops are written for
+// instruction count.  Results are identical to walk_resume_dir / walk_resume_bidir
+// (tests/test_hostsim_contours.py).
+FID_HD uint32_t idx9_packed(const uint32_t* plane, uint32_t tiles_per_row, uint32_t xy) {
+    const uint32_t x = xy & 0xFFFFu, y = xy >> 16;
+    const uint32_t qx = (x * 34953u) >> 20, qy = (y * 34953u) >> 20;
+    const uint32_t i = x - FID_HALO_T * qx;
+    const uint32_t* t = plane + ((qy * tiles_per_row + qx) * 32u + (y - FID_HALO_T * qy));
+    return ((t[0] >> i) & 7u) | (((t[1] >> i) & 7u) << 3) | (((t[2] >> i) & 7u) << 6);
+}
+FID_HD uint32_t entry_of_dir(int dir) { return (uint32_t)dir | (pack_move(dir) << 5); }
+#define FID_MOVE(xy, e) ((xy) + ((e) >> 5) - 65537u)
+
+// One-directional walk of at most `budget` steps (round 0).
+template <bool IS_RIGHT>
+FID_HD int walk_uni_fast(const WalkCtx& c, int x0, int y0, int max_len, int budget, WalkState* st) {
+    const uint32_t* plane = c.plane.base;
+    const uint32_t tpr = (uint32_t)c.plane.tiles_per_row;
+    const uint32_t* lut = IS_RIGHT ? c.lut_next : c.lut_prev;
+    const uint32_t xy0 = (uint32_t)x0 | ((uint32_t)y0 << 16);
+    const uint32_t ref = (uint32_t)(IS_RIGHT ? st->a0 : st->b0);
+    uint32_t xy = (uint32_t)st->x | ((uint32_t)st->y << 16);
+    uint32_t e = entry_of_dir(st->dir);
+    int result = WALK_CONTINUE, k = 0;
+    for (; k < budget; k++) {
+        xy = FID_MOVE(xy, e);
+        const uint32_t back = (e & 7u) ^ 4u;
+        if (xy == xy0 && back == ref) {
+            result = WALK_CANONICAL;
+            k++;
+            break;
+        }
+        e = lut_load(lut + idx9_packed(plane, tpr, xy) * 8u + back);
+        if ((e & 0x18u) && (xy < xy0 || (IS_RIGHT && (e & 8u) && xy == xy0))) {
+            result = WALK_ABORT;
+            k++;
+            break;
+        }
+    }
+    st->x = (int)(xy & 0xFFFFu);
+    st->y = (int)(xy >> 16);
+    st->dir = (int)(e & 7u);
+    st->n += k;
+    if (st->n > max_len && result != WALK_ABORT) result = WALK_TOO_LONG;
+    return result;
+}
+
+// Bidirectional walk of at most `budget` steps (budget/2 lock-step iterations).
+template <bool IS_RIGHT>
+FID_HD int walk_bidir_fast(const WalkCtx& c, int x0, int y0, int max_len, int budget, WalkState2* st) {
+    const uint32_t* plane = c.plane.base;
+    const uint32_t tpr = (uint32_t)c.plane.tiles_per_row;
+    const uint32_t xy0 = (uint32_t)x0 | ((uint32_t)y0 << 16);
+    uint32_t xyf = (uint32_t)st->xf | ((uint32_t)st->yf << 16), xyb = (uint32_t)st->xb | ((uint32_t)st->yb << 16);
+    uint32_t ef = entry_of_dir(st->df), eb = entry_of_dir(st->db);
+    const int iters = (budget + 1) >> 1;
+    int result = WALK_CONTINUE, it = 0, half = 0;
+    for (; it < iters; it++) {
+        // both moves and both table look-ups first (two independent chains), then the tests in walk order
+        const uint32_t xyf1 = FID_MOVE(xyf, ef), xyb1 = FID_MOVE(xyb, eb);
+        const uint32_t back_f = (ef & 7u) ^ 4u, back_b = (eb & 7u) ^ 4u;
+        const uint32_t ef1 = lut_load(c.lut_next + idx9_packed(plane, tpr, xyf1) * 8u + back_f);
+        const uint32_t eb1 = lut_load(c.lut_prev + idx9_packed(plane, tpr, xyb1) * 8u + back_b);
+        const uint32_t db = eb & 7u;
+        xyf = xyf1;
+        if (xyf1 == xyb && back_f == db) {  // the forward walker arrived on the backward walker's state
+            result = WALK_CANONICAL;
+            half = 1;
+            break;
+        }
+        ef = ef1;
+        if ((ef1 & 0x18u) && (xyf1 < xy0 || (IS_RIGHT && (ef1 & 8u) && xyf1 == xy0))) {
+            result = WALK_ABORT;
+            half = 1;
+            break;
+        }
+        xyb = xyb1;
+        if (xyb1 == xyf1 && back_b == (ef1 & 7u)) {  // the backward walker arrived on the forward walker's new state
+            result = WALK_CANONICAL;
+            half = 2;
+            break;
+        }
+        eb = eb1;
+        if ((eb1 & 0x18u) && (xyb1 < xy0 || (IS_RIGHT && (eb1 & 8u) && xyb1 == xy0))) {
+            result = WALK_ABORT;
+            half = 2;
+            break;
+        }
+    }
+    st->xf = (int)(xyf & 0xFFFFu);
+    st->yf = (int)(xyf >> 16);
+    st->df = (int)(ef & 7u);
+    st->xb = (int)(xyb & 0xFFFFu);
+    st->yb = (int)(xyb >> 16);
+    st->db = (int)(eb & 7u);
+    st->n += 2 * it + half;
+    st->nf += it + (half ? 1 : 0);
+    if (st->n > max_len && result != WALK_ABORT) result = WALK_TOO_LONG;
+    return result;
+}
+
 FID_HD int walk_resume(const WalkCtx& c, int x0, int y0, int is_right, int max_len, int budget, WalkState* st) {
     return is_right ? walk_resume_dir<true>(c, x0, y0, max_len, budget, st) : walk_resume_dir<false>(c, x0, y0, max_len, budget, st);
 }
@@ -360,23 +467,22 @@ struct WalkCkpt {
 // forward: points[off + t] = pixel after t steps, t = 0 .. count-1
 // backward: points[off - t] = pixel after t steps, t = 1 .. count
 FID_HD void trace_segment(const WalkCtx& c, const SegRec& s, uint32_t* points) {
-    int x = (int)(s.xy & 0xFFFF), y = (int)(s.xy >> 16), dir = (int)(s.dn & 7);
+    const uint32_t* plane = c.plane.base;
+    const uint32_t tpr = (uint32_t)c.plane.tiles_per_row;
+    uint32_t xy = s.xy, e = entry_of_dir((int)(s.dn & 7));
     const int count = (int)(s.dn >> 3);
+    uint32_t* out = points + s.off;
     if (s.meta & 1u) {
-        uint32_t* out = points + s.off;
         for (int t = 1; t <= count; t++) {
-            x += dir_dx(dir);
-            y += dir_dy(dir);
-            out[-t] = (uint32_t)x | ((uint32_t)y << 16);
-            dir = lut_load(c.lut_prev + c.plane.idx9(x, y) * 8 + ((dir + 4) & 7)) & 7;
+            xy = FID_MOVE(xy, e);
+            out[-t] = xy;
+            e = lut_load(c.lut_prev + idx9_packed(plane, tpr, xy) * 8u + ((e & 7u) ^ 4u));
         }
     } else {
-        uint32_t* out = points + s.off;
         for (int t = 0; t < count; t++) {
-            out[t] = (uint32_t)x | ((uint32_t)y << 16);
-            x += dir_dx(dir);
-            y += dir_dy(dir);
-            dir = lut_load(c.lut_next + c.plane.idx9(x, y) * 8 + ((dir + 4) & 7)) & 7;
+            out[t] = xy;
+            xy = FID_MOVE(xy, e);
+            e = lut_load(c.lut_next + idx9_packed(plane, tpr, xy) * 8u + ((e & 7u) ^ 4u));
         }
     }
 }
@@ -440,7 +546,7 @@ FID_HD void walk_checkpoint(const WalkState2& st, WalkCkpt* ck, int* last_f, int
 }
 
 // ---- start cracks of one halo-tile row -----------------------------------------------------------------
-// up / mid = words r-1 / r of a tile (r = 1..30); only interior bits 1..30 are reported.  Every
+// up / mid / dn = words r-1 / r / r+1 of a tile (r = 1..30); only interior bits 1..30 are reported.  Every
 // left/right crack is a potential Suzuki start; the ones that a walk would discard within its first
 // step are removed here with bit operations (all rules are exact -- they only drop cracks whose
 // walk provably aborts, so the set of canonical starts is unchanged):
@@ -449,14 +555,16 @@ FID_HD void walk_checkpoint(const WalkState2& st, WalkCkpt* ck, int* last_f, int
 //       (x+1,y-1), whose left neighbour (x,y-1) is an examined zero: raster-smaller left crack
 //   L2  up-left foreground, (x-2,y) and (x-2,y-1) zero               -> first backward step lands on
 //       (x-1,y-1) which owns a left crack
-// and the mirror images R0..R2 for right cracks (forward walk).
-FID_HD void halo_row_starts(uint32_t up, uint32_t mid, uint32_t* L, uint32_t* R) {
+// and the mirror images R0..R2 for right cracks (forward walk); I0 drops isolated pixels.
+FID_HD void halo_row_starts(uint32_t up, uint32_t mid, uint32_t dn, uint32_t* L, uint32_t* R) {
     const uint32_t interior = 0x7FFFFFFEu;
     const uint32_t up_l = up << 1, up_r = up >> 1, mid_l = mid << 1, mid_r = mid >> 1;
-    uint32_t l = mid & ~mid_l & ~(up & ~up_l);
+    // I0: an isolated pixel is a 1-point contour (walk_init gives up on it)
+    const uint32_t lone = mid & ~(up | up_l | up_r | mid_l | mid_r | dn | (dn << 1) | (dn >> 1));
+    uint32_t l = mid & ~mid_l & ~(up & ~up_l) & ~lone;
     l &= ~(~up & ~up_l & up_r);
     l &= ~(up_l & ~(mid << 2) & ~(up << 2) & 0xFFFFFFFCu);
-    uint32_t r = mid & ~mid_r & ~(up & ~up_r);
+    uint32_t r = mid & ~mid_r & ~(up & ~up_r) & ~lone;
     r &= ~(~up & ~up_r & up_l);
     r &= ~(up_r & ~(mid >> 2) & ~(up >> 2) & 0x3FFFFFFFu);
     *L = l & interior;

@@ -85,8 +85,8 @@ struct fid_detector {
     const uint8_t* hint_next = nullptr;
     int pf_idx = 0, pf_frames = 0, pf_w = 0, pf_h = 0;
     float* d_subpix_masks = nullptr;
-    uint8_t* d_lut_prev = nullptr;
-    uint8_t* d_lut_next = nullptr;
+    uint32_t* d_lut_prev = nullptr;
+    uint32_t* d_lut_next = nullptr;
     int walk_rounds = 0;
     int emit_blocks_per_sm = 8;
     int walk_budget[FID_WALK_MAX_ROUNDS]{};
@@ -325,14 +325,14 @@ extern "C" int fid_create(const fid_params* params, int device, int max_width, i
         CK(cudaMemcpy(h->d_subpix_masks, masks.data(), masks.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     {   // step tables of the border walk
-        std::vector<uint8_t> lp(FID_LUT_SIZE), ln(FID_LUT_SIZE);
+        std::vector<uint32_t> lp(FID_LUT_SIZE), ln(FID_LUT_SIZE);
         build_step_tables(lp.data(), ln.data());
         if ((rc = dalloc(&h->d_lut_prev, (size_t)FID_LUT_SIZE)) != FID_OK || (rc = dalloc(&h->d_lut_next, (size_t)FID_LUT_SIZE)) != FID_OK) {
             fid_destroy(h);
             return rc;
         }
-        CK(cudaMemcpy(h->d_lut_prev, lp.data(), FID_LUT_SIZE, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(h->d_lut_next, ln.data(), FID_LUT_SIZE, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->d_lut_prev, lp.data(), FID_LUT_SIZE * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(h->d_lut_next, ln.data(), FID_LUT_SIZE * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
     {   // walk plan: budgets per round, 'p' prefix = persistent lanes, 0 = unbounded (must be last)
         if (const char* e = getenv("FID_EMIT_BLOCKS")) h->emit_blocks_per_sm = std::max(1, atoi(e));
@@ -462,6 +462,9 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
         a.n_scales = P.n_scales;
         a.r_max = r_max_of(P);
         a.thresh_c = P.thresh_c;
+        a.starts = s.d_starts;
+        a.counters = s.d_counters;
+        a.max_starts = h->max_starts;
         bool fast = P.n_scales == 13;
         for (int i = 0; i < P.n_scales; i++) {
             a.win[i] = P.win[i];
@@ -476,22 +479,6 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
     }
     CK(cudaEventRecord(s.ev[ST_MASKS], st));
     if (stop_after == ST_THRESH) return FID_OK;
-    {  // start cracks
-        StartsArgs a{};
-        a.halo = s.d_halo;
-        a.starts = s.d_starts;
-        a.counters = s.d_counters;
-        a.max_starts = h->max_starts;
-        a.halo_tpr = g.halo_tpr;
-        a.halo_tiles_y = g.halo_tiles_y;
-        a.halo_scale_stride = g.halo_scale_stride;
-        a.halo_frame_stride = g.halo_frame_stride;
-        a.n_scales = P.n_scales;
-        a.n_frames = nf;
-        const long long total = (long long)nf * P.n_scales * (long long)g.halo_scale_stride;
-        k_starts<<<(unsigned int)((total + 255) / 256), 256, 0, st>>>(a);
-        launches++;
-    }
     CK(cudaEventRecord(s.ev[ST_WALK], st));
     const int mx = W > H ? W : H;
     const int min_len = (int)(P.min_perimeter_rate * mx), max_len = (int)(P.max_perimeter_rate * mx);

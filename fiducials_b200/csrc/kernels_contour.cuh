@@ -70,8 +70,8 @@ struct FrameGeom {
 // ---------------------------------------------------------------------------------------------------
 struct WalkArgs {
     const uint32_t* halo;
-    const uint8_t* lut_prev;
-    const uint8_t* lut_next;
+    const uint32_t* lut_prev;
+    const uint32_t* lut_next;
     const StartRec* starts;   // round 0 input: left items at [0, nL), right items at [max_starts-1 ...]
     const WalkRec* q_in;      // later rounds: left items at [0, nL), right items at [max_queue-1 ...]
     WalkRec* q_out;
@@ -173,7 +173,7 @@ __device__ __forceinline__ void walk_side(const WalkArgs& a, unsigned int n, uns
             const int x0 = sr.xy & 0xFFFF, y0 = sr.xy >> 16;
             WalkState st;
             if (walk_init(ctx, x0, y0, IS_RIGHT ? 1 : 0, &st) != WALK_CONTINUE) continue;
-            const int r = walk_resume_dir<IS_RIGHT>(ctx, x0, y0, a.max_len, a.budget, &st);
+            const int r = walk_uni_fast<IS_RIGHT>(ctx, x0, y0, a.max_len, a.budget, &st);
             WalkState2 s2;
             walk_split<IS_RIGHT>(x0, y0, st, &s2);
             walk_retire<IS_RIGHT>(a, r, sr.xy, sr.meta, s2, ctx, nullptr);
@@ -186,7 +186,7 @@ __device__ __forceinline__ void walk_side(const WalkArgs& a, unsigned int n, uns
             if (idx >= n) continue;
             WalkItem it;
             walk_load_item<IS_RIGHT>(a, idx, it);
-            const int r = walk_resume_bidir<IS_RIGHT>(it.ctx, it.x0, it.y0, a.max_len, a.budget, &it.st);
+            const int r = walk_bidir_fast<IS_RIGHT>(it.ctx, it.x0, it.y0, a.max_len, a.budget, &it.st);
             walk_retire<IS_RIGHT>(a, r, it.xy0, it.meta, it.st, it.ctx, nullptr);
         }
         return;
@@ -228,7 +228,7 @@ __device__ __forceinline__ void walk_side(const WalkArgs& a, unsigned int n, uns
         }
         if (active) {
             const int left = budget_end - it.st.n;
-            const int r = walk_resume_bidir<IS_RIGHT>(it.ctx, it.x0, it.y0, a.max_len, left < 16 ? left : 16, &it.st);
+            const int r = walk_bidir_fast<IS_RIGHT>(it.ctx, it.x0, it.y0, a.max_len, left < 16 ? left : 16, &it.st);
             if (r == WALK_CONTINUE && it.st.n < budget_end) {
                 walk_checkpoint(it.st, &ck, &last_f, &last_b);
             } else {
@@ -269,8 +269,8 @@ __global__ void __launch_bounds__(256) k_walk(const WalkArgs a) {
 // ---------------------------------------------------------------------------------------------------
 struct EmitArgs {
     const uint32_t* halo;
-    const uint8_t* lut_prev;
-    const uint8_t* lut_next;
+    const uint32_t* lut_prev;
+    const uint32_t* lut_next;
     const SegRec* segs;
     Pt16* points;
     const Counters* counters;

@@ -2,8 +2,8 @@
 //   k_gray       BGR8 -> gray (cv::cvtColor BGR2GRAY, 15-bit fixed point); 4 pixels per
 //                thread, 12-byte vector loads / 4-byte store
 //   k_threshold  gray -> n_scales adaptive-threshold planes, written directly as the
-//                bit-packed halo tiles the border walk reads (contour_walk.cuh, HaloView)
-//   k_starts     halo tiles -> start-crack queues (exact local prune), three words per thread
+//                bit-packed halo tiles the border walk reads (contour_walk.cuh, HaloView), plus the
+//                start-crack queues of the border walk (exact local prune) while the tiles are in registers
 //
 // k_threshold: one CTA per 120x60 output pixels = 4x2 halo tiles.  The CTA loads the gray region it
 // needs (output + 1 halo pixel + r_max on every side, replicate border) into shared memory, turns
@@ -78,6 +78,9 @@ struct ThreshArgs {
     int r_max;
     int thresh_c;
     int win[FID_MAX_SCALES];
+    StartRec* starts;      // start-crack queue: left cracks at [0, nL), right cracks at [max_starts-1 ...]
+    Counters* counters;
+    unsigned int max_starts;
 };
 
 __host__ __device__ inline size_t thresh_smem_bytes(int r_max) {
@@ -144,122 +147,112 @@ __global__ void __launch_bounds__(THR_THREADS, 2) k_threshold(const ThreshArgs a
         }
     }
     __syncthreads();
-    // D. one warp-iteration per tile word: unit = (tile row tyl, word r, tile column txl)
+    // D. one warp per halo tile: lane = bit position (column), loop over the 32 rows of the tile; lane r
+    //    keeps the word of row r for every scale, so at the end the warp holds the 13 finished tiles in
+    //    registers: one coalesced 128-byte store per scale, and the start cracks of the border walk
+    //    (contour_walk.cuh, halo_row_starts) come from two shuffles -- the planes are never read back.
+    //    Test: 2S >= (2g + 2C - 1) k^2 with an odd right-hand side  <=>  S >= g k^2 + ((2C-1) k^2 + 1)/2.
+    constexpr int NS = FAST ? 13 : FID_MAX_SCALES;
     const int twoC = 2 * a.thresh_c - 1;
-    for (int u = warp; u < THR_TILES_Y * 32 * THR_TILES_X; u += THR_THREADS / 32) {
-        const int txl = u % THR_TILES_X, r = (u / THR_TILES_X) & 31, tyl = u / (THR_TILES_X * 32);
-        const int tx = blockIdx.x * THR_TILES_X + txl, ty = blockIdx.y * THR_TILES_Y + tyl;
-        if (tx >= a.halo_tpr || ty >= a.halo_tiles_y) continue;  // warp-uniform
-        const int X = X0 + FID_HALO_T * txl - 1 + lane, Y = Y0 + FID_HALO_T * tyl - 1 + r;
-        const bool valid = X >= 0 && X < W && Y >= 0 && Y < H;
-        const int cx = FID_HALO_T * txl + lane + R, cy = FID_HALO_T * tyl + r + R;  // region coordinates
-        const uint32_t* p = sat + cy * SP + cx;  // table entry "above-left" of the pixel
-        const int g = (int)(p[SP + 1] - p[1] - p[SP] + p[0]);
-        const int g2 = 2 * g + twoC;
-        uint32_t* out = a.halo + (size_t)f * a.halo_frame_stride + ((size_t)ty * a.halo_tpr + tx) * 32 + r;
-        if (FAST) {
+    const int txl = warp % THR_TILES_X, tyl = warp / THR_TILES_X;
+    const int tx = blockIdx.x * THR_TILES_X + txl, ty = blockIdx.y * THR_TILES_Y + tyl;
+    if (tx >= a.halo_tpr || ty >= a.halo_tiles_y) return;  // warp-uniform; no block barrier below
+    uint32_t acc[NS];
+    int kk[NS], ck[NS], off_br[NS], off_bl[NS], off_tr[NS], off_tl[NS];
 #pragma unroll
-            for (int s = 0; s < 13; s++) {
-                const int rr = 1 + 2 * s, k = 2 * rr + 1;
-                const int S = (int)(p[(rr + 1) * SP + rr + 1] - p[(rr + 1) * SP - rr] - p[-rr * SP + rr + 1] + p[-rr * SP - rr]);
-                const uint32_t word = __ballot_sync(0xffffffffu, valid && (2 * S >= g2 * (k * k)));
-                if (lane == 0) out[(size_t)s * a.halo_scale_stride] = word;
+    for (int s = 0; s < NS; s++) {
+        acc[s] = 0;
+        const int k = FAST ? 3 + 4 * s : (s < a.n_scales ? a.win[s] : 1), rr = k >> 1;
+        kk[s] = k * k;
+        ck[s] = (twoC * k * k + 1) / 2;  // exact: odd * odd + 1 is even
+        off_br[s] = (rr + 1) * SP + rr + 1;
+        off_bl[s] = (rr + 1) * SP - rr;
+        off_tr[s] = -rr * SP + rr + 1;
+        off_tl[s] = -rr * SP - rr;
+    }
+    {
+        const int X = X0 + FID_HALO_T * txl - 1 + lane;
+        const bool col_ok = X >= 0 && X < W;
+        const uint32_t* pcol = sat + (FID_HALO_T * tyl + R) * SP + (FID_HALO_T * txl + lane + R);  // table entry "above-left" of the pixel
+        const int Ybase = Y0 + FID_HALO_T * tyl - 1;
+#pragma unroll 1
+        for (int r = 0; r < 32; r++) {
+            const int Y = Ybase + r;
+            const bool valid = col_ok && Y >= 0 && Y < H;
+            const uint32_t* p = pcol + r * SP;
+            const int g = (int)(p[SP + 1] - p[1] - p[SP] + p[0]);
+            const bool mine = lane == r;
+#pragma unroll
+            for (int s = 0; s < NS; s++) {
+                if (!FAST && s >= a.n_scales) break;
+                const int S = (int)(p[off_br[s]] - p[off_bl[s]] - p[off_tr[s]] + p[off_tl[s]]);
+                const uint32_t word = __ballot_sync(0xffffffffu, valid && S >= g * kk[s] + ck[s]);
+                acc[s] = mine ? word : acc[s];
             }
-        } else {
-            for (int s = 0; s < a.n_scales; s++) {
-                const int k = a.win[s], rr = k >> 1;
-                const int S = (int)(p[(rr + 1) * SP + rr + 1] - p[(rr + 1) * SP - rr] - p[-rr * SP + rr + 1] + p[-rr * SP - rr]);
-                const uint32_t word = __ballot_sync(0xffffffffu, valid && (2 * S >= g2 * (k * k)));
-                if (lane == 0) out[(size_t)s * a.halo_scale_stride] = word;
-            }
         }
     }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// k_starts: one thread per interior word (tile, r = 1..30) of every plane.  A left crack of (x,y) is
-// dominated when (x,y-1) is foreground with a zero left neighbour (that crack lies on the same
-// border and is raster smaller); same for right cracks -- exact prune, pure bit-ops.
-// ---------------------------------------------------------------------------------------------------
-struct StartsArgs {
-    const uint32_t* halo;
-    StartRec* starts;
-    Counters* counters;
-    unsigned int max_starts;
-    int halo_tpr, halo_tiles_y;
-    size_t halo_scale_stride, halo_frame_stride;
-    int n_scales, n_frames;
-};
-
-__global__ void __launch_bounds__(256) k_starts(const StartsArgs a) {
-    const long long words_per_plane = (long long)a.halo_tpr * a.halo_tiles_y * 32;
-    const long long total = (long long)a.n_frames * a.n_scales * words_per_plane;
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    uint32_t L = 0, Rr = 0;
-    int f = 0, s = 0, tile = 0, r = 0;
-    if (gid < total) {
-        const long long plane_id = gid / words_per_plane;
-        const int wi = (int)(gid - plane_id * words_per_plane);
-        f = (int)(plane_id / a.n_scales);
-        s = (int)(plane_id - (long long)f * a.n_scales);
-        tile = wi >> 5;
-        r = wi & 31;
-        if (r >= 1 && r <= FID_HALO_T) {
-            const uint32_t* t = a.halo + (size_t)f * a.halo_frame_stride + (size_t)s * a.halo_scale_stride + (size_t)wi;
-            const uint32_t mid = __ldg(t);
-            if (mid) halo_row_starts(__ldg(t - 1), mid, &L, &Rr);
-        }
-    }
-    // block-aggregated append (one atomic per block and side -- a per-warp atomic on two hot counters
-    // serialised in L2 and cost 4 ms per 128 frames): left cracks grow from the front of the buffer,
-    // right cracks from the back, so that every warp of the walk kernels sees a single direction
-    __shared__ unsigned int warp_tot[2][8];
-    __shared__ unsigned int block_base[2];
-    const int ty = tile / a.halo_tpr, tx = tile - ty * a.halo_tpr;
-    const uint32_t y = (uint32_t)(FID_HALO_T * ty - 1 + r);
-    const uint32_t meta_base = ((uint32_t)f << 8) | ((uint32_t)s << 1);
-    const int warp = threadIdx.x >> 5;
-    int excl[2];
+    uint32_t* out = a.halo + (size_t)f * a.halo_frame_stride + ((size_t)ty * a.halo_tpr + tx) * 32 + lane;
+    int cnt_l = 0, cnt_r = 0;
+    const bool row_ok = lane >= 1 && lane <= FID_HALO_T;
 #pragma unroll
-    for (int side = 0; side < 2; side++) {
-        const int cnt = __popc(side ? Rr : L);
-        int incl = cnt;
+    for (int s = 0; s < NS; s++) {
+        if (!FAST && s >= a.n_scales) break;
+        out[(size_t)s * a.halo_scale_stride] = acc[s];
+        const uint32_t up = __shfl_up_sync(0xffffffffu, acc[s], 1), dn = __shfl_down_sync(0xffffffffu, acc[s], 1);
+        uint32_t L = 0, Rr = 0;
+        if (row_ok && acc[s]) halo_row_starts(up, acc[s], dn, &L, &Rr);
+        cnt_l += __popc(L);
+        cnt_r += __popc(Rr);
+    }
+    // one queue reservation per warp and side (all scales of the tile): left cracks grow from the front of
+    // the buffer, right cracks from the back, so that every warp of the walk kernels sees a single direction
+    int incl_l = cnt_l, incl_r = cnt_r;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl += t;
+    for (int d = 1; d < 32; d <<= 1) {
+        const int tl = __shfl_up_sync(0xffffffffu, incl_l, d), tr = __shfl_up_sync(0xffffffffu, incl_r, d);
+        if (lane >= d) {
+            incl_l += tl;
+            incl_r += tr;
         }
-        excl[side] = incl - cnt;
-        if (lane == 31) warp_tot[side][warp] = (unsigned int)incl;
     }
-    __syncthreads();
-    if (threadIdx.x < 2) {
-        unsigned int tot = 0;
-        for (int w = 0; w < 8; w++) {
-            const unsigned int t = warp_tot[threadIdx.x][w];
-            warp_tot[threadIdx.x][w] = tot;
-            tot += t;
-        }
-        block_base[threadIdx.x] = tot ? atomicAdd(&a.counters->n_starts[threadIdx.x], tot) : 0u;
+    unsigned int base_l = 0, base_r = 0;
+    if (lane == 31) {
+        base_l = incl_l ? atomicAdd(&a.counters->n_starts[0], (unsigned int)incl_l) : 0u;
+        base_r = incl_r ? atomicAdd(&a.counters->n_starts[1], (unsigned int)incl_r) : 0u;
     }
-    __syncthreads();
+    unsigned int pos_l = __shfl_sync(0xffffffffu, base_l, 31) + (unsigned int)(incl_l - cnt_l);
+    unsigned int pos_r = __shfl_sync(0xffffffffu, base_r, 31) + (unsigned int)(incl_r - cnt_r);
+    const uint32_t yq = (uint32_t)(FID_HALO_T * ty - 1 + lane) << 16;
+    const int xb = FID_HALO_T * tx - 1;
+    const unsigned int cap = a.max_starts / 2;
+    bool overflow = false;
 #pragma unroll
-    for (int side = 0; side < 2; side++) {
-        uint32_t bitsv = side ? Rr : L;
-        unsigned int pos = block_base[side] + warp_tot[side][warp] + (unsigned int)excl[side];
-        while (bitsv) {
-            const int i = __ffs(bitsv) - 1;
-            bitsv &= bitsv - 1;
-            if (pos < a.max_starts / 2) {
-                const unsigned int slot = side ? a.max_starts - 1 - pos : pos;
-                a.starts[slot] = StartRec{(uint32_t)(FID_HALO_T * tx - 1 + i) | (y << 16), meta_base | (uint32_t)side};
-            } else {
-                atomicOr(&a.counters->overflow, 1u);
-            }
-            pos++;
+    for (int s = 0; s < NS; s++) {
+        if (!FAST && s >= a.n_scales) break;
+        const uint32_t up = __shfl_up_sync(0xffffffffu, acc[s], 1), dn = __shfl_down_sync(0xffffffffu, acc[s], 1);
+        uint32_t L = 0, Rr = 0;
+        if (row_ok && acc[s]) halo_row_starts(up, acc[s], dn, &L, &Rr);
+        const uint32_t meta = ((uint32_t)f << 8) | ((uint32_t)s << 1);
+        while (L) {
+            const int i = __ffs(L) - 1;
+            L &= L - 1;
+            if (pos_l < cap)
+                a.starts[pos_l] = StartRec{(uint32_t)(xb + i) | yq, meta};
+            else
+                overflow = true;
+            pos_l++;
+        }
+        while (Rr) {
+            const int i = __ffs(Rr) - 1;
+            Rr &= Rr - 1;
+            if (pos_r < cap)
+                a.starts[a.max_starts - 1 - pos_r] = StartRec{(uint32_t)(xb + i) | yq, meta | 1u};
+            else
+                overflow = true;
+            pos_r++;
         }
     }
+    if (overflow) atomicOr(&a.counters->overflow, 1u);
 }
 
 }  // namespace fid

@@ -31,8 +31,8 @@ struct Start {
 struct HostPlane {
     std::vector<uint32_t> halo;
     int tpr = 0, tiles_y = 0, W = 0, H = 0;
-    static std::vector<uint8_t>& lut(int which) {
-        static std::vector<uint8_t> p, n;
+    static std::vector<uint32_t>& lut(int which) {
+        static std::vector<uint32_t> p, n;
         if (p.empty()) {
             p.resize(FID_LUT_SIZE);
             n.resize(FID_LUT_SIZE);
@@ -69,7 +69,7 @@ static void find_starts(const HostPlane& hp, std::vector<Start>& starts) {
             for (int tx = 0; tx < hp.tpr; tx++) {
                 const uint32_t* t = hp.halo.data() + ((size_t)ty * hp.tpr + tx) * 32 + r;
                 uint32_t L = 0, R = 0;
-                if (t[0]) halo_row_starts(t[-1], t[0], &L, &R);
+                if (t[0]) halo_row_starts(t[-1], t[0], t[1], &L, &R);
                 const int y = FID_HALO_T * ty - 1 + r;
                 for (int i = 1; i <= FID_HALO_T; i++) {
                     if ((L >> i) & 1) starts.push_back({FID_HALO_T * tx - 1 + i, y, 0});
@@ -92,14 +92,15 @@ extern "C" {
 static int walk_and_emit(const WalkCtx& ctx, const Start& s, int max_len, int uni, int pass, int ck_step, std::vector<uint32_t>& pts, int* n_out) {
     WalkState st;
     if (walk_init(ctx, s.x, s.y, s.is_right, &st) != WALK_CONTINUE) return WALK_ABORT;
-    int r = uni > 0 ? walk_resume(ctx, s.x, s.y, s.is_right, max_len, uni, &st) : WALK_CONTINUE;
+    int r = WALK_CONTINUE;
+    if (uni > 0) r = s.is_right ? walk_uni_fast<true>(ctx, s.x, s.y, max_len, uni, &st) : walk_uni_fast<false>(ctx, s.x, s.y, max_len, uni, &st);
     WalkState2 s2;
     if (s.is_right) walk_split<true>(s.x, s.y, st, &s2); else walk_split<false>(s.x, s.y, st, &s2);
     WalkCkpt ck;
     ck.count[0] = ck.count[1] = 0;
     int last_f = 0, last_b = 0;
     while (r == WALK_CONTINUE) {
-        r = s.is_right ? walk_resume_bidir<true>(ctx, s.x, s.y, max_len, pass, &s2) : walk_resume_bidir<false>(ctx, s.x, s.y, max_len, pass, &s2);
+        r = s.is_right ? walk_bidir_fast<true>(ctx, s.x, s.y, max_len, pass, &s2) : walk_bidir_fast<false>(ctx, s.x, s.y, max_len, pass, &s2);
         if (r == WALK_CONTINUE && ck_step > 0) walk_checkpoint(s2, &ck, &last_f, &last_b, ck_step);
     }
     if (r != WALK_CANONICAL) return r;
@@ -140,7 +141,7 @@ int hs_find_contours_mode(const uint8_t* plane, int W, int H, int min_len, int m
             st = walk_start(hw.ctx(), s.x, s.y, s.is_right, max_len, &n);
         else
             st = walk_and_emit(hw.ctx(), s, max_len, mode == 1 ? 8 : 1, mode == 1 ? 16 : 2, mode == 1 ? FID_CKPT_STEP : 3, pts, &n);
-        if (st == WALK_CANONICAL && n >= min_len) chains.push_back({((int64_t)s.y * W + s.x) * 2 + s.is_right, s.x, s.y, s.is_right, n, std::move(pts)});
+        if (st == WALK_CANONICAL && n >= min_len && n <= max_len) chains.push_back({((int64_t)s.y * W + s.x) * 2 + s.is_right, s.x, s.y, s.is_right, n, std::move(pts)});
     }
     if (min_len <= 1) {  // isolated pixels are 1-point outer contours
         for (int y = 0; y < H; y++)
@@ -318,7 +319,7 @@ void hs_walk_sim2(const uint8_t* plane, int W, int H, int max_len, const int* bu
 // Every start crack of the plane walked one-directionally and bidirectionally (after `uni_steps` steps of
 // the one-directional walk, as the GPU does between round 0 and round 1): number of starts whose
 // (result, contour length) differ.  out[0] = starts, out[1] = canonical.
-int hs_walk_bidir_check(const uint8_t* plane, int W, int H, int max_len, int uni_steps, int chunk, int64_t* out) {
+int hs_walk_bidir_check(const uint8_t* plane, int W, int H, int max_len, int uni_steps, int chunk, int fast, int64_t* out) {
     HostPlane mask;
     pack_plane(plane, W, H, mask);
     std::vector<Start> starts;
@@ -335,20 +336,25 @@ int hs_walk_bidir_check(const uint8_t* plane, int W, int H, int max_len, int uni
         WalkState st;
         int r2 = walk_init(ctx, s.x, s.y, s.is_right, &st), n2 = 0;
         if (r2 == WALK_CONTINUE) {
-            r2 = uni_steps > 0 ? walk_resume(ctx, s.x, s.y, s.is_right, max_len, uni_steps, &st) : WALK_CONTINUE;
+            if (uni_steps <= 0) r2 = WALK_CONTINUE;
+            else if (!fast) r2 = walk_resume(ctx, s.x, s.y, s.is_right, max_len, uni_steps, &st);
+            else r2 = s.is_right ? walk_uni_fast<true>(ctx, s.x, s.y, max_len, uni_steps, &st) : walk_uni_fast<false>(ctx, s.x, s.y, max_len, uni_steps, &st);
             n2 = st.n;
             if (r2 == WALK_CONTINUE) {
                 WalkState2 s2;
                 if (s.is_right) walk_split<true>(s.x, s.y, st, &s2); else walk_split<false>(s.x, s.y, st, &s2);
                 do {
-                    r2 = s.is_right ? walk_resume_bidir<true>(ctx, s.x, s.y, max_len, chunk, &s2) : walk_resume_bidir<false>(ctx, s.x, s.y, max_len, chunk, &s2);
+                    if (!fast) r2 = s.is_right ? walk_resume_bidir<true>(ctx, s.x, s.y, max_len, chunk, &s2) : walk_resume_bidir<false>(ctx, s.x, s.y, max_len, chunk, &s2);
+                    else r2 = s.is_right ? walk_bidir_fast<true>(ctx, s.x, s.y, max_len, chunk, &s2) : walk_bidir_fast<false>(ctx, s.x, s.y, max_len, chunk, &s2);
                 } while (r2 == WALK_CONTINUE);
                 n2 = s2.n;
             }
         }
-        if (r1 == WALK_CANONICAL) out[1]++;
+        if (r1 == WALK_CANONICAL && n1 <= max_len) out[1]++;
         // ABORT and TOO_LONG both mean "no contour": which one is hit first depends on the direction walked
-        if ((r1 == WALK_CANONICAL) != (r2 == WALK_CANONICAL) || (r1 == WALK_CANONICAL && n1 != n2)) bad++;
+        // (and a lap that closes a step or a pass after max_len is "no contour" as well: k_walk drops it)
+        const bool c1 = r1 == WALK_CANONICAL && n1 <= max_len, c2 = r2 == WALK_CANONICAL && n2 <= max_len;
+        if (c1 != c2 || (c1 && n1 != n2)) bad++;
     }
     return bad;
 }

@@ -64,19 +64,19 @@ def test_find_contours_threshold_planes(cfg, seed):
             assert _same(ours, ref)
 
 
-def _bidir_mismatches(plane, max_len, uni_steps, chunk):
+def _bidir_mismatches(plane, max_len, uni_steps, chunk, fast):
     import ctypes as C
     lib = hs.load()
     lib.hs_walk_bidir_check.restype = C.c_int
-    lib.hs_walk_bidir_check.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.hs_walk_bidir_check.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
     plane = np.ascontiguousarray(plane, np.uint8)
     out = np.zeros(2, np.int64)
-    bad = lib.hs_walk_bidir_check(plane.ctypes.data, plane.shape[1], plane.shape[0], max_len, uni_steps, chunk, out.ctypes.data)
+    bad = lib.hs_walk_bidir_check(plane.ctypes.data, plane.shape[1], plane.shape[0], max_len, uni_steps, chunk, fast, out.ctypes.data)
     return bad, int(out[0]), int(out[1])
 
 
 def test_bidirectional_walk_equals_one_directional():
-    """walk_resume_bidir (rounds >= 1 of k_walk) decides every start crack exactly like the one-directional
+    """walk_resume_bidir / walk_bidir_fast (rounds >= 1 of k_walk) decide every start crack exactly like the one-directional
     walk that is pinned to cv2.findContours above: same verdict, same contour length."""
     rng = np.random.default_rng(11)
     planes = [(rng.random((90, 131)) < d).astype(np.uint8) for d in (0.3, 0.5, 0.62, 0.8)]
@@ -92,9 +92,10 @@ def test_bidirectional_walk_equals_one_directional():
     total = 0
     for plane in planes:
         for max_len, uni, chunk in [(1 << 20, 0, 2), (1 << 20, 8, 64), (1 << 20, 3, 16), (40, 8, 6), (41, 0, 1 << 20)]:
-            bad, n_starts, n_canon = _bidir_mismatches(plane, max_len, uni, chunk)
-            assert bad == 0
-            total += n_canon
+            for fast in (0, 1):  # the readable loops and the instruction-count-optimised ones the kernels run
+                bad, n_starts, n_canon = _bidir_mismatches(plane, max_len, uni, chunk, fast)
+                assert bad == 0
+                total += n_canon
     assert total > 1000
 
 
