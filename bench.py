@@ -266,12 +266,19 @@ def run_gpu_arm(args):
 
     launches = [0]
 
-    def step(on_device):
+    def submit(on_device):
+        # one batch (= one step's frames) into the library's queue; returns at once
         if on_device:
-            counts, ids, corners, tfs = det.detect_pose_batch(dptr.value, K, D, FIDUCIAL_LEN, on_device=True, n_frames=nf, width=W, height=H)
+            det.submit_batch(dptr.value, K, D, FIDUCIAL_LEN, on_device=True, n_frames=nf, width=W, height=H)
         else:
-            lib.fid_hint_next(det.h, hptr)  # streaming: the next step's first chunk uploads while this step computes
-            counts, ids, corners, tfs = det.detect_pose_batch(pinned, K, D, FIDUCIAL_LEN)
+            det.submit_batch(pinned, K, D, FIDUCIAL_LEN)  # H2D of this batch is queued here, inside the timed region
+
+    outs = [None, None]
+
+    def finish(k):
+        # results of the oldest batch in flight (host arrays) + its map update
+        outs[k & 1] = det.collect_batch(outs[k & 1])
+        counts, ids, corners, tfs = outs[k & 1]
         launches[0] += det.last_counters()["kernel_launches"]
         # fiducial_slam: the frames of this step are one camera stream -> one message per frame.  The
         # sequential fold is enqueued asynchronously so that it overlaps the detection of the next step
@@ -286,6 +293,18 @@ def run_gpu_arm(args):
         launches[0] += 1
         return counts
 
+    def run_steps(on_device, steps):
+        # software pipeline over steps: batch k+1 is submitted before batch k is collected, so the
+        # latency-bound tail of one batch (grouping, identification, pose, D2H) runs under the threshold /
+        # border-walk stages of the next.  Exactly `steps` batches are submitted AND collected in here.
+        total = 0
+        submit(on_device)
+        for k in range(steps):
+            if k + 1 < steps:
+                submit(on_device)
+            total += int(finish(k).sum())
+        return total
+
     def barrier():
         if dist is not None:
             dist.barrier()
@@ -296,9 +315,7 @@ def run_gpu_arm(args):
         launches[0] = 0
         _lib.check(lib.fid_timer_start(det.h))
         t0 = time.perf_counter()
-        total = 0
-        for _ in range(steps):
-            total += int(step(on_device).sum())
+        total = run_steps(on_device, steps)
         slam.sync()
         ms = C.c_float(0)
         _lib.check(lib.fid_timer_stop(det.h, C.byref(ms)))
@@ -309,9 +326,9 @@ def run_gpu_arm(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), float(t[1]), total, launches[0]
 
-    for _ in range(max(args.warmup, 3)):
-        step(True)
-    step(False)
+    run_steps(True, max(args.warmup, 3))
+    run_steps(False, 2)
+    slam.sync()
 
     sampler = ClockSampler(local_rank)
     sampler.start()

@@ -74,8 +74,16 @@ struct fid_detector {
     unsigned int max_starts = 0, max_chains = 0, max_points = 0, max_queue = 0, max_segs = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     // one compute stream per slot (chunk in flight): the latency-bound stages of one chunk overlap the
-    // issue-bound stages of the others.  FID_SLOTS (2..4, default 2)
-    int n_slots = 2;
+    // issue-bound stages of the others.  FID_SLOTS (2..4, default 4)
+    int n_slots = 4;
+    int stagger = 0;  // FID_STAGGER bit mask, see enqueue_pipeline
+    // fid_submit_batch / fid_collect_batch: FIFO of batches in flight
+    struct Pending {
+        int first_slot, n_chunks, n_frames, w, h;
+        int64_t launches;
+        bool pose;
+    } pending[MAX_SLOTS]{};
+    int pend_head = 0, pend_count = 0, slots_in_use = 0, slot_next = 0;
     cudaStream_t slot_stream[MAX_SLOTS] = {};
     Slot slot[MAX_SLOTS];
     // streaming prefetch (fid_hint_next): first chunk of the next call, ping-pong
@@ -299,6 +307,7 @@ extern "C" int fid_create(const fid_params* params, int device, int max_width, i
     h->max_queue = h->max_starts / 8 + 65536;  // walks that survive the first 32 steps: ~3 % of the start cracks
     CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    if (const char* e = getenv("FID_STAGGER")) h->stagger = atoi(e);
     if (const char* e = getenv("FID_SLOTS")) h->n_slots = std::max(2, std::min((int)MAX_SLOTS, atoi(e)));
     for (int i = 0; i < h->n_slots; i++) CK(cudaStreamCreateWithFlags(&h->slot_stream[i], cudaStreamNonBlocking));
     if ((rc = upload_constants()) != FID_OK || (rc = configure_kernels(h)) != FID_OK) {
@@ -426,12 +435,16 @@ static Camera make_camera(const fid_camera* c) {
 
 // Enqueue the whole pipeline for `nf` frames resident in d_bgr (geometry g) on stream `st`.
 static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, const FrameGeom& g, const uint8_t* d_bgr, const fid_camera* cam, double fiducial_len,
-                            int n_override, int stop_after /* -1 = all */) {
+                            int n_override, int stop_after /* -1 = all */, const Slot* prev = nullptr) {
     const DevParams& P = h->P;
     const int W = g.W, H = g.H;
     int launches = 0;
     CK(cudaMemsetAsync(s.d_counters, 0, sizeof(Counters), st));
     CK(cudaMemsetAsync(s.d_nraw, 0, sizeof(unsigned int) * nf, st));
+    // stagger: a stage of this chunk starts after the same stage of the previous chunk has finished, so the
+    // low-occupancy tails of one chunk (last walk round, grouping, identification, pose) run under the
+    // throughput-bound stages of the other instead of under its own twin
+    if (prev && (h->stagger & 1)) CK(cudaStreamWaitEvent(st, prev->ev[ST_MASKS], 0));
     CK(cudaEventRecord(s.ev[ST_THRESH], st));
     {  // gray + threshold (halo tiles)
         GrayArgs ga{};
@@ -480,6 +493,7 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
     CK(cudaEventRecord(s.ev[ST_MASKS], st));
     if (stop_after == ST_THRESH) return FID_OK;
     CK(cudaEventRecord(s.ev[ST_WALK], st));
+    if (prev && (h->stagger & 2)) CK(cudaStreamWaitEvent(st, prev->ev[ST_EMIT], 0));
     const int mx = W > H ? W : H;
     const int min_len = (int)(P.min_perimeter_rate * mx), max_len = (int)(P.max_perimeter_rate * mx);
     {  // walk, in rounds of growing budget
@@ -701,6 +715,7 @@ extern "C" int fid_detect_pose_batch(fid_detector* h, int n_frames, const uint8_
     if (!h || !bgr || !counts || n_frames < 0 || width < 16 || height < 16 || width > h->max_w || height > h->max_h || max_markers < 0) return FID_ERR_INVALID_ARG;
     if (row_stride < (size_t)width * 3 || frame_stride < row_stride * (size_t)height) return FID_ERR_INVALID_ARG;
     if (cam && !(fiducial_len > 0)) return FID_ERR_INVALID_ARG;
+    if (h->pend_count) return FID_ERR_INVALID_ARG;  // batches submitted with fid_submit_batch are still in flight
     CK(cudaSetDevice(h->device));
     int rc = upload_overrides(h, n_override, override_ids, override_lens);
     if (rc != FID_OK) return rc;
@@ -759,7 +774,7 @@ extern "C" int fid_detect_pose_batch(fid_detector* h, int n_frames, const uint8_
                 h->pf_h = height;
                 h->hint_next = nullptr;
             }
-            rc = enqueue_pipeline(h, s, cst, nf, g, d_in, cam, fiducial_len, n_override, -1);
+            rc = enqueue_pipeline(h, s, cst, nf, g, d_in, cam, fiducial_len, n_override, -1, c > 0 ? &h->slot[(c - 1) % NS] : nullptr);
             if (rc != FID_OK) return rc;
             rc = enqueue_d2h(h, s, cst, nf, cam != nullptr);
             if (rc != FID_OK) return rc;
@@ -774,6 +789,90 @@ extern "C" int fid_detect_pose_batch(fid_detector* h, int n_frames, const uint8_
             if (rc != FID_OK) status = rc;
         }
     }
+    return status;
+}
+
+extern "C" int fid_submit_batch(fid_detector* h, int n_frames, const uint8_t* bgr, int bgr_on_device, int width, int height, size_t row_stride, size_t frame_stride,
+                                const fid_camera* cam, double fiducial_len, int n_override, const int32_t* override_ids, const double* override_lens) {
+    if (!h || !bgr || n_frames <= 0 || width < 16 || height < 16 || width > h->max_w || height > h->max_h) return FID_ERR_INVALID_ARG;
+    if (row_stride < (size_t)width * 3 || frame_stride < row_stride * (size_t)height) return FID_ERR_INVALID_ARG;
+    if (cam && !(fiducial_len > 0)) return FID_ERR_INVALID_ARG;
+    const int B = h->max_batch, NS = h->n_slots;
+    const int n_chunks = (n_frames + B - 1) / B;
+    if (n_chunks > NS - h->slots_in_use || h->pend_count >= MAX_SLOTS) return FID_ERR_CAPACITY;
+    CK(cudaSetDevice(h->device));
+    if (n_override > 0)  // the override table is shared: batches in flight must be done with it
+        for (int i = 0; i < NS; i++) CK(cudaStreamSynchronize(h->slot_stream[i]));
+    int rc = upload_overrides(h, n_override, override_ids, override_lens);
+    if (rc != FID_OK) return rc;
+    h->last_w = width;
+    h->last_h = height;
+    const bool contiguous = row_stride == (size_t)width * 3 && frame_stride == row_stride * height;
+    const int first = h->slot_next;
+    h->counters[6] = 0;
+    for (int c = 0; c < n_chunks; c++) {
+        const int si = (first + c) % NS;
+        Slot& s = h->slot[si];
+        cudaStream_t cst = h->slot_stream[si];
+        const int nf = std::min(B, n_frames - c * B);
+        const uint8_t* src = bgr + (size_t)c * B * frame_stride;
+        const uint8_t* d_in;
+        FrameGeom g;
+        if (bgr_on_device) {
+            d_in = src;
+            g = make_geom(h, width, height, row_stride, frame_stride);
+        } else {
+            if (contiguous) {
+                CK(cudaMemcpyAsync(s.d_bgr, src, (size_t)nf * frame_stride, cudaMemcpyHostToDevice, h->copy_stream));
+            } else {
+                for (int f = 0; f < nf; f++)
+                    CK(cudaMemcpy2DAsync(s.d_bgr + (size_t)f * width * 3 * height, (size_t)width * 3, src + (size_t)f * frame_stride, row_stride, (size_t)width * 3, height,
+                                         cudaMemcpyHostToDevice, h->copy_stream));
+            }
+            CK(cudaEventRecord(s.copied, h->copy_stream));
+            CK(cudaStreamWaitEvent(cst, s.copied, 0));
+            d_in = s.d_bgr;
+            g = make_geom(h, width, height, (size_t)width * 3, (size_t)width * 3 * height);
+        }
+        const Slot* prev = (h->slots_in_use + c) > 0 ? &h->slot[(si + NS - 1) % NS] : nullptr;
+        rc = enqueue_pipeline(h, s, cst, nf, g, d_in, cam, fiducial_len, n_override, -1, prev);
+        if (rc != FID_OK) return rc;
+        rc = enqueue_d2h(h, s, cst, nf, cam != nullptr);
+        if (rc != FID_OK) return rc;
+        h->last_frames = nf;
+    }
+    fid_detector::Pending& pb = h->pending[(h->pend_head + h->pend_count) % MAX_SLOTS];
+    pb.first_slot = first;
+    pb.n_chunks = n_chunks;
+    pb.n_frames = n_frames;
+    pb.w = width;
+    pb.h = height;
+    pb.pose = cam != nullptr;
+    pb.launches = h->counters[6];
+    h->pend_count++;
+    h->slots_in_use += n_chunks;
+    h->slot_next = (first + n_chunks) % NS;
+    return FID_OK;
+}
+
+extern "C" int fid_collect_batch(fid_detector* h, int max_markers, int32_t* counts, int32_t* ids, float* corners, fid_transform* transforms) {
+    if (!h || !counts || max_markers < 0 || h->pend_count == 0) return FID_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    const fid_detector::Pending pb = h->pending[h->pend_head];
+    const int B = h->max_batch, NS = h->n_slots;
+    int status = FID_OK;
+    h->counters[6] = pb.launches;
+    h->stage_ms[ST_H2D] = 0;
+    for (int c = 0; c < pb.n_chunks; c++) {
+        Slot& s = h->slot[(pb.first_slot + c) % NS];
+        const int nf = std::min(B, pb.n_frames - c * B);
+        const int rc = collect(h, s, nf, max_markers, counts + (size_t)c * B, ids ? ids + (size_t)c * B * max_markers : nullptr,
+                               corners ? corners + (size_t)c * B * max_markers * 8 : nullptr, (transforms && pb.pose) ? transforms + (size_t)c * B * max_markers : nullptr, c == 0);
+        if (rc != FID_OK) status = rc;
+    }
+    h->pend_head = (h->pend_head + 1) % MAX_SLOTS;
+    h->pend_count--;
+    h->slots_in_use -= pb.n_chunks;
     return status;
 }
 

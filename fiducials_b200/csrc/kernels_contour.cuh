@@ -191,10 +191,18 @@ __device__ __forceinline__ void walk_side(const WalkArgs& a, unsigned int n, uns
         }
         return;
     }
-    // persistent lanes
+    // persistent lanes.  The first 32 * n_warps items are assigned statically, warp `my` taking items
+    // [32 my, 32 my + 32): when there are fewer items than lanes (the long-walk rounds) the work is packed
+    // into the lowest warps and every other warp -- and with it whole blocks and their registers -- retires
+    // at once, leaving the SMs to whatever runs on the other streams.  Later items go through the counter.
     const unsigned int lt_mask = (1u << lane) - 1u;
-    unsigned int next = 0, hi = 0;
+    const unsigned int static_end = n_warps * 32u;
+    unsigned int next = my * 32u, hi = next + 32u < n ? next + 32u : n;
     bool exhausted = false, active = false;
+    if (next >= n) {
+        if (static_end >= n) return;
+        hi = next;  // nothing static for this warp; go to the counter
+    }
     int budget_end = 0, last_f = 0, last_b = 0;
     WalkItem it;
     WalkCkpt ck;  // checkpoints of the current walk (local memory; touched once per FID_CKPT_STEP steps)
@@ -204,7 +212,7 @@ __device__ __forceinline__ void walk_side(const WalkArgs& a, unsigned int n, uns
         if (__popc(need) >= 16) {  // refill only when at least half the warp is idle
             if (!exhausted && next >= hi) {
                 unsigned int lo = 0;
-                if (lane == 0) lo = atomicAdd(&a.counters->work[a.round][IS_RIGHT ? 1 : 0], a.chunk);
+                if (lane == 0) lo = atomicAdd(&a.counters->work[a.round][IS_RIGHT ? 1 : 0], a.chunk) + static_end;
                 lo = __shfl_sync(0xffffffffu, lo, 0);
                 next = lo;
                 hi = lo + a.chunk < n ? lo + a.chunk : n;

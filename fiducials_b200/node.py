@@ -115,6 +115,35 @@ class Detector:
         _lib.check(st, "fid_detect_pose_batch")
         return counts, ids, corners.reshape(n, MAXM, 4, 2), tfs
 
+    def submit_batch(self, frames, K=None, D=None, fiducial_len=0.14, overrides=None, on_device=False, n_frames=None, width=None, height=None):
+        """fid_submit_batch: queue a batch and return at once (see detect_pose_batch for the arguments).  Host frames must
+        stay alive and unchanged until the matching collect_batch."""
+        if on_device:
+            n, H, W = int(n_frames), int(height), int(width)
+            ptr = C.c_void_p(int(frames))
+        else:
+            assert frames.dtype == np.uint8 and frames.flags["C_CONTIGUOUS"]
+            n, H, W = frames.shape[:3]
+            ptr = frames.ctypes.data_as(C.c_void_p)
+        cam = _camera(K, D) if K is not None else None
+        oi, ol, no = _overrides(overrides)
+        _lib.check(self.lib.fid_submit_batch(self.h, n, ptr, 1 if on_device else 0, W, H, W * 3, W * 3 * H, C.byref(cam) if cam is not None else None, float(fiducial_len), no,
+                                             oi.ctypes.data_as(C.c_void_p), ol.ctypes.data_as(C.c_void_p)), "fid_submit_batch")
+        if not hasattr(self, "_pending"):
+            self._pending = []
+        self._pending.append((n, cam is not None, frames))
+
+    def collect_batch(self, out=None):
+        """fid_collect_batch: results of the oldest submitted batch, as detect_pose_batch returns them.  `out` = a tuple
+        returned by an earlier call of the same shape, to reuse its buffers."""
+        n, with_pose, _keep = self._pending.pop(0)
+        if out is None:
+            out = (np.zeros(n, np.int32), np.zeros((n, MAXM), np.int32), np.zeros((n, MAXM, 4, 2), np.float32), (_lib.fid_transform * (n * MAXM))() if with_pose else None)
+        counts, ids, corners, tfs = out
+        _lib.check(self.lib.fid_collect_batch(self.h, MAXM, counts.ctypes.data_as(C.c_void_p), ids.ctypes.data_as(C.c_void_p), corners.ctypes.data_as(C.c_void_p),
+                                              C.cast(tfs, C.c_void_p) if tfs is not None else None), "fid_collect_batch")
+        return counts, ids, corners, tfs
+
     def debug_threshold(self, bgr):
         bgr = np.ascontiguousarray(bgr, np.uint8)
         H, W = bgr.shape[:2]

@@ -127,6 +127,19 @@ int fid_detect_pose_batch(fid_detector* h, int n_frames, const uint8_t* bgr, int
                           const fid_camera* cam, double fiducial_len, int n_override, const int32_t* override_ids, const double* override_lens,
                           int max_markers, int32_t* counts, int32_t* ids, float* corners, fid_transform* transforms);
 
+/* The same call split in two, for a camera stream: fid_submit_batch queues the uploads and kernels of a
+ * batch and returns at once; fid_collect_batch waits for the OLDEST submitted batch and writes its results
+ * (same layout as fid_detect_pose_batch).  While batch k finishes its latency-bound tail (grouping,
+ * identification, pose) batch k+1 already runs its threshold and border-walk stages -- the reference
+ * node has the same structure between its image callback and its publishers, one frame at a time.
+ * A batch needs ceil(n_frames / max_batch) free chunk slots; the handle has 4 of them (environment
+ * FID_SLOTS, 2..4).  FID_ERR_CAPACITY = not enough free slots, collect first.  The frames of
+ * a host `bgr` must stay valid and unchanged until the batch has been collected.
+ * fid_detect_pose_batch may only be called while nothing is in flight. */
+int fid_submit_batch(fid_detector* h, int n_frames, const uint8_t* bgr, int bgr_on_device, int width, int height, size_t row_stride, size_t frame_stride,
+                     const fid_camera* cam, double fiducial_len, int n_override, const int32_t* override_ids, const double* override_lens);
+int fid_collect_batch(fid_detector* h, int max_markers, int32_t* counts, int32_t* ids, float* corners, fid_transform* transforms);
+
 /* Streaming hint: `next_bgr` (pinned host memory, same frame count and geometry as the call that
  * follows this hint) will be the `bgr` argument of the call after that one.  The library then
  * uploads its first chunk in the background once the uploads of the call in progress are queued, so

@@ -216,6 +216,41 @@ def test_streaming_hint_prefetch(det_cache):
             assert np.array_equal(g, r)
 
 
+def test_submit_collect_pipeline(det_cache):
+    """fid_submit_batch / fid_collect_batch: batches in flight at the same time give exactly the results of
+    the synchronous call, in submission order; capacity and misuse are reported, not ignored."""
+    frames_a = np.ascontiguousarray(np.stack([synth.make_config_frame("C1", s)[0] for s in range(4)]))
+    frames_b = np.ascontiguousarray(np.stack([synth.make_config_frame("C1", 20 + s)[0] for s in range(3)]))
+    _, _, K, D, d = synth.make_config_frame("C1", 0)
+    det = det_cache(d, 640, 480, 2)  # 2-frame chunks: a = 2 chunks, b = 2 chunks -> all 4 slots busy
+    ref_a = [x.copy() for x in det.detect_pose_batch(frames_a, K, D, 0.14)[:3]]
+    ref_b = [x.copy() for x in det.detect_pose_batch(frames_b, K, D, 0.14)[:3]]
+    for _ in range(3):
+        det.submit_batch(frames_a, K, D, 0.14)
+        det.submit_batch(frames_b, K, D, 0.14)
+        with pytest.raises(RuntimeError):  # no free slot
+            det.submit_batch(frames_b, K, D, 0.14)
+        with pytest.raises(RuntimeError):  # synchronous call while batches are in flight
+            det.detect_pose_batch(frames_b, K, D, 0.14)
+        got_a = det.collect_batch()
+        det.submit_batch(frames_a, K, D, 0.14)  # slots of a are free again
+        got_b = det.collect_batch()
+        got_a2 = det.collect_batch()
+        for got, ref in ((got_a, ref_a), (got_b, ref_b), (got_a2, ref_a)):
+            assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+        assert got_a[3] is not None and got_a[3][0].fiducial_id == int(ref_a[1][0, 0])
+    # device-resident input, no camera
+    lib = det.lib
+    dptr = C.c_void_p()
+    assert lib.fid_device_alloc(det.h, frames_a.nbytes, C.byref(dptr)) == 0
+    assert lib.fid_memcpy_h2d(det.h, dptr, frames_a.ctypes.data_as(C.c_void_p), frames_a.nbytes) == 0
+    det.submit_batch(dptr.value, on_device=True, n_frames=4, width=640, height=480)
+    got = det.collect_batch()
+    assert np.array_equal(got[0], ref_a[0]) and np.array_equal(got[1], ref_a[1]) and np.array_equal(got[2], ref_a[2]) and got[3] is None
+    lib.fid_device_free(det.h, dptr)
+    assert lib.fid_collect_batch(det.h, 256, got[0].ctypes.data_as(C.c_void_p), None, None, None) == -1  # nothing in flight
+
+
 @pytest.mark.parametrize("kind", ["black", "white", "noise", "stripes"])
 def test_frames_without_markers(det_cache, kind):
     rng = np.random.default_rng(5)
