@@ -558,7 +558,9 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
         a.H = H;
         a.poly_accuracy_rate = P.poly_accuracy_rate;
         a.min_corner_dist_rate = P.min_corner_dist_rate;
-        k_approx<<<h->sm_count * 8, APPROX_THREADS, 0, st>>>(a);
+        k_approx_warp<<<h->sm_count * 8, APPROX_THREADS, 0, st>>>(a);
+        launches++;
+        k_approx<<<h->sm_count * 4, APPROX_THREADS, 0, st>>>(a);
         launches++;
     }
     CK(cudaEventRecord(s.ev[ST_GROUP], st));

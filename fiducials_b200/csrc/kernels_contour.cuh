@@ -26,7 +26,7 @@ struct Counters {
     unsigned int work[FID_WALK_MAX_ROUNDS][2]; // persistent-walker work counters, per direction
     unsigned int emit_work;
     unsigned int n_segs;       // contour segments queued for k_emit
-    unsigned int pad[1];
+    unsigned int approx_work;  // k_approx_warp work counter
 };
 
 struct WalkRec {       // a bidirectional border walk suspended between rounds (contour_walk.cuh, WalkState2)
@@ -315,6 +315,7 @@ __global__ void __launch_bounds__(64) k_emit(const EmitArgs a) {
 // k_approx: one block per contour.
 // ---------------------------------------------------------------------------------------------------
 #define APPROX_THREADS 128
+#define APPROX_WARP_MAX 1024  // contours up to this many points are handled by one warp (k_approx_warp)
 
 struct BlockReducer {
     int* sh_val;  // [APPROX_THREADS/32]
@@ -399,36 +400,121 @@ struct ApproxArgs {
     double poly_accuracy_rate, min_corner_dist_rate;
 };
 
+__device__ __forceinline__ void approx_emit_quad(const ApproxArgs& a, const ChainRec& c, const Pt16* q) {
+    if (!quad_passes_filters(q, (int)c.n, a.W, a.H, a.min_corner_dist_rate)) return;
+    const int f = c.meta >> 8, s = (c.meta >> 1) & 0x7F, is_right = c.meta & 1;
+    const unsigned int slot = atomicAdd(&a.n_raw[f], 1u);
+    if (slot < (unsigned int)a.max_raw) {
+        RawQuad r;
+        for (int k = 0; k < 4; k++) {
+            r.x[k] = q[k].x;
+            r.y[k] = q[k].y;
+        }
+        r.n_contour = (int)c.n;
+        r.order_hi = (uint32_t)s;
+        const uint32_t x = c.xy & 0xFFFF, y = c.xy >> 16;
+        r.order_lo = 0xFFFFFFFFu - ((y * (uint32_t)a.W + x) * 2u + (uint32_t)is_right);
+        a.raw[(size_t)f * a.max_raw + slot] = r;
+    } else {
+        atomicOr(&a.counters_rw->overflow, 8u);
+    }
+}
+
+// Contours longer than APPROX_WARP_MAX points: one block per contour.
 __global__ void __launch_bounds__(APPROX_THREADS) k_approx(const ApproxArgs a) {
     __shared__ int sh_val[APPROX_THREADS / 32], sh_idx[APPROX_THREADS / 32];
     unsigned int n = a.counters->n_chains;
     n = n < a.max_chains ? n : a.max_chains;
     BlockReducer red{sh_val, sh_idx};
     for (unsigned int i = blockIdx.x; i < n; i += gridDim.x) {
-        const ChainRec c = a.chains[i];
-        if (c.n == 0) continue;
+        const ChainRec c = a.chains[n - 1 - i];  // the long contours are at the end of the list
+        if (c.n <= APPROX_WARP_MAX) continue;
         const Pt16* p = a.points + c.offset;
         Pt16 q[FID_APPROX_MAX_V];
         const int nv = approx_poly_closed(red, p, (int)c.n, (double)c.n * a.poly_accuracy_rate, q);
         if (nv != 4) continue;
-        if (threadIdx.x == 0 && quad_passes_filters(q, (int)c.n, a.W, a.H, a.min_corner_dist_rate)) {
-            const int f = c.meta >> 8, s = (c.meta >> 1) & 0x7F, is_right = c.meta & 1;
-            const unsigned int slot = atomicAdd(&a.n_raw[f], 1u);
-            if (slot < (unsigned int)a.max_raw) {
-                RawQuad r;
-                for (int k = 0; k < 4; k++) {
-                    r.x[k] = q[k].x;
-                    r.y[k] = q[k].y;
-                }
-                r.n_contour = (int)c.n;
-                r.order_hi = (uint32_t)s;
-                const uint32_t x = c.xy & 0xFFFF, y = c.xy >> 16;
-                r.order_lo = 0xFFFFFFFFu - ((y * (uint32_t)a.W + x) * 2u + (uint32_t)is_right);
-                a.raw[(size_t)f * a.max_raw + slot] = r;
-            } else {
-                atomicOr(&a.counters_rw->overflow, 8u);
+        if (threadIdx.x == 0) approx_emit_quad(a, c, q);
+    }
+}
+
+// Contours of at most APPROX_WARP_MAX points (nearly all of them): one WARP per contour, the points staged
+// once in shared memory, every arg-max sweep a shuffle reduction -- no block barrier, no re-read from L2.
+// (One block per contour spent ~190 instructions per point and sweep on a 100-point contour, nearly all of
+// it in the block reduction.)
+struct WarpReducer {
+    __device__ ArgMax reduce(int best_v, int best_j) const {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const int ov = __shfl_xor_sync(0xffffffffu, best_v, d);
+            const int oj = __shfl_xor_sync(0xffffffffu, best_j, d);
+            if (ov > best_v || (ov == best_v && oj < best_j)) {
+                best_v = ov;
+                best_j = oj;
             }
         }
+        ArgMax r = {best_v, best_j};
+        if (r.value == 0) r.index = 0;
+        return r;
+    }
+    __device__ ArgMax farthest(const Pt16* p, int n, int pos0, int len) const {
+        const int sx = p[pos0].x, sy = p[pos0].y;
+        int bv = 0, bj = 0x7fffffff;
+        for (int j = 1 + (int)(threadIdx.x & 31); j < len; j += 32) {
+            int pos = pos0 + j;
+            pos = pos >= n ? pos - n : pos;
+            const Pt16 q = p[pos];
+            const int dx = q.x - sx, dy = q.y - sy;
+            const int d = dx * dx + dy * dy;
+            if (d > bv) {
+                bv = d;
+                bj = j;
+            }
+        }
+        return reduce(bv, bj);
+    }
+    __device__ ArgMax off_chord(const Pt16* p, int n, int s0, int s1) const {
+        const int sx = p[s0].x, sy = p[s0].y;
+        const int dx = p[s1].x - sx, dy = p[s1].y - sy;
+        int len = s1 - s0;
+        len = len <= 0 ? len + n : len;  // interior points are j = 1 .. len-1
+        int bv = 0, bj = 0x7fffffff;
+        for (int j = 1 + (int)(threadIdx.x & 31); j < len; j += 32) {
+            int pos = s0 + j;
+            pos = pos >= n ? pos - n : pos;
+            const Pt16 q = p[pos];
+            int d = (q.y - sy) * dx - (q.x - sx) * dy;
+            d = d < 0 ? -d : d;
+            if (d > bv) {
+                bv = d;
+                bj = j;
+            }
+        }
+        return reduce(bv, bj);
+    }
+};
+
+__global__ void __launch_bounds__(APPROX_THREADS) k_approx_warp(const ApproxArgs a) {
+    __shared__ uint32_t sh_pts[APPROX_THREADS / 32][APPROX_WARP_MAX];
+    unsigned int n = a.counters->n_chains;
+    n = n < a.max_chains ? n : a.max_chains;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* mine = sh_pts[warp];
+    const WarpReducer red;
+    for (;;) {
+        unsigned int i = 0;
+        if (lane == 0) i = atomicAdd(&a.counters_rw->approx_work, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n) break;
+        const ChainRec c = a.chains[i];
+        if (c.n == 0 || c.n > APPROX_WARP_MAX) continue;
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(a.points + c.offset);  // chains are 16-byte aligned
+        const int n4 = ((int)c.n + 3) >> 2;
+        for (int k = lane; k < n4; k += 32) reinterpret_cast<uint4*>(mine)[k] = reinterpret_cast<const uint4*>(src)[k];
+        __syncwarp();
+        Pt16 q[FID_APPROX_MAX_V];
+        const int nv = approx_poly_closed(red, reinterpret_cast<const Pt16*>(mine), (int)c.n, (double)c.n * a.poly_accuracy_rate, q);
+        if (nv == 4 && lane == 0) approx_emit_quad(a, c, q);
+        __syncwarp();
     }
 }
 
