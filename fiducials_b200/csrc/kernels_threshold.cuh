@@ -104,15 +104,46 @@ __global__ void __launch_bounds__(THR_THREADS, 2) k_threshold(const ThreshArgs a
     for (int i = tid; i < SP; i += THR_THREADS) sat[i] = 0;
     for (int i = tid; i <= RH; i += THR_THREADS) sat[i * SP] = 0;
     // A. gray region (replicate border): region (0,0) = image (X0-1-R, Y0-1-R)
-    for (int ry = warp; ry < RH; ry += THR_THREADS / 32) {
-        int y = Y0 - 1 - R + ry;
-        y = y < 0 ? 0 : (y > H - 1 ? H - 1 : y);
-        const uint8_t* grow = gray + (size_t)y * a.gray_pitch;
-        uint32_t* srow = sat + (ry + 1) * SP + 1;
-        for (int rx = lane; rx < RW; rx += 32) {
-            int x = X0 - 1 - R + rx;
-            x = x < 0 ? 0 : (x > W - 1 ? W - 1 : x);
-            srow[rx] = __ldg(grow + x);
+    const int XA = X0 - 1 - R - 2;  // 4-byte aligned when R = 25 (X0 is a multiple of 120): region column c = word column 4w - 2 + b
+    if (FAST && XA >= 0 && XA + 4 * ((RW + 2 + 3) / 4) <= a.gray_pitch && X0 - 1 - R + RW <= W) {
+        // interior CTA: 32-bit loads, all of a thread's loads in flight before the first use (the byte loop
+        // below exposes the global latency once per row group: "long scoreboard" was the top stall)
+        constexpr int WPR = (THR_OW + 2 + 2 * THR_FAST_R + 2 + 3) / 4;              // 44 words per row
+        constexpr int RHc = THR_OH + 2 + 2 * THR_FAST_R;                              // 112 rows
+        constexpr int PER = (WPR * RHc + THR_THREADS - 1) / THR_THREADS;              // 20 words per thread
+        uint32_t v[PER];
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int u = tid + k * THR_THREADS;
+            const int ry = u / WPR, w = u - ry * WPR;
+            int y = Y0 - 1 - R + ry;
+            y = y < 0 ? 0 : (y > H - 1 ? H - 1 : y);
+            v[k] = u < WPR * RHc ? __ldg(reinterpret_cast<const uint32_t*>(gray + (size_t)y * a.gray_pitch + XA) + w) : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            const int u = tid + k * THR_THREADS;
+            const int ry = u / WPR, w = u - ry * WPR;
+            if (u < WPR * RHc) {
+                uint32_t* srow = sat + (ry + 1) * SP + 1;
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    const int c = 4 * w - 2 + b;
+                    if (c >= 0 && c < RW) srow[c] = (v[k] >> (8 * b)) & 255u;
+                }
+            }
+        }
+    } else {
+        for (int ry = warp; ry < RH; ry += THR_THREADS / 32) {
+            int y = Y0 - 1 - R + ry;
+            y = y < 0 ? 0 : (y > H - 1 ? H - 1 : y);
+            const uint8_t* grow = gray + (size_t)y * a.gray_pitch;
+            uint32_t* srow = sat + (ry + 1) * SP + 1;
+            for (int rx = lane; rx < RW; rx += 32) {
+                int x = X0 - 1 - R + rx;
+                x = x < 0 ? 0 : (x > W - 1 ? W - 1 : x);
+                srow[rx] = __ldg(grow + x);
+            }
         }
     }
     __syncthreads();
