@@ -70,7 +70,7 @@ struct fid_detector {
     fid_params params{};
     DevParams P{};
     int max_w = 0, max_h = 0, max_batch = 0;
-    int max_raw = 4096, close_wpr = 128, max_sel = 512, max_markers = FID_MAX_MARKERS;
+    int max_raw = FID_GROUP_MAX_RAW, close_wpr = 128, max_sel = 512, max_markers = FID_MAX_MARKERS;
     unsigned int max_starts = 0, max_chains = 0, max_points = 0, max_queue = 0, max_segs = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     // one compute stream per slot (chunk in flight): the latency-bound stages of one chunk overlap the
@@ -181,6 +181,7 @@ static int upload_constants() {
     return FID_OK;
 }
 
+static size_t group_smem(int max_raw) { return (size_t)max_raw * (5 * sizeof(int) + 1); }
 static size_t ident_smem(const DevParams& P) { return (size_t)P.n_markers * 4 * 8 + IDENT_WARPS * 256 * 4 + IDENT_WARPS * FID_MAX_WARP_SIDE_SQ; }
 
 static int r_max_of(const DevParams& P) {
@@ -192,6 +193,7 @@ static int r_max_of(const DevParams& P) {
 static int configure_kernels(fid_detector* h) {
     CK(cudaFuncSetAttribute(k_threshold<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thresh_smem_bytes(THR_FAST_R)));
     CK(cudaFuncSetAttribute(k_threshold<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thresh_smem_bytes(FID_MAX_WIN_RADIUS)));
+    CK(cudaFuncSetAttribute(k_sort_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)group_smem(FID_GROUP_MAX_RAW)));
     CK(cudaFuncSetAttribute(k_identify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1000 * 4 * 8 + IDENT_WARPS * 256 * 4 + IDENT_WARPS * FID_MAX_WARP_SIDE_SQ)));
     return FID_OK;
 }
@@ -583,7 +585,7 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
         a.H = H;
         a.min_dist_to_border = P.min_dist_to_border;
         a.counters = s.d_counters;
-        k_sort_group<<<nf, GROUP_THREADS, 0, st>>>(a);
+        k_sort_group<<<nf, GROUP_THREADS, group_smem(h->max_raw), st>>>(a);
         launches++;
     }
     CK(cudaEventRecord(s.ev[ST_IDENT], st));
@@ -601,7 +603,7 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
         a.P = P;
         a.cand_id = s.d_cand_id;
         a.cand_corners = s.d_cand_corners;
-        dim3 grid((h->max_sel + IDENT_WARPS - 1) / IDENT_WARPS, nf);
+        dim3 grid(h->max_sel, nf);
         k_identify<<<grid, IDENT_WARPS * 32, ident_smem(P), st>>>(a);
         launches++;
     }

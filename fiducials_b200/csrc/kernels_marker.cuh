@@ -55,6 +55,7 @@ struct GroupArgs {
 };
 
 #define GROUP_THREADS 256
+#define FID_GROUP_MAX_RAW 4096  // >= fid_detector::max_raw
 
 __global__ void __launch_bounds__(GROUP_THREADS) k_sort_group(const GroupArgs a) {
     const int f = blockIdx.x;
@@ -90,7 +91,21 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_sort_group(const GroupArgs a)
         ps[rank] = pi;
     }
     __syncthreads();
-    // c. close-pair matrix, upper triangle; unit = (row i, 32-column word)
+    // c. close-pair matrix, upper triangle; unit = (row i, 32-column word).  The matrix is very sparse (a
+    //    marker scene has a few dozen close pairs among ~10^5): rows with at least one pair are flagged in
+    //    shared memory so that the serial pass below does not pay an L2 round trip per empty word.
+    __shared__ uint32_t row_any[(FID_GROUP_MAX_RAW + 31) / 32], grouped[(FID_GROUP_MAX_RAW + 31) / 32];
+    extern __shared__ int sm_group[];  // 5 * max_raw ints + max_raw bytes
+    int* sm_group_id = sm_group;
+    int* sm_members = sm_group + a.max_raw;
+    int* sm_next = sm_group + 2 * a.max_raw;
+    int* sm_head = sm_group + 3 * a.max_raw;
+    int* sm_tail = sm_group + 4 * a.max_raw;
+    uint8_t* sm_selected = reinterpret_cast<uint8_t*>(sm_group + 5 * a.max_raw);
+    __shared__ int s_warp_cnt[GROUP_THREADS / 32];
+    __shared__ int s_base;
+    for (int i = tid; i < (FID_GROUP_MAX_RAW + 31) / 32; i += GROUP_THREADS) row_any[i] = 0;
+    __syncthreads();
     const int wpr = (n + 31) >> 5;
     for (int u = tid; u < n * wpr; u += GROUP_THREADS) {
         const int i = u / wpr, w = u - i * wpr;
@@ -114,28 +129,48 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_sort_group(const GroupArgs a)
             }
         }
         cb[(size_t)i * a.close_wpr + w] = bits;
+        if (bits) atomicOr(&row_any[i >> 5], 1u << (i & 31));
     }
     __syncthreads();
     // d. order-dependent grouping (serial; the pair list is sparse)
     if (tid == 0) {
         const uint32_t* cbc = cb;
         const int cw = a.close_wpr;
-        auto close_word = [cbc, cw](int i, int w) -> uint32_t { return cbc[(size_t)i * cw + w]; };
-        group_candidates(n, qs, a.marker_size, a.border_bits, a.min_group_dist, close_word, a.fs.selected + fo, a.fs.group_id + fo, a.fs.group_members + fo,
-                         a.fs.next_in_group + fo, a.fs.group_head + fo, a.fs.group_tail + fo, a.fs.close_count + fo, a.fs.close_idx + fo, a.fs.close_off + fo);
-        int ns = 0;
-        for (int i = 0; i < n; i++) {
-            if (!a.fs.selected[fo + i]) continue;
-            if (quad_near_border(qs[i], a.W, a.H, a.min_dist_to_border)) continue;  // dropped silently, with its group
-            if (ns < a.max_sel) {
-                a.fs.sel_idx[fo + ns] = i;
-                ns++;
-            } else {
-                atomicOr(&a.counters->overflow, 16u);
-            }
-        }
-        a.n_sel[f] = ns;
+        const uint32_t* ra = row_any;
+        auto close_word = [cbc, cw, ra](int i, int w) -> uint32_t { return ((ra[i >> 5] >> (i & 31)) & 1u) ? cbc[(size_t)i * cw + w] : 0u; };
+        // scratch of the serial pass in shared memory (it is a chain of dependent look-ups: an L2 round trip
+        // per access made this the longest single-thread stretch of the whole pipeline)
+        group_candidates(n, qs, a.marker_size, a.border_bits, a.min_group_dist, close_word, sm_selected, sm_group_id, sm_members, sm_next, sm_head, sm_tail,
+                         a.fs.close_count + fo, a.fs.close_idx + fo, a.fs.close_off + fo, grouped);
+        s_base = 0;
     }
+    __syncthreads();
+    // e. selected candidates, in order, minus the ones near the frame border (dropped silently, with their group)
+    for (int c0 = 0; c0 < n; c0 += GROUP_THREADS) {
+        const int i = c0 + tid;
+        const bool keep = i < n && sm_selected[i] && !quad_near_border(qs[i], a.W, a.H, a.min_dist_to_border);
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        const int lane = tid & 31, warp = tid >> 5;
+        if (lane == 0) s_warp_cnt[warp] = __popc(m);
+        __syncthreads();
+        int off = s_base;
+        for (int w = 0; w < warp; w++) off += s_warp_cnt[w];
+        if (keep) {
+            const int pos = off + __popc(m & ((1u << lane) - 1u));
+            if (pos < a.max_sel)
+                a.fs.sel_idx[fo + pos] = i;
+            else
+                atomicOr(&a.counters->overflow, 16u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int tot = 0;
+            for (int w = 0; w < GROUP_THREADS / 32; w++) tot += s_warp_cnt[w];
+            s_base += tot;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) a.n_sel[f] = s_base < a.max_sel ? s_base : a.max_sel;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -177,44 +212,77 @@ struct IdentifyArgs {
     float* cand_corners; // [F][max_sel][8] rotated to marker order
 };
 
-#define IDENT_WARPS 4
+#define IDENT_WARPS 8
 
+// One block per selected candidate.  cv::aruco tries the selected quad first and then, in order, the
+// "close contours" of its group until one decodes; a non-marker group of a dozen nested
+// outlines used to cost a dozen identifications back to back in one warp -- the longest chain of the
+// launch.  Here warp w tries attempts w, w + 8, ... concurrently; the lowest successful attempt wins,
+// which is exactly the sequential first-success rule.
 __global__ void __launch_bounds__(IDENT_WARPS * 32) k_identify(const IdentifyArgs a) {
     extern __shared__ unsigned long long sm_dict[];  // n_markers*4 words, then per-warp scratch
+    __shared__ int s_best;                            // lowest successful attempt so far
+    __shared__ int s_id[IDENT_WARPS], s_rot[IDENT_WARPS], s_att[IDENT_WARPS];
+    const int f = blockIdx.y, k = blockIdx.x;
+    if (k >= a.n_sel[f]) return;
     const int n_words = a.P.n_markers * 4;
     for (int i = threadIdx.x; i < n_words; i += blockDim.x) sm_dict[i] = a.P.marker_size == 5 ? (unsigned long long)c_dict5[i] : c_dict6[i];
-    const int warp = threadIdx.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int* hist = reinterpret_cast<int*>(sm_dict + n_words) + warp * 256;
     uint8_t* img = reinterpret_cast<uint8_t*>(reinterpret_cast<int*>(sm_dict + n_words) + IDENT_WARPS * 256) + warp * (FID_MAX_WARP_SIDE_SQ);
+    if (threadIdx.x == 0) s_best = 0x7fffffff;
+    if (lane == 0) s_att[warp] = 0x7fffffff;
     __syncthreads();
-    const int f = blockIdx.y;
-    const int k = blockIdx.x * IDENT_WARPS + warp;
-    if (k >= a.n_sel[f]) return;
     const size_t fo = (size_t)f * a.max_raw;
     const int si = a.fs.sel_idx[fo + k];
     const uint8_t* gray = a.gray + (size_t)f * a.gray_frame_stride;
+    const int nc = a.fs.close_count[fo + si], co = a.fs.close_off[fo + si];
     WarpLanes L;
-    QuadF use = a.fs.quads[fo + si];
-    IdentifyResult r = identify_candidate(L, gray, a.W, a.H, (size_t)a.gray_pitch, use, a.P, sm_dict, img, hist);
-    if (r.id < 0) {
-        const int nc = a.fs.close_count[fo + si], co = a.fs.close_off[fo + si];
-        for (int c = 0; c < nc; c++) {
+    // attempt 0 (the selected quad) decodes for every real marker: warp 0 tries it alone, and only when it
+    // fails do all warps share the close contours (attempts 1 + w, 1 + w + 8, ...)
+    if (warp == 0) {
+        const IdentifyResult r = identify_candidate(L, gray, a.W, a.H, (size_t)a.gray_pitch, a.fs.quads[fo + si], a.P, sm_dict, img, hist);
+        if (r.id >= 0 && lane == 0) {
+            s_id[0] = r.id;
+            s_rot[0] = r.rotation;
+            s_att[0] = 0;
+            s_best = 0;
+        }
+    }
+    __syncthreads();
+    if (s_best != 0) {
+        for (int t = 1 + warp; t <= nc; t += IDENT_WARPS) {
+            if (t > *reinterpret_cast<volatile int*>(&s_best)) break;  // an earlier attempt already decoded
+            const QuadF quad = a.fs.quads[fo + a.fs.close_idx[fo + co + t - 1]];
+            const IdentifyResult r = identify_candidate(L, gray, a.W, a.H, (size_t)a.gray_pitch, quad, a.P, sm_dict, img, hist);
             __syncwarp();
-            const QuadF alt = a.fs.quads[fo + a.fs.close_idx[fo + co + c]];
-            r = identify_candidate(L, gray, a.W, a.H, (size_t)a.gray_pitch, alt, a.P, sm_dict, img, hist);
             if (r.id >= 0) {
-                use = alt;
-                break;
+                if (lane == 0) {
+                    s_id[warp] = r.id;
+                    s_rot[warp] = r.rotation;
+                    s_att[warp] = t;
+                    atomicMin(&s_best, t);
+                }
+                break;  // later attempts of this warp cannot win
             }
         }
     }
-    if ((threadIdx.x & 31) == 0) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
         const size_t o = (size_t)f * a.max_sel + k;
-        a.cand_id[o] = r.id;
-        if (r.id >= 0) {
+        int id = -1, rot = 0, att = 0;
+        for (int w = 0; w < IDENT_WARPS; w++)
+            if (s_att[w] == s_best && s_best != 0x7fffffff) {
+                id = s_id[w];
+                rot = s_rot[w];
+                att = s_att[w];
+            }
+        a.cand_id[o] = id;
+        if (id >= 0) {
+            const QuadF use = a.fs.quads[fo + (att == 0 ? si : a.fs.close_idx[fo + co + att - 1])];
             for (int c = 0; c < 4; c++) {  // correctCornerPosition: std::rotate(begin, begin + 4 - rotation, end)
-                a.cand_corners[o * 8 + 2 * c] = use.x[(c + 4 - r.rotation) & 3];
-                a.cand_corners[o * 8 + 2 * c + 1] = use.y[(c + 4 - r.rotation) & 3];
+                a.cand_corners[o * 8 + 2 * c] = use.x[(c + 4 - rot) & 3];
+                a.cand_corners[o * 8 + 2 * c + 1] = use.y[(c + 4 - rot) & 3];
             }
         }
     }

@@ -95,7 +95,8 @@ FID_HD void group_candidates(int n, const QuadF* quads, int marker_size, int bor
                              int* group_tail,      // [n]
                              int* close_count,     // [n]   number of close contours per candidate
                              int* close_idx,       // [n]   flat storage
-                             int* close_off)       // [n+1]
+                             int* close_off,       // [n+1]
+                             uint32_t* grouped)    // [(n+31)/32] scratch
 {
     int n_groups = 0;
     for (int i = 0; i < n; i++) {
@@ -105,33 +106,47 @@ FID_HD void group_candidates(int n, const QuadF* quads, int marker_size, int bor
         close_count[i] = 0;
     }
     const int n_words = (n + 31) >> 5;
+    for (int w = 0; w < n_words; w++) grouped[w] = 0;
+    // OpenCV visits the close pairs (i, j > i) in row-major order: both ungrouped -> new group; one
+    // grouped -> the other joins it; both grouped -> nothing (groups never merge).  The same marker seen at
+    // 13 scales gives hundreds of "both grouped" pairs per marker; the `grouped` bit mask skips them a
+    // word at a time (such a pair changes nothing: selected[] is already 0 for every grouped candidate).
     for (int i = 0; i < n; i++) {
         for (int w = (i + 1) >> 5; w < n_words; w++) {
-          uint32_t bits = close_word(i, w);
-          while (bits) {
-            const int j = (w << 5) + fid_ctz(bits);
-            bits &= bits - 1;
-            if (j <= i || j >= n) continue;
-            selected[i] = 0;
-            selected[j] = 0;
-            if (group_id[i] < 0 && group_id[j] < 0) {
-                const int g = n_groups++;
-                group_id[i] = group_id[j] = g;
-                group_head[g] = i;
-                next_in_group[i] = j;
-                group_tail[g] = j;
-            } else if (group_id[i] > -1 && group_id[j] == -1) {
-                const int g = group_id[i];
-                group_id[j] = g;
-                next_in_group[group_tail[g]] = j;
-                group_tail[g] = j;
-            } else if (group_id[j] > -1 && group_id[i] == -1) {
-                const int g = group_id[j];
-                group_id[i] = g;
-                next_in_group[group_tail[g]] = i;
-                group_tail[g] = i;
+            uint32_t bits = close_word(i, w);
+            if (w == ((i + 1) >> 5)) bits &= (i & 31) == 31 ? 0xFFFFFFFFu : ~((2u << (i & 31)) - 1u);  // j > i only
+            if (w == n_words - 1 && (n & 31)) bits &= (1u << (n & 31)) - 1u;                            // j < n only
+            while (bits) {
+                if (group_id[i] >= 0) {
+                    bits &= ~grouped[w];
+                    if (!bits) break;
+                }
+                const int j = (w << 5) + fid_ctz(bits);
+                bits &= bits - 1;
+                selected[i] = 0;
+                selected[j] = 0;
+                if (group_id[i] < 0 && group_id[j] < 0) {
+                    const int g = n_groups++;
+                    group_id[i] = group_id[j] = g;
+                    group_head[g] = i;
+                    next_in_group[i] = j;
+                    group_tail[g] = j;
+                    grouped[i >> 5] |= 1u << (i & 31);
+                    grouped[j >> 5] |= 1u << (j & 31);
+                } else if (group_id[i] > -1 && group_id[j] == -1) {
+                    const int g = group_id[i];
+                    group_id[j] = g;
+                    next_in_group[group_tail[g]] = j;
+                    group_tail[g] = j;
+                    grouped[j >> 5] |= 1u << (j & 31);
+                } else if (group_id[j] > -1 && group_id[i] == -1) {
+                    const int g = group_id[j];
+                    group_id[i] = g;
+                    next_in_group[group_tail[g]] = i;
+                    group_tail[g] = i;
+                    grouped[i >> 5] |= 1u << (i & 31);
+                }
             }
-          }
         }
     }
     // per group: sort members ascending (largest perimeter first), keep the first, collect the

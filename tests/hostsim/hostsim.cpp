@@ -455,6 +455,7 @@ int hs_detect(const uint8_t* gray, const uint8_t* planes, int W, int H, int dict
     }
     std::vector<uint8_t> selected(n);
     std::vector<int> gid(n), gmem(n), nxt(n), ghead(n), gtail(n), ccount(n), cidx(n), coff(n + 1);
+    std::vector<uint32_t> grouped_bits((size_t)(n + 31) / 32 + 1);
     const float rate = (float)P.min_marker_dist_rate;
     auto close_word = [&](int i, int w) -> uint32_t {
         uint32_t bits = 0;
@@ -465,7 +466,7 @@ int hs_detect(const uint8_t* gray, const uint8_t* planes, int W, int H, int dict
         return bits;
     };
     group_candidates(n, sq.data(), P.marker_size, P.marker_border_bits, (float)P.min_group_dist, close_word, selected.data(), gid.data(), gmem.data(), nxt.data(),
-                     ghead.data(), gtail.data(), ccount.data(), cidx.data(), coff.data());
+                     ghead.data(), gtail.data(), ccount.data(), cidx.data(), coff.data(), grouped_bits.data());
     std::vector<unsigned long long> dict;
     pack_dictionary(P, &dict);
     SerialLanes L;
