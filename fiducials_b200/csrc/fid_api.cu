@@ -1003,6 +1003,32 @@ extern "C" int fid_debug_threshold(fid_detector* h, const uint8_t* bgr, int widt
     return FID_OK;
 }
 
+extern "C" int fid_debug_time_threshold(fid_detector* h, int n_frames, const uint8_t* bgr_device, int width, int height, size_t row_stride, size_t frame_stride, int reps,
+                                        float* ms_per_pass) {
+    if (!h || !bgr_device || !ms_per_pass || n_frames < 1 || n_frames > h->max_batch || reps < 1 || width < 16 || height < 16 || width > h->max_w || height > h->max_h)
+        return FID_ERR_INVALID_ARG;
+    if (row_stride < (size_t)width * 3 || frame_stride < row_stride * (size_t)height || h->pend_count) return FID_ERR_INVALID_ARG;
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    Slot& s = h->slot[0];
+    const FrameGeom g = make_geom(h, width, height, row_stride, frame_stride);
+    if (!h->t0) {
+        CK(cudaEventCreate(&h->t0));
+        CK(cudaEventCreate(&h->t1));
+    }
+    float total = 0.f;
+    for (int r = -1; r < reps; r++) {  // one untimed pass first
+        const int rc = enqueue_pipeline(h, s, h->stream, n_frames, g, bgr_device, nullptr, 0.0, 0, ST_THRESH);
+        if (rc != FID_OK) return rc;
+        CK(cudaStreamSynchronize(h->stream));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, s.ev[ST_THRESH], s.ev[ST_MASKS]));
+        if (r >= 0) total += ms;
+    }
+    *ms_per_pass = total / (float)reps;
+    return FID_OK;
+}
+
 extern "C" int fid_debug_candidates(fid_detector* h, int max_candidates, int* n, int32_t* quads, int32_t* scale, int32_t* contour_len) {
     if (!h || !n) return FID_ERR_INVALID_ARG;
     CK(cudaSetDevice(h->device));

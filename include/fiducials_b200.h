@@ -164,6 +164,12 @@ int fid_memcpy_h2d(fid_detector* h, void* dst_device, const void* src_host, size
  *   planes: n_scales x H x W uint8 {0,1} (adaptiveThreshold per window size)
  * Runs only the threshold stage on one frame. */
 int fid_debug_threshold(fid_detector* h, const uint8_t* bgr, int width, int height, size_t stride, uint8_t* gray, uint8_t* planes, int* n_scales);
+/* Profiling aid: runs ONLY the threshold stage (k_gray + k_threshold) `reps` times on n_frames
+ * device-resident frames (n_frames <= max_batch), nothing else on the GPU, and returns the average device
+ * time of one pass in milliseconds (CUDA events on the launching stream).  bench.py reports the stage's
+ * roofline fraction from this figure next to the one measured inside the pipelined step. */
+int fid_debug_time_threshold(fid_detector* h, int n_frames, const uint8_t* bgr_device, int width, int height, size_t row_stride, size_t frame_stride, int reps,
+                             float* ms_per_pass);
 /* Quad candidates of the last fid_detect call on slot 0, in OpenCV's concatenation order
  * (scale-major, contour-list order): quads[n*8] int32 vertices (approxPolyDP order), scale[n],
  * contour_len[n]. */
