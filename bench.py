@@ -241,6 +241,8 @@ def run_gpu_arm(args):
         import torch.distributed as dist_mod
 
         dist = dist_mod
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # "NCCL version ..." goes to stdout, which must hold the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from fiducials_b200 import _lib, synth
