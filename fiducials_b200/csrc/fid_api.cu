@@ -77,6 +77,7 @@ struct fid_detector {
     // issue-bound stages of the others.  FID_SLOTS (2..4, default 4)
     int n_slots = 4;
     int stagger = 0;  // FID_STAGGER bit mask, see enqueue_pipeline
+    int enc = FID_ENC_BGR8, bpp = 3;  // fid_set_input_encoding
     // fid_submit_batch / fid_collect_batch: FIFO of batches in flight
     struct Pending {
         int first_slot, n_chunks, n_frames, w, h;
@@ -459,6 +460,7 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
         ga.bgr_frame_stride = g.bgr_frame_stride;
         ga.gray_pitch = g.gray_pitch;
         ga.gray_frame_stride = g.gray_frame_stride;
+        ga.enc = h->enc;
         const long long gq = (long long)nf * H * ((W + 3) / 4);
         k_gray<<<(unsigned int)((gq + 255) / 256), 256, 0, st>>>(ga);
         launches++;
@@ -717,7 +719,7 @@ extern "C" int fid_detect_pose_batch(fid_detector* h, int n_frames, const uint8_
                                      const fid_camera* cam, double fiducial_len, int n_override, const int32_t* override_ids, const double* override_lens,
                                      int max_markers, int32_t* counts, int32_t* ids, float* corners, fid_transform* transforms) {
     if (!h || !bgr || !counts || n_frames < 0 || width < 16 || height < 16 || width > h->max_w || height > h->max_h || max_markers < 0) return FID_ERR_INVALID_ARG;
-    if (row_stride < (size_t)width * 3 || frame_stride < row_stride * (size_t)height) return FID_ERR_INVALID_ARG;
+    if (row_stride < (size_t)width * h->bpp || frame_stride < row_stride * (size_t)height) return FID_ERR_INVALID_ARG;
     if (cam && !(fiducial_len > 0)) return FID_ERR_INVALID_ARG;
     if (h->pend_count) return FID_ERR_INVALID_ARG;  // batches submitted with fid_submit_batch are still in flight
     CK(cudaSetDevice(h->device));
@@ -741,7 +743,7 @@ extern "C" int fid_detect_pose_batch(fid_detector* h, int n_frames, const uint8_
             const uint8_t* src = bgr + (size_t)c * B * frame_stride;
             const uint8_t* d_in;
             FrameGeom g;
-            const bool contiguous = row_stride == (size_t)width * 3 && frame_stride == row_stride * height;
+            const bool contiguous = row_stride == (size_t)width * h->bpp && frame_stride == row_stride * height;
             if (bgr_on_device) {
                 d_in = src;
                 g = make_geom(h, width, height, row_stride, frame_stride);
@@ -749,21 +751,21 @@ extern "C" int fid_detect_pose_batch(fid_detector* h, int n_frames, const uint8_
                 // first chunk was uploaded in the background during the previous call (fid_hint_next)
                 CK(cudaStreamWaitEvent(h->slot_stream[0], h->pf_done[h->pf_idx], 0));
                 d_in = h->d_pf[h->pf_idx];
-                g = make_geom(h, width, height, (size_t)width * 3, (size_t)width * 3 * height);
+                g = make_geom(h, width, height, (size_t)width * h->bpp, (size_t)width * h->bpp * height);
                 h->pf_host = nullptr;
             } else {
                 // slot reuse: its previous results must have been collected (done below) before overwrite
-                if (row_stride == (size_t)width * 3 && frame_stride == row_stride * height) {
+                if (row_stride == (size_t)width * h->bpp && frame_stride == row_stride * height) {
                     CK(cudaMemcpyAsync(s.d_bgr, src, (size_t)nf * frame_stride, cudaMemcpyHostToDevice, h->copy_stream));
                 } else {
                     for (int f = 0; f < nf; f++)
-                        CK(cudaMemcpy2DAsync(s.d_bgr + (size_t)f * width * 3 * height, (size_t)width * 3, src + (size_t)f * frame_stride, row_stride, (size_t)width * 3, height,
+                        CK(cudaMemcpy2DAsync(s.d_bgr + (size_t)f * width * 3 * height, (size_t)width * h->bpp, src + (size_t)f * frame_stride, row_stride, (size_t)width * h->bpp, height,
                                              cudaMemcpyHostToDevice, h->copy_stream));
                 }
                 CK(cudaEventRecord(s.copied, h->copy_stream));
                 CK(cudaStreamWaitEvent(cst, s.copied, 0));
                 d_in = s.d_bgr;
-                g = make_geom(h, width, height, (size_t)width * 3, (size_t)width * 3 * height);
+                g = make_geom(h, width, height, (size_t)width * h->bpp, (size_t)width * h->bpp * height);
             }
             if (c == n_chunks - 1 && h->hint_next && !bgr_on_device && contiguous) {
                 // all uploads of this call are queued: start on the first chunk of the next call
@@ -799,7 +801,7 @@ extern "C" int fid_detect_pose_batch(fid_detector* h, int n_frames, const uint8_
 extern "C" int fid_submit_batch(fid_detector* h, int n_frames, const uint8_t* bgr, int bgr_on_device, int width, int height, size_t row_stride, size_t frame_stride,
                                 const fid_camera* cam, double fiducial_len, int n_override, const int32_t* override_ids, const double* override_lens) {
     if (!h || !bgr || n_frames <= 0 || width < 16 || height < 16 || width > h->max_w || height > h->max_h) return FID_ERR_INVALID_ARG;
-    if (row_stride < (size_t)width * 3 || frame_stride < row_stride * (size_t)height) return FID_ERR_INVALID_ARG;
+    if (row_stride < (size_t)width * h->bpp || frame_stride < row_stride * (size_t)height) return FID_ERR_INVALID_ARG;
     if (cam && !(fiducial_len > 0)) return FID_ERR_INVALID_ARG;
     const int B = h->max_batch, NS = h->n_slots;
     const int n_chunks = (n_frames + B - 1) / B;
@@ -811,7 +813,7 @@ extern "C" int fid_submit_batch(fid_detector* h, int n_frames, const uint8_t* bg
     if (rc != FID_OK) return rc;
     h->last_w = width;
     h->last_h = height;
-    const bool contiguous = row_stride == (size_t)width * 3 && frame_stride == row_stride * height;
+    const bool contiguous = row_stride == (size_t)width * h->bpp && frame_stride == row_stride * height;
     const int first = h->slot_next;
     h->counters[6] = 0;
     for (int c = 0; c < n_chunks; c++) {
@@ -830,13 +832,13 @@ extern "C" int fid_submit_batch(fid_detector* h, int n_frames, const uint8_t* bg
                 CK(cudaMemcpyAsync(s.d_bgr, src, (size_t)nf * frame_stride, cudaMemcpyHostToDevice, h->copy_stream));
             } else {
                 for (int f = 0; f < nf; f++)
-                    CK(cudaMemcpy2DAsync(s.d_bgr + (size_t)f * width * 3 * height, (size_t)width * 3, src + (size_t)f * frame_stride, row_stride, (size_t)width * 3, height,
+                    CK(cudaMemcpy2DAsync(s.d_bgr + (size_t)f * width * 3 * height, (size_t)width * h->bpp, src + (size_t)f * frame_stride, row_stride, (size_t)width * h->bpp, height,
                                          cudaMemcpyHostToDevice, h->copy_stream));
             }
             CK(cudaEventRecord(s.copied, h->copy_stream));
             CK(cudaStreamWaitEvent(cst, s.copied, 0));
             d_in = s.d_bgr;
-            g = make_geom(h, width, height, (size_t)width * 3, (size_t)width * 3 * height);
+            g = make_geom(h, width, height, (size_t)width * h->bpp, (size_t)width * h->bpp * height);
         }
         const Slot* prev = (h->slots_in_use + c) > 0 ? &h->slot[(si + NS - 1) % NS] : nullptr;
         rc = enqueue_pipeline(h, s, cst, nf, g, d_in, cam, fiducial_len, n_override, -1, prev);
@@ -914,6 +916,16 @@ extern "C" int fid_pose(fid_detector* h, int n, const int32_t* ids, const float*
     return FID_OK;
 }
 
+extern "C" int fid_set_input_encoding(fid_detector* h, int encoding) {
+    if (!h || h->pend_count) return FID_ERR_INVALID_ARG;
+    if (encoding != FID_ENC_BGR8 && encoding != FID_ENC_RGB8 && encoding != FID_ENC_MONO8) return FID_ERR_UNSUPPORTED;
+    h->enc = encoding;
+    h->bpp = encoding == FID_ENC_MONO8 ? 1 : 3;
+    h->pf_host = nullptr;  // a prefetched chunk was laid out for the old encoding
+    h->hint_next = nullptr;
+    return FID_OK;
+}
+
 extern "C" int fid_hint_next(fid_detector* h, const uint8_t* next_bgr) {
     if (!h) return FID_ERR_INVALID_ARG;
     h->hint_next = next_bgr;
@@ -979,11 +991,11 @@ extern "C" int fid_memcpy_h2d(fid_detector* h, void* dst_device, const void* src
 }
 
 extern "C" int fid_debug_threshold(fid_detector* h, const uint8_t* bgr, int width, int height, size_t stride, uint8_t* gray, uint8_t* planes, int* n_scales) {
-    if (!h || !bgr || width < 16 || height < 16 || width > h->max_w || height > h->max_h || stride < (size_t)width * 3) return FID_ERR_INVALID_ARG;
+    if (!h || !bgr || width < 16 || height < 16 || width > h->max_w || height > h->max_h || stride < (size_t)width * h->bpp) return FID_ERR_INVALID_ARG;
     CK(cudaSetDevice(h->device));
     Slot& s = h->slot[0];
-    CK(cudaMemcpy2DAsync(s.d_bgr, (size_t)width * 3, bgr, stride, (size_t)width * 3, height, cudaMemcpyHostToDevice, h->stream));
-    const FrameGeom g = make_geom(h, width, height, (size_t)width * 3, (size_t)width * 3 * height);
+    CK(cudaMemcpy2DAsync(s.d_bgr, (size_t)width * h->bpp, bgr, stride, (size_t)width * h->bpp, height, cudaMemcpyHostToDevice, h->stream));
+    const FrameGeom g = make_geom(h, width, height, (size_t)width * h->bpp, (size_t)width * h->bpp * height);
     const int rc = enqueue_pipeline(h, s, h->stream, 1, g, s.d_bgr, nullptr, 0.0, 0, ST_THRESH);
     if (rc != FID_OK) return rc;
     CK(cudaStreamSynchronize(h->stream));
@@ -1007,7 +1019,7 @@ extern "C" int fid_debug_time_threshold(fid_detector* h, int n_frames, const uin
                                         float* ms_per_pass) {
     if (!h || !bgr_device || !ms_per_pass || n_frames < 1 || n_frames > h->max_batch || reps < 1 || width < 16 || height < 16 || width > h->max_w || height > h->max_h)
         return FID_ERR_INVALID_ARG;
-    if (row_stride < (size_t)width * 3 || frame_stride < row_stride * (size_t)height || h->pend_count) return FID_ERR_INVALID_ARG;
+    if (row_stride < (size_t)width * h->bpp || frame_stride < row_stride * (size_t)height || h->pend_count) return FID_ERR_INVALID_ARG;
     CK(cudaSetDevice(h->device));
     CK(cudaDeviceSynchronize());
     Slot& s = h->slot[0];

@@ -434,6 +434,60 @@ extern "C" int fid_map_entries(fid_map* m, int instance, int max_entries, int* n
     return st.overflow ? FID_ERR_CAPACITY : FID_OK;
 }
 
+// links (map.cpp:217-222, saved by saveMap :557-559): the device keeps them as a slot x slot bit matrix.
+extern "C" int fid_map_links(fid_map* m, int instance, int max_pairs, int* n_pairs, int32_t* pairs) {
+    if (!m || instance < 0 || instance >= m->p.n_instances || !n_pairs || max_pairs < 0) return FID_ERR_INVALID_ARG;
+    CK(cudaSetDevice(m->device));
+    CK(cudaStreamSynchronize(m->stream));
+    MapState st;
+    CK(cudaMemcpy(&st, m->d_state + instance, sizeof(st), cudaMemcpyDeviceToHost));
+    const int cap = m->p.max_fiducials, wpr = (cap + 31) / 32;
+    std::vector<MapEntry> e(st.n);
+    std::vector<uint32_t> rows((size_t)st.n * wpr);
+    if (st.n) {
+        CK(cudaMemcpy(e.data(), m->d_entries + (size_t)instance * st.capacity, sizeof(MapEntry) * st.n, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(rows.data(), m->d_links + (size_t)instance * cap * wpr, sizeof(uint32_t) * rows.size(), cudaMemcpyDeviceToHost));
+    }
+    std::vector<std::pair<int32_t, int32_t>> out;
+    for (int i = 0; i < st.n; i++)
+        for (int j = 0; j < st.n; j++)
+            if ((rows[(size_t)i * wpr + (j >> 5)] >> (j & 31)) & 1u) out.emplace_back(e[i].id, e[j].id);
+    std::sort(out.begin(), out.end());  // std::map<int, Fiducial> / std::set<int> links iterate ascending
+    *n_pairs = (int)out.size();
+    if ((int)out.size() > max_pairs) return FID_ERR_CAPACITY;
+    for (size_t k = 0; k < out.size() && pairs; k++) {
+        pairs[2 * k] = out[k].first;
+        pairs[2 * k + 1] = out[k].second;
+    }
+    return FID_OK;
+}
+
+extern "C" int fid_map_add_links(fid_map* m, int instance, int n_pairs, const int32_t* pairs) {
+    if (!m || instance < 0 || instance >= m->p.n_instances || n_pairs < 0 || (n_pairs > 0 && !pairs)) return FID_ERR_INVALID_ARG;
+    if (n_pairs == 0) return FID_OK;
+    CK(cudaSetDevice(m->device));
+    CK(cudaStreamSynchronize(m->stream));
+    MapState st;
+    CK(cudaMemcpy(&st, m->d_state + instance, sizeof(st), cudaMemcpyDeviceToHost));
+    const int cap = m->p.max_fiducials, wpr = (cap + 31) / 32;
+    std::vector<MapEntry> e(st.n);
+    std::vector<uint32_t> rows((size_t)st.n * wpr);
+    if (!st.n) return FID_OK;
+    CK(cudaMemcpy(e.data(), m->d_entries + (size_t)instance * st.capacity, sizeof(MapEntry) * st.n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(rows.data(), m->d_links + (size_t)instance * cap * wpr, sizeof(uint32_t) * rows.size(), cudaMemcpyDeviceToHost));
+    auto slot_of = [&](int32_t id) {
+        for (int i = 0; i < st.n; i++)
+            if (e[i].id == id) return i;
+        return -1;
+    };
+    for (int k = 0; k < n_pairs; k++) {
+        const int i = slot_of(pairs[2 * k]), j = slot_of(pairs[2 * k + 1]);
+        if (i >= 0 && j >= 0) rows[(size_t)i * wpr + (j >> 5)] |= 1u << (j & 31);  // a link to a fiducial that is not in the map cannot be kept
+    }
+    CK(cudaMemcpy(m->d_links + (size_t)instance * cap * wpr, rows.data(), sizeof(uint32_t) * rows.size(), cudaMemcpyHostToDevice));
+    return FID_OK;
+}
+
 extern "C" int fid_map_export_device(fid_map* m, int instance, void** device_table, size_t* bytes) {
     if (!m || instance < 0 || instance >= m->p.n_instances || !device_table || !bytes) return FID_ERR_INVALID_ARG;
     CK(cudaSetDevice(m->device));

@@ -29,6 +29,7 @@ struct GrayArgs {
     size_t bgr_row_stride, bgr_frame_stride;
     int gray_pitch;
     size_t gray_frame_stride;
+    int enc;  // FID_ENC_*: what cv_bridge::toCvCopy(msg, BGR8) would have been given (aruco_detect.cpp:348)
 };
 
 __device__ __forceinline__ uint32_t gray_of(uint32_t b, uint32_t g, uint32_t r) { return (3735u * b + 19235u * g + 9798u * r + 16384u) >> 15; }
@@ -42,19 +43,34 @@ __global__ void __launch_bounds__(256) k_gray(const GrayArgs a) {
     const long long t = gid / quads;
     const int y = (int)(t % a.H), f = (int)(t / a.H);
     const int x = q * 4;
-    const uint8_t* src = a.bgr + (size_t)f * a.bgr_frame_stride + (size_t)y * a.bgr_row_stride + 3 * (size_t)x;
     uint8_t* dst = a.gray + (size_t)f * a.gray_frame_stride + (size_t)y * a.gray_pitch + x;
+    if (a.enc == 2) {  // MONO8: toCvCopy replicates the channel and BGR2GRAY of (g,g,g) is g exactly ((32768 g + 16384) >> 15)
+        const uint8_t* src = a.bgr + (size_t)f * a.bgr_frame_stride + (size_t)y * a.bgr_row_stride + (size_t)x;
+        if (x + 3 < a.W && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
+            *reinterpret_cast<uint32_t*>(dst) = __ldg(reinterpret_cast<const uint32_t*>(src));
+        } else {
+            for (int k = 0; k < 4 && x + k < a.W; k++) dst[k] = src[k];
+        }
+        return;
+    }
+    const uint8_t* src = a.bgr + (size_t)f * a.bgr_frame_stride + (size_t)y * a.bgr_row_stride + 3 * (size_t)x;
+    const bool rgb = a.enc == 1;  // RGB8: toCvCopy swaps the channels first, i.e. the first byte is R
     if (x + 3 < a.W && ((reinterpret_cast<uintptr_t>(src) & 3) == 0)) {
         const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(src));      // B0 G0 R0 B1
         const uint32_t w1 = __ldg(reinterpret_cast<const uint32_t*>(src) + 1);  // G1 R1 B2 G2
         const uint32_t w2 = __ldg(reinterpret_cast<const uint32_t*>(src) + 2);  // R2 B3 G3 R3
-        const uint32_t g0 = gray_of(w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u);
-        const uint32_t g1 = gray_of(w0 >> 24, w1 & 255u, (w1 >> 8) & 255u);
-        const uint32_t g2 = gray_of((w1 >> 16) & 255u, w1 >> 24, w2 & 255u);
-        const uint32_t g3 = gray_of((w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24);
-        *reinterpret_cast<uint32_t*>(dst) = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);  // gray_pitch and x are multiples of 4
+        uint32_t c0[4] = {w0 & 255u, w0 >> 24, (w1 >> 16) & 255u, (w2 >> 8) & 255u};
+        const uint32_t c1[4] = {(w0 >> 8) & 255u, w1 & 255u, w1 >> 24, (w2 >> 16) & 255u};
+        uint32_t c2[4] = {(w0 >> 16) & 255u, (w1 >> 8) & 255u, w2 & 255u, w2 >> 24};
+        uint32_t out = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) out |= (rgb ? gray_of(c2[k], c1[k], c0[k]) : gray_of(c0[k], c1[k], c2[k])) << (8 * k);
+        *reinterpret_cast<uint32_t*>(dst) = out;  // gray_pitch and x are multiples of 4
     } else {
-        for (int k = 0; k < 4 && x + k < a.W; k++) dst[k] = (uint8_t)gray_of(src[3 * k], src[3 * k + 1], src[3 * k + 2]);
+        for (int k = 0; k < 4 && x + k < a.W; k++) {
+            const uint32_t p0 = src[3 * k], p1 = src[3 * k + 1], p2 = src[3 * k + 2];
+            dst[k] = (uint8_t)(rgb ? gray_of(p2, p1, p0) : gray_of(p0, p1, p2));
+        }
     }
 }
 

@@ -9,6 +9,9 @@
 #include <map>
 #include <stdexcept>
 #include <string>
+#include <sstream>
+#include <cstdio>
+#include <cmath>
 #include <vector>
 
 #include "../../include/fiducials_b200.h"
@@ -190,6 +193,56 @@ class FiducialSlam {
         FiducialMapEntryArray out;
         for (int i = 0; i < n; i++) out.fiducials.push_back(FiducialMapEntry{e[i].fiducial_id, e[i].x, e[i].y, e[i].z, e[i].rx, e[i].ry, e[i].rz});
         return out;
+    }
+
+    // Map::saveMap, map.cpp:541-566
+    bool saveMap(const std::string& filename) {
+        std::vector<fid_map_entry> e(cap);
+        int n = 0, np = 0;
+        check(fid_map_entries(map, 0, cap, &n, e.data()), "fid_map_entries");
+        std::vector<int32_t> pairs((size_t)2 * cap * cap);
+        check(fid_map_links(map, 0, cap * cap, &np, pairs.data()), "fid_map_links");
+        FILE* fp = fopen(filename.c_str(), "w");
+        if (fp == NULL) return false;
+        for (int i = 0; i < n; i++) {
+            fprintf(fp, "%d %lf %lf %lf %lf %lf %lf %lf %d", e[i].fiducial_id, e[i].x, e[i].y, e[i].z, e[i].rx * 180.0 / M_PI, e[i].ry * 180.0 / M_PI, e[i].rz * 180.0 / M_PI,
+                    e[i].variance, e[i].num_obs);
+            for (int k = 0; k < np; k++)
+                if (pairs[2 * k] == e[i].fiducial_id) fprintf(fp, " %d", pairs[2 * k + 1]);
+            fprintf(fp, "\n");
+        }
+        fclose(fp);
+        return true;
+    }
+
+    // Map::loadMap(filename), map.cpp:572-625 (same sscanf format; invalid lines are skipped)
+    bool loadMap(const std::string& filename) {
+        FILE* fp = fopen(filename.c_str(), "r");
+        if (fp == NULL) return false;
+        const int BUFSIZE = 2048;
+        char linebuf[BUFSIZE], linkbuf[BUFSIZE];
+        std::vector<fid_map_file_entry> rows;
+        std::vector<int32_t> pairs;
+        while (!feof(fp)) {
+            if (fgets(linebuf, BUFSIZE - 1, fp) == NULL) break;
+            fid_map_file_entry r;
+            r.num_obs = 0;
+            linkbuf[0] = '\0';
+            const int nElems = sscanf(linebuf, "%d %lf %lf %lf %lf %lf %lf %lf %d%[^\t\n]*s", &r.fiducial_id, &r.x, &r.y, &r.z, &r.roll_deg, &r.pitch_deg, &r.yaw_deg, &r.variance,
+                                      &r.num_obs, linkbuf);
+            if (nElems != 9 && nElems != 10) continue;
+            rows.push_back(r);
+            std::istringstream ss(linkbuf);
+            std::string tok;
+            while (getline(ss, tok, ' '))
+                if (!tok.empty()) {
+                    pairs.push_back(r.fiducial_id);
+                    pairs.push_back(std::stoi(tok));
+                }
+        }
+        fclose(fp);
+        if (fid_map_load(map, 0, (int)rows.size(), rows.data()) != FID_OK) return false;
+        return fid_map_add_links(map, 0, (int)pairs.size() / 2, pairs.data()) == FID_OK;
     }
 
    private:

@@ -11,6 +11,7 @@ parity tests and bench.py; the C++ twin for a real ROS node is fiducials_b200/cs
 from __future__ import annotations
 
 import ctypes as C
+import math
 from typing import Dict, Iterable, List, Optional, Sequence
 
 import numpy as np
@@ -49,6 +50,7 @@ class Detector:
     def __init__(self, params=None, device=0, max_width=1920, max_height=1080, max_batch=1):
         self.lib = _lib.load()
         self.params = params if params is not None else default_params()
+        self.bpp = 3
         self.h = C.c_void_p()
         _lib.check(self.lib.fid_create(C.byref(self.params), device, max_width, max_height, max_batch, C.byref(self.h)), "fid_create")
         self.max_batch = max_batch
@@ -69,6 +71,14 @@ class Detector:
         _lib.check(self.lib.fid_set_params(self.h, C.byref(params)))
         self.params = params
 
+    ENCODINGS = {"bgr8": 0, "rgb8": 1, "mono8": 2}
+
+    def set_input_encoding(self, encoding: str):
+        """fid_set_input_encoding: the camera's own sensor_msgs/Image encoding ("bgr8", "rgb8", "mono8"; frames are then
+        [n,H,W,3] or [n,H,W]) instead of the BGR8 copy cv_bridge makes for the reference (aruco_detect.cpp:348)."""
+        _lib.check(self.lib.fid_set_input_encoding(self.h, self.ENCODINGS[encoding]), "fid_set_input_encoding")
+        self.bpp = 1 if encoding == "mono8" else 3
+
     def detect(self, bgr: np.ndarray):
         """fid_detect: (ids int32[n], corners float32[n,4,2])."""
         bgr = np.ascontiguousarray(bgr, np.uint8)
@@ -76,7 +86,7 @@ class Detector:
         ids = np.zeros(MAXM, np.int32)
         corners = np.zeros((MAXM, 8), np.float32)
         n = C.c_int(0)
-        _lib.check(self.lib.fid_detect(self.h, bgr.ctypes.data_as(C.c_void_p), W, H, W * 3, MAXM, C.byref(n), ids.ctypes.data_as(C.c_void_p),
+        _lib.check(self.lib.fid_detect(self.h, bgr.ctypes.data_as(C.c_void_p), W, H, W * self.bpp, MAXM, C.byref(n), ids.ctypes.data_as(C.c_void_p),
                                        corners.ctypes.data_as(C.c_void_p)), "fid_detect")
         return ids[: n.value].copy(), corners[: n.value].reshape(-1, 4, 2).copy()
 
@@ -109,7 +119,7 @@ class Detector:
             self._out_key = key
         counts, ids, corners, tfs = self._out
         oi, ol, no = _overrides(overrides)
-        st = self.lib.fid_detect_pose_batch(self.h, n, ptr, 1 if on_device else 0, W, H, W * 3, W * 3 * H, C.byref(cam) if cam is not None else None, float(fiducial_len), no,
+        st = self.lib.fid_detect_pose_batch(self.h, n, ptr, 1 if on_device else 0, W, H, W * self.bpp, W * self.bpp * H, C.byref(cam) if cam is not None else None, float(fiducial_len), no,
                                             oi.ctypes.data_as(C.c_void_p), ol.ctypes.data_as(C.c_void_p), MAXM, counts.ctypes.data_as(C.c_void_p),
                                             ids.ctypes.data_as(C.c_void_p), corners.ctypes.data_as(C.c_void_p), C.cast(tfs, C.c_void_p) if tfs is not None else None)
         _lib.check(st, "fid_detect_pose_batch")
@@ -127,7 +137,7 @@ class Detector:
             ptr = frames.ctypes.data_as(C.c_void_p)
         cam = _camera(K, D) if K is not None else None
         oi, ol, no = _overrides(overrides)
-        _lib.check(self.lib.fid_submit_batch(self.h, n, ptr, 1 if on_device else 0, W, H, W * 3, W * 3 * H, C.byref(cam) if cam is not None else None, float(fiducial_len), no,
+        _lib.check(self.lib.fid_submit_batch(self.h, n, ptr, 1 if on_device else 0, W, H, W * self.bpp, W * self.bpp * H, C.byref(cam) if cam is not None else None, float(fiducial_len), no,
                                              oi.ctypes.data_as(C.c_void_p), ol.ctypes.data_as(C.c_void_p)), "fid_submit_batch")
         if not hasattr(self, "_pending"):
             self._pending = []
@@ -150,7 +160,7 @@ class Detector:
         gray = np.zeros((H, W), np.uint8)
         planes = np.zeros((16, H, W), np.uint8)
         ns = C.c_int(0)
-        _lib.check(self.lib.fid_debug_threshold(self.h, bgr.ctypes.data_as(C.c_void_p), W, H, W * 3, gray.ctypes.data_as(C.c_void_p), planes.ctypes.data_as(C.c_void_p),
+        _lib.check(self.lib.fid_debug_threshold(self.h, bgr.ctypes.data_as(C.c_void_p), W, H, W * self.bpp, gray.ctypes.data_as(C.c_void_p), planes.ctypes.data_as(C.c_void_p),
                                                 C.byref(ns)))
         return gray, planes[: ns.value]
 
@@ -323,6 +333,48 @@ class FiducialSlam:
             arr[i].x, arr[i].y, arr[i].z, arr[i].roll_deg, arr[i].pitch_deg, arr[i].yaw_deg, arr[i].variance = [float(v) for v in e[1:8]]
             arr[i].num_obs = int(e[8]) if len(e) > 8 else 0
         _lib.check(self.lib.fid_map_load(self.h, instance, len(entries), C.cast(arr, C.c_void_p)))
+
+    def links(self, instance=0):
+        """fid_map_links: {fiducial_id: sorted linked ids} (Fiducial::links, map.h:87)."""
+        cap = self.p.max_fiducials
+        pairs = np.zeros((cap * cap, 2), np.int32)
+        n = C.c_int(0)
+        _lib.check(self.lib.fid_map_links(self.h, instance, cap * cap, C.byref(n), pairs.ctypes.data_as(C.c_void_p)))
+        out: Dict[int, List[int]] = {}
+        for a, b in pairs[: n.value]:
+            out.setdefault(int(a), []).append(int(b))
+        return out
+
+    def saveMap(self, filename, instance=0):
+        """Map::saveMap, map.cpp:541-566: `id x y z rx ry rz(deg) variance numObs links...`, %lf formatting."""
+        links = self.links(instance)
+        with open(filename, "w") as fp:
+            for e in self.entries(instance):
+                rad2deg = lambda a: a * 180.0 / math.pi  # helpers.h:8
+                fp.write("%d %f %f %f %f %f %f %f %d" % (e.fiducial_id, e.x, e.y, e.z, rad2deg(e.rx), rad2deg(e.ry), rad2deg(e.rz), e.variance, e.num_obs))
+                fp.write("".join(" %d" % k for k in links.get(e.fiducial_id, [])) + "\n")
+        return True
+
+    def loadMapFile(self, filename, instance=0):
+        """Map::loadMap(filename), map.cpp:572-625.  Returns the number of entries read (invalid lines are skipped
+        like the reference's ROS_WARN("Invalid line"))."""
+        rows, pairs = [], []
+        with open(filename) as fp:
+            for line in fp:
+                tok = line.split("\t")[0].split()
+                try:
+                    row = [int(tok[0])] + [float(v) for v in tok[1:8]] + [int(tok[8])]
+                    if len(row) != 9:
+                        raise ValueError
+                except (ValueError, IndexError):
+                    continue
+                rows.append(row)
+                pairs += [(row[0], int(v)) for v in tok[9:]]
+        self.loadMap(rows, instance)
+        if pairs:
+            arr = np.ascontiguousarray(np.array(pairs, np.int32))
+            _lib.check(self.lib.fid_map_add_links(self.h, instance, len(pairs), arr.ctypes.data_as(C.c_void_p)))
+        return len(rows)
 
     @staticmethod
     def _obs(transforms):

@@ -140,6 +140,15 @@ int fid_submit_batch(fid_detector* h, int n_frames, const uint8_t* bgr, int bgr_
                      const fid_camera* cam, double fiducial_len, int n_override, const int32_t* override_ids, const double* override_lens);
 int fid_collect_batch(fid_detector* h, int max_markers, int32_t* counts, int32_t* ids, float* corners, fid_transform* transforms);
 
+/* Pixel format of the frames handed to every entry point that takes `bgr` (default FID_ENC_BGR8).  The
+ * reference converts whatever the camera publishes with cv_bridge::toCvCopy(msg, BGR8)
+ * (aruco_detect.cpp:348) before detectMarkers turns it into gray again; the library takes the camera's own
+ * encoding and produces the identical gray plane: RGB8 = channels swapped, MONO8 = the plane itself (one
+ * byte per pixel: a third of the upload).  Strides are in bytes of that encoding.  Not while batches are
+ * in flight. */
+enum { FID_ENC_BGR8 = 0, FID_ENC_RGB8 = 1, FID_ENC_MONO8 = 2 };
+int fid_set_input_encoding(fid_detector* h, int encoding);
+
 /* Streaming hint: `next_bgr` (pinned host memory, same frame count and geometry as the call that
  * follows this hint) will be the `bgr` argument of the call after that one.  The library then
  * uploads its first chunk in the background once the uploads of the call in progress are queued, so
@@ -213,6 +222,12 @@ typedef struct fid_map_file_entry {
     double x, y, z, roll_deg, pitch_deg, yaw_deg, variance;
 } fid_map_file_entry;
 int fid_map_load(fid_map* m, int instance, int n, const fid_map_file_entry* entries);
+
+/* The link sets of the map (Fiducial::links, map.h:87; filled by updateMap map.cpp:217-222, written after
+ * numObs on every line of the map file, saveMap :557-559 / loadMap :608-615) as (fiducial_id, linked_id) pairs in
+ * ascending order.  fid_map_add_links is the loadMap direction; a link to an id that is not in the map is dropped. */
+int fid_map_links(fid_map* m, int instance, int max_pairs, int* n_pairs, int32_t* pairs);
+int fid_map_add_links(fid_map* m, int instance, int n_pairs, const int32_t* pairs);
 
 /* 7-vector transform: x y z qx qy qz qw (what the host obtains from tf, map.cpp:258-273). */
 typedef struct fid_tf {

@@ -362,6 +362,40 @@ class Map:
         return out
 
 
+def save_map_text(m: "Map") -> str:
+    """Map::saveMap, map.cpp:541-566: one line per fiducial in ascending id,
+    `id x y z rx ry rz(deg) variance numObs link link ...` with C's %lf (six decimals)."""
+    lines = []
+    for fid in sorted(m.fiducials):
+        f = m.fiducials[fid]
+        r, p, y = get_rpy(f.pose.R)
+        rad2deg = lambda a: a * 180.0 / math.pi  # helpers.h:8
+        head = "%d %f %f %f %f %f %f %f %d" % (f.id, f.pose.t[0], f.pose.t[1], f.pose.t[2], rad2deg(r), rad2deg(p), rad2deg(y), f.pose.var, f.numObs)
+        lines.append(head + "".join(" %d" % k for k in sorted(f.links)))
+    return "".join(line + "\n" for line in lines)
+
+
+def load_map_text(m: "Map", text: str) -> int:
+    """Map::loadMap, map.cpp:572-625: sscanf("%d %lf %lf %lf %lf %lf %lf %lf %d%[^\t\n]*s"); a line is accepted when
+    the nine leading fields parse (nElems 9 or 10), the rest of the line is a blank-separated list of linked ids.
+    Returns the number of entries read."""
+    n = 0
+    for line in text.splitlines():
+        tok = line.split("\t")[0].split()
+        try:
+            fid = int(tok[0])
+            vals = [float(v) for v in tok[1:8]]
+            num_obs = int(tok[8])
+            if len(vals) != 7:
+                raise ValueError
+        except (ValueError, IndexError):
+            continue  # ROS_WARN("Invalid line")
+        links = [int(v) for v in tok[9:]]
+        m.load_entry(fid, *vals, num_obs=num_obs, links=links)
+        n += 1
+    return n
+
+
 def merge_maps(tables):
     """Deterministic merge of per-rank map tables (NEW -- no reference counterpart; parity
     unpinned, checked only against this restatement).  ``tables`` = list (rank order) of lists of

@@ -43,6 +43,12 @@ int main(int argc, char** argv) {
         for (int i = 0; i < 13; i++) slam.transformCallback(fta, &ident, &ident, &robot);
         for (const auto& e : slam.publishMap().fiducials) std::printf("M %d %.17g %.17g %.17g %.17g %.17g %.17g\n", e.fiducial_id, e.x, e.y, e.z, e.rx, e.ry, e.rz);
         std::printf("R %d %.17g %.17g %.17g\n", robot.valid, robot.t[0], robot.t[1], robot.t[2]);
+        // saveMap / loadMap round trip through the reference's text format (map.cpp:541-625)
+        const std::string path = std::string(argv[1]) + ".map.txt";
+        if (!slam.saveMap(path)) return 6;
+        fid_glue::FiducialSlam slam2(64);
+        if (!slam2.loadMap(path) || !slam2.saveMap(path + "2")) return 7;
+        std::printf("F %s\n", path.c_str());
     } catch (const std::exception& e) {
         std::fprintf(stderr, "error: %s\n", e.what());
         return 1;

@@ -251,6 +251,41 @@ def test_submit_collect_pipeline(det_cache):
     assert lib.fid_collect_batch(det.h, 256, got[0].ctypes.data_as(C.c_void_p), None, None, None) == -1  # nothing in flight
 
 
+def test_input_encodings(det_cache):
+    """fid_set_input_encoding: rgb8 and mono8 frames give exactly what the reference gets after
+    cv_bridge::toCvCopy(msg, BGR8) (aruco_detect.cpp:348) -- checked against the oracle on the converted frame."""
+    import cv2
+    from fiducials_b200.node import Detector, default_params
+
+    bgr, _, K, D, d = synth.make_config_frame("C1", 6)
+    bgr = bgr.copy()
+    bgr[..., 0] = np.clip(bgr[..., 0].astype(int) + 25, 0, 255)  # make the channels differ so that a swap would show
+    bgr[..., 2] = np.clip(bgr[..., 2].astype(int) - 30, 0, 255)
+    det = Detector(default_params(dictionary=d), 0, 640, 480, 2)
+    try:
+        ref_ids, ref_c = det.detect(bgr)
+        oi, oc = ao.detect(bgr, d)
+        assert ref_ids.tolist() == oi.tolist() and len(oi) >= 3
+        det.set_input_encoding("rgb8")
+        ids, c = det.detect(np.ascontiguousarray(bgr[..., ::-1]))
+        assert ids.tolist() == ref_ids.tolist() and np.array_equal(c, ref_c)
+        det.set_input_encoding("mono8")
+        mono = cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY)
+        oi, oc = ao.detect(cv2.cvtColor(mono, cv2.COLOR_GRAY2BGR), d)  # what toCvCopy(mono8 -> BGR8) hands to detectMarkers
+        ids, c = det.detect(mono)
+        assert ids.tolist() == oi.tolist() and np.abs(c - oc).max() <= 1e-3
+        g, planes = det.debug_threshold(mono)
+        assert np.array_equal(g, mono)
+        counts, bids, bc, tfs = det.detect_pose_batch(np.stack([mono, mono, mono]), K, D, 0.14)  # 3 frames, 2-frame chunks
+        for f in range(3):
+            assert bids[f, : counts[f]].tolist() == ids.tolist() and np.array_equal(bc[f, : counts[f]], c)
+        det.set_input_encoding("bgr8")
+        ids, c = det.detect(bgr)
+        assert ids.tolist() == ref_ids.tolist() and np.array_equal(c, ref_c)
+    finally:
+        det.close()
+
+
 @pytest.mark.parametrize("kind", ["black", "white", "noise", "stripes"])
 def test_frames_without_markers(det_cache, kind):
     rng = np.random.default_rng(5)

@@ -52,6 +52,43 @@ def test_create_map_sequence(kat):
     assert [f.fiducial_id for f in msg.fiducials] == sorted(ents)
 
 
+def test_save_and_load_map_file(kat, tmp_path):
+    """saveMap / loadMap (map.cpp:541-625) through the device map: after the create_map sequence the file written
+    from the GPU state equals the oracle's line for line (ids, numObs and links exactly, values to the file's %lf
+    precision); loading it into a fresh handle and replaying gives the oracle's result for the same history."""
+    from fiducials_b200.node import FiducialSlam
+
+    tr = _bag_transforms(kat)
+    ident = so.TWV.identity()
+    ref = so.Map()
+    ref.load_entry(111, 0, 0, 0, 0, 0, 0, 0, 0)
+    slam = FiducialSlam(max_fiducials=32)
+    slam.loadMap([[111, 0, 0, 0, 0, 0, 0, 0, 0]])
+    for _ in range(15):
+        ref.update(so.observations_from_transforms(tr), ident, ident)
+        slam.transformCallback(tr, _tf7(ident), _tf7(ident))
+    path = tmp_path / "map.txt"
+    assert slam.saveMap(str(path))
+    got = [l.split() for l in path.read_text().splitlines()]
+    exp = [l.split() for l in so.save_map_text(ref).splitlines()]
+    assert len(got) == len(exp) == len(ref.fiducials) and len(exp) > 3
+    for g, e in zip(got, exp):
+        assert g[0] == e[0] and g[8:] == e[8:] and len(g) > 9  # id, numObs, links
+        assert np.abs(np.array(g[1:8], float) - np.array(e[1:8], float)).max() <= 2e-6
+    # load into fresh maps (device and oracle) and keep going: same history -> same result
+    slam2 = FiducialSlam(max_fiducials=32)
+    assert slam2.loadMapFile(str(path)) == len(exp)
+    assert slam2.links() == slam.links()
+    ref2 = so.Map()
+    so.load_map_text(ref2, path.read_text())
+    for _ in range(5):
+        ref2.update(so.observations_from_transforms(tr), ident, ident)
+        slam2.transformCallback(tr, _tf7(ident), _tf7(ident))
+    _cmp_entries(slam2.entries(), ref2.entries(), 1e-9)
+    slam.close()
+    slam2.close()
+
+
 def test_auto_init_403_golden(kat):
     from fiducials_b200.node import Detector, FiducialSlam, default_params
 

@@ -56,3 +56,11 @@ def test_node_glue_messages_match_oracle(tmp_path):
         vals = np.array(t[2:], float)
         assert np.abs(vals[:3] - fields[i]["translation"]).max() < 1e-3 and np.abs(vals[3:7] - fields[i]["rotation"]).max() < 1e-3
     assert sorted(int(m[1]) for m in M) == sorted(ids.tolist())
+    # saveMap -> loadMap -> saveMap through the reference's text format: same ids, numObs and links, values to %lf precision
+    path = [l.split()[1] for l in r.stdout.splitlines() if l.startswith("F ")][0]
+    a = [l.split() for l in open(path).read().splitlines()]
+    b = [l.split() for l in open(path + "2").read().splitlines()]
+    assert len(a) == len(ids) and [int(l[0]) for l in a] == sorted(ids.tolist())
+    for la, lb in zip(a, b):
+        assert la[0] == lb[0] and la[8:] == lb[8:] and len(la) == 9 + len(ids) - 1  # every marker of the frame links to the others
+        assert np.abs(np.array(la[1:8], float) - np.array(lb[1:8], float)).max() <= 2e-6

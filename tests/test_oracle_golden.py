@@ -155,3 +155,30 @@ def test_tv_outlier_with_large_variance():  # :79-107
 def test_tv_different_with_similar_variance():  # :109-126
     out = so.average_transforms(_twv(0.0, 0.1), _twv(1.0, 0.2, (1, 0, 0)))
     assert 0 < out.t[0] < 1.0 and 0 < _angle(out) < 1.0 and out.var > 0.2
+
+
+def test_map_file_format_reference_fixtures(tmp_path):
+    """saveMap / loadMap text format (fiducial_slam/src/map.cpp:541-625).  The two map files the reference ships
+    (fiducial_slam/test/111_initial_map.txt, 610_initial_map.txt -- one line each, quoted here) load into the
+    poses its launch tests expect, and a map with links survives save -> load -> save byte for byte."""
+    from oracle import slam_oracle as so
+
+    m = so.Map()
+    assert so.load_map_text(m, "111 0 0 0 0 0 0 0 0\n") == 1  # 111_initial_map.txt
+    f = m.fiducials[111]
+    assert f.pose.t == [0.0, 0.0, 0.0] and f.pose.var == 0.0 and f.numObs == 0 and not f.links
+    assert np.allclose(np.array(f.pose.R), np.eye(3), atol=1e-15)
+    m = so.Map()
+    assert so.load_map_text(m, "610 0 0 0 180 0 180 0 0\n") == 1  # 610_initial_map.txt
+    R = np.array(m.fiducials[610].pose.R)
+    assert np.allclose(R, np.diag([-1.0, 1.0, -1.0]), atol=1e-12)  # setRPY(180, 0, 180 deg): a half turn about y
+    # invalid lines are skipped (nElems != 9, 10), links are the rest of the line
+    m = so.Map()
+    text = "7 1.5 -2 0.25 10 20 30 0.001 4 8 9\nnot a line\n8 0 0 0 0 0 0 1 2 7\n9 1 2 3 4 5 6 7\n"
+    assert so.load_map_text(m, text) == 2 and sorted(m.fiducials) == [7, 8]
+    assert m.fiducials[7].links == {8, 9} and m.fiducials[8].links == {7} and m.fiducials[7].numObs == 4
+    out = so.save_map_text(m)
+    assert out.splitlines()[0].startswith("7 1.500000 -2.000000 0.250000 10.000000 20.000000 30.000000 0.001000 4 8 9")
+    m2 = so.Map()
+    so.load_map_text(m2, out)
+    assert so.save_map_text(m2) == out
