@@ -38,6 +38,7 @@ sys.path.insert(0, ROOT)
 WORKLOAD = "C2"
 FIDUCIAL_LEN = 0.14
 FRAMES_PER_STEP = int(os.environ.get("FID_BENCH_FRAMES", "128"))  # distinct frames per step; 128 x 6.2 MB = 796 MB >> 126 MB L2
+DEPTH = int(os.environ.get("FID_BENCH_DEPTH", "2"))            # batches in flight (each takes FRAMES/SLOT of the library's FID_SLOTS chunk slots)
 SLOT_FRAMES = int(os.environ.get("FID_BENCH_SLOT", "64"))     # frames per in-flight chunk inside the library (two chunks pipeline)
 HBM_FALLBACK_GBS = 6650.0
 
@@ -275,12 +276,12 @@ def run_gpu_arm(args):
         else:
             det.submit_batch(pinned, K, D, FIDUCIAL_LEN)  # H2D of this batch is queued here, inside the timed region
 
-    outs = [None, None]
+    outs = [None] * 4
 
     def finish(k):
         # results of the oldest batch in flight (host arrays) + its map update
-        outs[k & 1] = det.collect_batch(outs[k & 1])
-        counts, ids, corners, tfs = outs[k & 1]
+        outs[k & 3] = det.collect_batch(outs[k & 3])
+        counts, ids, corners, tfs = outs[k & 3]
         launches[0] += det.last_counters()["kernel_launches"]
         # fiducial_slam: the frames of this step are one camera stream -> one message per frame.  The
         # sequential fold is enqueued asynchronously so that it overlaps the detection of the next step
@@ -300,9 +301,11 @@ def run_gpu_arm(args):
         # latency-bound tail of one batch (grouping, identification, pose, D2H) runs under the threshold /
         # border-walk stages of the next.  Exactly `steps` batches are submitted AND collected in here.
         total = 0
-        submit(on_device)
+        ahead = min(DEPTH - 1, steps)
+        for _ in range(ahead):
+            submit(on_device)
         for k in range(steps):
-            if k + 1 < steps:
+            if k + ahead < steps:
                 submit(on_device)
             total += int(finish(k).sum())
         return total

@@ -27,7 +27,7 @@ using namespace fid;
 
 enum { ST_H2D = 0, ST_THRESH, ST_MASKS, ST_WALK, ST_EMIT, ST_APPROX, ST_GROUP, ST_IDENT, ST_SUBPIX_POSE, ST_POSE_UNUSED, ST_D2H, ST_COUNT };
 enum { N_WALK_ROUNDS = FID_WALK_MAX_ROUNDS };
-enum { MAX_SLOTS = 4 };
+enum { MAX_SLOTS = 8 };
 
 struct Slot {
     uint8_t* d_bgr = nullptr;
@@ -74,7 +74,7 @@ struct fid_detector {
     unsigned int max_starts = 0, max_chains = 0, max_points = 0, max_queue = 0, max_segs = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     // one compute stream per slot (chunk in flight): the latency-bound stages of one chunk overlap the
-    // issue-bound stages of the others.  FID_SLOTS (2..4, default 4)
+    // issue-bound stages of the others.  FID_SLOTS (2..8, default 4)
     int n_slots = 4;
     int stagger = 0;  // FID_STAGGER bit mask, see enqueue_pipeline
     int enc = FID_ENC_BGR8, bpp = 3;  // fid_set_input_encoding

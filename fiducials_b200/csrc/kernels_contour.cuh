@@ -1,8 +1,10 @@
 // CUDA kernels, contour half of the per-frame pipeline (sm_100a); the threshold stage that feeds it
 // is in kernels_threshold.cuh:
-//   k_walk          one thread per start crack / suspended walk: border walk, canonical test, length (A.3b)
-//   k_emit          one thread per surviving border: ordered contour points
-//   k_approx        one block per contour: approxPolyDP + quad filters             (A.4)
+//   k_walk          one thread per start crack / suspended walk, in rounds: round 0 one-directional, later
+//                   rounds bidirectional; canonical test, contour length, emission segments      (A.3b)
+//   k_emit          one thread per contour segment: ordered contour points
+//   k_approx_warp   one warp per contour (<= 1024 points): approxPolyDP + quad filters             (A.4)
+//   k_approx        one block per longer contour
 // All kernels take a batch of frames (blockIdx.z / queue entries carry the frame index) so that a
 // launch has enough independent work to fill 148 SMs.
 #pragma once
@@ -66,7 +68,8 @@ struct FrameGeom {
 // at most its budget and re-queues the undecided walks, which keeps the lanes of a warp within one
 // budget of each other; the last, long rounds run "persistent" (a lane that finishes pulls the next
 // queue item when at least half the warp is idle).  Left-crack (backwards) and right-crack
-// (forwards) walks live in separate queue regions, so a warp executes a single direction.
+// (forwards) walks live in separate queue regions, so a warp executes a single code path (the crack
+// type decides the tie rule and, in round 0, the direction; rounds >= 1 walk both ways, contour_walk.cuh).
 // ---------------------------------------------------------------------------------------------------
 struct WalkArgs {
     const uint32_t* halo;

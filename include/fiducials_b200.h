@@ -133,7 +133,7 @@ int fid_detect_pose_batch(fid_detector* h, int n_frames, const uint8_t* bgr, int
  * identification, pose) batch k+1 already runs its threshold and border-walk stages -- the reference
  * node has the same structure between its image callback and its publishers, one frame at a time.
  * A batch needs ceil(n_frames / max_batch) free chunk slots; the handle has 4 of them (environment
- * FID_SLOTS, 2..4).  FID_ERR_CAPACITY = not enough free slots, collect first.  The frames of
+ * FID_SLOTS, 2..8).  FID_ERR_CAPACITY = not enough free slots, collect first.  The frames of
  * a host `bgr` must stay valid and unchanged until the batch has been collected.
  * fid_detect_pose_batch may only be called while nothing is in flight. */
 int fid_submit_batch(fid_detector* h, int n_frames, const uint8_t* bgr, int bgr_on_device, int width, int height, size_t row_stride, size_t frame_stride,
@@ -185,7 +185,7 @@ int fid_debug_time_threshold(fid_detector* h, int n_frames, const uint8_t* bgr_d
 int fid_debug_candidates(fid_detector* h, int max_candidates, int* n, int32_t* quads, int32_t* scale, int32_t* contour_len);
 
 /* Per-stage device times (milliseconds, CUDA events) of the last batch call:
- * [0] h2d copy, [1] threshold, [2] masks+starts, [3] border walk, [4] chain emit, [5] polygon+filters,
+ * [0] h2d copy, [1] threshold (+ start cracks), [2] unused (reads 0), [3] border walk, [4] chain emit, [5] polygon+filters,
  * [6] group, [7] identify, [8] subpix+pose, [9] unused, [10] d2h, [11..18] the border-walk rounds
  * (unused rounds read 0); n_stages returns 19. */
 int fid_last_stage_ms(fid_detector* h, float* ms, int max_stages, int* n_stages);
