@@ -347,6 +347,28 @@ def test_set_params_no_refine(det_cache):
     assert ids.tolist() == rids.tolist() and np.array_equal(corners, rc)
 
 
+@pytest.mark.parametrize("wmin,wmax,wstep,const", [(5, 21, 8, 7), (3, 23, 10, 7), (4, 30, 6, 3), (51, 51, 4, 7)])
+def test_other_threshold_windows(det_cache, wmin, wmax, wstep, const):
+    """dynamic_reconfigure can change the adaptive threshold windows (configCallback, aruco_detect.cpp:257-298):
+    any other window set than the node's default 3..53 step 4 runs the generic instance of the threshold kernel
+    (runtime table offsets instead of immediates).  Planes bit-exact, detection equal to the oracle's."""
+    from fiducials_b200.node import default_params
+
+    bgr, _, K, D, d = synth.make_config_frame("C1", 5)
+    det = det_cache(d, 640, 480)
+    kw = dict(adaptiveThreshWinSizeMin=wmin, adaptiveThreshWinSizeMax=wmax, adaptiveThreshWinSizeStep=wstep, adaptiveThreshConstant=float(const))
+    det.set_params(default_params(dictionary=d, **kw))
+    try:
+        g, planes = det.debug_threshold(bgr)
+        ref = ao.threshold_planes(ao.gray(bgr), dict(ao.REFERENCE_PARAMS, **kw))
+        assert planes.shape == ref.shape and np.array_equal(planes, ref)
+        ids, corners = det.detect(bgr)
+        rids, rc = ao.detect(bgr, d, **kw)
+        assert ids.tolist() == rids.tolist() and (len(rids) == 0 or np.abs(corners - rc).max() <= 1e-3)
+    finally:
+        det.set_params(default_params(dictionary=d))
+
+
 def test_unsupported_dictionary_rejected():
     from fiducials_b200 import _lib
     from fiducials_b200.node import Detector, default_params
