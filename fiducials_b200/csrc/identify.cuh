@@ -21,6 +21,13 @@ struct SerialLanes {
     FID_HD int min_i(int v) const { return v; }
     FID_HD unsigned long long or_u64(unsigned long long v) const { return v; }
     FID_HD void hist_add(int* h, int bin) const { h[bin]++; }
+    FID_HD uint32_t ballot(bool p) const { return p ? 1u : 0u; }
+    FID_HD int shfl_i(int v, int) const { return v; }
+    FID_HD int atomic_add(int* p, int v) const {
+        const int old = *p;
+        *p += v;
+        return old;
+    }
 };
 
 // getPerspectiveTransform(src quad -> dst square) : 8x8 LU with partial pivoting, double.

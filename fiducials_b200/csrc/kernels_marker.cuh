@@ -54,6 +54,35 @@ struct GroupArgs {
     Counters* counters;
 };
 
+// One warp as a lane group (identify.cuh, quad_group.cuh); tests/hostsim plugs SerialLanes (one lane).
+struct WarpLanes {
+    __device__ int lane() const { return threadIdx.x & 31; }
+    __device__ int count() const { return 32; }
+    __device__ void sync() const { __syncwarp(); }
+    __device__ long long sum(long long v) const {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        return v;
+    }
+    __device__ int min_i(int v) const {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const int o = __shfl_xor_sync(0xffffffffu, v, d);
+            v = o < v ? o : v;
+        }
+        return v;
+    }
+    __device__ unsigned long long or_u64(unsigned long long v) const {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, d);
+        return v;
+    }
+    __device__ void hist_add(int* h, int bin) const { atomicAdd(h + bin, 1); }
+    __device__ uint32_t ballot(bool p) const { return __ballot_sync(0xffffffffu, p); }
+    __device__ int shfl_i(int v, int src) const { return __shfl_sync(0xffffffffu, v, src); }
+    __device__ int atomic_add(int* p, int v) const { return atomicAdd(p, v); }
+};
+
 #define GROUP_THREADS 256
 #define FID_GROUP_MAX_RAW 4096  // >= fid_detector::max_raw
 
@@ -95,13 +124,13 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_sort_group(const GroupArgs a)
     //    marker scene has a few dozen close pairs among ~10^5): rows with at least one pair are flagged in
     //    shared memory so that the serial pass below does not pay an L2 round trip per empty word.
     __shared__ uint32_t row_any[(FID_GROUP_MAX_RAW + 31) / 32], grouped[(FID_GROUP_MAX_RAW + 31) / 32];
-    extern __shared__ int sm_group[];  // 5 * max_raw ints + max_raw bytes
+    extern __shared__ int sm_group[];  // 6 * max_raw ints + max_raw bytes
     int* sm_group_id = sm_group;
-    int* sm_members = sm_group + a.max_raw;
-    int* sm_next = sm_group + 2 * a.max_raw;
-    int* sm_head = sm_group + 3 * a.max_raw;
-    int* sm_tail = sm_group + 4 * a.max_raw;
-    uint8_t* sm_selected = reinterpret_cast<uint8_t*>(sm_group + 5 * a.max_raw);
+    int* sm_members = sm_group + a.max_raw;  // 2 * max_raw: members + accepted ids of every group
+    int* sm_next = sm_group + 3 * a.max_raw;
+    int* sm_head = sm_group + 4 * a.max_raw;
+    int* sm_tail = sm_group + 5 * a.max_raw;
+    uint8_t* sm_selected = reinterpret_cast<uint8_t*>(sm_group + 6 * a.max_raw);
     __shared__ int s_warp_cnt[GROUP_THREADS / 32];
     __shared__ int s_base;
     for (int i = tid; i < (FID_GROUP_MAX_RAW + 31) / 32; i += GROUP_THREADS) row_any[i] = 0;
@@ -132,17 +161,29 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_sort_group(const GroupArgs a)
         if (bits) atomicOr(&row_any[i >> 5], 1u << (i & 31));
     }
     __syncthreads();
-    // d. order-dependent grouping (serial; the pair list is sparse)
+    // d. order-dependent grouping.  Pass 1 (the close pairs in row-major order -> groups) is inherently serial
+    //    and runs in one thread on shared-memory scratch; pass 2 (per group: sort, pick the leader, collect the
+    //    close contours that differ from the running reference) runs one warp per group.
+    __shared__ int s_n_groups, s_total_close, s_members_used;
     if (tid == 0) {
-        const uint32_t* cbc = cb;
-        const int cw = a.close_wpr;
-        const uint32_t* ra = row_any;
-        auto close_word = [cbc, cw, ra](int i, int w) -> uint32_t { return ((ra[i >> 5] >> (i & 31)) & 1u) ? cbc[(size_t)i * cw + w] : 0u; };
-        // scratch of the serial pass in shared memory (it is a chain of dependent look-ups: an L2 round trip
-        // per access made this the longest single-thread stretch of the whole pipeline)
-        group_candidates(n, qs, a.marker_size, a.border_bits, a.min_group_dist, close_word, sm_selected, sm_group_id, sm_members, sm_next, sm_head, sm_tail,
-                         a.fs.close_count + fo, a.fs.close_idx + fo, a.fs.close_off + fo, grouped);
+        struct CloseWordDev {
+            const uint32_t* cb;
+            int cw;
+            const uint32_t* ra;
+            __device__ uint32_t operator()(int i, int w) const { return cb[(size_t)i * cw + w]; }
+            __device__ bool row_any(int i) const { return (ra[i >> 5] >> (i & 31)) & 1u; }
+        } close_word{cb, a.close_wpr, row_any};
+        s_n_groups = group_pairs(n, close_word, sm_selected, sm_group_id, sm_next, sm_head, sm_tail, a.fs.close_count + fo, grouped);
+        s_total_close = 0;
+        s_members_used = 0;
         s_base = 0;
+    }
+    __syncthreads();
+    {
+        const WarpLanes L;
+        for (int g = tid >> 5; g < s_n_groups; g += GROUP_THREADS / 32)
+            group_finish_lanes(L, g, qs, a.marker_size, a.border_bits, a.min_group_dist, sm_selected, sm_members, &s_members_used, sm_next, sm_head, a.fs.close_count + fo,
+                               a.fs.close_idx + fo, a.fs.close_off + fo, &s_total_close);
     }
     __syncthreads();
     // e. selected candidates, in order, minus the ones near the frame border (dropped silently, with their group)
@@ -174,30 +215,6 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_sort_group(const GroupArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------------
-struct WarpLanes {
-    __device__ int lane() const { return threadIdx.x & 31; }
-    __device__ int count() const { return 32; }
-    __device__ void sync() const { __syncwarp(); }
-    __device__ long long sum(long long v) const {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-        return v;
-    }
-    __device__ int min_i(int v) const {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            const int o = __shfl_xor_sync(0xffffffffu, v, d);
-            v = o < v ? o : v;
-        }
-        return v;
-    }
-    __device__ unsigned long long or_u64(unsigned long long v) const {
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, d);
-        return v;
-    }
-    __device__ void hist_add(int* h, int bin) const { atomicAdd(h + bin, 1); }
-};
 
 struct IdentifyArgs {
     const uint8_t* gray;

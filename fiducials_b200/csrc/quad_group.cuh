@@ -80,24 +80,11 @@ FID_HD float quad_module_size(const QuadF& q, int marker_size, int border_bits) 
     return s;
 }
 
-// Serial grouping over candidates already sorted by descending perimeter (stable).  `close_word(i,w)`
-// returns bits [32w, 32w+32) of row i of the pair predicate avgDist(i,j) < perimeter[j] *
-// minMarkerDistanceRate (upper triangle, j > i), evaluated by the caller (in parallel on the GPU).
-// The matrix is sparse, so only set bits are visited -- in the same (i, j) order as OpenCV's loops.  Outputs: selected[i] and, for group leaders, the list of
-// close contours (indices) in close_idx[close_off[i] .. close_off[i+1]).
-// Scratch: group_id[n], group_of[..] arrays supplied by the caller.
+// Pass 1 (order dependent, serial): the close pairs in row-major order -> groups as linked lists.
+// Returns the number of groups.  selected[i] = 1 for candidates that are in no group.
 template <class CloseWord>
-FID_HD void group_candidates(int n, const QuadF* quads, int marker_size, int border_bits, float min_group_dist, const CloseWord& close_word, uint8_t* selected,
-                             int* group_id,        // [n]
-                             int* group_members,   // [n]   members of all groups, appended per group via linked lists
-                             int* next_in_group,   // [n]   linked list
-                             int* group_head,      // [n]   head per group
-                             int* group_tail,      // [n]
-                             int* close_count,     // [n]   number of close contours per candidate
-                             int* close_idx,       // [n]   flat storage
-                             int* close_off,       // [n+1]
-                             uint32_t* grouped)    // [(n+31)/32] scratch
-{
+FID_HD int group_pairs(int n, const CloseWord& close_word, uint8_t* selected, int* group_id, int* next_in_group, int* group_head, int* group_tail, int* close_count,
+                       uint32_t* grouped) {
     int n_groups = 0;
     for (int i = 0; i < n; i++) {
         selected[i] = 1;
@@ -112,6 +99,7 @@ FID_HD void group_candidates(int n, const QuadF* quads, int marker_size, int bor
     // 13 scales gives hundreds of "both grouped" pairs per marker; the `grouped` bit mask skips them a
     // word at a time (such a pair changes nothing: selected[] is already 0 for every grouped candidate).
     for (int i = 0; i < n; i++) {
+        if (!close_word.row_any(i)) continue;
         for (int w = (i + 1) >> 5; w < n_words; w++) {
             uint32_t bits = close_word(i, w);
             if (w == ((i + 1) >> 5)) bits &= (i & 31) == 31 ? 0xFFFFFFFFu : ~((2u << (i & 31)) - 1u);  // j > i only
@@ -149,36 +137,103 @@ FID_HD void group_candidates(int n, const QuadF* quads, int marker_size, int bor
             }
         }
     }
-    // per group: sort members ascending (largest perimeter first), keep the first, collect the
-    // "close contours" that differ enough from the running reference.
-    int total_close = 0;
-    for (int g = 0; g < n_groups; g++) {
-        int m = 0;
-        for (int k = group_head[g]; k >= 0; k = next_in_group[k]) group_members[m++] = k;
-        for (int a = 1; a < m; a++) {  // insertion sort (groups are small)
-            const int v = group_members[a];
-            int b = a - 1;
-            while (b >= 0 && group_members[b] > v) {
-                group_members[b + 1] = group_members[b];
+    return n_groups;
+}
+
+// Pass 2 for one group, executed by a lane group (a CUDA warp in k_sort_group, a single lane in tests/hostsim;
+// identify.cuh has the Lanes interface): sort the members ascending (largest perimeter first), keep the first,
+// collect the "close contours" that differ enough from the running reference -- the lanes test the next
+// count() members against the reference at once and the first hit becomes the new reference, which is the
+// sequential rule.  members: scratch shared by all groups (2 ints per candidate), *members_used /
+// *total_close: reservation counters (atomics on the device).
+template <class Lanes>
+FID_HD void group_finish_lanes(const Lanes& L, int g, const QuadF* quads, int marker_size, int border_bits, float min_group_dist, uint8_t* selected, int* members,
+                               int* members_used, const int* next_in_group, const int* group_head, int* close_count, int* close_idx, int* close_off, int* total_close) {
+    const int lane = L.lane(), width = L.count();
+    int m = 0, base = 0;
+    if (lane == 0) {
+        for (int k = group_head[g]; k >= 0; k = next_in_group[k]) m++;
+        base = L.atomic_add(members_used, 2 * m);  // m members + up to m accepted ids
+        int w = 0;
+        for (int k = group_head[g]; k >= 0; k = next_in_group[k]) members[base + w++] = k;
+    }
+    m = L.shfl_i(m, 0);
+    base = L.shfl_i(base, 0);
+    int* mem = members + base;
+    int* acc = mem + m;
+    L.sync();
+    if (m <= width) {  // rank sort, one member per lane
+        const int mine = lane < m ? mem[lane] : 0x7fffffff;
+        int rank = 0;
+        for (int k = 0; k < m; k++) rank += L.shfl_i(mine, k) < mine ? 1 : 0;
+        L.sync();
+        if (lane < m) mem[rank] = mine;
+    } else if (lane == 0) {
+        for (int x = 1; x < m; x++) {  // insertion sort (rare: more members than lanes)
+            const int v = mem[x];
+            int b = x - 1;
+            while (b >= 0 && mem[b] > v) {
+                mem[b + 1] = mem[b];
                 b--;
             }
-            group_members[b + 1] = v;
-        }
-        const int lead = group_members[0];
-        int cur = lead;
-        selected[lead] = 1;
-        close_off[lead] = total_close;
-        for (int a = 1; a < m; a++) {
-            const int id = group_members[a];
-            const float dist = quad_avg_distance(quads[id], quads[cur]);
-            const float module = quad_module_size(quads[id], marker_size, border_bits);
-            if (dist > min_group_dist * module) {
-                cur = id;
-                close_idx[total_close++] = id;
-                close_count[lead]++;
-            }
+            mem[b + 1] = v;
         }
     }
+    L.sync();
+    const int lead = mem[0];
+    int cur = lead, n_acc = 0, pos = 1;
+    while (pos < m) {
+        const int x = pos + lane;
+        bool ok = false;
+        if (x < m) {
+            const int id = mem[x];
+            const QuadF q = quads[id];
+            ok = quad_avg_distance(q, quads[cur]) > min_group_dist * quad_module_size(q, marker_size, border_bits);
+        }
+        const uint32_t hits = L.ballot(ok);
+        if (!hits) {
+            pos += width;
+            continue;
+        }
+        const int first = pos + fid_ctz(hits);
+        cur = mem[first];
+        if (lane == 0) acc[n_acc] = cur;
+        n_acc++;
+        pos = first + 1;
+    }
+    L.sync();
+    int off = 0;
+    if (lane == 0) {
+        off = L.atomic_add(total_close, n_acc);
+        selected[lead] = 1;
+        close_off[lead] = off;
+        close_count[lead] = n_acc;
+    }
+    off = L.shfl_i(off, 0);
+    for (int k = lane; k < n_acc; k += width) close_idx[off + k] = acc[k];
+}
+
+// Both passes, serial (CPU harness).  `close_word(i, w)` returns bits [32w, 32w+32) of row i of the pair
+// predicate avgDist(i,j) < perimeter[j] * minMarkerDistanceRate (upper triangle, j > i), `close_word.row_any(i)`
+// whether row i has any bit.  Outputs: selected[i] and, for group leaders, the list of close contours
+// (indices) in close_idx[close_off[i] .. close_off[i] + close_count[i]).
+template <class Lanes, class CloseWord>
+FID_HD void group_candidates(const Lanes& L, int n, const QuadF* quads, int marker_size, int border_bits, float min_group_dist, const CloseWord& close_word, uint8_t* selected,
+                             int* group_id,        // [n]
+                             int* group_members,   // [2n]  scratch
+                             int* next_in_group,   // [n]   linked list
+                             int* group_head,      // [n]   head per group
+                             int* group_tail,      // [n]
+                             int* close_count,     // [n]   number of close contours per candidate
+                             int* close_idx,       // [n]   flat storage
+                             int* close_off,       // [n+1]
+                             uint32_t* grouped)    // [(n+31)/32] scratch
+{
+    const int n_groups = group_pairs(n, close_word, selected, group_id, next_in_group, group_head, group_tail, close_count, grouped);
+    int total_close = 0, members_used = 0;
+    for (int g = 0; g < n_groups; g++)
+        group_finish_lanes(L, g, quads, marker_size, border_bits, min_group_dist, selected, group_members, &members_used, next_in_group, group_head, close_count, close_idx, close_off,
+                           &total_close);
 }
 
 }  // namespace fid

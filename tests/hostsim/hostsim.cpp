@@ -454,18 +454,25 @@ int hs_detect(const uint8_t* gray, const uint8_t* planes, int W, int H, int dict
         sper[i] = per[order[i]];
     }
     std::vector<uint8_t> selected(n);
-    std::vector<int> gid(n), gmem(n), nxt(n), ghead(n), gtail(n), ccount(n), cidx(n), coff(n + 1);
+    std::vector<int> gid(n), gmem(2 * (size_t)n + 2), nxt(n), ghead(n), gtail(n), ccount(n), cidx(n), coff(n + 1);
     std::vector<uint32_t> grouped_bits((size_t)(n + 31) / 32 + 1);
     const float rate = (float)P.min_marker_dist_rate;
-    auto close_word = [&](int i, int w) -> uint32_t {
-        uint32_t bits = 0;
-        for (int b = 0; b < 32; b++) {
-            const int j = 32 * w + b;
-            if (j > i && j < n && quad_avg_distance(sq[i], sq[j]) < sper[j] * rate) bits |= 1u << b;
+    struct CloseWordHost {
+        const std::vector<QuadF>* sq;
+        const std::vector<float>* sper;
+        int n;
+        float rate;
+        uint32_t operator()(int i, int w) const {
+            uint32_t bits = 0;
+            for (int b = 0; b < 32; b++) {
+                const int j = 32 * w + b;
+                if (j > i && j < n && quad_avg_distance((*sq)[i], (*sq)[j]) < (*sper)[j] * rate) bits |= 1u << b;
+            }
+            return bits;
         }
-        return bits;
-    };
-    group_candidates(n, sq.data(), P.marker_size, P.marker_border_bits, (float)P.min_group_dist, close_word, selected.data(), gid.data(), gmem.data(), nxt.data(),
+        bool row_any(int) const { return true; }
+    } close_word{&sq, &sper, n, rate};
+    group_candidates(SerialLanes(), n, sq.data(), P.marker_size, P.marker_border_bits, (float)P.min_group_dist, close_word, selected.data(), gid.data(), gmem.data(), nxt.data(),
                      ghead.data(), gtail.data(), ccount.data(), cidx.data(), coff.data(), grouped_bits.data());
     std::vector<unsigned long long> dict;
     pack_dictionary(P, &dict);
