@@ -182,7 +182,7 @@ static int upload_constants() {
     return FID_OK;
 }
 
-static size_t group_smem(int max_raw) { return (size_t)max_raw * (6 * sizeof(int) + 1); }
+static size_t group_smem(int max_raw) { return (size_t)max_raw * 6 * sizeof(int) + (((size_t)max_raw + 15) & ~(size_t)15) + GROUP_CLOSE_SMEM_WORDS * sizeof(uint32_t); }
 static size_t ident_smem(const DevParams& P) { return (size_t)P.n_markers * 4 * 8 + IDENT_WARPS * 256 * 4 + IDENT_WARPS * FID_MAX_WARP_SIDE_SQ; }
 
 static int r_max_of(const DevParams& P) {

@@ -85,6 +85,7 @@ struct WarpLanes {
 
 #define GROUP_THREADS 256
 #define FID_GROUP_MAX_RAW 4096  // >= fid_detector::max_raw
+#define GROUP_CLOSE_SMEM_WORDS 12288  // 48 KB of the close-pair matrix in shared memory
 
 __global__ void __launch_bounds__(GROUP_THREADS) k_sort_group(const GroupArgs a) {
     const int f = blockIdx.x;
@@ -97,7 +98,6 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_sort_group(const GroupArgs a)
     float* pt = a.fs.per_tmp + fo;
     QuadF* qs = a.fs.quads + fo;
     float* ps = a.fs.per + fo;
-    uint32_t* cb = a.fs.close_bits + fo * a.close_wpr;
     if (tid == 0) a.n_raw_clamped[f] = n;
     // a. clockwise + perimeter
     for (int i = tid; i < n; i += GROUP_THREADS) {
@@ -136,6 +136,13 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_sort_group(const GroupArgs a)
     for (int i = tid; i < (FID_GROUP_MAX_RAW + 31) / 32; i += GROUP_THREADS) row_any[i] = 0;
     __syncthreads();
     const int wpr = (n + 31) >> 5;
+    // the matrix lives in shared memory when it fits (n <= ~600 candidates): the serial pass below reads it
+    // word by word, each read feeding the next decision -- from global memory that was an L2 round trip
+    // per word and 2/3 of this kernel's time
+    uint32_t* sm_close = reinterpret_cast<uint32_t*>(sm_selected + ((a.max_raw + 15) & ~15));
+    const bool close_in_smem = n * wpr <= GROUP_CLOSE_SMEM_WORDS;
+    uint32_t* cb = close_in_smem ? sm_close : a.fs.close_bits + fo * a.close_wpr;
+    const int cb_pitch = close_in_smem ? wpr : a.close_wpr;
     for (int u = tid; u < n * wpr; u += GROUP_THREADS) {
         const int i = u / wpr, w = u - i * wpr;
         uint32_t bits = 0;
@@ -157,7 +164,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_sort_group(const GroupArgs a)
                 if (quad_avg_distance(qi, qj) < thr) bits |= 1u << b;
             }
         }
-        cb[(size_t)i * a.close_wpr + w] = bits;
+        cb[(size_t)i * cb_pitch + w] = bits;
         if (bits) atomicOr(&row_any[i >> 5], 1u << (i & 31));
     }
     __syncthreads();
@@ -172,7 +179,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_sort_group(const GroupArgs a)
             const uint32_t* ra;
             __device__ uint32_t operator()(int i, int w) const { return cb[(size_t)i * cw + w]; }
             __device__ bool row_any(int i) const { return (ra[i >> 5] >> (i & 31)) & 1u; }
-        } close_word{cb, a.close_wpr, row_any};
+        } close_word{cb, cb_pitch, row_any};
         s_n_groups = group_pairs(n, close_word, sm_selected, sm_group_id, sm_next, sm_head, sm_tail, a.fs.close_count + fo, grouped);
         s_total_close = 0;
         s_members_used = 0;
