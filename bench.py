@@ -348,6 +348,23 @@ def run_gpu_arm(args):
     e2e_s, e2e_wall, _, _ = timed(False, args.steps)
     clocks = sampler.stop()
 
+    # extra (not the metric): latency of ONE frame through the synchronous per-frame call the reference node makes
+    # (imageCallback + poseEstimateCallback), host frame in, host results out, nothing else on the GPU
+    single_ms = None
+    if rank == 0:
+        try:
+            det1 = Detector(default_params(dictionary=dict_id), local_rank, W, H, 1)
+            one = np.ascontiguousarray(pinned[:1])
+            for _ in range(3):
+                det1.detect_pose_batch(one, K, D, FIDUCIAL_LEN)
+            t0 = time.perf_counter()
+            for i in range(20):
+                det1.detect_pose_batch(np.ascontiguousarray(pinned[i % nf : i % nf + 1]), K, D, FIDUCIAL_LEN)
+            single_ms = (time.perf_counter() - t0) / 20 * 1e3
+            det1.close()
+        except Exception as e:  # pragma: no cover
+            print("single-frame latency probe failed: %r" % (e,), file=sys.stderr)
+
     frames_total = nf * args.steps * world
     value = frames_total / dev_s
     e2e_value = frames_total / e2e_s
@@ -424,6 +441,7 @@ def run_gpu_arm(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
             "wallclock_s": {"device_resident": dev_wall, "e2e": e2e_wall},
+            "single_frame_latency_ms": single_ms,
         }
         print(json.dumps(out))
     lib.fid_device_free(det.h, dptr)
