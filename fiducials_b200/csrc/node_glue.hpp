@@ -9,6 +9,7 @@
 #include <map>
 #include <stdexcept>
 #include <string>
+#include <fstream>
 #include <sstream>
 #include <cstdio>
 #include <cmath>
@@ -215,32 +216,25 @@ class FiducialSlam {
         return true;
     }
 
-    // Map::loadMap(filename), map.cpp:572-625 (same sscanf format; invalid lines are skipped)
+    // Map::loadMap(filename), map.cpp:572-625: one fiducial per line, nine leading fields (id, x y z, roll pitch yaw
+    // in degrees, variance, numObs), then the linked ids up to a tab or the end of the line; a line whose nine
+    // fields do not parse is skipped (the reference logs "Invalid line").
     bool loadMap(const std::string& filename) {
-        FILE* fp = fopen(filename.c_str(), "r");
-        if (fp == NULL) return false;
-        const int BUFSIZE = 2048;
-        char linebuf[BUFSIZE], linkbuf[BUFSIZE];
+        std::ifstream in(filename);
+        if (!in) return false;
         std::vector<fid_map_file_entry> rows;
         std::vector<int32_t> pairs;
-        while (!feof(fp)) {
-            if (fgets(linebuf, BUFSIZE - 1, fp) == NULL) break;
-            fid_map_file_entry r;
-            r.num_obs = 0;
-            linkbuf[0] = '\0';
-            const int nElems = sscanf(linebuf, "%d %lf %lf %lf %lf %lf %lf %lf %d%[^\t\n]*s", &r.fiducial_id, &r.x, &r.y, &r.z, &r.roll_deg, &r.pitch_deg, &r.yaw_deg, &r.variance,
-                                      &r.num_obs, linkbuf);
-            if (nElems != 9 && nElems != 10) continue;
+        std::string line;
+        while (std::getline(in, line)) {
+            std::istringstream fields(line.substr(0, line.find('\t')));
+            fid_map_file_entry r{};
+            if (!(fields >> r.fiducial_id >> r.x >> r.y >> r.z >> r.roll_deg >> r.pitch_deg >> r.yaw_deg >> r.variance >> r.num_obs)) continue;
             rows.push_back(r);
-            std::istringstream ss(linkbuf);
-            std::string tok;
-            while (getline(ss, tok, ' '))
-                if (!tok.empty()) {
-                    pairs.push_back(r.fiducial_id);
-                    pairs.push_back(std::stoi(tok));
-                }
+            for (int32_t linked; fields >> linked;) {
+                pairs.push_back(r.fiducial_id);
+                pairs.push_back(linked);
+            }
         }
-        fclose(fp);
         if (fid_map_load(map, 0, (int)rows.size(), rows.data()) != FID_OK) return false;
         return fid_map_add_links(map, 0, (int)pairs.size() / 2, pairs.data()) == FID_OK;
     }
