@@ -125,72 +125,101 @@ def _cpu_worker_frame(i):
     return len(ids)
 
 
-def cpu_reference_fps(frames, dict_id, K, D, budget_s=12.0):
-    """Times the reference's CPU path on a bounded sample in both modes:
+class CpuArm:
+    """The reference's CPU path on a bounded sample, in both modes:
     reference mode  = one process, OpenCV threads = all cores (what the single-threaded node does);
-    throughput mode = one single-threaded worker process per core, frames round-robin.
-    Returns dict(value=best fps, cores, sample)."""
-    import multiprocessing as mp
-    import tempfile
+    throughput mode = single-threaded worker processes, frames round-robin: one per logical core and one per
+                      physical core (half of them on an SMT box -- the detector is memory bound and ran 30 % faster
+                      that way on the 128-thread host of the B200 box).
+    The worker pools are spawned once (spawn, so OpenCV's thread pool is never forked) and reused by every
+    measure() call: --impl reference times K steps without paying K pool start-ups."""
 
-    import cv2
+    def __init__(self, frames, dict_id, K, D):
+        import multiprocessing as mp
+        import tempfile
 
-    from oracle import aruco_oracle as ao
-
-    ncores = os.cpu_count() or 1
-
-    def one(i):
-        return ao.detect_and_pose(frames[i % len(frames)], dict_id, K, D, FIDUCIAL_LEN)
-
-    # reference mode
-    cv2.setNumThreads(ncores)
-    one(0)
-    t0 = time.perf_counter()
-    n_ref = 0
-    while (time.perf_counter() - t0 < budget_s / 2 and n_ref < 4 * len(frames)) or n_ref < 3:
-        one(n_ref)
-        n_ref += 1
-    fps_ref = n_ref / (time.perf_counter() - t0)
-    # throughput mode: one worker per logical core, and one per physical core (half of them on an SMT box --
-    # the detector is memory bound and ran 30 % faster that way on the 128-thread host of the B200 box)
-    fps_thr, n_thr, nproc, tried = 0.0, 0, max(1, ncores), []
-    tmp = tempfile.NamedTemporaryFile(suffix=".npy", delete=False)
-    try:
-        np.save(tmp, np.ascontiguousarray(frames))
-        tmp.close()
-        ctx = mp.get_context("spawn")
-        counts = [max(1, ncores)] + ([ncores // 2] if ncores >= 8 else [])
-        for npr in counts:
-            with ctx.Pool(npr, initializer=_cpu_worker_init, initargs=(1, tmp.name, dict_id, K, D)) as pool:
+        self.frames, self.dict_id, self.K, self.D = frames, dict_id, K, D
+        self.ncores = os.cpu_count() or 1
+        self.pools = []
+        self.tmp = tempfile.NamedTemporaryFile(suffix=".npy", delete=False)
+        np.save(self.tmp, np.ascontiguousarray(frames))
+        self.tmp.close()
+        try:
+            ctx = mp.get_context("spawn")
+            for npr in [max(1, self.ncores)] + ([self.ncores // 2] if self.ncores >= 8 else []):
+                pool = ctx.Pool(npr, initializer=_cpu_worker_init, initargs=(1, self.tmp.name, dict_id, K, D))
                 pool.map(_cpu_worker_frame, range(npr), chunksize=1)  # warm-up (imports, first-call setup)
+                self.pools.append((npr, pool))
+        except Exception as e:  # pragma: no cover
+            print("throughput-mode CPU baseline unavailable: %r" % (e,), file=sys.stderr)
+
+    def close(self):
+        for _, pool in self.pools:
+            pool.terminate()
+            pool.join()
+        self.pools = []
+        try:
+            os.unlink(self.tmp.name)
+        except OSError:
+            pass
+
+    def measure(self, budget_s=12.0):
+        """dict(value=best fps, cores, kind, sample)."""
+        import cv2
+
+        from oracle import aruco_oracle as ao
+
+        frames, ncores = self.frames, self.ncores
+
+        def one(i):
+            return ao.detect_and_pose(frames[i % len(frames)], self.dict_id, self.K, self.D, FIDUCIAL_LEN)
+
+        n_modes = 1 + len(self.pools)
+        # reference mode
+        cv2.setNumThreads(ncores)
+        one(0)
+        t0 = time.perf_counter()
+        n_ref = 0
+        while (time.perf_counter() - t0 < budget_s / n_modes and n_ref < 4 * len(frames)) or n_ref < 3:
+            one(n_ref)
+            n_ref += 1
+        fps_ref = n_ref / (time.perf_counter() - t0)
+        # throughput mode
+        fps_thr, n_thr, nproc, tried = 0.0, 0, max(1, ncores), []
+        for npr, pool in self.pools:
+            try:
                 t0 = time.perf_counter()
                 pool.map(_cpu_worker_frame, range(npr), chunksize=1)
                 per_round = time.perf_counter() - t0
-                rounds = int(max(1, min(8, (budget_s / (2 * len(counts))) / max(per_round, 1e-3))))
+                rounds = int(max(1, min(8, (budget_s / n_modes) / max(per_round, 1e-3))))
                 n = npr * rounds
                 t0 = time.perf_counter()
                 pool.map(_cpu_worker_frame, range(n), chunksize=1)
                 fps = n / (time.perf_counter() - t0)
+            except Exception as e:  # pragma: no cover
+                print("throughput-mode CPU baseline failed: %r" % (e,), file=sys.stderr)
+                continue
             tried.append("%d procs %.2f fps" % (npr, fps))
             if fps > fps_thr:
                 fps_thr, n_thr, nproc = fps, n, npr
-    except Exception as e:  # pragma: no cover
-        print("throughput-mode CPU baseline failed: %r" % (e,), file=sys.stderr)
+        best = max(fps_ref, fps_thr)
+        return {
+            "value": best,
+            "unit": "frames/s",
+            "cores": ncores if fps_ref >= fps_thr else nproc,
+            "kind": "reference",
+            "sample": "cv2 %s ArucoDetector(reference params)+solvePnP+projectPoints on %s frames: reference mode (1 proc, %d OpenCV threads) %d frames %.2f fps; "
+                      "throughput mode (%d procs x 1 thread) %d frames %.2f fps [%s]; value = best of all; os.cpu_count=%d"
+                      % (cv2.__version__, WORKLOAD, ncores, n_ref, fps_ref, nproc, n_thr, fps_thr, ", ".join(tried), ncores),
+        }
+
+
+def cpu_reference_fps(frames, dict_id, K, D, budget_s=12.0):
+    arm = CpuArm(frames, dict_id, K, D)
+    try:
+        return arm.measure(budget_s)
     finally:
-        try:
-            os.unlink(tmp.name)
-        except OSError:
-            pass
-    best = max(fps_ref, fps_thr)
-    return {
-        "value": best,
-        "unit": "frames/s",
-        "cores": ncores if fps_ref >= fps_thr else nproc,
-        "kind": "reference",
-        "sample": "cv2 %s ArucoDetector(reference params)+solvePnP+projectPoints on %s frames: reference mode (1 proc, %d OpenCV threads) %d frames %.2f fps; "
-                  "throughput mode (%d procs x 1 thread) %d frames %.2f fps [%s]; value = best of all; os.cpu_count=%d"
-                  % (cv2.__version__, WORKLOAD, ncores, n_ref, fps_ref, nproc, n_thr, fps_thr, ", ".join(tried), ncores),
-    }
+        arm.close()
 
 
 def run_reference_arm(args):
@@ -202,12 +231,16 @@ def run_reference_arm(args):
     frames, truths, K, D, dict_id = synth.make_config_stream(WORKLOAD, 8, seed=0)
     per_step = []
     detail = None
-    budget = max(4.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
-    for i in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        detail = cpu_reference_fps(frames, dict_id, K, D, budget_s=budget)
-        if i >= args.warmup:
-            per_step.append((detail["value"], time.perf_counter() - t0))
+    budget = max(4.0, min(20.0, 150.0 / max(1, args.steps + args.warmup)))  # whole run: a few minutes
+    arm = CpuArm(frames, dict_id, K, D)
+    try:
+        for i in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            detail = arm.measure(budget_s=budget)
+            if i >= args.warmup:
+                per_step.append((detail["value"], time.perf_counter() - t0))
+    finally:
+        arm.close()
     fps = float(np.median([p[0] for p in per_step]))
     ms = float(np.mean([p[1] for p in per_step]) * 1e3)
     detail["value"] = fps
