@@ -49,6 +49,29 @@ FID_HD int fid_popc(uint32_t v) {
 #endif
 }
 
+// cv::cvtColor(BGR2GRAY) of one 8-bit pixel: 15-bit fixed point
+FID_HD uint32_t gray_of_bgr(uint32_t b, uint32_t g, uint32_t r) { return (3735u * b + 19235u * g + 9798u * r + 16384u) >> 15; }
+
+// Gray image accessors for the stages that sample a few pixels (identification, cornerSubPix): either
+// a gray plane, or the frame itself in the encoding cv_bridge::toCvCopy(msg, BGR8) was given
+// (aruco_detect.cpp:348) -- the tensor-core threshold kernel never writes a gray plane to HBM.
+struct GrayPlane {
+    const uint8_t* p;
+    size_t pitch;
+    FID_HD int at(int x, int y) const { return p[(size_t)y * pitch + x]; }
+};
+struct FrameImg {
+    const uint8_t* p;
+    size_t row_stride;
+    int enc;  // 0 bgr8, 1 rgb8, 2 mono8
+    FID_HD int at(int x, int y) const {
+        const uint8_t* q = p + (size_t)y * row_stride;
+        if (enc == 2) return q[x];
+        q += 3 * (size_t)x;
+        return (int)(enc == 1 ? gray_of_bgr(q[2], q[1], q[0]) : gray_of_bgr(q[0], q[1], q[2]));
+    }
+};
+
 // Detector parameters as consumed by the device code.  Mirrors the 21 fields of
 // aruco_detect/cfg/DetectorParams.cfg that aruco_detect.cpp:690-727 sets, plus the two OpenCV-4.13
 // fields the oracle fixes.

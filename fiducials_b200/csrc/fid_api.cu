@@ -1,5 +1,6 @@
 // C-ABI of the detector (include/fiducials_b200.h): handle management, batch orchestration on CUDA
 // streams, stage timing.  No CPU fallback: every entry point that computes needs a CUDA device.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -11,6 +12,7 @@
 #include "../../include/fiducials_b200.h"
 #include "kernels_contour.cuh"
 #include "kernels_threshold.cuh"
+#include "kernels_threshold_mma.cuh"
 #include "kernels_marker.cuh"
 #include "params_host.h"
 
@@ -96,6 +98,7 @@ struct fid_detector {
     float* d_subpix_masks = nullptr;
     uint32_t* d_lut_prev = nullptr;
     uint32_t* d_lut_next = nullptr;
+    int thresh_mode = 0;  // 0 = summed-area-table kernel (kernels_threshold.cuh, default: faster end to end), 1 = tensor-core kernel (kernels_threshold_mma.cuh; FID_THRESH=mma)
     int walk_rounds = 0;
     int emit_blocks_per_sm = 8;
     int walk_budget[FID_WALK_MAX_ROUNDS]{};
@@ -157,6 +160,8 @@ static FrameGeom make_geom(const fid_detector* h, int W, int H, size_t row_strid
     g.halo_tiles_y = (H + FID_HALO_T - 1) / FID_HALO_T;
     g.halo_scale_stride = halo_plane_words(W, H);
     g.halo_frame_stride = g.halo_scale_stride * h->P.n_scales;
+    g.magic_tpr = (uint32_t)((0x100000000ull + (uint64_t)g.halo_tpr - 1) / (uint64_t)g.halo_tpr);
+    g.magic_tiles_y = (uint32_t)((0x100000000ull + (uint64_t)g.halo_tiles_y - 1) / (uint64_t)g.halo_tiles_y);
     return g;
 }
 
@@ -185,6 +190,34 @@ static int upload_constants() {
 static size_t group_smem(int max_raw) { return (size_t)max_raw * 6 * sizeof(int) + (((size_t)max_raw + 15) & ~(size_t)15) + GROUP_CLOSE_SMEM_WORDS * sizeof(uint32_t); }
 static size_t ident_smem(const DevParams& P) { return (size_t)P.n_markers * 4 * 8 + IDENT_WARPS * 256 * 4 + IDENT_WARPS * FID_MAX_WARP_SIDE_SQ; }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+        cudaGetLastError();
+    }
+    return fn;
+}
+// u32 view of 3-byte-per-pixel rows: dims (3W/4, H, frames), box TM_BOXW x TM_BOXH x 1.  False when the layout cannot be described
+// (then every tile takes the clamping global-load path).
+static bool make_bgr_tensor_map(CUtensorMap* tm, const uint8_t* src, int W, int H, int nf, size_t row_stride, size_t frame_stride) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn || (W & 3) || (row_stride & 15) || (frame_stride & 15) || (reinterpret_cast<uintptr_t>(src) & 15) || 3 * W / 4 < TM_BOXW || H < TM_BOXH) return false;
+    const cuuint64_t gdim[3] = {(cuuint64_t)(3 * W / 4), (cuuint64_t)H, (cuuint64_t)nf};
+    const cuuint64_t gstr[2] = {(cuuint64_t)row_stride, (cuuint64_t)frame_stride};
+    const cuuint32_t box[3] = {TM_BOXW, TM_BOXH, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<uint8_t*>(src), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 static int r_max_of(const DevParams& P) {
     int r = 1;
     for (int i = 0; i < P.n_scales; i++) r = std::max(r, P.win[i] / 2);
@@ -194,6 +227,8 @@ static int r_max_of(const DevParams& P) {
 static int configure_kernels(fid_detector* h) {
     CK(cudaFuncSetAttribute(k_threshold<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thresh_smem_bytes(THR_FAST_R)));
     CK(cudaFuncSetAttribute(k_threshold<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thresh_smem_bytes(FID_MAX_WIN_RADIUS)));
+    CK(cudaFuncSetAttribute(k_threshold_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM_BYTES));
+    CK(cudaFuncSetAttribute(k_threshold_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_sort_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)group_smem(FID_GROUP_MAX_RAW)));
     CK(cudaFuncSetAttribute(k_identify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1000 * 4 * 8 + IDENT_WARPS * 256 * 4 + IDENT_WARPS * FID_MAX_WARP_SIDE_SQ)));
     return FID_OK;
@@ -286,6 +321,7 @@ extern "C" int fid_create(const fid_params* params, int device, int max_width, i
         cudaGetLastError();
         return FID_ERR_NO_DEVICE;
     }
+    if ((long long)max_batch * halo_tiles_x(max_width) * ((max_height + FID_HALO_T - 1) / FID_HALO_T) > ((1ll << FID_START_TILE_BITS) - 1)) return FID_ERR_INVALID_ARG;  // StartRec tile field (all ones = null record)
     DevParams P;
     int rc = make_dev_params(*params, &P);
     if (rc != FID_OK) return rc;
@@ -297,8 +333,17 @@ extern "C" int fid_create(const fid_params* params, int device, int max_width, i
     h->max_w = max_width;
     h->max_h = max_height;
     h->max_batch = max_batch;
+#define CKH(call)                                                                                      \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) {                                                                       \
+            fprintf(stderr, "[fiducials_b200] CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            fid_destroy(h);                                                                            \
+            return FID_ERR_CUDA;                                                                       \
+        }                                                                                              \
+    } while (0)
     cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
+    CKH(cudaGetDeviceProperties(&prop, device));
     h->sm_count = prop.multiProcessorCount;
     const size_t px = (size_t)max_width * max_height * max_batch;
     // Worst case measured on uniform-noise frames with the reference's 13 scales: 4.9 start cracks and
@@ -308,11 +353,12 @@ extern "C" int fid_create(const fid_params* params, int device, int max_width, i
     h->max_points = (unsigned int)std::min<size_t>(px * 4 + 65536, 0x7fffffffu);
     h->max_segs = h->max_chains * 4;  // two per contour + checkpoints of the long ones
     h->max_queue = h->max_starts / 8 + 65536;  // walks that survive the first 32 steps: ~3 % of the start cracks
-    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    CKH(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CKH(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
     if (const char* e = getenv("FID_STAGGER")) h->stagger = atoi(e);
+    if (const char* e = getenv("FID_THRESH")) h->thresh_mode = strcmp(e, "mma") == 0 ? 1 : 0;
     if (const char* e = getenv("FID_SLOTS")) h->n_slots = std::max(2, std::min((int)MAX_SLOTS, atoi(e)));
-    for (int i = 0; i < h->n_slots; i++) CK(cudaStreamCreateWithFlags(&h->slot_stream[i], cudaStreamNonBlocking));
+    for (int i = 0; i < h->n_slots; i++) CKH(cudaStreamCreateWithFlags(&h->slot_stream[i], cudaStreamNonBlocking));
     if ((rc = upload_constants()) != FID_OK || (rc = configure_kernels(h)) != FID_OK) {
         fid_destroy(h);
         return rc;
@@ -334,7 +380,7 @@ extern "C" int fid_create(const fid_params* params, int device, int max_width, i
             fid_destroy(h);
             return rc;
         }
-        CK(cudaMemcpy(h->d_subpix_masks, masks.data(), masks.size() * sizeof(float), cudaMemcpyHostToDevice));
+        CKH(cudaMemcpy(h->d_subpix_masks, masks.data(), masks.size() * sizeof(float), cudaMemcpyHostToDevice));
     }
     {   // step tables of the border walk
         std::vector<uint32_t> lp(FID_LUT_SIZE), ln(FID_LUT_SIZE);
@@ -343,8 +389,8 @@ extern "C" int fid_create(const fid_params* params, int device, int max_width, i
             fid_destroy(h);
             return rc;
         }
-        CK(cudaMemcpy(h->d_lut_prev, lp.data(), FID_LUT_SIZE * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(h->d_lut_next, ln.data(), FID_LUT_SIZE * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CKH(cudaMemcpy(h->d_lut_prev, lp.data(), FID_LUT_SIZE * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CKH(cudaMemcpy(h->d_lut_next, ln.data(), FID_LUT_SIZE * sizeof(uint32_t), cudaMemcpyHostToDevice));
     }
     {   // walk plan: budgets per round, 'p' prefix = persistent lanes, 0 = unbounded (must be last)
         if (const char* e = getenv("FID_EMIT_BLOCKS")) h->emit_blocks_per_sm = std::max(1, atoi(e));
@@ -379,7 +425,7 @@ extern "C" int fid_create(const fid_params* params, int device, int max_width, i
             fid_destroy(h);
             return rc;
         }
-        CK(cudaEventCreateWithFlags(&h->pf_done[i], cudaEventDisableTiming));
+        CKH(cudaEventCreateWithFlags(&h->pf_done[i], cudaEventDisableTiming));
     }
     if ((rc = dalloc(&h->d_override_ids, 1024)) != FID_OK || (rc = dalloc(&h->d_override_lens, 1024)) != FID_OK || (rc = dalloc(&h->d_pose_ids, 4096)) != FID_OK ||
         (rc = dalloc(&h->d_pose_corners, 4096 * 8)) != FID_OK || (rc = dalloc(&h->d_pose_out, 4096)) != FID_OK) {
@@ -388,6 +434,7 @@ extern "C" int fid_create(const fid_params* params, int device, int max_width, i
     }
     *out = h;
     return FID_OK;
+#undef CKH
 }
 
 extern "C" int fid_destroy(fid_detector* h) {
@@ -449,50 +496,101 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
     // throughput-bound stages of the other instead of under its own twin
     if (prev && (h->stagger & 1)) CK(cudaStreamWaitEvent(st, prev->ev[ST_MASKS], 0));
     CK(cudaEventRecord(s.ev[ST_THRESH], st));
-    {  // gray + threshold (halo tiles)
-        GrayArgs ga{};
-        ga.bgr = d_bgr;
-        ga.gray = s.d_gray;
-        ga.W = W;
-        ga.H = H;
-        ga.n_frames = nf;
-        ga.bgr_row_stride = g.bgr_row_stride;
-        ga.bgr_frame_stride = g.bgr_frame_stride;
-        ga.gray_pitch = g.gray_pitch;
-        ga.gray_frame_stride = g.gray_frame_stride;
-        ga.enc = h->enc;
-        const long long gq = (long long)nf * H * ((W + 3) / 4);
-        k_gray<<<(unsigned int)((gq + 255) / 256), 256, 0, st>>>(ga);
-        launches++;
-        ThreshArgs a{};
-        a.gray = s.d_gray;
-        a.halo = s.d_halo;
-        a.W = W;
-        a.H = H;
-        a.n_frames = nf;
-        a.gray_pitch = g.gray_pitch;
-        a.gray_frame_stride = g.gray_frame_stride;
-        a.halo_tpr = g.halo_tpr;
-        a.halo_tiles_y = g.halo_tiles_y;
-        a.halo_scale_stride = g.halo_scale_stride;
-        a.halo_frame_stride = g.halo_frame_stride;
-        a.n_scales = P.n_scales;
-        a.r_max = r_max_of(P);
-        a.thresh_c = P.thresh_c;
-        a.starts = s.d_starts;
-        a.counters = s.d_counters;
-        a.max_starts = h->max_starts;
+    {  // threshold stage: gray + 13 adaptive thresholds -> halo tiles + start cracks
         bool fast = P.n_scales == 13;
-        for (int i = 0; i < P.n_scales; i++) {
-            a.win[i] = P.win[i];
-            fast = fast && P.win[i] == 3 + 4 * i;
+        for (int i = 0; i < P.n_scales; i++) fast = fast && P.win[i] == 3 + 4 * i;
+        if (fast && h->thresh_mode == 1) {
+            // tensor-core kernel: persistent, one CTA per SM; BGR staged by TMA where the layout allows
+            ThreshMmaArgs a{};
+            a.src = d_bgr;
+            a.enc = h->enc;
+            a.bpp = h->bpp;
+            a.row_stride = g.bgr_row_stride;
+            a.frame_stride = g.bgr_frame_stride;
+            a.halo = s.d_halo;
+            a.W = W;
+            a.H = H;
+            a.n_frames = nf;
+            a.halo_tpr = g.halo_tpr;
+            a.halo_tiles_y = g.halo_tiles_y;
+            a.halo_scale_stride = g.halo_scale_stride;
+            a.halo_frame_stride = g.halo_frame_stride;
+            a.thresh_c = P.thresh_c;
+            a.tiles_x = (g.halo_tpr + THR_TILES_X - 1) / THR_TILES_X;
+            a.tiles_y = (g.halo_tiles_y + THR_TILES_Y - 1) / THR_TILES_Y;
+            a.starts = s.d_starts;
+            a.counters = s.d_counters;
+            a.max_starts = h->max_starts;
+            CUtensorMap tmap;
+            memset(&tmap, 0, sizeof(tmap));
+            static const bool tma_off = getenv("FID_THRESH_TMA") && atoi(getenv("FID_THRESH_TMA")) == 0;  // debugging switch
+            a.use_tma = (!tma_off && h->enc != FID_ENC_MONO8 && make_bgr_tensor_map(&tmap, d_bgr, W, H, nf, g.bgr_row_stride, g.bgr_frame_stride)) ? 1 : 0;
+            const long long total = (long long)a.tiles_x * a.tiles_y * nf;
+            const int grid = (int)std::min<long long>(total, h->sm_count);
+            static const bool prof_on = getenv("FID_THRESH_PROF") && atoi(getenv("FID_THRESH_PROF")) != 0;  // debugging: per-warp wait cycles
+            static long long* d_prof = nullptr;
+            if (prof_on && !d_prof) cudaMalloc((void**)&d_prof, sizeof(long long) * 256 * 16 * TM_PROF_KINDS);
+            a.prof = prof_on ? d_prof : nullptr;
+            if (prof_on)
+                k_threshold_mma<true><<<grid, TM_THREADS, TM_SMEM_BYTES, st>>>(a, tmap);
+            else
+                k_threshold_mma<false><<<grid, TM_THREADS, TM_SMEM_BYTES, st>>>(a, tmap);
+            launches++;
+            if (prof_on && stop_after == ST_THRESH) {  // fid_debug_time_threshold: print the wait profile of a few CTAs
+                cudaStreamSynchronize(st);
+                std::vector<long long> hp((size_t)256 * 16 * TM_PROF_KINDS);
+                cudaMemcpy(hp.data(), d_prof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost);
+                static int printed = 0;
+                if (printed++ < 2)
+                    for (int b : {0, 1, 77}) {
+                        for (int w = 0; w < 16; w++) {
+                            fprintf(stderr, "[thr prof] cta %3d warp %2d:", b, w);
+                            for (int k = 0; k < TM_PROF_KINDS; k++) fprintf(stderr, " %8lld", hp[((size_t)b * 16 + w) * TM_PROF_KINDS + k]);
+                            fprintf(stderr, "\n");
+                        }
+                    }
+            }
+        } else {
+            GrayArgs ga{};
+            ga.bgr = d_bgr;
+            ga.gray = s.d_gray;
+            ga.W = W;
+            ga.H = H;
+            ga.n_frames = nf;
+            ga.bgr_row_stride = g.bgr_row_stride;
+            ga.bgr_frame_stride = g.bgr_frame_stride;
+            ga.gray_pitch = g.gray_pitch;
+            ga.gray_frame_stride = g.gray_frame_stride;
+            ga.enc = h->enc;
+            const long long gq = (long long)nf * H * ((W + 3) / 4);
+            k_gray<<<(unsigned int)((gq + 255) / 256), 256, 0, st>>>(ga);
+            launches++;
+            ThreshArgs a{};
+            a.gray = s.d_gray;
+            a.halo = s.d_halo;
+            a.W = W;
+            a.H = H;
+            a.n_frames = nf;
+            a.gray_pitch = g.gray_pitch;
+            a.gray_frame_stride = g.gray_frame_stride;
+            a.halo_tpr = g.halo_tpr;
+            a.halo_tiles_y = g.halo_tiles_y;
+            a.halo_scale_stride = g.halo_scale_stride;
+            a.halo_frame_stride = g.halo_frame_stride;
+            a.n_scales = P.n_scales;
+            a.r_max = r_max_of(P);
+            a.thresh_c = P.thresh_c;
+            a.starts = s.d_starts;
+            a.counters = s.d_counters;
+            a.max_starts = h->max_starts;
+            for (int i = 0; i < P.n_scales; i++) a.win[i] = P.win[i];
+            dim3 grid((g.halo_tpr + THR_TILES_X - 1) / THR_TILES_X, (g.halo_tiles_y + THR_TILES_Y - 1) / THR_TILES_Y, nf);
+            if (fast)
+                k_threshold<true><<<grid, THR_THREADS, thresh_smem_bytes(THR_FAST_R), st>>>(a);
+            else
+                k_threshold<false><<<grid, THR_THREADS, thresh_smem_bytes(a.r_max), st>>>(a);
+            launches++;
         }
-        dim3 grid((g.halo_tpr + THR_TILES_X - 1) / THR_TILES_X, (g.halo_tiles_y + THR_TILES_Y - 1) / THR_TILES_Y, nf);
-        if (fast)
-            k_threshold<true><<<grid, THR_THREADS, thresh_smem_bytes(THR_FAST_R), st>>>(a);
-        else
-            k_threshold<false><<<grid, THR_THREADS, thresh_smem_bytes(a.r_max), st>>>(a);
-        launches++;
     }
     CK(cudaEventRecord(s.ev[ST_MASKS], st));
     if (stop_after == ST_THRESH) return FID_OK;
@@ -593,9 +691,10 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
     CK(cudaEventRecord(s.ev[ST_IDENT], st));
     {  // identify
         IdentifyArgs a{};
-        a.gray = s.d_gray;
-        a.gray_frame_stride = g.gray_frame_stride;
-        a.gray_pitch = g.gray_pitch;
+        a.src = d_bgr;
+        a.row_stride = g.bgr_row_stride;
+        a.frame_stride = g.bgr_frame_stride;
+        a.enc = h->enc;
         a.W = W;
         a.H = H;
         a.fs = s.fs;
@@ -612,9 +711,10 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
     CK(cudaEventRecord(s.ev[ST_SUBPIX_POSE], st));
     {  // finish
         FinishArgs a{};
-        a.gray = s.d_gray;
-        a.gray_frame_stride = g.gray_frame_stride;
-        a.gray_pitch = g.gray_pitch;
+        a.src = d_bgr;
+        a.row_stride = g.bgr_row_stride;
+        a.frame_stride = g.bgr_frame_stride;
+        a.enc = h->enc;
         a.W = W;
         a.H = H;
         a.n_sel = s.d_nsel;
@@ -759,7 +859,7 @@ extern "C" int fid_detect_pose_batch(fid_detector* h, int n_frames, const uint8_
                     CK(cudaMemcpyAsync(s.d_bgr, src, (size_t)nf * frame_stride, cudaMemcpyHostToDevice, h->copy_stream));
                 } else {
                     for (int f = 0; f < nf; f++)
-                        CK(cudaMemcpy2DAsync(s.d_bgr + (size_t)f * width * 3 * height, (size_t)width * h->bpp, src + (size_t)f * frame_stride, row_stride, (size_t)width * h->bpp, height,
+                        CK(cudaMemcpy2DAsync(s.d_bgr + (size_t)f * width * h->bpp * height, (size_t)width * h->bpp, src + (size_t)f * frame_stride, row_stride, (size_t)width * h->bpp, height,
                                              cudaMemcpyHostToDevice, h->copy_stream));
                 }
                 CK(cudaEventRecord(s.copied, h->copy_stream));
@@ -832,7 +932,7 @@ extern "C" int fid_submit_batch(fid_detector* h, int n_frames, const uint8_t* bg
                 CK(cudaMemcpyAsync(s.d_bgr, src, (size_t)nf * frame_stride, cudaMemcpyHostToDevice, h->copy_stream));
             } else {
                 for (int f = 0; f < nf; f++)
-                    CK(cudaMemcpy2DAsync(s.d_bgr + (size_t)f * width * 3 * height, (size_t)width * h->bpp, src + (size_t)f * frame_stride, row_stride, (size_t)width * h->bpp, height,
+                    CK(cudaMemcpy2DAsync(s.d_bgr + (size_t)f * width * h->bpp * height, (size_t)width * h->bpp, src + (size_t)f * frame_stride, row_stride, (size_t)width * h->bpp, height,
                                          cudaMemcpyHostToDevice, h->copy_stream));
             }
             CK(cudaEventRecord(s.copied, h->copy_stream));
@@ -893,6 +993,7 @@ extern "C" int fid_detect(fid_detector* h, const uint8_t* bgr, int width, int he
 extern "C" int fid_pose(fid_detector* h, int n, const int32_t* ids, const float* corners, const fid_camera* cam, double fiducial_len, int n_override,
                         const int32_t* override_ids, const double* override_lens, fid_transform* out) {
     if (!h || n < 0 || n > 4096 || !cam || !(fiducial_len > 0) || (n > 0 && (!ids || !corners || !out))) return FID_ERR_INVALID_ARG;
+    if (h->pend_count) return FID_ERR_INVALID_ARG;  // batches in flight read the shared override table
     if (n == 0) return FID_OK;
     CK(cudaSetDevice(h->device));
     int rc = upload_overrides(h, n_override, override_ids, override_lens);
@@ -992,12 +1093,29 @@ extern "C" int fid_memcpy_h2d(fid_detector* h, void* dst_device, const void* src
 
 extern "C" int fid_debug_threshold(fid_detector* h, const uint8_t* bgr, int width, int height, size_t stride, uint8_t* gray, uint8_t* planes, int* n_scales) {
     if (!h || !bgr || width < 16 || height < 16 || width > h->max_w || height > h->max_h || stride < (size_t)width * h->bpp) return FID_ERR_INVALID_ARG;
+    if (h->pend_count) return FID_ERR_INVALID_ARG;  // slot 0 may belong to a batch in flight
     CK(cudaSetDevice(h->device));
     Slot& s = h->slot[0];
     CK(cudaMemcpy2DAsync(s.d_bgr, (size_t)width * h->bpp, bgr, stride, (size_t)width * h->bpp, height, cudaMemcpyHostToDevice, h->stream));
     const FrameGeom g = make_geom(h, width, height, (size_t)width * h->bpp, (size_t)width * h->bpp * height);
     const int rc = enqueue_pipeline(h, s, h->stream, 1, g, s.d_bgr, nullptr, 0.0, 0, ST_THRESH);
     if (rc != FID_OK) return rc;
+    if (gray) {  // the tensor-core threshold kernel keeps the gray tile on chip: produce the plane for the caller
+        GrayArgs ga{};
+        ga.bgr = s.d_bgr;
+        ga.gray = s.d_gray;
+        ga.W = width;
+        ga.H = height;
+        ga.n_frames = 1;
+        ga.bgr_row_stride = g.bgr_row_stride;
+        ga.bgr_frame_stride = g.bgr_frame_stride;
+        ga.gray_pitch = g.gray_pitch;
+        ga.gray_frame_stride = g.gray_frame_stride;
+        ga.enc = h->enc;
+        const long long gq = (long long)height * ((width + 3) / 4);
+        k_gray<<<(unsigned int)((gq + 255) / 256), 256, 0, h->stream>>>(ga);
+        CK(cudaGetLastError());
+    }
     CK(cudaStreamSynchronize(h->stream));
     if (gray) CK(cudaMemcpy2D(gray, width, s.d_gray, g.gray_pitch, width, height, cudaMemcpyDeviceToHost));
     if (planes) {
@@ -1042,7 +1160,7 @@ extern "C" int fid_debug_time_threshold(fid_detector* h, int n_frames, const uin
 }
 
 extern "C" int fid_debug_candidates(fid_detector* h, int max_candidates, int* n, int32_t* quads, int32_t* scale, int32_t* contour_len) {
-    if (!h || !n) return FID_ERR_INVALID_ARG;
+    if (!h || !n || h->pend_count) return FID_ERR_INVALID_ARG;
     CK(cudaSetDevice(h->device));
     Slot& s = h->slot[0];
     unsigned int cnt = 0;

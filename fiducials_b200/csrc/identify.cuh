@@ -106,7 +106,8 @@ FID_HD int round_half_even_to_int(double v) {
 }
 
 // warpPerspective(INTER_NEAREST, BORDER_CONSTANT 0) sample for destination pixel (x,y).
-FID_HD int warp_nearest_sample(const uint8_t* gray, int W, int H, size_t pitch, const double Mi[9], int x, int y) {
+template <class Img>
+FID_HD int warp_nearest_sample(const Img& gray, int W, int H, const double Mi[9], int x, int y) {
     const double X0 = Mi[1] * y + Mi[2];
     const double Y0 = Mi[4] * y + Mi[5];
     const double W0 = Mi[7] * y + Mi[8];
@@ -117,7 +118,7 @@ FID_HD int warp_nearest_sample(const uint8_t* gray, int W, int H, size_t pitch, 
     fx = fx < -2147483648.0 ? -2147483648.0 : (fx > 2147483647.0 ? 2147483647.0 : fx);
     fy = fy < -2147483648.0 ? -2147483648.0 : (fy > 2147483647.0 ? 2147483647.0 : fy);
     const int sx = round_half_even_to_int(fx), sy = round_half_even_to_int(fy);
-    if ((unsigned)sx < (unsigned)W && (unsigned)sy < (unsigned)H) return gray[(size_t)sy * pitch + sx];
+    if ((unsigned)sx < (unsigned)W && (unsigned)sy < (unsigned)H) return gray.at(sx, sy);
     return 0;
 }
 
@@ -154,9 +155,9 @@ struct IdentifyResult {
 
 // `img` : S*S bytes of scratch, `hist`: 256 ints of scratch (zeroed by this function).
 // dict  : n_markers x 4 rotations packed as little-endian byte strings in 64-bit words.
-template <class Lanes>
-FID_HD IdentifyResult identify_candidate(const Lanes& L, const uint8_t* gray, int W, int H, size_t pitch, const QuadF& quad, const DevParams& P,
-                                         const unsigned long long* dict, uint8_t* img, int* hist) {
+template <class Lanes, class Img>
+FID_HD IdentifyResult identify_candidate(const Lanes& L, const Img& gray, int W, int H, const QuadF& quad, const DevParams& P, const unsigned long long* dict, uint8_t* img,
+                                         int* hist) {
     IdentifyResult res = {-1, 0};
     const int cells = P.marker_size + 2 * P.marker_border_bits;
     const int cell = P.px_per_cell;
@@ -171,7 +172,7 @@ FID_HD IdentifyResult identify_candidate(const Lanes& L, const uint8_t* gray, in
     long long s1 = 0, s2 = 0;
     for (int p = L.lane(); p < S * S; p += L.count()) {
         const int y = p / S, x = p - y * S;
-        const int v = warp_nearest_sample(gray, W, H, pitch, Mi, x, y);
+        const int v = warp_nearest_sample(gray, W, H, Mi, x, y);
         img[p] = (uint8_t)v;
         L.hist_add(hist, v);
         if (x >= half && x < S - half && y >= half && y < S - half) {

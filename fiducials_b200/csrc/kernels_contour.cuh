@@ -40,10 +40,14 @@ struct WalkRec {       // a bidirectional border walk suspended between rounds (
     uint32_t nf;       // steps of the forward walker
 };
 
+// A start crack as the threshold kernel queues it: 4 bytes, relative to its halo tile.  The side (left /
+// right crack) is the queue region it sits in.  [tile within the chunk : 18][scale : 4][tile row : 5][bit : 5]
 struct StartRec {
-    uint32_t xy;    // x | y << 16
-    uint32_t meta;  // frame << 8 | scale << 1 | is_right
+    uint32_t v;
 };
+#define FID_START_TILE_BITS 18
+#define FID_START_NULL 0xFFFFFFFFu  // padding of a partly used queue block (kernels_threshold_mma.cuh); tile field all ones never occurs
+FID_HD uint32_t start_rec_pack(uint32_t tile, uint32_t scale, uint32_t row, uint32_t col) { return (tile << 14) | (scale << 10) | (row << 5) | col; }
 
 struct ChainRec {
     uint32_t xy;
@@ -59,7 +63,19 @@ struct FrameGeom {
     size_t gray_frame_stride;
     int halo_tpr, halo_tiles_y;  // 30x30(+halo) tiles per tile row / tile rows
     size_t halo_scale_stride, halo_frame_stride;  // in words (see HaloView)
+    uint32_t magic_tpr, magic_tiles_y;  // ceil(2^32 / d): __umulhi(t, magic) == t / d for t < 2^18, d < 2^14
 };
+
+// start record -> (pixel, meta = frame << 8 | scale << 1 | is_right)
+__device__ __forceinline__ void start_rec_unpack(const FrameGeom& g, uint32_t v, uint32_t is_right, uint32_t* xy, uint32_t* meta) {
+    const uint32_t tile = v >> 14, scale = (v >> 10) & 15u, row = (v >> 5) & 31u, col = v & 31u;
+    const uint32_t trow = __umulhi(tile, g.magic_tpr);            // f * tiles_y + ty
+    const uint32_t tx = tile - trow * (uint32_t)g.halo_tpr;
+    const uint32_t f = __umulhi(trow, g.magic_tiles_y);
+    const uint32_t ty = trow - f * (uint32_t)g.halo_tiles_y;
+    *xy = (FID_HALO_T * tx - 1u + col) | ((FID_HALO_T * ty - 1u + row) << 16);
+    *meta = (f << 8) | (scale << 1) | is_right;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // Border walk in rounds of growing step budget.  Walk lengths are heavy tailed (most start cracks
@@ -171,15 +187,18 @@ __device__ __forceinline__ void walk_side(const WalkArgs& a, unsigned int n, uns
         for (unsigned int base = my * 32; base < n; base += n_warps * 32) {
             const unsigned int idx = base + lane;
             if (idx >= n) continue;
-            const StartRec sr = a.starts[IS_RIGHT ? a.max_starts - 1 - idx : idx];
-            const WalkCtx ctx = walk_ctx_of(a, sr.meta);
-            const int x0 = sr.xy & 0xFFFF, y0 = sr.xy >> 16;
+            uint32_t sxy, smeta;
+            const uint32_t srec = a.starts[IS_RIGHT ? a.max_starts - 1 - idx : idx].v;
+            if (srec == FID_START_NULL) continue;
+            start_rec_unpack(a.g, srec, IS_RIGHT ? 1u : 0u, &sxy, &smeta);
+            const WalkCtx ctx = walk_ctx_of(a, smeta);
+            const int x0 = sxy & 0xFFFF, y0 = sxy >> 16;
             WalkState st;
             if (walk_init(ctx, x0, y0, IS_RIGHT ? 1 : 0, &st) != WALK_CONTINUE) continue;
             const int r = walk_uni_fast<IS_RIGHT>(ctx, x0, y0, a.max_len, a.budget, &st);
             WalkState2 s2;
             walk_split<IS_RIGHT>(x0, y0, st, &s2);
-            walk_retire<IS_RIGHT>(a, r, sr.xy, sr.meta, s2, ctx, nullptr);
+            walk_retire<IS_RIGHT>(a, r, sxy, smeta, s2, ctx, nullptr);
         }
         return;
     }

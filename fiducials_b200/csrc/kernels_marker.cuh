@@ -224,9 +224,9 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_sort_group(const GroupArgs a)
 // ---------------------------------------------------------------------------------------------------
 
 struct IdentifyArgs {
-    const uint8_t* gray;
-    size_t gray_frame_stride;
-    int gray_pitch, W, H;
+    const uint8_t* src;  // the frames as given (encoding enc): gray is computed per sample, no gray plane
+    size_t row_stride, frame_stride;
+    int enc, W, H;
     FrameScratch fs;
     const int* n_sel;
     int max_raw;
@@ -259,13 +259,13 @@ __global__ void __launch_bounds__(IDENT_WARPS * 32) k_identify(const IdentifyArg
     __syncthreads();
     const size_t fo = (size_t)f * a.max_raw;
     const int si = a.fs.sel_idx[fo + k];
-    const uint8_t* gray = a.gray + (size_t)f * a.gray_frame_stride;
+    const FrameImg gray{a.src + (size_t)f * a.frame_stride, a.row_stride, a.enc};
     const int nc = a.fs.close_count[fo + si], co = a.fs.close_off[fo + si];
     WarpLanes L;
     // attempt 0 (the selected quad) decodes for every real marker: warp 0 tries it alone, and only when it
     // fails do all warps share the close contours (attempts 1 + w, 1 + w + 8, ...)
     if (warp == 0) {
-        const IdentifyResult r = identify_candidate(L, gray, a.W, a.H, (size_t)a.gray_pitch, a.fs.quads[fo + si], a.P, sm_dict, img, hist);
+        const IdentifyResult r = identify_candidate(L, gray, a.W, a.H, a.fs.quads[fo + si], a.P, sm_dict, img, hist);
         if (r.id >= 0 && lane == 0) {
             s_id[0] = r.id;
             s_rot[0] = r.rotation;
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(IDENT_WARPS * 32) k_identify(const IdentifyArg
         for (int t = 1 + warp; t <= nc; t += IDENT_WARPS) {
             if (t > *reinterpret_cast<volatile int*>(&s_best)) break;  // an earlier attempt already decoded
             const QuadF quad = a.fs.quads[fo + a.fs.close_idx[fo + co + t - 1]];
-            const IdentifyResult r = identify_candidate(L, gray, a.W, a.H, (size_t)a.gray_pitch, quad, a.P, sm_dict, img, hist);
+            const IdentifyResult r = identify_candidate(L, gray, a.W, a.H, quad, a.P, sm_dict, img, hist);
             __syncwarp();
             if (r.id >= 0) {
                 if (lane == 0) {
@@ -314,9 +314,9 @@ __global__ void __launch_bounds__(IDENT_WARPS * 32) k_identify(const IdentifyArg
 
 // ---------------------------------------------------------------------------------------------------
 struct FinishArgs {
-    const uint8_t* gray;
-    size_t gray_frame_stride;
-    int gray_pitch, W, H;
+    const uint8_t* src;
+    size_t row_stride, frame_stride;
+    int enc, W, H;
     const int* n_sel;
     const int* cand_id;
     const float* cand_corners;
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(FINISH_THREADS) k_finish(const FinishArgs a) {
     }
     __syncthreads();
     const int n = s_n;
-    const uint8_t* gray = a.gray + (size_t)f * a.gray_frame_stride;
+    const FrameImg gray{a.src + (size_t)f * a.frame_stride, a.row_stride, a.enc};
     float* oc = a.out_corners + (size_t)f * a.max_markers * 8;
     // corners (+ sub-pixel refinement), one thread per corner
     for (int c = tid; c < 4 * n; c += FINISH_THREADS) {
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(FINISH_THREADS) k_finish(const FinishArgs a) {
             win = win < 1 ? 1 : win;
             win = win < a.P.refine_win ? win : a.P.refine_win;
             float patch[(2 * FID_SUBPIX_MAX_WIN + 3) * (2 * FID_SUBPIX_MAX_WIN + 3)];
-            corner_subpix(gray, a.W, a.H, (size_t)a.gray_pitch, &x, &y, win, a.subpix_masks + subpix_mask_offset(win), a.P.refine_max_iter,
+            corner_subpix(gray, a.W, a.H, &x, &y, win, a.subpix_masks + subpix_mask_offset(win), a.P.refine_max_iter,
                           a.P.refine_min_acc * a.P.refine_min_acc, patch);
         }
         oc[(size_t)m * 8 + 2 * ci] = x;

@@ -19,6 +19,7 @@
 
 #include "common.cuh"
 #include "contour_walk.cuh"
+#include "kernels_threshold_tail.cuh"  // tail shared by both threshold kernels
 
 namespace fid {
 
@@ -32,7 +33,7 @@ struct GrayArgs {
     int enc;  // FID_ENC_*: what cv_bridge::toCvCopy(msg, BGR8) would have been given (aruco_detect.cpp:348)
 };
 
-__device__ __forceinline__ uint32_t gray_of(uint32_t b, uint32_t g, uint32_t r) { return (3735u * b + 19235u * g + 9798u * r + 16384u) >> 15; }
+__device__ __forceinline__ uint32_t gray_of(uint32_t b, uint32_t g, uint32_t r) { return gray_of_bgr(b, g, r); }
 
 __global__ void __launch_bounds__(256) k_gray(const GrayArgs a) {
     const int quads = (a.W + 3) >> 2;
@@ -238,68 +239,8 @@ __global__ void __launch_bounds__(THR_THREADS, 2) k_threshold(const ThreshArgs a
             }
         }
     }
-    uint32_t* out = a.halo + (size_t)f * a.halo_frame_stride + ((size_t)ty * a.halo_tpr + tx) * 32 + lane;
-    int cnt_l = 0, cnt_r = 0;
-    const bool row_ok = lane >= 1 && lane <= FID_HALO_T;
-#pragma unroll
-    for (int s = 0; s < NS; s++) {
-        if (!FAST && s >= a.n_scales) break;
-        out[(size_t)s * a.halo_scale_stride] = acc[s];
-        const uint32_t up = __shfl_up_sync(0xffffffffu, acc[s], 1), dn = __shfl_down_sync(0xffffffffu, acc[s], 1);
-        uint32_t L = 0, Rr = 0;
-        if (row_ok && acc[s]) halo_row_starts(up, acc[s], dn, &L, &Rr);
-        cnt_l += __popc(L);
-        cnt_r += __popc(Rr);
-    }
-    // one queue reservation per warp and side (all scales of the tile): left cracks grow from the front of
-    // the buffer, right cracks from the back, so that every warp of the walk kernels sees a single direction
-    int incl_l = cnt_l, incl_r = cnt_r;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int tl = __shfl_up_sync(0xffffffffu, incl_l, d), tr = __shfl_up_sync(0xffffffffu, incl_r, d);
-        if (lane >= d) {
-            incl_l += tl;
-            incl_r += tr;
-        }
-    }
-    unsigned int base_l = 0, base_r = 0;
-    if (lane == 31) {
-        base_l = incl_l ? atomicAdd(&a.counters->n_starts[0], (unsigned int)incl_l) : 0u;
-        base_r = incl_r ? atomicAdd(&a.counters->n_starts[1], (unsigned int)incl_r) : 0u;
-    }
-    unsigned int pos_l = __shfl_sync(0xffffffffu, base_l, 31) + (unsigned int)(incl_l - cnt_l);
-    unsigned int pos_r = __shfl_sync(0xffffffffu, base_r, 31) + (unsigned int)(incl_r - cnt_r);
-    const uint32_t yq = (uint32_t)(FID_HALO_T * ty - 1 + lane) << 16;
-    const int xb = FID_HALO_T * tx - 1;
-    const unsigned int cap = a.max_starts / 2;
-    bool overflow = false;
-#pragma unroll
-    for (int s = 0; s < NS; s++) {
-        if (!FAST && s >= a.n_scales) break;
-        const uint32_t up = __shfl_up_sync(0xffffffffu, acc[s], 1), dn = __shfl_down_sync(0xffffffffu, acc[s], 1);
-        uint32_t L = 0, Rr = 0;
-        if (row_ok && acc[s]) halo_row_starts(up, acc[s], dn, &L, &Rr);
-        const uint32_t meta = ((uint32_t)f << 8) | ((uint32_t)s << 1);
-        while (L) {
-            const int i = __ffs(L) - 1;
-            L &= L - 1;
-            if (pos_l < cap)
-                a.starts[pos_l] = StartRec{(uint32_t)(xb + i) | yq, meta};
-            else
-                overflow = true;
-            pos_l++;
-        }
-        while (Rr) {
-            const int i = __ffs(Rr) - 1;
-            Rr &= Rr - 1;
-            if (pos_r < cap)
-                a.starts[a.max_starts - 1 - pos_r] = StartRec{(uint32_t)(xb + i) | yq, meta | 1u};
-            else
-                overflow = true;
-            pos_r++;
-        }
-    }
-    if (overflow) atomicOr(&a.counters->overflow, 1u);
+    thr_store_tile_and_starts<NS>(acc, FAST ? 13 : a.n_scales, f, tx, ty, lane, a.halo, a.halo_frame_stride, a.halo_scale_stride, a.halo_tpr, a.halo_tiles_y, a.starts, a.counters,
+                                  a.max_starts);
 }
 
 }  // namespace fid

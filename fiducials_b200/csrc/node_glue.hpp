@@ -201,8 +201,10 @@ class FiducialSlam {
         std::vector<fid_map_entry> e(cap);
         int n = 0, np = 0;
         check(fid_map_entries(map, 0, cap, &n, e.data()), "fid_map_entries");
-        std::vector<int32_t> pairs((size_t)2 * cap * cap);
-        check(fid_map_links(map, 0, cap * cap, &np, pairs.data()), "fid_map_links");
+        std::vector<int32_t> pairs;
+        fid_map_links(map, 0, 0, &np, nullptr);  // FID_ERR_CAPACITY by design: this call only asks for the count
+        pairs.resize(2 * (size_t)np + 2);
+        check(fid_map_links(map, 0, np, &np, pairs.data()), "fid_map_links");
         FILE* fp = fopen(filename.c_str(), "w");
         if (fp == NULL) return false;
         for (int i = 0; i < n; i++) {
@@ -226,11 +228,16 @@ class FiducialSlam {
         std::vector<int32_t> pairs;
         std::string line;
         while (std::getline(in, line)) {
-            std::istringstream fields(line.substr(0, line.find('\t')));
+            // sscanf("%d %lf %lf %lf %lf %lf %lf %lf %d%[^\t\n]"): the nine numbers may be separated by any white space (tabs
+            // included); only the link list that follows them ends at the first tab
+            std::istringstream fields(line);
             fid_map_file_entry r{};
             if (!(fields >> r.fiducial_id >> r.x >> r.y >> r.z >> r.roll_deg >> r.pitch_deg >> r.yaw_deg >> r.variance >> r.num_obs)) continue;
             rows.push_back(r);
-            for (int32_t linked; fields >> linked;) {
+            std::string rest;
+            std::getline(fields, rest);
+            std::istringstream links(rest.substr(0, rest.find('\t')));
+            for (int32_t linked; links >> linked;) {
                 pairs.push_back(r.fiducial_id);
                 pairs.push_back(linked);
             }

@@ -203,7 +203,6 @@ struct RobotPose {  // T_mapBase after updatePose
     double var;
 };
 
-#define FID_MAX_OBS 64
 
 FID_HD void map_hash_rebuild(const MapHash& h, const MapEntry* e, int n) {
     for (int i = 0; i < h.size; i++) h.keys[i] = 0;
@@ -226,26 +225,31 @@ FID_HD int map_find(const MapState& st, const MapEntry* e, int id, const MapHash
 
 FID_HD bool isnan3(const double t[3]) { return t[0] != t[0] || t[1] != t[1] || t[2] != t[2]; }
 
+// T_camFid of one observation with its variance (Observation::Observation, map.cpp:53-59; transformCallback :91-97)
+FID_HD Twv obs_cam_fid(const Obs& o, double weighting_scale, int use_area) {
+    Twv t;
+    q_to_m(o.q, t.R);
+    t.t[0] = o.t[0];
+    t.t[1] = o.t[1];
+    t.t[2] = o.t[2];
+    t.var = use_area ? weighting_scale / o.area : weighting_scale * o.object_error;
+    return t;
+}
+
 // links: capacity x capacity bit matrix (row = slot, bit = other slot), may be null.
+// var_scratch / slot_scratch: n_obs entries each of caller-owned scratch (the per-observation variance updatePose writes back
+// for updateMap, map.cpp:298, and the slots of the link pass) -- a message may hold any number of observations, like the
+// reference's std::vector<Observation>.
 FID_HD void map_update(MapState& st, MapEntry* e, uint32_t* links, const Obs* obs_in, int n_obs, const Twv* T_baseCam /*null = lookup failed*/,
                        const Twv* T_camBase /*null = lookup failed*/, double weighting_scale, int use_area, double systematic_error, RobotPose* robot,
-                       const MapHash* hash = nullptr) {
+                       const MapHash* hash, double* var_scratch, int* slot_scratch) {
     if (hash && hash->size > 0 && !st.hash_valid) {
         map_hash_rebuild(*hash, e, st.n);
         st.hash_valid = 1;
     }
     robot->valid = 0;
     robot->n_estimates = 0;
-    if (n_obs > FID_MAX_OBS) n_obs = FID_MAX_OBS;
-    // transformCallback: observations with T_camFid, T_fidCam, variance
-    Twv camFid[FID_MAX_OBS];
-    for (int i = 0; i < n_obs; i++) {
-        q_to_m(obs_in[i].q, camFid[i].R);
-        camFid[i].t[0] = obs_in[i].t[0];
-        camFid[i].t[1] = obs_in[i].t[1];
-        camFid[i].t[2] = obs_in[i].t[2];
-        camFid[i].var = use_area ? weighting_scale / obs_in[i].area : weighting_scale * obs_in[i].object_error;
-    }
+    // transformCallback: observations with T_camFid, T_fidCam, variance (recomputed from the message where needed)
     st.frame_num++;
     if (n_obs > 0 && st.n == 0) st.initializing = 1;
     if (st.initializing) {
@@ -254,7 +258,8 @@ FID_HD void map_update(MapState& st, MapEntry* e, uint32_t* links, const Obs* ob
             int idx = -1;
             double smallest = -1.0;
             for (int i = 0; i < n_obs; i++) {
-                const double d = camFid[i].t[0] * camFid[i].t[0] + camFid[i].t[1] * camFid[i].t[1] + camFid[i].t[2] * camFid[i].t[2];
+                const double* ct = obs_in[i].t;
+                const double d = ct[0] * ct[0] + ct[1] * ct[1] + ct[2] * ct[2];
                 if (smallest < 0 || d < smallest) {
                     smallest = d;
                     idx = i;
@@ -262,10 +267,11 @@ FID_HD void map_update(MapState& st, MapEntry* e, uint32_t* links, const Obs* ob
             }
             if (idx >= 0 && st.capacity > 0) {
                 st.origin_fid = obs_in[idx].id;
-                Twv T = camFid[idx];
+                const Twv cf = obs_cam_fid(obs_in[idx], weighting_scale, use_area);
+                Twv T = cf;
                 if (T_baseCam) {
-                    T = twv_mul(*T_baseCam, camFid[idx]);
-                    T.var = camFid[idx].var;
+                    T = twv_mul(*T_baseCam, cf);
+                    T.var = cf.var;
                 }
                 e[0].id = obs_in[idx].id;
                 e[0].num_obs = 0;
@@ -278,10 +284,11 @@ FID_HD void map_update(MapState& st, MapEntry* e, uint32_t* links, const Obs* ob
         } else {
             for (int i = 0; i < n_obs; i++) {
                 if (obs_in[i].id == st.origin_fid) {
-                    Twv T = camFid[i];
+                    const Twv cf = obs_cam_fid(obs_in[i], weighting_scale, use_area);
+                    Twv T = cf;
                     if (T_baseCam) {
-                        T = twv_mul(*T_baseCam, camFid[i]);
-                        T.var = camFid[i].var;
+                        T = twv_mul(*T_baseCam, cf);
+                        T.var = cf.var;
                     }
                     const int slot = map_find(st, e, st.origin_fid, hash);
                     if (slot >= 0) {
@@ -315,14 +322,16 @@ FID_HD void map_update(MapState& st, MapEntry* e, uint32_t* links, const Obs* ob
     int n_est = 0;
     Twv mapBase;
     for (int i = 0; i < n_obs; i++) {
+        const Twv cf = obs_cam_fid(obs_in[i], weighting_scale, use_area);
+        var_scratch[i] = cf.var;
         const int slot = map_find(st, e, obs_in[i].id, hash);
         if (slot < 0) continue;
-        Twv fidCam = twv_inverse(camFid[i]);
+        Twv fidCam = twv_inverse(cf);
         Twv p = twv_mul(e[slot].pose, fidCam);
         p = twv_mul(p, camBase);
         double roll, pitch, yaw;
         get_rpy(p.R, &roll, &pitch, &yaw);
-        const double* c = camFid[i].t;
+        const double* c = cf.t;
         const double zr = p.t[2] / c[2];
         const double s1 = (zr * zr) * (c[0] * c[0] + c[1] * c[1]);
         const double len2 = p.t[0] * p.t[0] + p.t[1] * p.t[1] + p.t[2] * p.t[2];
@@ -330,7 +339,7 @@ FID_HD void map_update(MapState& st, MapEntry* e, uint32_t* links, const Obs* ob
         const double s2 = len2 * (sr * sr);
         const double s3 = len2 * (spt * spt);
         p.var = s1 + s2 + s3 + systematic_error;
-        camFid[i].var = p.var;  // write-back used by updateMap
+        var_scratch[i] = p.var;  // write-back used by updateMap
         if (isnan3(p.t)) continue;
         if (n_est == 0) {
             mapBase = p;
@@ -351,7 +360,9 @@ FID_HD void map_update(MapState& st, MapEntry* e, uint32_t* links, const Obs* ob
     // ---- updateMap
     if (n_obs > 1 && !st.read_only) {
         for (int i = 0; i < n_obs; i++) {
-            const Twv mapFid = twv_mul(mapCam, camFid[i]);
+            Twv cf = obs_cam_fid(obs_in[i], weighting_scale, use_area);
+            cf.var = var_scratch[i];
+            const Twv mapFid = twv_mul(mapCam, cf);
             if (isnan3(mapFid.t)) continue;
             int slot = map_find(st, e, obs_in[i].id, hash);
             if (slot < 0) {
@@ -373,7 +384,7 @@ FID_HD void map_update(MapState& st, MapEntry* e, uint32_t* links, const Obs* ob
         // links (map.cpp:217-222): every fiducial seen in this frame links to every other one
         if (links) {
             const int wpr = (st.capacity + 31) / 32;
-            int slots[FID_MAX_OBS];
+            int* slots = slot_scratch;
             for (int i = 0; i < n_obs; i++) slots[i] = map_find(st, e, obs_in[i].id, hash);
             for (int i = 0; i < n_obs; i++) {
                 if (slots[i] < 0) continue;

@@ -10,7 +10,8 @@ namespace fid {
 #define FID_SUBPIX_MAX_WIN 5  // cornerRefinementWinSize upper bound supported (reference uses 5)
 
 // getRectSubPix(8u -> 32f) of a (2*win+3)^2 patch centred at (cx,cy); replicate border.
-FID_HD void rect_subpix(const uint8_t* gray, int W, int H, size_t pitch, float cx, float cy, int win, float* patch) {
+template <class Img>
+FID_HD void rect_subpix(const Img& gray, int W, int H, float cx, float cy, int win, float* patch) {
     const int pw = 2 * win + 3;
     cx -= (pw - 1) * 0.5f;
     cy -= (pw - 1) * 0.5f;
@@ -24,21 +25,20 @@ FID_HD void rect_subpix(const uint8_t* gray, int W, int H, size_t pitch, float c
             y0 = y0 < 0 ? 0 : (y0 > H - 1 ? H - 1 : y0);
             y1 = y1 < 0 ? 0 : (y1 > H - 1 ? H - 1 : y1);
         }
-        const uint8_t* r0 = gray + (size_t)y0 * pitch;
-        const uint8_t* r1 = gray + (size_t)y1 * pitch;
         for (int j = 0; j < pw; j++) {
             int x0 = ix + j, x1 = ix + j + 1;
             if (!inside) {
                 x0 = x0 < 0 ? 0 : (x0 > W - 1 ? W - 1 : x0);
                 x1 = x1 < 0 ? 0 : (x1 > W - 1 ? W - 1 : x1);
             }
-            patch[i * pw + j] = r0[x0] * a11 + r0[x1] * a12 + r1[x0] * a21 + r1[x1] * a22;
+            patch[i * pw + j] = gray.at(x0, y0) * a11 + gray.at(x1, y0) * a12 + gray.at(x0, y1) * a21 + gray.at(x1, y1) * a22;
         }
     }
 }
 
 // mask[(2win+1)^2] is the separable exp window computed on the host (libm expf, as OpenCV does).
-FID_HD void corner_subpix(const uint8_t* gray, int W, int H, size_t pitch, float* px, float* py, int win, const float* mask, int max_iters, double eps_sq,
+template <class Img>
+FID_HD void corner_subpix(const Img& gray, int W, int H, float* px, float* py, int win, const float* mask, int max_iters, double eps_sq,
                           float* patch /* (2win+3)^2 scratch */) {
     const int ww = 2 * win + 1, pw = ww + 2;
     const float tx = *px, ty = *py;
@@ -46,7 +46,7 @@ FID_HD void corner_subpix(const uint8_t* gray, int W, int H, size_t pitch, float
     int iter = 0;
     double err = 0.0;
     do {
-        rect_subpix(gray, W, H, pitch, cx, cy, win, patch);
+        rect_subpix(gray, W, H, cx, cy, win, patch);
         double a = 0, b = 0, c = 0, bb1 = 0, bb2 = 0;
         for (int i = 0, k = 0; i < ww; i++) {
             const float* sp = patch + (i + 1) * pw + 1;

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import re
 from typing import Dict, Iterable, List, Optional, Sequence
 
 import numpy as np
@@ -361,15 +362,18 @@ class FiducialSlam:
         rows, pairs = [], []
         with open(filename) as fp:
             for line in fp:
-                tok = line.split("\t")[0].split()
+                # sscanf("%d %lf ... %d%[^\t\n]"): nine numbers separated by any white space (tabs too), then the links up to a tab
+                m = re.match(r"\s*(\S+)\s+(\S+)\s+(\S+)\s+(\S+)\s+(\S+)\s+(\S+)\s+(\S+)\s+(\S+)\s+([+-]?\d+)([^\t\n]*)", line)
                 try:
-                    row = [int(tok[0])] + [float(v) for v in tok[1:8]] + [int(tok[8])]
-                    if len(row) != 9:
+                    if m is None:
                         raise ValueError
-                except (ValueError, IndexError):
+                    tok = m.groups()
+                    row = [int(tok[0])] + [float(v) for v in tok[1:8]] + [int(tok[8])]
+                    links = [int(v) for v in tok[9].split()]
+                except ValueError:
                     continue
                 rows.append(row)
-                pairs += [(row[0], int(v)) for v in tok[9:]]
+                pairs += [(row[0], v) for v in links]
         self.loadMap(rows, instance)
         if pairs:
             arr = np.ascontiguousarray(np.array(pairs, np.int32))
@@ -466,13 +470,39 @@ class FiducialSlam:
     def clear(self, instance=0):
         _lib.check(self.lib.fid_map_clear(self.h, instance))
 
-    # multi-GPU merge (new)
+    # multi-GPU merged view (new): local instances are never overwritten by a merge
     def export_table(self, instance=0) -> np.ndarray:
         cap = self.p.max_fiducials
         arr = (_lib.fid_map_record * cap)()
         _lib.check(self.lib.fid_map_export(self.h, instance, C.cast(arr, C.c_void_p)))
         return np.frombuffer(arr, dtype=np.uint8).copy()
 
-    def merge_tables(self, tables: np.ndarray, n_tables: int, instance=0):
+    def merge_tables(self, tables: np.ndarray, n_tables: int):
+        """Fold n_tables gathered tables (rank order) into the merged view (rebuilt from scratch: idempotent)."""
         tables = np.ascontiguousarray(tables, np.uint8)
-        _lib.check(self.lib.fid_map_merge(self.h, instance, n_tables, tables.ctypes.data_as(C.c_void_p)))
+        _lib.check(self.lib.fid_map_merge(self.h, n_tables, tables.ctypes.data_as(C.c_void_p)))
+
+    def merged_entries(self):
+        cap = self.p.max_fiducials
+        arr = (_lib.fid_map_entry * cap)()
+        n = C.c_int(0)
+        _lib.check(self.lib.fid_map_merged_entries(self.h, cap, C.byref(n), C.cast(arr, C.c_void_p)))
+        return [arr[i] for i in range(n.value)]
+
+    def adopt_merged(self, instance=0):
+        _lib.check(self.lib.fid_map_adopt_merged(self.h, instance))
+
+    @property
+    def table_bytes(self) -> int:
+        return self.p.max_fiducials * C.sizeof(_lib.fid_map_record)
+
+    def cuda_stream(self) -> int:
+        st = C.c_void_p()
+        _lib.check(self.lib.fid_map_stream(self.h, C.byref(st)))
+        return st.value or 0
+
+    def export_async(self, device_ptr: int, instance=0):
+        _lib.check(self.lib.fid_map_export_async(self.h, instance, C.c_void_p(device_ptr)))
+
+    def merge_device_async(self, device_ptr: int, n_tables: int):
+        _lib.check(self.lib.fid_map_merge_device_async(self.h, n_tables, C.c_void_p(device_ptr)))

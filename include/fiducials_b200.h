@@ -278,10 +278,15 @@ int fid_map_sync(fid_map* m);
 /* publishMap (map.cpp:629-654): entries in ascending fiducial id. */
 int fid_map_entries(fid_map* m, int instance, int max_entries, int* n, fid_map_entry* entries);
 
-/* Multi-GPU merge (NEW, no reference counterpart -- SURVEY 8e).  Export an instance as a fixed-size
- * table (max_fiducials records), exchange tables with ncclAllGather / torch.distributed.all_gather,
- * then every rank folds the gathered tables in rank order (ids ascending, fused with
- * TransformWithVariance::update, variance-0 entries win) into the instance. */
+/* Multi-GPU merged map (NEW, no reference counterpart -- SURVEY 8e; parity unpinned, checked against
+ * oracle/slam_oracle.py::merge_maps).  Every rank keeps its own LOCAL map instances (the reference's
+ * sequential fold over its own camera stream).  Once per merge epoch each rank exports its instance as a
+ * fixed-size table (max_fiducials records, ids ascending, unused records -1 at the end), the tables are
+ * exchanged with ONE all-gather (ncclAllGather / torch.distributed.all_gather_into_tensor), and every
+ * rank folds the gathered tables -- ranks in order, TransformWithVariance::update
+ * (transform_with_variance.cpp:43-78), variance-0 entries win -- into a MERGED VIEW that is separate from
+ * the local instances and rebuilt from scratch by every merge: merging is idempotent and nothing that was
+ * exchanged at one epoch is fused again at the next. */
 typedef struct fid_map_record {
     int32_t fiducial_id; /* -1 = empty slot */
     int32_t num_obs;
@@ -290,10 +295,20 @@ typedef struct fid_map_record {
     double variance;
 } fid_map_record;
 int fid_map_export(fid_map* m, int instance, fid_map_record* table /* [max_fiducials] */);
-int fid_map_merge(fid_map* m, int instance, int n_tables, const fid_map_record* tables /* [n_tables][max_fiducials] */);
-/* Device pointer + byte size of the instance's export table, for in-place NCCL all-gather. */
+/* Device pointer + byte size of the instance's export table (synchronous). */
 int fid_map_export_device(fid_map* m, int instance, void** device_table, size_t* bytes);
-int fid_map_merge_device(fid_map* m, int instance, int n_tables, const void* device_tables);
+/* Stream-ordered forms for an exchange that never blocks the host: fid_map_stream returns the
+ * cudaStream_t every asynchronous fid_map_* call is ordered on; enqueue the export into a caller-owned
+ * device buffer, the all-gather on that same stream, then the merge of the gathered buffer. */
+int fid_map_stream(fid_map* m, void** cuda_stream);
+int fid_map_export_async(fid_map* m, int instance, void* device_dst /* [max_fiducials] fid_map_record */);
+int fid_map_merge_device_async(fid_map* m, int n_tables, const void* device_tables /* [n_tables][max_fiducials] */);
+int fid_map_merge_device(fid_map* m, int n_tables, const void* device_tables);
+int fid_map_merge(fid_map* m, int n_tables, const fid_map_record* tables /* host, [n_tables][max_fiducials] */);
+/* The merged view as FiducialMapEntry fields (ids ascending), like fid_map_entries. */
+int fid_map_merged_entries(fid_map* m, int max_entries, int* n, fid_map_entry* entries);
+/* Replace an instance's fiducials by the merged view (explicit; its links are cleared). */
+int fid_map_adopt_merged(fid_map* m, int instance);
 
 #ifdef __cplusplus
 }

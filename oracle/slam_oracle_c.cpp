@@ -52,11 +52,14 @@ int slam_c_replay(int capacity, int n_seed, const double* seed, int n_msgs, cons
         cb.t[2] = cam_base[2];
         cb.var = 0;
     }
-    Obs buf[FID_MAX_OBS];
+    int max_n = 1;
+    for (int k = 0; k < n_msgs; k++) max_n = offsets[k + 1] - offsets[k] > max_n ? offsets[k + 1] - offsets[k] : max_n;
+    Obs* buf = (Obs*)calloc((size_t)max_n, sizeof(Obs));
+    double* var_scratch = (double*)calloc((size_t)max_n, sizeof(double));
+    int* slot_scratch = (int*)calloc((size_t)max_n, sizeof(int));
     RobotPose rp;
     for (int k = 0; k < n_msgs; k++) {
         int n = offsets[k + 1] - offsets[k];
-        if (n > FID_MAX_OBS) n = FID_MAX_OBS;
         for (int i = 0; i < n; i++) {
             const double* o = obs + 10 * (size_t)(offsets[k] + i);
             buf[i].id = (int)o[0];
@@ -70,7 +73,7 @@ int slam_c_replay(int capacity, int n_seed, const double* seed, int n_msgs, cons
             buf[i].object_error = o[8];
             buf[i].area = o[9];
         }
-        map_update(st, e, NULL, buf, n, base_cam ? &bc : NULL, cam_base ? &cb : NULL, 1e9, 0, 0.01, &rp);
+        map_update(st, e, NULL, buf, n, base_cam ? &bc : NULL, cam_base ? &cb : NULL, 1e9, 0, 0.01, &rp, NULL, var_scratch, slot_scratch);
         if (robot_out) {
             double* r = robot_out + 9 * (size_t)k;
             r[0] = rp.valid;
@@ -93,6 +96,9 @@ int slam_c_replay(int capacity, int n_seed, const double* seed, int n_msgs, cons
     }
     const int n = st.n;
     free(e);
+    free(buf);
+    free(var_scratch);
+    free(slot_scratch);
     return n;
 }
 }

@@ -487,11 +487,11 @@ int hs_detect(const uint8_t* gray, const uint8_t* planes, int W, int H, int dict
         if (quad_near_border(sq[i], W, H, P.min_dist_to_border)) continue;
         n_sel++;
         QuadF use = sq[i];
-        IdentifyResult r = identify_candidate(L, gray, W, H, (size_t)W, use, P, dict.data(), img.data(), hist);
+        IdentifyResult r = identify_candidate(L, GrayPlane{gray, (size_t)W}, W, H, use, P, dict.data(), img.data(), hist);
         if (r.id < 0) {
             for (int k = 0; k < ccount[i]; k++) {
                 const QuadF& alt = sq[cidx[coff[i] + k]];
-                r = identify_candidate(L, gray, W, H, (size_t)W, alt, P, dict.data(), img.data(), hist);
+                r = identify_candidate(L, GrayPlane{gray, (size_t)W}, W, H, alt, P, dict.data(), img.data(), hist);
                 if (r.id >= 0) {
                     use = alt;
                     break;
@@ -518,7 +518,7 @@ int hs_detect(const uint8_t* gray, const uint8_t* planes, int W, int H, int dict
             win = win < P.refine_win ? win : P.refine_win;
             subpix_mask(win, mask);
             for (int k = 0; k < 4; k++)
-                corner_subpix(gray, W, H, (size_t)W, &cx[k], &cy[k], win, mask, P.refine_max_iter, P.refine_min_acc * P.refine_min_acc, patch.data());
+                corner_subpix(GrayPlane{gray, (size_t)W}, W, H, &cx[k], &cy[k], win, mask, P.refine_max_iter, P.refine_min_acc * P.refine_min_acc, patch.data());
         }
         ids[n_out] = r.id;
         for (int k = 0; k < 4; k++) {
@@ -539,7 +539,7 @@ void hs_corner_subpix(const uint8_t* gray, int W, int H, float* pts, int n, int 
     float mask[121];
     float patch[13 * 13];
     subpix_mask(win, mask);
-    for (int i = 0; i < n; i++) corner_subpix(gray, W, H, (size_t)W, &pts[2 * i], &pts[2 * i + 1], win, mask, max_iters, eps * eps, patch);
+    for (int i = 0; i < n; i++) corner_subpix(GrayPlane{gray, (size_t)W}, W, H, &pts[2 * i], &pts[2 * i + 1], win, mask, max_iters, eps * eps, patch);
 }
 
 // Pose of n markers; out: n x 19 doubles (rvec3 tvec3 image_error object_error area quat4 iters pad..)
@@ -606,7 +606,9 @@ int hs_map_update(void* h, int n, const double* obs, const double* baseCam, cons
         cb.var = 0;
     }
     RobotPose rp;
-    map_update(m->st, m->e.data(), m->links.data(), o.data(), n, baseCam ? &bc : nullptr, camBase ? &cb : nullptr, 1e9, 0, 0.01, &rp);
+    std::vector<double> var_scratch((size_t)n + 1);
+    std::vector<int> slot_scratch((size_t)n + 1);
+    map_update(m->st, m->e.data(), m->links.data(), o.data(), n, baseCam ? &bc : nullptr, camBase ? &cb : nullptr, 1e9, 0, 0.01, &rp, nullptr, var_scratch.data(), slot_scratch.data());
     robot[0] = rp.valid;
     robot[1] = rp.n_estimates;
     for (int k = 0; k < 3; k++) robot[2 + k] = rp.t[k];

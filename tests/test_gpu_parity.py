@@ -401,3 +401,102 @@ def test_full_size_round_trip(det_cache, cfg):
         proj, _ = cv2.projectPoints(obj, np.array(t.rvec), np.array(t.translation), K, D)
         assert np.abs(proj.reshape(4, 2) - corners[i]).max() < 1.0
         assert t.image_error < 1.0
+
+
+# ---- the tensor-core threshold kernel (tcgen05.mma kind::i8 + TMEM + TMA; opt-in with FID_THRESH=mma) -------------------
+from fiducials_b200.node import MAXM, Detector, default_params  # noqa: E402
+
+@pytest.fixture
+def mma_threshold(monkeypatch):
+    monkeypatch.setenv("FID_THRESH", "mma")  # read by fid_create
+
+
+@pytest.mark.parametrize("case", ["C1", "C2", "noise", "odd", "flat", "kat", "mono", "rgb"])
+def test_mma_threshold_planes_bit_exact(mma_threshold, kat, case):
+    """kernels_threshold_mma.cuh gives the same 13 planes as cv2.adaptiveThreshold: interior tiles (TMA staged), replicate-border
+    tiles, image sizes that are no multiple of the tile, layouts TMA cannot describe (odd width -> every tile clamps), mono8 / rgb8."""
+    rng = np.random.default_rng(12)
+    enc = "bgr8"
+    if case in ("C1", "C2"):
+        bgr = synth.make_config_frame(case, 1)[0]
+    elif case == "noise":
+        bgr = rng.integers(0, 256, (360, 640, 3), dtype=np.uint8)
+    elif case == "odd":
+        bgr = rng.integers(0, 256, (131, 203, 3), dtype=np.uint8)
+    elif case == "flat":
+        bgr = np.full((96, 160, 3), 200, np.uint8)
+    elif case == "kat":
+        bgr = kat.frame("tag01")
+    elif case == "mono":
+        bgr, enc = rng.integers(0, 256, (300, 480), dtype=np.uint8), "mono8"
+    else:
+        bgr, enc = rng.integers(0, 256, (300, 480, 3), dtype=np.uint8), "rgb8"
+    H, W = bgr.shape[:2]
+    det = Detector(default_params(dictionary=7), 0, max(W, 16), max(H, 16), 1)
+    try:
+        if enc != "bgr8":
+            det.set_input_encoding(enc)
+        g, planes = det.debug_threshold(bgr)
+    finally:
+        det.close()
+    as_bgr = bgr if enc == "bgr8" else (np.repeat(bgr[:, :, None], 3, axis=2) if enc == "mono8" else np.ascontiguousarray(bgr[:, :, ::-1]))
+    rg = ao.gray(as_bgr)
+    assert np.array_equal(g, rg)
+    rp = ao.threshold_planes(rg)
+    assert np.array_equal(planes, rp), [int((planes[s] != rp[s]).sum()) for s in range(len(rp))]
+
+
+@pytest.mark.parametrize("cfg,seed", [("C1", 0), ("C3", 1), ("C2", 3)])
+def test_mma_threshold_full_pipeline(mma_threshold, cfg, seed):
+    """Start cracks queued by the tensor-core kernel (column-domain prune, block-allocated queue with null padding) feed the
+    same border walk: ids, order, corners and poses equal the oracle's on whole frames, batches included."""
+    bgr, truth, K, D, dict_id = synth.make_config_frame(cfg, seed)
+    H, W = bgr.shape[:2]
+    det = Detector(default_params(dictionary=dict_id), 0, W, H, 2)
+    try:
+        frames = np.ascontiguousarray(np.stack([bgr, bgr[::-1].copy(), bgr]))
+        counts, ids, corners, tfs = det.detect_pose_batch(frames, K, D, 0.14)
+        for i, fr in enumerate(frames):
+            oi, oc, rv, tv, fields = ao.detect_and_pose(fr, dict_id, K, D, 0.14)
+            n = int(counts[i])
+            assert ids[i, :n].tolist() == oi.tolist()
+            if n:
+                assert np.abs(corners[i, :n] - oc).max() <= 1e-3
+                for m in range(n):
+                    t = tfs[i * MAXM + m]
+                    assert np.abs(np.array(t.translation[:]) - fields[m]["translation"]).max() <= 1e-3
+                    assert np.abs(np.array(t.rotation[:]) - fields[m]["rotation"]).max() <= 1e-3
+    finally:
+        det.close()
+
+
+def test_mono8_strided_multi_frame():
+    """a padded mono8 batch (row stride > width, frame stride > rows) must land frame f at f*W*H in the slot
+    buffer (bytes per pixel of the ENCODING, not 3): every frame of the batch decodes like the contiguous call."""
+    bgr, truth, K, D, dict_id = synth.make_config_frame("C1", 2)
+    H, W = bgr.shape[:2]
+    mono = np.ascontiguousarray(bgr[:, :, 0])
+    frames = [mono, mono[::-1].copy(), mono]
+    pitch, rows = W + 24, H + 3
+    padded = np.zeros((len(frames), rows, pitch), np.uint8)
+    for i, fr in enumerate(frames):
+        padded[i, :H, :W] = fr
+    det = Detector(default_params(dictionary=dict_id), 0, W, H, 4)
+    try:
+        det.set_input_encoding("mono8")
+        lib = det.lib
+        n = len(frames)
+        counts = np.zeros(n, np.int32)
+        ids = np.zeros((n, MAXM), np.int32)
+        corners = np.zeros((n, MAXM, 8), np.float32)
+        from fiducials_b200 import _lib
+
+        _lib.check(lib.fid_detect_pose_batch(det.h, n, padded.ctypes.data_as(C.c_void_p), 0, W, H, pitch, pitch * rows, None, 0.0, 0, None, None, MAXM,
+                                             counts.ctypes.data_as(C.c_void_p), ids.ctypes.data_as(C.c_void_p), corners.ctypes.data_as(C.c_void_p), None))
+        ref = det.detect_pose_batch(np.ascontiguousarray(np.stack(frames)))
+        assert counts.tolist() == ref[0].tolist() and counts[0] > 0
+        for i in range(n):
+            assert ids[i, : counts[i]].tolist() == ref[1][i, : counts[i]].tolist()
+            assert np.array_equal(corners[i, : counts[i]].reshape(-1, 4, 2), ref[2][i, : counts[i]])
+    finally:
+        det.close()

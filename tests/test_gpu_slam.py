@@ -188,16 +188,32 @@ def test_merge_matches_oracle_merge():
         refs.append(r)
     slam.replay(halves, _tf7(ident), _tf7(ident))
     tables = np.concatenate([slam.export_table(0), slam.export_table(1)])
-    slam.merge_tables(tables, 2, instance=0)
+    local_before = [(e.fiducial_id, e.x, e.rz, e.variance, e.num_obs) for e in slam.entries(0)]
+    slam.merge_tables(tables, 2)
     merged = so.merge_maps([[(f.id, f.pose, f.numObs) for f in r.fiducials.values()] for r in refs])
-    ents = slam.entries(0)
-    assert [e.fiducial_id for e in ents] == sorted(merged)
-    for e in ents:
-        pose, n = merged[e.fiducial_id]
-        rr = so.get_rpy(pose.R)
-        assert np.abs(np.array([e.x, e.y, e.z]) - np.array(pose.t)).max() < 1e-9
-        assert np.abs(np.array([e.rx, e.ry, e.rz]) - np.array(rr)).max() < 1e-9
-        assert e.num_obs == n
+
+    def check(ents):
+        assert [e.fiducial_id for e in ents] == sorted(merged)
+        for e in ents:
+            pose, n = merged[e.fiducial_id]
+            rr = so.get_rpy(pose.R)
+            assert np.abs(np.array([e.x, e.y, e.z]) - np.array(pose.t)).max() < 1e-9
+            assert np.abs(np.array([e.rx, e.ry, e.rz]) - np.array(rr)).max() < 1e-9
+            assert e.num_obs == n
+            assert abs(e.variance - pose.var) <= 1e-9 * max(1.0, abs(pose.var))
+
+    check(slam.merged_entries())
+    # the merge writes a separate view: the local instances are untouched, so a second merge of the same
+    # (re-exported) tables gives the same view (idempotence; round 1 folded the view back into the local map)
+    assert [(e.fiducial_id, e.x, e.rz, e.variance, e.num_obs) for e in slam.entries(0)] == local_before
+    first = [(e.fiducial_id, e.x, e.y, e.z, e.rx, e.ry, e.rz, e.variance, e.num_obs) for e in slam.merged_entries()]
+    tables2 = np.concatenate([slam.export_table(0), slam.export_table(1)])
+    assert np.array_equal(tables, tables2)
+    slam.merge_tables(tables2, 2)
+    assert [(e.fiducial_id, e.x, e.y, e.z, e.rx, e.ry, e.rz, e.variance, e.num_obs) for e in slam.merged_entries()] == first
+    # explicit adoption: the view replaces an instance
+    slam.adopt_merged(1)
+    check(slam.entries(1))
 
 
 def test_c5_pose_graph_sequence():
@@ -228,3 +244,100 @@ def test_c5_pose_graph_sequence():
         ei = many.entries(i)
         assert [a.fiducial_id for a in ei] == [a.fiducial_id for a in e0]
         assert all(a.x == b.x and a.rz == b.rz for a, b in zip(ei, e0))  # deterministic across instances
+
+
+def test_links_follow_the_fiducials(kat, tmp_path):
+    """fiducials.clear() (clearCallback, map.cpp:809-817) drops the link sets with the fiducials; loadMap builds a
+    fresh Fiducial for an id it replaces (map.cpp:600-606) -- no stale links may survive either on the device's slot x slot matrix."""
+    from fiducials_b200.node import FiducialSlam
+
+    tr = _bag_transforms(kat)
+    ident = so.TWV.identity()
+    slam = FiducialSlam(max_fiducials=32)
+    slam.loadMap([[111, 0, 0, 0, 0, 0, 0, 0, 0]])
+    for _ in range(3):
+        slam.transformCallback(tr, _tf7(ident), _tf7(ident))
+    links = slam.links()
+    assert links and all(v for v in links.values())
+    some = next(k for k in links if k != 111)
+    # replacing one fiducial through loadMap: its own links and the links to it are gone, the others stay
+    slam.loadMap([[some, 1, 2, 3, 0, 0, 0, 0.5, 0]])
+    after = slam.links()
+    assert some not in after and all(some not in v for v in after.values())
+    assert any(after.values())
+    # clear, then a different map: nothing of the old link matrix may show up under the new slot order
+    slam.clear()
+    assert slam.entries() == [] and slam.links() == {}
+    slam.loadMap([[7, 0, 0, 0, 0, 0, 0, 0, 0], [9, 1, 0, 0, 0, 0, 0, 1, 0]])
+    assert slam.links() == {}
+    slam.close()
+
+
+def test_load_map_file_with_tabs(tmp_path):
+    """Map::loadMap's sscanf accepts tabs between the nine numbers; only the link list ends at the first tab (map.cpp:590-615)."""
+    from fiducials_b200.node import FiducialSlam
+
+    path = tmp_path / "tabs.txt"
+    path.write_text("5\t1.0\t2.0 3.0\t0 0 90\t0.25\t4 6 7\textra words\n6 0 0 0 0 0 0 1 0 5\nnot a line\n7\t0\t0\t0\t0\t0\t0\t1\t2\n")
+    slam = FiducialSlam(max_fiducials=8)
+    assert slam.loadMapFile(str(path)) == 3
+    ents = slam.entries()
+    assert [e.fiducial_id for e in ents] == [5, 6, 7] and ents[0].num_obs == 4 and abs(ents[0].y - 2.0) < 1e-12 and abs(ents[0].rz - np.pi / 2) < 1e-12
+    assert slam.links() == {5: [6, 7], 6: [5]}
+    slam.close()
+
+
+def test_messages_with_more_than_64_observations():
+    """A FiducialTransformArray has no size limit (Map::update takes a std::vector<Observation>, map.cpp:152); round 1 clamped
+    a message to 64 observations silently.  100 fiducials in every message, through all three entry points."""
+    from fiducials_b200 import _lib
+    from fiducials_b200.node import FiducialSlam
+
+    rng = np.random.default_rng(5)
+    n_fid = 100
+    grid = [(float(i % 10), float(i // 10), 2.5) for i in range(n_fid)]
+    msgs = []
+    for k in range(6):
+        cam = np.array([4.0 + 0.3 * k, 4.5 - 0.2 * k, 0.0])
+        order = list(range(n_fid))
+        rng.shuffle(order)
+        m = []
+        for i in order:
+            t = np.array(grid[i]) - cam + rng.normal(0, 0.004, 3)
+            q = so.q_from_rpy(math.pi + rng.normal(0, 0.01), rng.normal(0, 0.01), math.pi + rng.normal(0, 0.01))
+            m.append(dict(fiducial_id=100 + i, translation=t, rotation=np.array(q), image_error=0.1, object_error=float(rng.uniform(1e-4, 1e-2)), fiducial_area=900.0))
+        msgs.append(m)
+    ident = so.TWV.identity()
+    ref = so.Map()
+    ref.load_entry(100, grid[0][0], grid[0][1], grid[0][2], 180, 0, 180, 0, 0)
+    for m in msgs:
+        ref.update(so.observations_from_transforms(m), ident, ident)
+    assert len(ref.fiducials) == n_fid
+    seed = [[100, grid[0][0], grid[0][1], grid[0][2], 180, 0, 180, 0, 0]]
+    a = FiducialSlam(max_fiducials=128)
+    a.loadMap(seed)
+    for m in msgs:
+        r = a.transformCallback(m, _tf7(ident), _tf7(ident))  # fid_map_update
+    assert r.valid == 1 and r.n_estimates == n_fid
+    _cmp_entries(a.entries(), ref.entries(), 1e-9)
+    b = FiducialSlam(max_fiducials=128)
+    b.loadMap(seed)
+    b.replay([msgs], _tf7(ident), _tf7(ident))  # fid_map_update_sequence
+    _cmp_entries(b.entries(), ref.entries(), 1e-9)
+    assert b.links() == a.links() and len(a.links()[100]) == n_fid - 1
+    # fid_map_update_frames: the dense per-frame layout of the detector (FID_MAX_MARKERS slots per frame)
+    c = FiducialSlam(max_fiducials=128)
+    c.loadMap(seed)
+    from fiducials_b200.node import MAXM
+
+    tfs = (_lib.fid_transform * (len(msgs) * MAXM))()
+    counts = np.zeros(len(msgs), np.int32)
+    for f, m in enumerate(msgs):
+        counts[f] = len(m)
+        arr = FiducialSlam._obs(m)
+        for i in range(len(m)):
+            tfs[f * MAXM + i] = arr[i]
+    c.update_frames(counts, tfs, _tf7(ident), _tf7(ident))
+    _cmp_entries(c.entries(), ref.entries(), 1e-9)
+    for s in (a, b, c):
+        s.close()

@@ -15,7 +15,6 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from fiducials_b200 import synth  # noqa: E402
-from fiducials_b200.node import FiducialSlam  # noqa: E402
 
 
 def cpu_replay(msgs, seed_entry, reps=5):
@@ -33,10 +32,31 @@ def cpu_replay(msgs, seed_entry, reps=5):
         n = lib.slam_c_replay(512, 1, seed.ctypes.data_as(C.c_void_p), len(msgs), off.ctypes.data_as(C.c_void_p), flat.ctypes.data_as(C.c_void_p),
                               ident.ctypes.data_as(C.c_void_p), ident.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), None)
         best = min(best, time.perf_counter() - t0)
+    cpu_replay.last_entries = out[:n].copy()
     return best, n
 
 
+def cpu_fold_seconds(msgs, seed_entry, reps=3):
+    """Seconds for the whole sequence on one host core (bench.py --workload C5 cpu_baseline)."""
+    return cpu_replay(msgs, seed_entry, reps)[0]
+
+
+def cpu_fold_entries(msgs, seed_entry):
+    """Map after the sequence as rows (id, x, y, z, roll, pitch, yaw), ids ascending (publishMap read-out)."""
+    from oracle import slam_oracle as so
+
+    cpu_replay(msgs, seed_entry, 1)
+    rows = []
+    for r in cpu_replay.last_entries:
+        R = [list(r[4:7]), list(r[7:10]), list(r[10:13])]
+        rr = so.get_rpy(R)
+        rows.append((int(r[0]), r[1], r[2], r[3], rr[0], rr[1], rr[2]))
+    return sorted(rows)
+
+
 def main():
+    from fiducials_b200.node import FiducialSlam
+
     msgs, seed_entry = synth.make_c5_sequence(1000, seed=0)
     n_obs = sum(len(m) for m in msgs)
     res = {"config": "C5: 500 fiducials, %d frames, %d observations" % (len(msgs), n_obs)}
