@@ -106,7 +106,7 @@ EXPORTS = [
     "fid_detect_pose_batch", "fid_submit_batch", "fid_collect_batch", "fid_hint_next", "fid_set_input_encoding", "fid_timer_start", "fid_timer_stop", "fid_host_alloc", "fid_host_free", "fid_device_alloc", "fid_device_free", "fid_memcpy_h2d", "fid_debug_threshold", "fid_debug_time_threshold",
     "fid_debug_candidates", "fid_last_stage_ms", "fid_last_counters", "fid_map_default_params", "fid_map_create", "fid_map_destroy", "fid_map_clear",
     "fid_map_load", "fid_map_links", "fid_map_add_links", "fid_map_update", "fid_map_update_sequence", "fid_map_update_frames", "fid_map_update_frames_async", "fid_map_sync", "fid_map_entries", "fid_map_export", "fid_map_merge", "fid_map_export_device",
-    "fid_map_merge_device", "fid_map_merge_device_async", "fid_map_export_async", "fid_map_stream", "fid_map_merged_entries", "fid_map_adopt_merged",
+    "fid_map_merge_device", "fid_map_merge_device_async", "fid_map_export_async", "fid_map_stream", "fid_map_merged_entries", "fid_map_adopt_merged", "fid_map_add_fiducial",
 ]
 
 _lib = None
@@ -169,6 +169,7 @@ def load():
     lib.fid_map_stream.argtypes = [vp, C.POINTER(vp)]
     lib.fid_map_merged_entries.argtypes = [vp, i32, C.POINTER(C.c_int), vp]
     lib.fid_map_adopt_merged.argtypes = [vp, i32]
+    lib.fid_map_add_fiducial.argtypes = [vp, i32, i32, C.POINTER(fid_tf)]
     for name in EXPORTS:
         getattr(lib, name)  # AttributeError if the build lost a symbol
     _lib = lib

@@ -100,6 +100,7 @@ struct fid_detector {
     uint32_t* d_lut_next = nullptr;
     int thresh_mode = 0;  // 0 = summed-area-table kernel (kernels_threshold.cuh, default: faster end to end), 1 = tensor-core kernel (kernels_threshold_mma.cuh; FID_THRESH=mma)
     int walk_rounds = 0;
+    int walk_refill = 16, walk_pass = 16;  // persistent rounds: idle lanes that trigger a refill, steps per pass (FID_WALK_REFILL / FID_WALK_PASS)
     int emit_blocks_per_sm = 8;
     int walk_budget[FID_WALK_MAX_ROUNDS]{};
     int walk_persist[FID_WALK_MAX_ROUNDS]{};
@@ -394,6 +395,8 @@ extern "C" int fid_create(const fid_params* params, int device, int max_width, i
     }
     {   // walk plan: budgets per round, 'p' prefix = persistent lanes, 0 = unbounded (must be last)
         if (const char* e = getenv("FID_EMIT_BLOCKS")) h->emit_blocks_per_sm = std::max(1, atoi(e));
+        if (const char* e = getenv("FID_WALK_REFILL")) h->walk_refill = std::max(1, std::min(32, atoi(e)));
+        if (const char* e = getenv("FID_WALK_PASS")) h->walk_pass = std::max(2, atoi(e)) & ~1;
         const char* plan = getenv("FID_WALK_PLAN");
         if (!plan || !*plan) plan = "8,64,512,p0";
         h->walk_rounds = 0;
@@ -624,6 +627,8 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
             a.q_in = r > 0 ? s.d_queue[(r - 1) & 1] : nullptr;
             a.q_out = s.d_queue[r & 1];
             a.chunk = r == 0 ? 256u : 32u;
+            a.refill_min = h->walk_refill;
+            a.pass_steps = h->walk_pass;
             const int blocks = r == 0 ? h->sm_count * 8 : (r == 1 ? h->sm_count * 8 : h->sm_count * 4);
             k_walk<<<blocks, 256, 0, st>>>(a);
             launches++;

@@ -288,6 +288,7 @@ static int reset_state(fid_map* m, int inst_lo, int inst_hi) {
         memset(&s, 0, sizeof(s));
         s.capacity = m->p.max_fiducials;
         s.origin_fid = -1;
+        s.fiducial_to_add = -1;
         s.read_only = m->p.read_only_map;
         s.hash_size = m->hash_size;
         s.hash_valid = 0;
@@ -360,6 +361,22 @@ extern "C" int fid_map_clear(fid_map* m, int instance) {
     CK(cudaMemcpy(m->d_state + instance, &st, sizeof(st), cudaMemcpyHostToDevice));
     const size_t wpr = (m->p.max_fiducials + 31) / 32;
     CK(cudaMemset(m->d_links + (size_t)instance * m->p.max_fiducials * wpr, 0, sizeof(uint32_t) * (size_t)m->p.max_fiducials * wpr));
+    return FID_OK;
+}
+
+extern "C" int fid_map_add_fiducial(fid_map* m, int instance, int fiducial_id, const fid_tf* T_mapBase) {
+    if (!m || instance < 0 || instance >= m->p.n_instances || fiducial_id < 0) return FID_ERR_INVALID_ARG;
+    CK(cudaSetDevice(m->device));
+    CK(cudaStreamSynchronize(m->stream));
+    MapState st;
+    CK(cudaMemcpy(&st, m->d_state + instance, sizeof(st), cudaMemcpyDeviceToHost));
+    st.fiducial_to_add = fiducial_id;  // addFiducialCallback (map.cpp:821-828); handled by the next update (handleAddFiducial :489-535)
+    st.add_have_map_base = T_mapBase ? 1 : 0;
+    if (T_mapBase) {
+        for (int k = 0; k < 3; k++) st.add_map_base[k] = T_mapBase->t[k];
+        for (int k = 0; k < 4; k++) st.add_map_base[3 + k] = T_mapBase->q[k];
+    }
+    CK(cudaMemcpy(m->d_state + instance, &st, sizeof(st), cudaMemcpyHostToDevice));
     return FID_OK;
 }
 

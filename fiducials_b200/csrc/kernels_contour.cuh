@@ -103,6 +103,8 @@ struct WalkArgs {
     int min_len, max_len, budget;
     int persistent;
     unsigned int chunk;       // persistent mode: queue items a warp takes per atomic
+    int refill_min;           // persistent mode: refill the warp's idle lanes from the queue when at least this many are idle
+    int pass_steps;           // persistent mode: steps every active lane walks between two refill checks
 };
 
 struct WalkItem {
@@ -231,7 +233,7 @@ __device__ __forceinline__ void walk_side(const WalkArgs& a, unsigned int n, uns
     ck.count[0] = ck.count[1] = 0;
     for (;;) {
         const uint32_t need = __ballot_sync(0xffffffffu, !active);
-        if (__popc(need) >= 16) {  // refill only when at least half the warp is idle
+        if (__popc(need) >= a.refill_min) {  // refill when enough lanes are idle
             if (!exhausted && next >= hi) {
                 unsigned int lo = 0;
                 if (lane == 0) lo = atomicAdd(&a.counters->work[a.round][IS_RIGHT ? 1 : 0], a.chunk) + static_end;
@@ -258,7 +260,7 @@ __device__ __forceinline__ void walk_side(const WalkArgs& a, unsigned int n, uns
         }
         if (active) {
             const int left = budget_end - it.st.n;
-            const int r = walk_bidir_fast<IS_RIGHT>(it.ctx, it.x0, it.y0, a.max_len, left < 16 ? left : 16, &it.st);
+            const int r = walk_bidir_fast<IS_RIGHT>(it.ctx, it.x0, it.y0, a.max_len, left < a.pass_steps ? left : a.pass_steps, &it.st);
             if (r == WALK_CONTINUE && it.st.n < budget_end) {
                 walk_checkpoint(it.st, &ck, &last_f, &last_b);
             } else {

@@ -155,6 +155,40 @@ class FiducialsNode {
     Header last;
 };
 
+// tf2 LinearMath pieces of the published pose (setRotation / getRotation / getRPY's yaw)
+inline void tf2_q_to_m(const double q[4], double m[9]) {
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    const double s = 2.0 / (x * x + y * y + z * z + w * w);
+    const double xs = x * s, ys = y * s, zs = z * s, wx = w * xs, wy = w * ys, wz = w * zs, xx = x * xs, xy = x * ys, xz = x * zs, yy = y * ys, yz = y * zs, zz = z * zs;
+    const double r[9] = {1.0 - (yy + zz), xy - wz, xz + wy, xy + wz, 1.0 - (xx + zz), yz - wx, xz - wy, yz + wx, 1.0 - (xx + yy)};
+    for (int i = 0; i < 9; i++) m[i] = r[i];
+}
+inline void tf2_m_to_q(const double m[9], double q[4]) {
+    const double tr = m[0] + m[4] + m[8];
+    if (tr > 0.0) {
+        double s = sqrt(tr + 1.0);
+        q[3] = s * 0.5;
+        s = 0.5 / s;
+        q[0] = (m[7] - m[5]) * s;
+        q[1] = (m[2] - m[6]) * s;
+        q[2] = (m[3] - m[1]) * s;
+    } else {
+        const int i = m[0] < m[4] ? (m[4] < m[8] ? 2 : 1) : (m[0] < m[8] ? 2 : 0);
+        const int j = (i + 1) % 3, k = (i + 2) % 3;
+        double s = sqrt(m[i * 3 + i] - m[j * 3 + j] - m[k * 3 + k] + 1.0);
+        q[i] = s * 0.5;
+        s = 0.5 / s;
+        q[3] = (m[k * 3 + j] - m[j * 3 + k]) * s;
+        q[j] = (m[j * 3 + i] + m[i * 3 + j]) * s;
+        q[k] = (m[k * 3 + i] + m[i * 3 + k]) * s;
+    }
+}
+inline double tf2_get_yaw(const double m[9]) {  // third angle of tf2::Matrix3x3::getRPY
+    if (fabs(m[6]) >= 1.0) return 0.0;
+    const double c = cos(-asin(m[6]));
+    return atan2(m[3] / c, m[0] / c);
+}
+
 // fiducial_slam's FiducialSlam + Map, minus ROS transport and tf (the two tf lookups of
 // Map::updatePose, map.cpp:258-273, are passed in by the caller; nullptr = lookup failed).
 class FiducialSlam {
@@ -184,6 +218,58 @@ class FiducialSlam {
             o.image_error = ft.image_error; o.object_error = ft.object_error; o.fiducial_area = ft.fiducial_area;
         }
         return fid_map_update(map, 0, (int)obs.size(), obs.data(), T_baseCam, T_camBase, robot) == FID_OK;
+    }
+
+    // add_fiducial service (addFiducialCallback, map.cpp:821-828; handled by the next update, handleAddFiducial :489-535).
+    // T_mapBase = the tf lookup map -> base, nullptr when it fails.
+    bool addFiducial(int fiducial_id, const fid_tf* T_mapBase) { return fid_map_add_fiducial(map, 0, fiducial_id, T_mapBase) == FID_OK; }
+
+    // ---- published pose: host-side message packing of updatePose's tail (map.cpp:337-379) ----
+    bool overridePublishedCovariance = false;  // rosparam covariance_diagonal, map.cpp:110-125
+    double covarianceDiagonal[6] = {0, 0, 0, 0, 0, 0};
+    bool publish_6dof_pose = false;            // map.cpp:107
+    // six values, all non-zero, or the parameter is ignored (map.cpp:112-124)
+    void setCovarianceDiagonal(const std::vector<double>& d) {
+        overridePublishedCovariance = d.size() == 6;
+        for (size_t i = 0; i < 6; i++) covarianceDiagonal[i] = overridePublishedCovariance ? d[i] : 0.0;
+        for (size_t i = 0; overridePublishedCovariance && i < 6; i++)
+            if (d[i] == 0) {
+                overridePublishedCovariance = false;
+                for (double& v : covarianceDiagonal) v = 0.0;
+            }
+    }
+    // covariance of the PoseWithCovarianceStamped on /fiducial_pose: toPose (transform_with_variance.h:69-84) + override (:341-345)
+    void robotPoseCovariance(const fid_robot_pose& robot, double cov[36]) const {
+        for (int i = 0; i < 36; i++) cov[i] = 0.0;
+        for (int i = 0; i < 6; i++) cov[i * 6 + i] = overridePublishedCovariance ? covarianceDiagonal[i] : robot.variance;
+    }
+    // the transform broadcast as map -> odom (T_odomBase given) or map -> base: basePose * odom^-1 (:351-365), squashed to
+    // x, y, yaw unless publish_6dof_pose (:369-379)
+    Transform poseTf(const fid_robot_pose& robot, const fid_tf* T_odomBase) const {
+        double R[9], t[3] = {robot.t[0], robot.t[1], robot.t[2]};
+        tf2_q_to_m(robot.q, R);
+        if (T_odomBase) {
+            double Ro[9], Ri[9], ti[3], Rn[9];
+            tf2_q_to_m(T_odomBase->q, Ro);
+            for (int i = 0; i < 3; i++)
+                for (int j = 0; j < 3; j++) Ri[i * 3 + j] = Ro[j * 3 + i];
+            for (int i = 0; i < 3; i++) ti[i] = Ri[i * 3] * -T_odomBase->t[0] + Ri[i * 3 + 1] * -T_odomBase->t[1] + Ri[i * 3 + 2] * -T_odomBase->t[2];
+            for (int i = 0; i < 3; i++) {
+                for (int j = 0; j < 3; j++) Rn[i * 3 + j] = R[i * 3] * Ri[j] + R[i * 3 + 1] * Ri[3 + j] + R[i * 3 + 2] * Ri[6 + j];
+                t[i] = (R[i * 3] * ti[0] + R[i * 3 + 1] * ti[1] + R[i * 3 + 2] * ti[2]) + robot.t[i];
+            }
+            for (int i = 0; i < 9; i++) R[i] = Rn[i];
+        }
+        if (!publish_6dof_pose) {
+            t[2] = 0.0;
+            const double yaw = tf2_get_yaw(R);
+            const double ch = cos(yaw), sh = sin(yaw);  // setRPY(0, 0, yaw)
+            const double Rz[9] = {ch, -sh, 0, sh, ch, 0, 0, 0, 1};
+            for (int i = 0; i < 9; i++) R[i] = Rz[i];
+        }
+        double q[4];
+        tf2_m_to_q(R, q);
+        return Transform{t[0], t[1], t[2], q[0], q[1], q[2], q[3]};
     }
 
     // publishMap, map.cpp:629-654

@@ -166,6 +166,9 @@ struct MapState {  // Map members map.h:118-134 that carry arithmetic state
     int32_t overflow;    // set if an insertion did not fit
     int32_t hash_size;   // power of two >= 2*capacity; 0 = no hash table (linear search)
     int32_t hash_valid;  // 0 = rebuild the id -> slot table from the entries before the next update
+    int32_t fiducial_to_add;     // add_fiducial service request, -1 = none (Map::fiducialToAdd, map.cpp:821-828)
+    int32_t add_have_map_base;   // the map -> base tf lookup of handleAddFiducial (map.cpp:514-517) succeeded
+    double add_map_base[7];      // ... x y z qx qy qz qw
 };
 
 // id -> slot open-addressing table (linear probing); key = id + 1 (0 = empty), value = slot.
@@ -240,9 +243,9 @@ FID_HD Twv obs_cam_fid(const Obs& o, double weighting_scale, int use_area) {
 // var_scratch / slot_scratch: n_obs entries each of caller-owned scratch (the per-observation variance updatePose writes back
 // for updateMap, map.cpp:298, and the slots of the link pass) -- a message may hold any number of observations, like the
 // reference's std::vector<Observation>.
-FID_HD void map_update(MapState& st, MapEntry* e, uint32_t* links, const Obs* obs_in, int n_obs, const Twv* T_baseCam /*null = lookup failed*/,
-                       const Twv* T_camBase /*null = lookup failed*/, double weighting_scale, int use_area, double systematic_error, RobotPose* robot,
-                       const MapHash* hash, double* var_scratch, int* slot_scratch) {
+FID_HD void map_update_core(MapState& st, MapEntry* e, uint32_t* links, const Obs* obs_in, int n_obs, const Twv* T_baseCam /*null = lookup failed*/,
+                            const Twv* T_camBase /*null = lookup failed*/, double weighting_scale, int use_area, double systematic_error, RobotPose* robot,
+                            const MapHash* hash, double* var_scratch, int* slot_scratch) {
     if (hash && hash->size > 0 && !st.hash_valid) {
         map_hash_rebuild(*hash, e, st.n);
         st.hash_valid = 1;
@@ -395,6 +398,55 @@ FID_HD void map_update(MapState& st, MapEntry* e, uint32_t* links, const Obs* ob
             }
         }
     }
+}
+
+// Map::handleAddFiducial, map.cpp:489-535 (called at the end of every Map::update, :173)
+FID_HD void map_handle_add_fiducial(MapState& st, MapEntry* e, const Obs* obs_in, int n_obs, const Twv* T_baseCam, double weighting_scale, int use_area,
+                                    const MapHash* hash) {
+    if (st.fiducial_to_add == -1) return;
+    if (map_find(st, e, st.fiducial_to_add, hash) >= 0) {  // "already in map - ignoring add request"
+        st.fiducial_to_add = -1;
+        return;
+    }
+    for (int i = 0; i < n_obs; i++) {
+        if (obs_in[i].id != st.fiducial_to_add) continue;
+        Twv T = obs_cam_fid(obs_in[i], weighting_scale, use_area);
+        const double var = T.var;
+        if (T_baseCam) T = twv_mul(*T_baseCam, T);  // tf2::Transform * TransformWithVariance: the variance stays T's
+        if (st.add_have_map_base) {
+            Twv mb;
+            q_to_m(st.add_map_base + 3, mb.R);
+            mb.t[0] = st.add_map_base[0];
+            mb.t[1] = st.add_map_base[1];
+            mb.t[2] = st.add_map_base[2];
+            mb.var = 0.0;
+            T = twv_mul(mb, T);
+        }
+        T.var = var;
+        if (st.n >= st.capacity) {
+            st.overflow = 1;
+        } else {
+            const int slot = st.n++;
+            e[slot].id = obs_in[i].id;
+            e[slot].num_obs = 0;
+            e[slot].pose = T;
+            if (hash && hash->size > 0) map_hash_insert(*hash, obs_in[i].id, slot);
+            // fiducials[originFid].pose.variance = 0.0 -- only where originFid names a fiducial (with originFid == -1 the
+            // reference's operator[] inserts a default-constructed Fiducial with uninitialised members: not restated)
+            const int os = st.origin_fid != -1 ? map_find(st, e, st.origin_fid, hash) : -1;
+            if (os >= 0) e[os].pose.var = 0.0;
+        }
+        st.initializing = 0;
+        st.fiducial_to_add = -1;
+        return;
+    }
+}
+
+FID_HD void map_update(MapState& st, MapEntry* e, uint32_t* links, const Obs* obs_in, int n_obs, const Twv* T_baseCam /*null = lookup failed*/,
+                       const Twv* T_camBase /*null = lookup failed*/, double weighting_scale, int use_area, double systematic_error, RobotPose* robot,
+                       const MapHash* hash, double* var_scratch, int* slot_scratch) {
+    map_update_core(st, e, links, obs_in, n_obs, T_baseCam, T_camBase, weighting_scale, use_area, systematic_error, robot, hash, var_scratch, slot_scratch);
+    map_handle_add_fiducial(st, e, obs_in, n_obs, T_baseCam, weighting_scale, use_area, hash);
 }
 
 }  // namespace fid

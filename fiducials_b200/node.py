@@ -470,6 +470,22 @@ class FiducialSlam:
     def clear(self, instance=0):
         _lib.check(self.lib.fid_map_clear(self.h, instance))
 
+    def addFiducial(self, fiducial_id, T_mapBase=None, instance=0):
+        """add_fiducial service (addFiducialCallback, map.cpp:821-828): handled by the next transformCallback that observes the id
+        (handleAddFiducial, map.cpp:489-535).  T_mapBase = the tf lookup map -> base (7-vector) or None when it fails."""
+        mb = _tf(T_mapBase)
+        _lib.check(self.lib.fid_map_add_fiducial(self.h, instance, int(fiducial_id), C.byref(mb) if mb is not None else None))
+
+    # ---- published pose (host-side message packing, map.cpp:337-379) ----
+    covariance_diagonal = None   # rosparam covariance_diagonal (map.cpp:110-125): six non-zero values or ignored
+    publish_6dof_pose = False    # map.cpp:107
+
+    def robotPoseCovariance(self, robot):
+        return robot_pose_covariance(robot.variance, self.covariance_diagonal)
+
+    def poseTf(self, robot, T_odomBase=None):
+        return pose_tf(robot.t[:], robot.q[:], T_odomBase, self.publish_6dof_pose)
+
     # multi-GPU merged view (new; SURVEY 8e): local instances are never overwritten by a merge
     def export_table(self, instance=0) -> np.ndarray:
         cap = self.p.max_fiducials
@@ -506,3 +522,80 @@ class FiducialSlam:
 
     def merge_device_async(self, device_ptr: int, n_tables: int):
         _lib.check(self.lib.fid_map_merge_device_async(self.h, n_tables, C.c_void_p(device_ptr)))
+
+
+def robot_pose_covariance(variance, covariance_diagonal=None):
+    """Row-major 6x6 covariance of the PoseWithCovarianceStamped on /fiducial_pose: toPose fills the diagonal with the scalar
+    variance (transform_with_variance.h:69-84); a covariance_diagonal of six non-zero values overrides it (map.cpp:110-125,341-345)."""
+    cov = [0.0] * 36
+    diag = [float(variance)] * 6
+    if covariance_diagonal is not None and len(covariance_diagonal) == 6 and all(v != 0 for v in covariance_diagonal):
+        diag = [float(v) for v in covariance_diagonal]
+    for i in range(6):
+        cov[i * 6 + i] = diag[i]
+    return cov
+
+
+def pose_tf(t, q, T_odomBase=None, publish_6dof_pose=False):
+    """The transform broadcast as map -> odom (or map -> base): outPose = basePose * odom^-1 when the odom lookup succeeded
+    (map.cpp:351-365), squashed to x, y, yaw unless publish_6dof_pose (map.cpp:369-379).  Returns (t[3], q_xyzw[4])."""
+    t = np.array(t, np.float64)
+    R = _q_to_R(q)
+    if T_odomBase is not None:
+        Ro = _q_to_R(T_odomBase[3:7])
+        to = np.array(T_odomBase[:3], np.float64)
+        Rinv = Ro.T
+        tinv = Rinv @ (-to)
+        t = R @ tinv + t
+        R = R @ Rinv
+    if not publish_6dof_pose:
+        t[2] = 0.0
+        yaw = _get_rpy(R)[2]
+        R = _set_rpy(0.0, 0.0, yaw)
+    return t, _R_to_q(R)
+
+
+# ---- tf2 LinearMath pieces used by the host-side message packing above ------------------------------------
+def _q_to_R(q):  # tf2::Matrix3x3::setRotation
+    x, y, z, w = [float(v) for v in q]
+    d = x * x + y * y + z * z + w * w
+    s = 2.0 / d
+    xs, ys, zs = x * s, y * s, z * s
+    wx, wy, wz, xx, xy, xz, yy, yz, zz = w * xs, w * ys, w * zs, x * xs, x * ys, x * zs, y * ys, y * zs, z * zs
+    return np.array([[1.0 - (yy + zz), xy - wz, xz + wy], [xy + wz, 1.0 - (xx + zz), yz - wx], [xz - wy, yz + wx, 1.0 - (xx + yy)]])
+
+
+def _R_to_q(m):  # tf2::Matrix3x3::getRotation
+    tr = m[0][0] + m[1][1] + m[2][2]
+    q = [0.0] * 4
+    if tr > 0.0:
+        s = math.sqrt(tr + 1.0)
+        q[3] = s * 0.5
+        s = 0.5 / s
+        q[0], q[1], q[2] = (m[2][1] - m[1][2]) * s, (m[0][2] - m[2][0]) * s, (m[1][0] - m[0][1]) * s
+    else:
+        i = (2 if m[1][1] < m[2][2] else 1) if m[0][0] < m[1][1] else (2 if m[0][0] < m[2][2] else 0)
+        j, k = (i + 1) % 3, (i + 2) % 3
+        s = math.sqrt(m[i][i] - m[j][j] - m[k][k] + 1.0)
+        q[i] = s * 0.5
+        s = 0.5 / s
+        q[3] = (m[k][j] - m[j][k]) * s
+        q[j] = (m[j][i] + m[i][j]) * s
+        q[k] = (m[k][i] + m[i][k]) * s
+    return np.array(q)
+
+
+def _get_rpy(m):  # tf2::Matrix3x3::getRPY
+    if abs(m[2][0]) >= 1.0:
+        delta = math.atan2(m[2][1], m[2][2])
+        return (delta, math.pi / 2.0, 0.0) if m[2][0] < 0 else (delta, -math.pi / 2.0, 0.0)
+    pitch = -math.asin(m[2][0])
+    c = math.cos(pitch)
+    return math.atan2(m[2][1] / c, m[2][2] / c), pitch, math.atan2(m[1][0] / c, m[0][0] / c)
+
+
+def _set_rpy(roll, pitch, yaw):  # tf2::Matrix3x3::setRPY
+    ci, cj, ch = math.cos(roll), math.cos(pitch), math.cos(yaw)
+    si, sj, sh = math.sin(roll), math.sin(pitch), math.sin(yaw)
+    cc, cs, sc, ss = ci * ch, ci * sh, si * ch, si * sh
+    return np.array([[cj * ch, sj * sc - cs, sj * cc + ss], [cj * sh, sj * ss + cc, sj * cs - sc], [-sj, cj * si, cj * ci]])

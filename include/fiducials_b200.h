@@ -235,6 +235,13 @@ typedef struct fid_tf {
     double q[4];
 } fid_tf;
 
+/* add_fiducial service (addFiducialCallback, map.cpp:821-828): the next update that sees `fiducial_id` inserts it
+ * (Map::handleAddFiducial, map.cpp:489-535, called by every Map::update at :173) as T_mapBase * T_baseCam * T_camFid with the
+ * observation's variance, pins the origin fiducial's variance to 0 and ends map initialisation; a request for an id that is
+ * already in the map is dropped.  T_mapBase = the host's tf lookup map -> base (map.cpp:514-517), NULL when it failed
+ * ("Placing robot at the origin"). */
+int fid_map_add_fiducial(fid_map* m, int instance, int fiducial_id, const fid_tf* T_mapBase);
+
 typedef struct fid_robot_pose { /* geometry for /fiducial_pose (map.cpp:337-345) */
     int32_t valid;
     int32_t n_estimates;

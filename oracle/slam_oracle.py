@@ -241,6 +241,8 @@ class Map:
         self.originFid = -1
         self.isInitializingMap = False
         self.readOnly = read_only
+        self.fiducialToAdd = -1          # add_fiducial service (map.cpp:821-828)
+        self.addMapBase = None           # tf lookup map -> base at the time of handleAddFiducial (map.cpp:514-517), None = failed
 
     def load_entry(self, fid, x, y, z, roll_deg, pitch_deg, yaw_deg, variance, num_obs=0, links=()):
         """One line of loadMap, map.cpp:595-606 (degrees -> setRPY)."""
@@ -261,7 +263,35 @@ class Map:
             n, T_mapCam, robot = self.update_pose(obs, T_baseCam, T_camBase)
             if n > 0 and len(obs) > 1 and not self.readOnly:
                 self.update_map(obs, T_mapCam)
+        self.handle_add_fiducial(obs, T_baseCam)  # :173
         return robot
+
+    # map.cpp:489-535
+    def handle_add_fiducial(self, obs, T_baseCam: TWV | None):
+        if self.fiducialToAdd == -1:
+            return
+        if self.fiducialToAdd in self.fiducials:
+            self.fiducialToAdd = -1
+            return
+        for o in obs:
+            if o.fid == self.fiducialToAdd:
+                T = o.T_camFid.copy()
+                if T_baseCam is not None:  # T.setData(T_baseCam * T): tf2::Transform * TransformWithVariance keeps T's variance
+                    var = T.var
+                    T = T_baseCam.mul(T, add_var=False)
+                    T.var = var
+                if self.addMapBase is not None:
+                    var = T.var
+                    T = self.addMapBase.mul(T, add_var=False)
+                    T.var = var
+                self.fiducials[o.fid] = Fiducial(o.fid, T)
+                # `fiducials[originFid].pose.variance = 0.0`: with originFid == -1 (map from a file) the reference's operator[]
+                # inserts a default-constructed Fiducial with uninitialised members under key -1; only the defined case is restated
+                if self.originFid in self.fiducials:
+                    self.fiducials[self.originFid].pose.var = 0.0
+                self.isInitializingMap = False
+                self.fiducialToAdd = -1
+                return
 
     # map.cpp:181-225
     def update_map(self, obs, T_mapCam: TWV):
@@ -416,3 +446,39 @@ def merge_maps(tables):
                 cur.update(pose)
                 merged[fid] = (cur, n + int(num_obs))
     return merged
+
+
+# ----------------------------- published pose (map.cpp:337-379) --------------------------
+def pose_covariance(variance, covariance_diagonal=None):
+    """toPose (transform_with_variance.h:69-84) + the covariance_diagonal override (map.cpp:110-125,341-345): the 36-entry
+    row-major covariance of the PoseWithCovarianceStamped on /fiducial_pose.  The override is ignored unless it has six non-zero values."""
+    cov = [0.0] * 36
+    diag = [variance] * 6
+    if covariance_diagonal is not None and len(covariance_diagonal) == 6 and all(v != 0 for v in covariance_diagonal):
+        diag = [float(v) for v in covariance_diagonal]
+    for i in range(6):
+        cov[i * 6 + i] = diag[i]
+    return cov
+
+
+def set_rpy_matrix(roll, pitch, yaw):
+    """tf2::Matrix3x3::setRPY == setEulerYPR(yaw, pitch, roll)."""
+    ci, cj, ch = math.cos(roll), math.cos(pitch), math.cos(yaw)
+    si, sj, sh = math.sin(roll), math.sin(pitch), math.sin(yaw)
+    cc, cs, sc, ss = ci * ch, ci * sh, si * ch, si * sh
+    return [[cj * ch, sj * sc - cs, sj * cc + ss], [cj * sh, sj * ss + cc, sj * cs - sc], [-sj, cj * si, cj * ci]]
+
+
+def published_pose_tf(T_mapBase: TWV, T_odomBase: TWV | None = None, publish_6dof_pose=False):
+    """The map -> odom (or map -> base) transform of updatePose's tail, map.cpp:351-379: outPose = basePose * odom^-1 when the
+    odom lookup succeeded, then squashed to x, y, yaw unless publish_6dof_pose."""
+    out = T_mapBase.copy()
+    if T_odomBase is not None:
+        var = out.var
+        out = out.mul(T_odomBase.inverse(), add_var=False)
+        out.var = var
+    if not publish_6dof_pose:
+        out.t[2] = 0.0
+        _r, _p, yaw = get_rpy(out.R)
+        out.R = set_rpy_matrix(0.0, 0.0, yaw)
+    return out

@@ -26,6 +26,7 @@ int slam_c_replay(int capacity, int n_seed, const double* seed, int n_msgs, cons
     memset(&st, 0, sizeof(st));
     st.capacity = capacity;
     st.origin_fid = -1;
+    st.fiducial_to_add = -1;
     MapEntry* e = (MapEntry*)calloc((size_t)capacity, sizeof(MapEntry));
     for (int i = 0; i < n_seed; i++) {
         e[i].id = (int)seed[9 * i];

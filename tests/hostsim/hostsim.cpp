@@ -573,6 +573,7 @@ void* hs_map_create(int capacity, int read_only) {
     memset(&m->st, 0, sizeof(m->st));
     m->st.capacity = capacity;
     m->st.origin_fid = -1;
+    m->st.fiducial_to_add = -1;
     m->st.read_only = read_only;
     m->e.resize(capacity);
     m->links.assign((size_t)capacity * ((capacity + 31) / 32), 0u);

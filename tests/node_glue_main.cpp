@@ -43,6 +43,29 @@ int main(int argc, char** argv) {
         for (int i = 0; i < 13; i++) slam.transformCallback(fta, &ident, &ident, &robot);
         for (const auto& e : slam.publishMap().fiducials) std::printf("M %d %.17g %.17g %.17g %.17g %.17g %.17g\n", e.fiducial_id, e.x, e.y, e.z, e.rx, e.ry, e.rz);
         std::printf("R %d %.17g %.17g %.17g\n", robot.valid, robot.t[0], robot.t[1], robot.t[2]);
+        // published pose: covariance override + 2-D squashing of map -> odom (map.cpp:337-379)
+        {
+            fid_robot_pose rp{};
+            rp.valid = 1;
+            rp.t[0] = 1.25; rp.t[1] = -0.5; rp.t[2] = 0.3;
+            rp.q[0] = 0.18257418583505536; rp.q[1] = 0.3651483716701107; rp.q[2] = 0.5477225575051661; rp.q[3] = 0.7302967433402214;
+            rp.variance = 0.125;
+            fid_tf odom{{0.4, 0.2, 0.0}, {0, 0, 0.3826834323650898, 0.9238795325112867}};
+            double cov[36];
+            slam.robotPoseCovariance(rp, cov);
+            std::printf("C %.17g %.17g %.17g\n", cov[0], cov[7], cov[35]);
+            slam.setCovarianceDiagonal({1, 2, 3, 4, 5, 6});
+            slam.robotPoseCovariance(rp, cov);
+            std::printf("C %.17g %.17g %.17g\n", cov[0], cov[7], cov[35]);
+            slam.setCovarianceDiagonal({1, 2, 0, 4, 5, 6});
+            slam.robotPoseCovariance(rp, cov);
+            std::printf("C %.17g %.17g %.17g\n", cov[0], cov[7], cov[35]);
+            fid_glue::Transform p2 = slam.poseTf(rp, &odom);
+            std::printf("P %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", p2.tx, p2.ty, p2.tz, p2.qx, p2.qy, p2.qz, p2.qw);
+            slam.publish_6dof_pose = true;
+            fid_glue::Transform p6 = slam.poseTf(rp, nullptr);
+            std::printf("P %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", p6.tx, p6.ty, p6.tz, p6.qx, p6.qy, p6.qz, p6.qw);
+        }
         // saveMap / loadMap round trip through the reference's text format (map.cpp:541-625)
         const std::string path = std::string(argv[1]) + ".map.txt";
         if (!slam.saveMap(path)) return 6;

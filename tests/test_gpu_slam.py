@@ -341,3 +341,49 @@ def test_messages_with_more_than_64_observations():
     _cmp_entries(c.entries(), ref.entries(), 1e-9)
     for s in (a, b, c):
         s.close()
+
+
+def test_add_fiducial_service():
+    """add_fiducial (addFiducialCallback map.cpp:821-828, handleAddFiducial :489-535, called from every Map::update :173) on a
+    read-only map: the requested id is inserted from the next message that observes it as T_mapBase * T_baseCam * T_camFid with
+    the observation's variance; a request for an id that is already mapped is dropped; nothing else is added."""
+    from fiducials_b200.node import FiducialSlam
+
+    rng = np.random.default_rng(9)
+    msgs, grid = _random_walk_messages(rng, 12, 20, 5)
+    base_cam = so.TWV.from_qt(so.q_from_rpy(0.02, -0.03, 0.4), [0.1, -0.05, 0.3])
+    cam_base = base_cam.inverse()
+    map_base = so.TWV.from_qt(so.q_from_rpy(0.0, 0.0, 0.7), [1.5, -2.0, 0.0])
+    seed = [100, grid[0][0], grid[0][1], grid[0][2], 180, 0, 180, 0, 0]
+    ref = so.Map(read_only=True)
+    ref.load_entry(*seed)
+    slam = FiducialSlam(max_fiducials=32, read_only_map=True)
+    slam.loadMap([seed])
+    seen = sorted({t["fiducial_id"] for m in msgs for t in m} - {100})
+    want, again = seen[0], seen[1]
+
+    def step(m):
+        r = ref.update(so.observations_from_transforms(m), base_cam, cam_base)
+        g = slam.transformCallback(m, _tf7(base_cam), _tf7(cam_base))
+        return r, g
+
+    step(msgs[0])
+    ref.fiducialToAdd, ref.addMapBase = want, map_base
+    slam.addFiducial(want, _tf7(map_base))
+    for m in msgs[1:8]:
+        step(m)
+    ref.fiducialToAdd, ref.addMapBase = again, None  # tf lookup failed: "Placing robot at the origin"
+    slam.addFiducial(again, None)
+    for m in msgs[8:14]:
+        step(m)
+    ref.fiducialToAdd, ref.addMapBase = want, None   # already in the map: the request is dropped
+    slam.addFiducial(want, None)
+    for m in msgs[14:]:
+        step(m)
+    assert ref.fiducialToAdd == -1
+    ids = [e.fiducial_id for e in slam.entries()]
+    assert ids == sorted(ref.fiducials) and set(ids) <= {100, want, again} and want in ids
+    _cmp_entries(slam.entries(), ref.entries(), 1e-9)
+    for e in slam.entries():
+        assert abs(e.variance - ref.fiducials[e.fiducial_id].pose.var) <= 1e-9 * max(1.0, abs(e.variance))
+    slam.close()

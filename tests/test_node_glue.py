@@ -64,3 +64,15 @@ def test_node_glue_messages_match_oracle(tmp_path):
     for la, lb in zip(a, b):
         assert la[0] == lb[0] and la[8:] == lb[8:] and len(la) == 9 + len(ids) - 1  # every marker of the frame links to the others
         assert np.abs(np.array(la[1:8], float) - np.array(lb[1:8], float)).max() <= 2e-6
+    # published pose (map.cpp:337-379): covariance (scalar variance / covariance_diagonal / ignored when a value is 0), 2-D squash
+    from oracle import slam_oracle as so
+
+    Cl = [np.array(l.split()[1:], float) for l in r.stdout.splitlines() if l.startswith("C ")]
+    assert np.allclose(Cl[0], [0.125, 0.125, 0.125]) and np.allclose(Cl[1], [1, 2, 6]) and np.allclose(Cl[2], [0.125, 0.125, 0.125])
+    Pl = [np.array(l.split()[1:], float) for l in r.stdout.splitlines() if l.startswith("P ")]
+    base = so.TWV.from_qt([0.18257418583505536, 0.3651483716701107, 0.5477225575051661, 0.7302967433402214], [1.25, -0.5, 0.3], 0.125)
+    odom = so.TWV.from_qt([0, 0, 0.3826834323650898, 0.9238795325112867], [0.4, 0.2, 0.0])
+    for got, exp in ((Pl[0], so.published_pose_tf(base, odom, False)), (Pl[1], so.published_pose_tf(base, None, True))):
+        assert np.abs(got[:3] - np.array(exp.t)).max() < 1e-12
+        q = np.array(so.m_to_q(exp.R))
+        assert min(np.abs(got[3:] - q).max(), np.abs(got[3:] + q).max()) < 1e-12
