@@ -72,7 +72,7 @@ struct fid_detector {
     fid_params params{};
     DevParams P{};
     int max_w = 0, max_h = 0, max_batch = 0;
-    int max_raw = FID_GROUP_MAX_RAW, close_wpr = 128, max_sel = 512, max_markers = FID_MAX_MARKERS;
+    int max_raw = FID_GROUP_MAX_RAW, close_wpr = 128, max_sel = FID_MAX_SEL, max_markers = FID_MAX_MARKERS;
     unsigned int max_starts = 0, max_chains = 0, max_points = 0, max_queue = 0, max_segs = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     // one compute stream per slot (chunk in flight): the latency-bound stages of one chunk overlap the
@@ -725,6 +725,8 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
         a.n_sel = s.d_nsel;
         a.cand_id = s.d_cand_id;
         a.cand_corners = s.d_cand_corners;
+        a.fs = s.fs;
+        a.max_raw = h->max_raw;
         a.max_sel = h->max_sel;
         a.max_markers = h->max_markers;
         a.P = P;

@@ -320,6 +320,8 @@ struct FinishArgs {
     const int* n_sel;
     const int* cand_id;
     const float* cand_corners;
+    FrameScratch fs;  // selected candidates' quads (candidate hierarchy)
+    int max_raw;
     int max_sel, max_markers;
     DevParams P;
     const float* subpix_masks;  // windows 1..5 concatenated: offsets 0, 9, 34, 83, 164
@@ -337,6 +339,7 @@ struct FinishArgs {
 };
 
 #define FINISH_THREADS 128
+#define FID_MAX_SEL 512  // selected candidates per frame (fid_detector::max_sel)
 
 __device__ __forceinline__ int subpix_mask_offset(int win) {
     int off = 0;
@@ -347,12 +350,58 @@ __device__ __forceinline__ int subpix_mask_offset(int win) {
 __global__ void __launch_bounds__(FINISH_THREADS) k_finish(const FinishArgs a) {
     __shared__ int s_n;
     __shared__ int s_src[FID_MAX_MARKERS];
+    __shared__ short s_parent[FID_MAX_SEL], s_depth[FID_MAX_SEL];
+    __shared__ unsigned char s_was[FID_MAX_SEL];
     const int f = blockIdx.x, tid = threadIdx.x;
+    const int ns = a.n_sel[f] < FID_MAX_SEL ? a.n_sel[f] : FID_MAX_SEL;
+    // OpenCV 4.13 candidate hierarchy: candidates are in descending-perimeter order; the parent of i is the
+    // nearest larger candidate whose quad contains all four corners of i
+    {
+        const size_t fo = (size_t)f * a.max_raw;
+        for (int i = tid; i < ns; i += FINISH_THREADS) {
+            const QuadF qi = a.fs.quads[fo + a.fs.sel_idx[fo + i]];
+            int parent = -1;
+            for (int j = i - 1; j >= 0; j--)
+                if (quad_inside_quad(qi, a.fs.quads[fo + a.fs.sel_idx[fo + j]])) {
+                    parent = j;
+                    break;
+                }
+            s_parent[i] = (short)parent;
+            s_depth[i] = 0;
+            s_was[i] = 0;
+        }
+    }
+    __syncthreads();
     if (tid == 0) {
+        // depth: leaves 0, a parent one more than its deepest child (children have larger indices)
+        int max_depth = 0;
+        for (int i = ns - 1; i >= 0; i--) {
+            const int p = s_parent[i];
+            if (p >= 0 && s_depth[p] < s_depth[i] + 1) s_depth[p] = (short)(s_depth[i] + 1);
+            max_depth = s_depth[i] > max_depth ? s_depth[i] : max_depth;
+        }
+        // identification runs level by level, innermost first, `while (counter < ncandidates)`: an identified candidate
+        // counts all its not yet visited ancestors, every candidate of a level counts itself once more -- so the loop can end
+        // before the outer levels are reached (a marker that encloses an identified marker is then never looked at), but a
+        // level that is reached is identified completely.  s_was[i] bit 1 = level reached ("processed").
+        int counter = 0;
+        for (int depth = 0; depth <= max_depth && counter < ns; depth++) {
+            for (int v = 0; v < ns; v++)
+                if (s_depth[v] == depth) s_was[v] |= 3;
+            for (int v = 0; v < ns; v++) {
+                if (s_depth[v] != depth) continue;
+                if (a.cand_id[(size_t)f * a.max_sel + v] >= 0)
+                    for (int p = s_parent[v]; p != -1; p = s_parent[p])
+                        if (!(s_was[p] & 1)) {
+                            s_was[p] |= 1;
+                            counter++;
+                        }
+                counter++;
+            }
+        }
         int n = 0;
-        const int ns = a.n_sel[f];
         for (int k = 0; k < ns; k++) {
-            if (a.cand_id[(size_t)f * a.max_sel + k] < 0) continue;
+            if (a.cand_id[(size_t)f * a.max_sel + k] < 0 || !(s_was[k] & 2)) continue;
             if (n < a.max_markers && n < FID_MAX_MARKERS) {
                 s_src[n++] = k;
             } else {

@@ -11,6 +11,32 @@ struct QuadF {
     float x[4], y[4];
 };
 
+// cv::pointPolygonTest(quad, pt, measureDist=false) > 0 for a float quad (crossing number with OpenCV's edge rules): strictly inside.
+FID_HD bool point_strictly_in_quad(const QuadF& q, float px, float py) {
+    int counter = 0;
+    float vx = q.x[3], vy = q.y[3];
+    for (int i = 0; i < 4; i++) {
+        const float v0x = vx, v0y = vy;
+        vx = q.x[i];
+        vy = q.y[i];
+        if ((v0y <= py && vy <= py) || (v0y > py && vy > py) || (v0x < px && vx < px)) {
+            if (py == vy && (px == vx || (py == v0y && ((v0x <= px && px <= vx) || (vx <= px && px <= v0x))))) return false;  // on the boundary
+            continue;
+        }
+        double dist = (double)(py - v0y) * (vx - v0x) - (double)(px - v0x) * (vy - v0y);
+        if (dist == 0) return false;
+        if (vy < v0y) dist = -dist;
+        counter += dist > 0 ? 1 : 0;
+    }
+    return (counter & 1) != 0;
+}
+// checkMarker1InMarker2 of OpenCV 4.13's candidate hierarchy: all four corners of `inner` lie inside `outer`
+FID_HD bool quad_inside_quad(const QuadF& inner, const QuadF& outer) {
+    for (int k = 0; k < 4; k++)
+        if (!point_strictly_in_quad(outer, inner.x[k], inner.y[k])) return false;
+    return true;
+}
+
 // Raw candidate emitted by the approximation kernel.
 struct RawQuad {
     int16_t x[4], y[4];  // approxPolyDP vertex order

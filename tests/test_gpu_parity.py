@@ -500,3 +500,49 @@ def test_mono8_strided_multi_frame():
             assert np.array_equal(corners[i, : counts[i]].reshape(-1, 4, 2), ref[2][i, : counts[i]])
     finally:
         det.close()
+
+
+def _nested_marker_frames():
+    """A valid marker inside a white cell of a bigger valid marker, without and with a second depth-1 candidate
+    (a black frame around a black square) elsewhere in the image."""
+    import cv2
+
+    d = cv2.aruco.getPredefinedDictionary(10)
+    big = cv2.aruco.generateImageMarker(d, 5, 640)
+    img = np.full((900, 1400), 200, np.uint8)
+    img[100:740, 150:790] = big
+    cells = big.reshape(8, 80, 8, 80).mean(axis=(1, 3))
+    ys, xs = np.where(cells[1:7, 1:7] > 128)
+    cy, cx = ys[3] + 1, xs[3] + 1
+    y0, x0 = 100 + cy * 80 + 16, 150 + cx * 80 + 16
+    img[y0 : y0 + 48, x0 : x0 + 48] = cv2.aruco.generateImageMarker(d, 7, 48)
+    alone = cv2.GaussianBlur(img, (0, 0), 0.8)
+    cv2.rectangle(img, (1050, 200), (1350, 500), 20, -1)
+    cv2.rectangle(img, (1080, 230), (1320, 470), 235, -1)
+    cv2.rectangle(img, (1150, 300), (1250, 400), 20, -1)
+    both = cv2.GaussianBlur(img, (0, 0), 0.8)
+    return [np.repeat(g[:, :, None], 3, axis=2) for g in (alone, both)]
+
+
+def test_candidate_hierarchy_nested_markers():
+    """OpenCV 4.13 identifies candidates level by level, innermost first, and stops as soon as every candidate is accounted for:
+    a marker that encloses an identified marker is never looked at when it is alone on its level (first frame: only id 7), but is
+    reported when its level is reached because of another candidate (second frame: ids 5 and 7).  Same ids / order / corners / poses."""
+    K = np.array([[800.0, 0, 700], [0, 800, 450], [0, 0, 1]])
+    D = np.zeros(5)
+    expect = ([7], [5, 7])
+    det = Detector(default_params(dictionary=10), 0, 1400, 900, 2)
+    try:
+        frames = np.ascontiguousarray(np.stack(_nested_marker_frames()))
+        counts, ids, corners, tfs = det.detect_pose_batch(frames, K, D, 0.14)
+        for i, fr in enumerate(frames):
+            oi, oc, rv, tv, fields = ao.detect_and_pose(fr, 10, K, D, 0.14)
+            assert oi.tolist() == expect[i]  # what cv2 4.13 does (pins the oracle's behaviour as well)
+            n = int(counts[i])
+            assert ids[i, :n].tolist() == oi.tolist()
+            assert np.abs(corners[i, :n] - oc).max() <= 1e-3
+            for m in range(n):
+                t = tfs[i * MAXM + m]
+                assert np.abs(np.array(t.translation[:]) - fields[m]["translation"]).max() <= 1e-3
+    finally:
+        det.close()

@@ -137,3 +137,55 @@ def test_is_convex_vs_cv2():
     for _ in range(3000):
         q = rng.integers(0, 40, (4, 2)).astype(np.int32)
         assert hs.is_convex(q) == bool(cv2.isContourConvex(q.reshape(4, 1, 2)))
+
+
+def test_approx_poly_fuzz_spurred_marker_outlines():
+    """VERDICT r1 weak-10 / SURVEY 7.3-4: approxPolyDP on SELF-TOUCHING outlines.  Marker-like quadrilaterals (random pose, 40..400 px)
+    are rasterised with 1-pixel spurs, notches and pinches on their borders, every border cv2.findContours returns is run through
+    cv2.approxPolyDP and through the device function (approx_quad.cuh, compiled for the host): the 4-gon decision must agree in
+    BOTH directions and the four vertices must be identical -- a wrong "4" is a spurious candidate, a missed one a lost marker."""
+    rng = np.random.default_rng(17)
+    total = quads = touching = 0
+    for trial in range(260):
+        W = H = 480
+        img = np.zeros((H, W), np.uint8)
+        side = rng.uniform(40, 400)
+        c = np.array([W / 2, H / 2]) + rng.uniform(-20, 20, 2)
+        ang = rng.uniform(0, 2 * np.pi)
+        base = np.array([[-1, -1], [1, -1], [1, 1], [-1, 1]], np.float64) * side / 2
+        base += rng.uniform(-0.12, 0.12, (4, 2)) * side
+        R = np.array([[np.cos(ang), -np.sin(ang)], [np.sin(ang), np.cos(ang)]])
+        quad = (base @ R.T + c).astype(np.int32)
+        cv2.fillPoly(img, [quad.reshape(-1, 1, 2)], 255)
+        inner = ((base * rng.uniform(0.5, 0.8)) @ R.T + c).astype(np.int32)
+        if trial % 3 == 0:
+            cv2.fillPoly(img, [inner.reshape(-1, 1, 2)], 0)  # a ring: outer + hole border
+        # spurs (1-px lines sticking out / cut in), notches and single-pixel bridges along the border
+        border = cv2.findContours(img.copy(), cv2.RETR_LIST, cv2.CHAIN_APPROX_NONE)[0]
+        for b in border:
+            pts = b.reshape(-1, 2)
+            for _ in range(int(rng.integers(2, 14))):
+                x, y = pts[rng.integers(0, len(pts))]
+                dx, dy = rng.integers(-1, 2, 2)
+                ln = int(rng.integers(1, 4))
+                val = 255 if rng.random() < 0.5 else 0
+                for t in range(1, ln + 1):
+                    xx, yy = x + dx * t, y + dy * t
+                    if 1 <= xx < W - 1 and 1 <= yy < H - 1:
+                        img[yy, xx] = val
+        plane = (img > 0).astype(np.uint8)
+        for cnt in ao.find_contours(plane):
+            n = len(cnt)
+            if n < 40:
+                continue
+            uniq = len({(int(p[0]), int(p[1])) for p in cnt})
+            touching += uniq < n
+            ref = cv2.approxPolyDP(cnt.reshape(-1, 1, 2), n * 0.01, True).reshape(-1, 2)
+            k, ours = hs.approx_poly(cnt, n * 0.01)
+            total += 1
+            if len(ref) == 4:
+                quads += 1
+                assert k == 4 and np.array_equal(ours, ref), (trial, n, ref.tolist(), k)
+            else:
+                assert k != 4, (trial, n, len(ref))
+    assert total > 300 and quads > 100 and touching > 100, (total, quads, touching)
