@@ -108,6 +108,27 @@ def pin_to_gpu_numa_node(index):
 
 
 # ------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """stdout must carry ONE JSON line: everything any library prints to fd 1 (NCCL's version banner, ...) goes to stderr instead."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    line = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
+
+
 def rank_info():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
@@ -332,10 +353,10 @@ def run_reference_arm(args):
         "cpu_baseline": detail,
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out))
+    emit(out)
 
 
-DTYPE = "u8/i32 (threshold on int8 tensor cores with s32 accumulators, contours), f32/f64 (sub-pixel, pose, map)"
+DTYPE = "u8/i32 (threshold, contours), f32/f64 (sub-pixel, pose, map)"
 METRIC = {"C2": "frames/sec 1920x1080 (detect+pose)", "C3": "frames/sec 1280x720 per-GPU camera streams (detect+pose)", "C4": "frames/sec 3840x2160 (detect+pose)",
           "C5": "map updates/sec (500 fiducials, 10k observations)"}
 
@@ -535,7 +556,7 @@ def run_gpu_arm(args):
             pass
         roofline = {
             "bound": "hbm",
-            "kernel": "k_threshold_mma (threshold stage: BGR->gray, 13 adaptive thresholds on the int8 tensor cores, halo tiles + start cracks; one launch)",
+            "kernel": ("k_threshold_mma (BGR->gray + 13 adaptive thresholds on the int8 tensor cores + halo tiles + start cracks, one launch)" if os.environ.get("FID_THRESH") == "mma" else "k_gray + k_threshold<FAST> (threshold stage: gray, summed-area table in shared memory, 13 thresholds, halo tiles + start cracks)"),
             "achieved": achieved,
             "peak": peak,
             "unit": "GB/s",
@@ -594,7 +615,7 @@ def run_gpu_arm(args):
             "wallclock_s": {"device_resident": dev_wall, "e2e": e2e_wall},
             "single_frame_latency_ms": single_ms,
         }
-        print(json.dumps(out))
+        emit(out)
     lib.fid_device_free(det.h, dptr)
     lib.fid_host_free(hptr)
     det.close()
@@ -634,7 +655,7 @@ def run_c5(args, reference):
                "cpu_baseline": {"value": val, "unit": "observations/s", "cores": 1, "kind": "port", "cpu_model": model, "physical_cores": phys, "logical_cpus": logical,
                                 "sample": "the whole sequence through oracle/_ref/libslam_oracle.so (map.cpp / transform_with_variance.cpp restated, g++ -O2), one core"},
                "e2e": {"value": val, "unit": "observations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(out))
+        emit(out)
         return
     import torch
 
@@ -707,7 +728,7 @@ def run_c5(args, reference):
                "cpu_baseline": {"value": n_obs / cpu_dt, "unit": "observations/s", "cores": 1, "kind": "port", "cpu_model": model, "physical_cores": phys, "logical_cpus": logical,
                                 "sample": "the whole sequence through oracle/_ref/libslam_oracle.so, one core, %.2f ms" % (cpu_dt * 1e3)},
                "roofline": {"bound": "latency", "note": "sequential scalar-variance fold (SURVEY 8d): no roofline fraction is meaningful; report observations/s and ms per sequence"}}
-        print(json.dumps(out))
+        emit(out)
     slam.close()
     if dist is not None:
         dist.barrier()
@@ -724,6 +745,7 @@ def main():
     args = ap.parse_args()
     global WORKLOAD
     WORKLOAD = args.workload
+    claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:

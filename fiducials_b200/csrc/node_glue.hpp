@@ -47,6 +47,18 @@ struct FiducialTransformArray {  // FiducialTransformArray.msg:3-5
     int32_t image_seq = 0;
     std::vector<FiducialTransform> transforms;
 };
+struct ObjectHypothesisWithPose {  // vision_msgs, as aruco_detect.cpp:463-476 fills it
+    int32_t id = 0;
+    double score = 0;
+    Transform pose;  // position + orientation
+};
+struct Detection2D {
+    std::vector<ObjectHypothesisWithPose> results;
+};
+struct Detection2DArray {
+    Header header;
+    std::vector<Detection2D> detections;
+};
 struct FiducialMapEntry {  // FiducialMapEntry.msg:2-10
     int32_t fiducial_id = 0;
     double x = 0, y = 0, z = 0, rx = 0, ry = 0, rz = 0;
@@ -136,6 +148,20 @@ class FiducialsNode {
             ft.object_error = t.object_error;
             ft.fiducial_area = t.fiducial_area;
             fta->transforms.push_back(ft);
+        }
+        return true;
+    }
+
+    // vis_msgs variant (aruco_detect.cpp:403,462-478,534): vision_msgs/Detection2DArray with score = exp(-2 object_error)
+    bool poseEstimateCallbackVis(Detection2DArray* vma) {
+        FiducialTransformArray fta;
+        if (!poseEstimateCallback(&fta)) return false;
+        vma->header = fta.header;
+        vma->detections.clear();
+        for (const FiducialTransform& ft : fta.transforms) {
+            Detection2D d;
+            d.results.push_back(ObjectHypothesisWithPose{ft.fiducial_id, exp(-2.0 * ft.object_error), ft.transform});
+            vma->detections.push_back(d);
         }
         return true;
     }

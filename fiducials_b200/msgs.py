@@ -69,3 +69,22 @@ class FiducialMapEntry:  # FiducialMapEntry.msg:2-10
 @dataclass
 class FiducialMapEntryArray:  # FiducialMapEntryArray.msg
     fiducials: List[FiducialMapEntry] = field(default_factory=list)
+
+
+@dataclass
+class ObjectHypothesisWithPose:  # vision_msgs/ObjectHypothesisWithPose as the reference fills it (aruco_detect.cpp:463-476)
+    id: int = 0
+    score: float = 0.0           # exp(-2 * object_error): [0, inf) -> (0, 1]
+    position: Tuple[float, float, float] = (0.0, 0.0, 0.0)
+    orientation: Tuple[float, float, float, float] = (0.0, 0.0, 0.0, 1.0)  # x y z w
+
+
+@dataclass
+class Detection2D:  # vision_msgs/Detection2D: the reference only fills results[0]
+    results: List[ObjectHypothesisWithPose] = field(default_factory=list)
+
+
+@dataclass
+class Detection2DArray:  # published instead of FiducialTransformArray when the vis_msgs parameter is set (:403,:534,:666)
+    header: Header = field(default_factory=Header)
+    detections: List[Detection2D] = field(default_factory=list)

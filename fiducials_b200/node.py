@@ -18,7 +18,7 @@ from typing import Dict, Iterable, List, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from .msgs import (Fiducial, FiducialArray, FiducialMapEntry, FiducialMapEntryArray, FiducialTransform, FiducialTransformArray, Header, Transform)
+from .msgs import (Detection2D, Detection2DArray, ObjectHypothesisWithPose, Fiducial, FiducialArray, FiducialMapEntry, FiducialMapEntryArray, FiducialTransform, FiducialTransformArray, Header, Transform)
 
 MAXM = _lib.FID_MAX_MARKERS
 
@@ -215,6 +215,7 @@ class FiducialsNode:
         self.frameId = ""
         self.frameNum = 0
         self.enable_detections = True
+        self.vis_msgs = False  # pnh.param vis_msgs (:614)
         self.ids = np.zeros(0, np.int32)
         self.corners = np.zeros((0, 4, 2), np.float32)
         self._last_header = Header()
@@ -262,6 +263,13 @@ class FiducialsNode:
             tfs = self.det.pose(self.ids, self.corners, self.K, self.D, self.fiducial_len, self.fiducialLens)
         except _lib.FidError:
             return fta
+        if self.vis_msgs:  # :403, :462-478: vision_msgs/Detection2DArray instead of FiducialTransformArray
+            vma = Detection2DArray(header=Header(0, header.stamp, self.frameId))
+            for t in tfs:
+                if t.fiducial_id in self.ignoreIds:
+                    continue
+                vma.detections.append(Detection2D([ObjectHypothesisWithPose(int(t.fiducial_id), math.exp(-2.0 * float(t.object_error)), tuple(t.translation), tuple(t.rotation))]))
+            return vma
         for t in tfs:
             if t.fiducial_id in self.ignoreIds:
                 continue  # :440

@@ -4,6 +4,7 @@ BASELINE.json's full sizes.  Tolerances: ids identical a
 order; corners within 1e-3 px; rvec/tvec within 1e-3; image/object error and area within 1e-6
 relative; integer stages (gray, threshold planes, quad candidates) bit-exact."""
 import ctypes as C
+import math
 
 import numpy as np
 import pytest
@@ -154,6 +155,13 @@ def test_node_mirror_messages(kat):
     assert [t.fiducial_id for t in fta.transforms] == [245] and fta.header.frame_id == "camera"
     i = kat["tag245_ids"].tolist().index(245)
     assert np.abs(np.array(fta.transforms[0].transform.translation) - kat["tag245_tvecs"][i]).max() < 1e-3
+    # vis_msgs parameter (:403,:462-478): vision_msgs/Detection2DArray with score = exp(-2 object_error), same pose
+    node.vis_msgs = True
+    vma = node.poseEstimateCallback(fva)
+    assert len(vma.detections) == 1 and len(vma.detections[0].results) == 1
+    h = vma.detections[0].results[0]
+    assert h.id == 245 and abs(h.score - math.exp(-2.0 * fta.transforms[0].object_error)) < 1e-15 and 0.0 < h.score <= 1.0
+    assert h.position == fta.transforms[0].transform.translation and h.orientation == fta.transforms[0].transform.rotation
     node2 = FiducialsNode(dictionary=7, max_width=64, max_height=64)
     assert node2.poseEstimateCallback(None) is None  # no camera info -> nothing published (:417-422)
 
