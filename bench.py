@@ -704,6 +704,24 @@ def run_c5(args, reference):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t[0])
     ents = slam.entries(0)
+    # the north-star's batched SE(3) Gauss-Newton over the same observations (fid_map_refine; new, parity unpinned): cost, the
+    # reference's plane-fit metric (fiducial_slam/scripts/fit_plane.py; the synthetic ceiling is the plane z = 2.5) and wall time
+    refine = None
+    if rank == 0:
+        from oracle import refine_oracle as ro
+
+        pts0 = [[e.x, e.y, e.z] for e in ents]
+        truth = np.array([[float(e.fiducial_id % 25), float(e.fiducial_id // 25), 2.5] for e in ents])
+        t0 = time.perf_counter()
+        st = slam.refine(msgs)
+        refine_s = time.perf_counter() - t0
+        ents_r = slam.entries(0)
+        pts1 = [[e.x, e.y, e.z] for e in ents_r]
+        refine = {"seconds": refine_s, "edges": st.n_edges, "free_poses": st.n_free, "gauss_newton_steps": st.iterations, "kernel_launches": st.kernel_launches,
+                  "cost_initial": st.initial_cost, "cost_final": st.final_cost,
+                  "plane_fit_residual_before": ro.plane_fit_residual(pts0), "plane_fit_residual_after": ro.plane_fit_residual(pts1),
+                  "max_position_error_before_m": float(np.abs(np.array(pts0) - truth).max()), "max_position_error_after_m": float(np.abs(np.array(pts1) - truth).max()),
+                  "rms_position_error_before_m": float(np.sqrt(np.mean((np.array(pts0) - truth) ** 2))), "rms_position_error_after_m": float(np.sqrt(np.mean((np.array(pts1) - truth) ** 2)))}
     # parity gate: the numpy restatement over a 250-message prefix is covered by tests/test_gpu_slam.py::test_c5_pose_graph_sequence;
     # here: the host-compiled fold of the FULL sequence must agree with the device's map to 1e-8
     sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -724,7 +742,7 @@ def run_c5(args, reference):
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": {"workload": workload, "parallelism": "replicas only: every rank folds its own copy of the sequence (the fold is sequential per map)", "map_fiducials": len(ents)},
                "e2e": {"value": val, "unit": "observations/s", "h2d_bytes_per_step": int(obs.nbytes + offsets.nbytes), "d2h_bytes_per_step": 0, "note": "value already includes the H2D of the observations"},
-               "gpu_launches": args.steps, "parity": {"max_entry_diff_vs_host_fold": worst, "entries": len(ents)},
+               "gpu_launches": args.steps, "parity": {"max_entry_diff_vs_host_fold": worst, "entries": len(ents)}, "batch_gauss_newton_refine": refine,
                "cpu_baseline": {"value": n_obs / cpu_dt, "unit": "observations/s", "cores": 1, "kind": "port", "cpu_model": model, "physical_cores": phys, "logical_cpus": logical,
                                 "sample": "the whole sequence through oracle/_ref/libslam_oracle.so, one core, %.2f ms" % (cpu_dt * 1e3)},
                "roofline": {"bound": "latency", "note": "sequential scalar-variance fold (SURVEY 8d): no roofline fraction is meaningful; report observations/s and ms per sequence"}}

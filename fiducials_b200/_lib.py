@@ -96,6 +96,14 @@ class fid_map_entry(C.Structure):
     _fields_ = [("fiducial_id", C.c_int32), ("num_obs", C.c_int32)] + [(k, C.c_double) for k in ("x", "y", "z", "rx", "ry", "rz", "variance")]
 
 
+class fid_refine_params(C.Structure):
+    _fields_ = [("max_iterations", C.c_int32), ("pcg_iterations", C.c_int32), ("pcg_tolerance", C.c_double), ("damping", C.c_double), ("translation_weight", C.c_double)]
+
+
+class fid_refine_stats(C.Structure):
+    _fields_ = [("initial_cost", C.c_double), ("final_cost", C.c_double), ("iterations", C.c_int32), ("n_edges", C.c_int32), ("n_free", C.c_int32), ("kernel_launches", C.c_int32)]
+
+
 class fid_map_record(C.Structure):
     _fields_ = [("fiducial_id", C.c_int32), ("num_obs", C.c_int32), ("t", C.c_double * 3), ("q", C.c_double * 4), ("variance", C.c_double)]
 
@@ -106,7 +114,7 @@ EXPORTS = [
     "fid_detect_pose_batch", "fid_submit_batch", "fid_collect_batch", "fid_hint_next", "fid_set_input_encoding", "fid_timer_start", "fid_timer_stop", "fid_host_alloc", "fid_host_free", "fid_device_alloc", "fid_device_free", "fid_memcpy_h2d", "fid_debug_threshold", "fid_debug_time_threshold",
     "fid_debug_candidates", "fid_last_stage_ms", "fid_last_counters", "fid_map_default_params", "fid_map_create", "fid_map_destroy", "fid_map_clear",
     "fid_map_load", "fid_map_links", "fid_map_add_links", "fid_map_update", "fid_map_update_sequence", "fid_map_update_frames", "fid_map_update_frames_async", "fid_map_sync", "fid_map_entries", "fid_map_export", "fid_map_merge", "fid_map_export_device",
-    "fid_map_merge_device", "fid_map_merge_device_async", "fid_map_export_async", "fid_map_stream", "fid_map_merged_entries", "fid_map_adopt_merged", "fid_map_add_fiducial",
+    "fid_map_merge_device", "fid_map_merge_device_async", "fid_map_export_async", "fid_map_stream", "fid_map_merged_entries", "fid_map_adopt_merged", "fid_map_add_fiducial", "fid_map_refine_default_params", "fid_map_refine",
 ]
 
 _lib = None
@@ -170,6 +178,8 @@ def load():
     lib.fid_map_merged_entries.argtypes = [vp, i32, C.POINTER(C.c_int), vp]
     lib.fid_map_adopt_merged.argtypes = [vp, i32]
     lib.fid_map_add_fiducial.argtypes = [vp, i32, i32, C.POINTER(fid_tf)]
+    lib.fid_map_refine_default_params.argtypes = [C.POINTER(fid_refine_params)]
+    lib.fid_map_refine.argtypes = [vp, i32, i32, vp, vp, C.POINTER(fid_refine_params), C.POINTER(fid_refine_stats)]
     for name in EXPORTS:
         getattr(lib, name)  # AttributeError if the build lost a symbol
     _lib = lib

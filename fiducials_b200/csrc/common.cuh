@@ -20,7 +20,7 @@ namespace fid {
 
 #define FID_MAX_SCALES 16
 #define FID_MAX_WIN_RADIUS 31   // adaptive-threshold window <= 63
-#define FID_MAX_WARP_SIDE 64    // (markerSize + 2*border) * pixelPerCell <= 64
+#define FID_MAX_WARP_SIDE 72    // (markerSize + 2*border) * pixelPerCell: 7x7 markers with the reference's 8 pixels per cell
 #define FID_MAX_WARP_SIDE_SQ (FID_MAX_WARP_SIDE * FID_MAX_WARP_SIDE)
 
 struct Pt16 {
@@ -102,6 +102,7 @@ struct DevParams {
     int n_markers;
     int max_correction_bits;
     int dict_nbytes;                // (ms*ms+7)/8
+    int dict_table;                 // index into kDictTables (host side)
 };
 
 }  // namespace fid

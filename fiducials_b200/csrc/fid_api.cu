@@ -96,6 +96,7 @@ struct fid_detector {
     const uint8_t* hint_next = nullptr;
     int pf_idx = 0, pf_frames = 0, pf_w = 0, pf_h = 0;
     float* d_subpix_masks = nullptr;
+    unsigned long long* d_dict = nullptr;  // active dictionary, kMaxDictMarkers * 4 words
     uint32_t* d_lut_prev = nullptr;
     uint32_t* d_lut_next = nullptr;
     int thresh_mode = 0;  // 0 = summed-area-table kernel (kernels_threshold.cuh, default: faster end to end), 1 = tensor-core kernel (kernels_threshold_mma.cuh; FID_THRESH=mma)
@@ -166,25 +167,11 @@ static FrameGeom make_geom(const fid_detector* h, int W, int H, size_t row_strid
     return g;
 }
 
-static int upload_constants() {
-    static bool done[64] = {false};
-    int dev = 0;
-    CK(cudaGetDevice(&dev));
-    if (dev < 64 && done[dev]) return FID_OK;
-    std::vector<uint32_t> d5(4000);
-    std::vector<unsigned long long> d6(4000);
-    for (int m = 0; m < 1000; m++)
-        for (int r = 0; r < 4; r++) {
-            uint32_t v5 = 0;
-            for (int k = 0; k < 4; k++) v5 |= (uint32_t)kDictBytes5x5[m * 16 + r * 4 + k] << (8 * k);
-            d5[m * 4 + r] = v5;
-            unsigned long long v6 = 0;
-            for (int k = 0; k < 5; k++) v6 |= (unsigned long long)kDictBytes6x6[m * 20 + r * 5 + k] << (8 * k);
-            d6[m * 4 + r] = v6;
-        }
-    CK(cudaMemcpyToSymbol(c_dict5, d5.data(), sizeof(uint32_t) * 4000));
-    CK(cudaMemcpyToSymbol(c_dict6, d6.data(), sizeof(unsigned long long) * 4000));
-    if (dev < 64) done[dev] = true;
+// the active dictionary -> device (n_markers x 4 rotations of 64-bit words)
+static int upload_dictionary(fid_detector* h) {
+    std::vector<unsigned long long> words;
+    pack_dictionary(h->P, &words);
+    CK(cudaMemcpy(h->d_dict, words.data(), words.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
     return FID_OK;
 }
 
@@ -231,7 +218,7 @@ static int configure_kernels(fid_detector* h) {
     CK(cudaFuncSetAttribute(k_threshold_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_threshold_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_sort_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)group_smem(FID_GROUP_MAX_RAW)));
-    CK(cudaFuncSetAttribute(k_identify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(1000 * 4 * 8 + IDENT_WARPS * 256 * 4 + IDENT_WARPS * FID_MAX_WARP_SIDE_SQ)));
+    CK(cudaFuncSetAttribute(k_identify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxDictMarkers * 4 * 8 + IDENT_WARPS * 256 * 4 + IDENT_WARPS * FID_MAX_WARP_SIDE_SQ)));
     return FID_OK;
 }
 
@@ -360,7 +347,7 @@ extern "C" int fid_create(const fid_params* params, int device, int max_width, i
     if (const char* e = getenv("FID_THRESH")) h->thresh_mode = strcmp(e, "mma") == 0 ? 1 : 0;
     if (const char* e = getenv("FID_SLOTS")) h->n_slots = std::max(2, std::min((int)MAX_SLOTS, atoi(e)));
     for (int i = 0; i < h->n_slots; i++) CKH(cudaStreamCreateWithFlags(&h->slot_stream[i], cudaStreamNonBlocking));
-    if ((rc = upload_constants()) != FID_OK || (rc = configure_kernels(h)) != FID_OK) {
+    if ((rc = dalloc(&h->d_dict, (size_t)kMaxDictMarkers * 4)) != FID_OK || (rc = upload_dictionary(h)) != FID_OK || (rc = configure_kernels(h)) != FID_OK) {
         fid_destroy(h);
         return rc;
     }
@@ -445,7 +432,7 @@ extern "C" int fid_destroy(fid_detector* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (int i = 0; i < MAX_SLOTS; i++) free_slot(h->slot[i]);
-    void* ptrs[] = {h->d_pf[0], h->d_pf[1], h->d_lut_prev, h->d_lut_next, h->d_subpix_masks, h->d_override_ids, h->d_override_lens, h->d_pose_ids, h->d_pose_corners, h->d_pose_out};
+    void* ptrs[] = {h->d_dict, h->d_pf[0], h->d_pf[1], h->d_lut_prev, h->d_lut_next, h->d_subpix_masks, h->d_override_ids, h->d_override_lens, h->d_pose_ids, h->d_pose_corners, h->d_pose_out};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 2; i++)
@@ -465,9 +452,13 @@ extern "C" int fid_set_params(fid_detector* h, const fid_params* params) {
     DevParams P;
     const int rc = make_dev_params(*params, &P);
     if (rc != FID_OK) return rc;
+    if (h->pend_count) return FID_ERR_INVALID_ARG;  // between frames only (configCallback, aruco_detect.cpp:257-298)
+    CK(cudaSetDevice(h->device));
+    for (int i = 0; i < h->n_slots; i++) CK(cudaStreamSynchronize(h->slot_stream[i]));
+    CK(cudaStreamSynchronize(h->stream));
     h->params = *params;
     h->P = P;
-    return FID_OK;
+    return upload_dictionary(h);
 }
 
 static Camera make_camera(const fid_camera* c) {
@@ -707,6 +698,7 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
         a.max_raw = h->max_raw;
         a.max_sel = h->max_sel;
         a.P = P;
+        a.dict = h->d_dict;
         a.cand_id = s.d_cand_id;
         a.cand_corners = s.d_cand_corners;
         dim3 grid(h->max_sel, nf);

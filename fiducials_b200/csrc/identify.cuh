@@ -190,29 +190,37 @@ FID_HD IdentifyResult identify_candidate(const Lanes& L, const Img& gray, int W,
     double var = (double)s2 * scale - mean * mean;
     var = var > 0.0 ? var : 0.0;
     const double stddev = sqrt(var);
-    unsigned long long bits = 0;  // bit (y*cells + x)
+    // cell c = y*cells + x: bit c of bits_lo for c < 64, bit c-64 of bits_hi otherwise (7x7 markers have 81 cells)
+    unsigned long long bits_lo = 0, bits_hi = 0;
     if (stddev < P.min_otsu_stddev) {
-        if (mean > 127.0) bits = cells * cells >= 64 ? ~0ull : ((1ull << (cells * cells)) - 1ull);
+        if (mean > 127.0) bits_lo = bits_hi = ~0ull;  // all white (bits beyond cells*cells are never read)
     } else {
         const int t = otsu_threshold(hist, S * S);
         const int win = cell - 2 * margin;
-        unsigned long long mine = 0;
+        unsigned long long mine = 0, mine_hi = 0;
         for (int c = L.lane(); c < cells * cells; c += L.count()) {
             const int cy = c / cells, cx = c - cy * cells;
             int nz = 0;
             for (int yy = 0; yy < win; yy++)
                 for (int xx = 0; xx < win; xx++) nz += img[(cy * cell + margin + yy) * S + cx * cell + margin + xx] > t ? 1 : 0;
-            if (nz > (win * win) / 2) mine |= 1ull << c;
+            if (nz > (win * win) / 2) {
+                if (c < 64)
+                    mine |= 1ull << c;
+                else
+                    mine_hi |= 1ull << (c - 64);
+            }
         }
-        bits = L.or_u64(mine);
+        bits_lo = L.or_u64(mine);
+        bits_hi = cells * cells > 64 ? L.or_u64(mine_hi) : 0ull;
     }
+    auto cell_bit = [&](int c) -> int { return (int)(((c < 64 ? bits_lo >> c : bits_hi >> (c - 64))) & 1ull); };
     // border errors (_getBorderErrors) -- number of white bits in the border ring
     const int bb = P.marker_border_bits, ms = P.marker_size;
     int border_errors = 0;
     for (int y = 0; y < cells; y++)
         for (int x = 0; x < cells; x++) {
             const bool in_border = y < bb || y >= cells - bb || x < bb || x >= cells - bb;
-            if (in_border && ((bits >> (y * cells + x)) & 1ull)) border_errors++;
+            if (in_border && cell_bit(y * cells + x)) border_errors++;
         }
     const int max_border = (int)((double)(ms * ms) * P.max_err_border_rate);
     if (border_errors > max_border) return res;
@@ -223,7 +231,7 @@ FID_HD IdentifyResult identify_candidate(const Lanes& L, const Img& gray, int W,
         const int total = ms * ms;
         for (int y = 0; y < ms; y++)
             for (int x = 0; x < ms; x++) {
-                const int b = (int)((bits >> ((y + bb) * cells + x + bb)) & 1ull);
+                const int b = cell_bit((y + bb) * cells + x + bb);
                 cur = (cur << 1) | b;
                 nbits++;
                 k++;

@@ -17,11 +17,9 @@
 
 namespace fid {
 
-// Dictionaries live in constant memory (immutable, shared by every handle): 5x5 family as 25-bit
-// words, 6x6 family as 36-bit words; both hold 1000 markers x 4 rotations (prefix property of
-// OpenCV's predefined dictionaries, tools/gen_dict_tables.py).
-__constant__ uint32_t c_dict5[1000 * 4];
-__constant__ unsigned long long c_dict6[1000 * 4];
+// The active dictionary lives in global memory as n_markers x 4 rotations of 64-bit words (params_host.h, pack_dictionary;
+// any OpenCV predefined dictionary, up to 2320 markers x 32 B = 74 KB -- more than constant memory holds) and is staged into
+// shared memory by every identification block.
 
 struct FrameScratch {     // per-frame global scratch, all arrays sized max_raw
     QuadF* quads_tmp;     // clockwise quads, unsorted
@@ -232,6 +230,7 @@ struct IdentifyArgs {
     int max_raw;
     int max_sel;
     DevParams P;
+    const unsigned long long* dict;  // n_markers * 4 words
     int* cand_id;        // [F][max_sel]  -1 rejected
     float* cand_corners; // [F][max_sel][8] rotated to marker order
 };
@@ -250,7 +249,7 @@ __global__ void __launch_bounds__(IDENT_WARPS * 32) k_identify(const IdentifyArg
     const int f = blockIdx.y, k = blockIdx.x;
     if (k >= a.n_sel[f]) return;
     const int n_words = a.P.n_markers * 4;
-    for (int i = threadIdx.x; i < n_words; i += blockDim.x) sm_dict[i] = a.P.marker_size == 5 ? (unsigned long long)c_dict5[i] : c_dict6[i];
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) sm_dict[i] = __ldg(a.dict + i);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int* hist = reinterpret_cast<int*>(sm_dict + n_words) + warp * 256;
     uint8_t* img = reinterpret_cast<uint8_t*>(reinterpret_cast<int*>(sm_dict + n_words) + IDENT_WARPS * 256) + warp * (FID_MAX_WARP_SIDE_SQ);

@@ -81,16 +81,17 @@ inline int make_dev_params(const fid_params& p, DevParams* dp) {
     dp->n_markers = info->n_markers;
     dp->max_correction_bits = info->max_correction_bits;
     dp->dict_nbytes = (info->marker_size * info->marker_size + 7) / 8;
+    dp->dict_table = info->table;
     if (p.markerBorderBits < 1 || p.perspectiveRemovePixelPerCell < 1) return FID_ERR_INVALID_ARG;
     const int cells = dp->marker_size + 2 * dp->marker_border_bits;
-    if (cells * dp->px_per_cell > FID_MAX_WARP_SIDE || cells * cells > 64) return FID_ERR_UNSUPPORTED;
+    if (cells * dp->px_per_cell > FID_MAX_WARP_SIDE || cells * cells > 128 || dp->marker_size * dp->marker_size > 64) return FID_ERR_UNSUPPORTED;
     if (dp->corner_refine && (dp->refine_win < 1 || dp->refine_win > 5 || dp->refine_max_iter < 1 || !(dp->refine_min_acc > 0))) return FID_ERR_UNSUPPORTED;
     return FID_OK;
 }
 
 // Dictionary as n_markers x 4 rotations of 64-bit words (byte k of the rotation in bits 8k..8k+7).
 inline void pack_dictionary(const DevParams& dp, std::vector<unsigned long long>* out) {
-    const uint8_t* tab = dp.marker_size == 5 ? kDictBytes5x5 : kDictBytes6x6;
+    const uint8_t* tab = kDictTables[dp.dict_table];
     const int nb = dp.dict_nbytes;
     out->assign((size_t)dp.n_markers * 4, 0ull);
     for (int m = 0; m < dp.n_markers; m++)

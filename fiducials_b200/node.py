@@ -494,6 +494,25 @@ class FiducialSlam:
     def poseTf(self, robot, T_odomBase=None):
         return pose_tf(robot.t[:], robot.q[:], T_odomBase, self.publish_6dof_pose)
 
+    def refine(self, messages, instance=0, **params):
+        """fid_map_refine: batch SE(3) Gauss-Newton over the relative poses the recorded messages contain (new).
+        messages = list of messages (lists of FiducialTransform-like dicts).  Returns fid_refine_stats."""
+        flat, offsets = [], [0]
+        for m in messages:
+            flat.extend(m)
+            offsets.append(len(flat))
+        arr = self._obs(flat)
+        off = np.ascontiguousarray(np.array(offsets, np.int32))
+        p = _lib.fid_refine_params()
+        _lib.check(self.lib.fid_map_refine_default_params(C.byref(p)))
+        for k, v in params.items():
+            if not hasattr(p, k):
+                raise AttributeError("unknown refine parameter %r" % k)
+            setattr(p, k, v)
+        st = _lib.fid_refine_stats()
+        _lib.check(self.lib.fid_map_refine(self.h, instance, len(messages), off.ctypes.data_as(C.c_void_p), C.cast(arr, C.c_void_p), C.byref(p), C.byref(st)), "fid_map_refine")
+        return st
+
     # multi-GPU merged view (new; SURVEY 8e): local instances are never overwritten by a merge
     def export_table(self, instance=0) -> np.ndarray:
         cap = self.p.max_fiducials

@@ -34,12 +34,14 @@ def dictionary_info(dict_id: int):
     if not _dict_cache:
         z = np.load(_DICT_NPZ)
         _dict_cache["info"] = {int(r[0]): (int(r[1]), int(r[2]), int(r[3])) for r in z["info"]}
-        _dict_cache[5] = z["bytes_5x5"]
-        _dict_cache[6] = z["bytes_6x6"]
+        names = {0: "4x4", 1: "4x4", 2: "4x4", 3: "4x4", 4: "5x5", 5: "5x5", 6: "5x5", 7: "5x5", 8: "6x6", 9: "6x6", 10: "6x6", 11: "6x6", 12: "7x7", 13: "7x7",
+                 14: "7x7", 15: "7x7", 16: "original", 17: "apriltag16h5", 18: "apriltag25h9", 19: "apriltag36h10", 20: "apriltag36h11", 21: "mip36h12"}
+        for e, nm in names.items():
+            _dict_cache[("bytes", e)] = z["bytes_" + nm]
     if dict_id not in _dict_cache["info"]:
-        raise ValueError("unsupported dictionary enum %d (supported: 4..11)" % dict_id)
+        raise ValueError("unsupported dictionary enum %d (supported: 0..21)" % dict_id)
     ms, n, mc = _dict_cache["info"][dict_id]
-    return ms, n, mc, _dict_cache[ms][:n]
+    return ms, n, mc, _dict_cache[("bytes", dict_id)][:n]
 
 
 def marker_bits(dict_id: int, marker_id: int) -> np.ndarray:

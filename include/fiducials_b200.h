@@ -285,6 +285,28 @@ int fid_map_sync(fid_map* m);
 /* publishMap (map.cpp:629-654): entries in ascending fiducial id. */
 int fid_map_entries(fid_map* m, int instance, int max_entries, int* n, fid_map_entry* entries);
 
+/* Batch SE(3) Gauss-Newton refinement of a map instance over a recorded message sequence (NEW -- SURVEY 8f-3, the north-star's
+ * "batched SE(3) Gauss-Newton"; the reference only has the sequential fold above and the co-visibility links of map.cpp:217-222;
+ * parity unpinned, stated and checked by oracle/refine_oracle.py, quality metric = fiducial_slam/scripts/fit_plane.py).
+ * Unknowns: the instance's fiducial poses, entries with variance 0 stay fixed.  Every message that observes mapped fiducials a, b
+ * (a before b) contributes the relative pose T_camFid_a^-1 T_camFid_b with weight 1 / (object_error_a + object_error_b + 1e-9);
+ * cost = sum w (|Log(Z_R^T R_a^T R_b)|^2 + translation_weight |R_a^T (t_b - t_a) - Z_t|^2).  The poses are updated in place
+ * (variances and observation counts are left alone).  Messages: obs[offsets[k] .. offsets[k+1]). */
+typedef struct fid_refine_params {
+    int32_t max_iterations;    /* Gauss-Newton steps, 1..64 (default 8) */
+    int32_t pcg_iterations;    /* preconditioned conjugate-gradient iterations per step, upper bound (default 100) */
+    double pcg_tolerance;      /* relative residual at which the linear solve stops (default 1e-10) */
+    double damping;            /* Levenberg term on the diagonal (default 1e-6) */
+    double translation_weight; /* lambda_t (default 1) */
+} fid_refine_params;
+typedef struct fid_refine_stats {
+    double initial_cost, final_cost;
+    int32_t iterations, n_edges, n_free, kernel_launches;
+} fid_refine_stats;
+int fid_map_refine_default_params(fid_refine_params* p);
+int fid_map_refine(fid_map* m, int instance, int n_msgs, const int32_t* offsets, const fid_transform* obs, const fid_refine_params* params /* NULL = defaults */,
+                   fid_refine_stats* stats /* optional */);
+
 /* Multi-GPU merged map (NEW, no reference counterpart -- SURVEY 8e; parity unpinned, checked against
  * oracle/slam_oracle.py::merge_maps).  Every rank keeps its own LOCAL map instances (the reference's
  * sequential fold over its own camera stream).  Once per merge epoch each rank exports its instance as a

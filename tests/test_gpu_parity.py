@@ -382,7 +382,7 @@ def test_unsupported_dictionary_rejected():
     from fiducials_b200.node import Detector, default_params
 
     with pytest.raises(_lib.FidError) as e:
-        Detector(default_params(dictionary=16), 0, 64, 64, 1)  # DICT_ARUCO_ORIGINAL
+        Detector(default_params(dictionary=22), 0, 64, 64, 1)  # not an OpenCV predefined dictionary (0..21 are supported)
     assert e.value.status == -4
 
 
@@ -554,3 +554,39 @@ def test_candidate_hierarchy_nested_markers():
                 assert np.abs(np.array(t.translation[:]) - fields[m]["translation"]).max() <= 1e-3
     finally:
         det.close()
+
+
+@pytest.mark.parametrize("dict_id", [0, 3, 7, 12, 15, 16, 17, 18, 19, 20, 21])
+def test_every_predefined_dictionary(dict_id):
+    """The reference takes any OpenCV predefined dictionary by enum value (aruco_detect.cpp:611,671; default 7 = DICT_5X5_1000):
+    4x4 .. 7x7 families (7x7: 81 cells incl. the border), ARUCO_ORIGINAL, the AprilTag families (up to 2320 markers), MIP_36h12."""
+    import cv2
+
+    d = cv2.aruco.getPredefinedDictionary(dict_id)
+    n = d.bytesList.shape[0]
+    rng = np.random.default_rng(dict_id)
+    ids = sorted(set([0, n - 1] + [int(v) for v in rng.integers(0, n, 4)]))[:6]
+    img = np.full((600, 900), 205, np.uint8)
+    for k, mid in enumerate(ids):
+        side = 120 + 10 * k
+        m = cv2.aruco.generateImageMarker(d, mid, side)
+        y0, x0 = 60 + 270 * (k // 3), 50 + 290 * (k % 3)
+        img[y0 : y0 + side, x0 : x0 + side] = m
+    M = cv2.getRotationMatrix2D((450, 300), 11.0, 0.95)
+    img = cv2.warpAffine(img, M, (900, 600), borderValue=205)
+    img = cv2.GaussianBlur(img, (0, 0), 0.9)
+    bgr = np.repeat(img[:, :, None], 3, axis=2)
+    K = np.array([[700.0, 0, 450], [0, 700, 300], [0, 0, 1]])
+    D = np.zeros(5)
+    oi, oc, rv, tv, fields = ao.detect_and_pose(bgr, dict_id, K, D, 0.14)
+    assert sorted(oi.tolist()) == ids  # the oracle finds them all
+    det = Detector(default_params(dictionary=dict_id), 0, 900, 600, 1)
+    try:
+        counts, gi, gc, tfs = det.detect_pose_batch(bgr[None], K, D, 0.14)
+    finally:
+        det.close()
+    nn = int(counts[0])
+    assert gi[0, :nn].tolist() == oi.tolist()
+    assert np.abs(gc[0, :nn] - oc).max() <= 1e-3
+    for m in range(nn):
+        assert np.abs(np.array(tfs[m].translation[:]) - fields[m]["translation"]).max() <= 1e-3

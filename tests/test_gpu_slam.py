@@ -387,3 +387,42 @@ def test_add_fiducial_service():
     for e in slam.entries():
         assert abs(e.variance - ref.fiducials[e.fiducial_id].pose.var) <= 1e-9 * max(1.0, abs(e.variance))
     slam.close()
+
+
+def test_batch_gauss_newton_refine_matches_oracle():
+    """fid_map_refine (NEW; parity unpinned -- the reference has no batch solver): the matrix-free PCG Gauss-Newton on the
+    device lands on the poses of the dense numpy statement of the same problem (oracle/refine_oracle.py) -- same edges, weights,
+    residuals, local parametrisation, damping and iteration count -- and the cost goes down monotonically from the sequential fold's map."""
+    from fiducials_b200 import synth
+    from fiducials_b200.node import FiducialSlam
+    from oracle import refine_oracle as ro
+
+    msgs, seed = synth.make_c5_sequence(120, seed=1, cols=6, rows=5, visible=6)
+    ident = so.TWV.identity()
+    slam = FiducialSlam(max_fiducials=64)
+    slam.loadMap([seed])
+    slam.replay([msgs], _tf7(ident), _tf7(ident))
+    before = slam.entries()
+    ids = [e.fiducial_id for e in before]
+    R0 = [np.array(so.set_rpy_matrix(e.rx, e.ry, e.rz)) for e in before]
+    t0 = [np.array([e.x, e.y, e.z]) for e in before]
+    fixed = [e.variance == 0.0 for e in before]
+    assert sum(fixed) == 1 and len(ids) == 30
+    edges = ro.build_edges(ids, msgs)
+    iters = 5
+    Rr, tr, costs = ro.refine(R0, t0, fixed, edges, iterations=iters, damping=1e-6, lambda_t=2.0)
+    st = slam.refine(msgs, max_iterations=iters, pcg_iterations=400, pcg_tolerance=1e-14, damping=1e-6, translation_weight=2.0)
+    assert st.n_edges == len(edges) and st.n_free == 29 and st.iterations == iters
+    assert abs(st.initial_cost - costs[0]) <= 1e-9 * costs[0] and abs(st.final_cost - costs[-1]) <= 1e-7 * costs[-1]
+    assert st.final_cost < st.initial_cost and all(b <= a * (1 + 1e-12) for a, b in zip(costs, costs[1:]))
+    after = slam.entries()
+    assert [e.fiducial_id for e in after] == ids
+    for e, R, t, f, b in zip(after, Rr, tr, fixed, before):
+        assert np.abs(np.array([e.x, e.y, e.z]) - t).max() < 1e-7
+        assert np.abs(np.array(so.set_rpy_matrix(e.rx, e.ry, e.rz)) - R).max() < 1e-7
+        assert e.variance == b.variance and e.num_obs == b.num_obs  # only the poses move
+        if f:
+            assert (e.x, e.y, e.z, e.rx, e.ry, e.rz) == (b.x, b.y, b.z, b.rx, b.ry, b.rz)  # pinned entries stay put
+    # the reference's map-quality metric (fiducial_slam/scripts/fit_plane.py) stays at the noise level of the observations
+    assert ro.plane_fit_residual([[e.x, e.y, e.z] for e in after]) < 0.05
+    slam.close()
