@@ -101,7 +101,7 @@ class fid_refine_params(C.Structure):
 
 
 class fid_refine_stats(C.Structure):
-    _fields_ = [("initial_cost", C.c_double), ("final_cost", C.c_double), ("iterations", C.c_int32), ("n_edges", C.c_int32), ("n_free", C.c_int32), ("kernel_launches", C.c_int32)]
+    _fields_ = [("initial_cost", C.c_double), ("final_cost", C.c_double), ("solve_ms", C.c_double), ("iterations", C.c_int32), ("n_edges", C.c_int32), ("n_free", C.c_int32), ("kernel_launches", C.c_int32)]
 
 
 class fid_map_record(C.Structure):

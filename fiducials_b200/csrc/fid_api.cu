@@ -545,28 +545,16 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
                     }
             }
         } else {
-            GrayArgs ga{};
-            ga.bgr = d_bgr;
-            ga.gray = s.d_gray;
-            ga.W = W;
-            ga.H = H;
-            ga.n_frames = nf;
-            ga.bgr_row_stride = g.bgr_row_stride;
-            ga.bgr_frame_stride = g.bgr_frame_stride;
-            ga.gray_pitch = g.gray_pitch;
-            ga.gray_frame_stride = g.gray_frame_stride;
-            ga.enc = h->enc;
-            const long long gq = (long long)nf * H * ((W + 3) / 4);
-            k_gray<<<(unsigned int)((gq + 255) / 256), 256, 0, st>>>(ga);
-            launches++;
             ThreshArgs a{};
-            a.gray = s.d_gray;
+            a.src = d_bgr;
+            a.src_row_stride = g.bgr_row_stride;
+            a.src_frame_stride = g.bgr_frame_stride;
+            a.enc = h->enc;
+            a.aligned4 = (W % 4 == 0) && (g.bgr_row_stride % 4 == 0) && (g.bgr_frame_stride % 4 == 0) && ((uintptr_t)d_bgr % 4 == 0);
             a.halo = s.d_halo;
             a.W = W;
             a.H = H;
             a.n_frames = nf;
-            a.gray_pitch = g.gray_pitch;
-            a.gray_frame_stride = g.gray_frame_stride;
             a.halo_tpr = g.halo_tpr;
             a.halo_tiles_y = g.halo_tiles_y;
             a.halo_scale_stride = g.halo_scale_stride;

@@ -12,11 +12,14 @@
 //   residual      e_R = Log(Z_R^T R_a^T R_b),  e_t = R_a^T (t_b - t_a) - Z_t          cost = sum w (|e_R|^2 + lambda_t |e_t|^2)
 //   step          Gauss-Newton, R <- R Exp(dtheta), t <- t + dt, Levenberg damping mu
 //
-// The normal equations are never formed: J^T W J is applied edge by edge (one thread per edge, 6x6 blocks A, B kept from the
-// linearisation, double atomics into the 6 N vector) inside a block-Jacobi preconditioned conjugate gradient whose scalars stay on
-// the device -- a GN step is a fixed sequence of launches with no host synchronisation.  At C5's size (500 poses, 45 k edges,
+// The normal equations are never formed: J^T W J is applied as u = W J p (one thread per edge, 6x6 blocks A, B kept from the
+// linearisation) followed by a gather J^T u per node over its incident edges (a warp per node, no atomics) inside a block-Jacobi
+// preconditioned conjugate gradient.  The whole refinement -- every Gauss-Newton step and every CG iteration -- is ONE cooperative
+// kernel with grid-wide barriers between the phases: no host round trips, no launch gaps (a first version with three launches per
+// CG iteration and double atomics spent 105 ms on C5's graph).  At C5's size (500 poses, 45 k edges,
 // 432 flops per edge and product) the 6x6 block products are far below anything a tensor-core tile could use; the work
 // is latency bound, so the design goal is "no host round trips", not flops.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <string.h>
@@ -28,6 +31,7 @@
 #include "fid_map_internal.h"
 
 using namespace fid;
+namespace cg = cooperative_groups;
 
 namespace {
 
@@ -120,230 +124,212 @@ __device__ void edge_terms(const MapEntry& Xa, const MapEntry& Xb, const Edge& e
 struct RefineBufs {
     const Edge* edges;
     EdgeLin* lin;
+    double* u;                 // per edge: W (A p_a + B p_b), 6 doubles
+    const int32_t* node_off;   // CSR of the incident edges of every node: adj[node_off[n] .. node_off[n+1])
+    const uint32_t* adj;       // edge index | (1u << 31 if the node is the edge's b side)
     int n_edges, n_nodes;      // n_nodes = fiducials of the instance
     MapEntry* entries;
-    double *g, *x, *r, *z, *p, *q, *Hd;  // 6 n vectors; Hd = block diagonal, 36 per node
-    double* scal;              // [0] cost  [1] rz  [2] pq  [3] rz_new  [4] r0 norm^2  [5] r norm^2
+    double *g, *x, *r, *z, *p, *q, *Minv;  // 6 n vectors; Minv = inverted block diagonal, 36 per node
+    double* cost;              // [gn iteration]  (+1: final)
+    double *pq, *rz, *rr;      // [gn iteration][pcg iteration + 1] accumulators (zeroed by the host)
+    int max_iterations, pcg_iterations;
     double lambda_t, damping, pcg_tol2;
 };
 
 __device__ __forceinline__ double wk(const RefineBufs& b, double w, int k) { return k < 3 ? w : w * b.lambda_t; }
-
-// linearise: residuals, Jacobian blocks, gradient g = J^T W e, block diagonal of J^T W J, cost
-__global__ void k_gn_linearize(const RefineBufs b) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    double c = 0.0;
-    if (i < b.n_edges) {
-        const Edge ed = b.edges[i];
-        EdgeLin L;
-        edge_terms(b.entries[ed.a], b.entries[ed.b], ed, &L);
-        b.lin[i] = L;
-        for (int k = 0; k < 6; k++) c += wk(b, ed.w, k) * L.e[k] * L.e[k];
-        for (int col = 0; col < 6; col++) {
-            double ga = 0, gb = 0;
-            for (int k = 0; k < 6; k++) {
-                ga += L.A[k * 6 + col] * wk(b, ed.w, k) * L.e[k];
-                gb += L.B[k * 6 + col] * wk(b, ed.w, k) * L.e[k];
-            }
-            atomicAdd(&b.g[6 * ed.a + col], ga);
-            atomicAdd(&b.g[6 * ed.b + col], gb);
-            for (int row = 0; row < 6; row++) {
-                double ha = 0, hb = 0;
-                for (int k = 0; k < 6; k++) {
-                    ha += L.A[k * 6 + row] * wk(b, ed.w, k) * L.A[k * 6 + col];
-                    hb += L.B[k * 6 + row] * wk(b, ed.w, k) * L.B[k * 6 + col];
-                }
-                atomicAdd(&b.Hd[36 * ed.a + row * 6 + col], ha);
-                atomicAdd(&b.Hd[36 * ed.b + row * 6 + col], hb);
-            }
-        }
-    }
-    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-    if ((threadIdx.x & 31) == 0 && c != 0.0) atomicAdd(&b.scal[0], c);
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
 }
 
-// per node: invert the damped 6x6 diagonal block (Cholesky); fixed nodes get a zero block.  Also PCG start: x = 0, r = -g (free), z = M^-1 r, p = z
-__global__ void k_gn_precondition(const RefineBufs b) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= b.n_nodes) return;
-    double* H = b.Hd + 36 * n;
-    const bool fixed = b.entries[n].pose.var == 0.0;
-    double Lm[36], inv[36];
-    bool ok = !fixed;
-    if (ok) {
-        for (int i = 0; i < 6; i++) H[i * 6 + i] += b.damping;
-        for (int i = 0; i < 6 && ok; i++)
-            for (int j = 0; j <= i; j++) {
-                double s = H[i * 6 + j];
-                for (int k = 0; k < j; k++) s -= Lm[i * 6 + k] * Lm[j * 6 + k];
-                if (i == j) {
-                    if (s <= 0.0) {
-                        ok = false;
-                        break;
+// One cooperative kernel runs the whole refinement: Gauss-Newton steps of {linearise (per edge) -> gradient + block diagonal
+// (gather per node over its incident edges, no atomics) -> preconditioned conjugate gradient (per edge: u = W J p; per node:
+// q = J^T u) -> apply}, the phases separated by grid-wide barriers.  A warp owns a node, its lanes stride over the node's edges.
+__global__ void __launch_bounds__(256) k_gn_solve(const RefineBufs b) {
+    cg::grid_group grid = cg::this_grid();
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+    const int lane = threadIdx.x & 31, warp = tid >> 5, nwarps = nthreads >> 5;
+    const int slots = b.pcg_iterations + 1;
+    for (int it = 0; it <= b.max_iterations; it++) {
+        // ---- linearise (the extra pass it == max_iterations only evaluates the final cost) ----
+        double c = 0.0;
+        for (int i = tid; i < b.n_edges; i += nthreads) {
+            const Edge ed = b.edges[i];
+            EdgeLin L;
+            edge_terms(b.entries[ed.a], b.entries[ed.b], ed, &L);
+            if (it < b.max_iterations) b.lin[i] = L;
+            for (int k = 0; k < 6; k++) c += wk(b, ed.w, k) * L.e[k] * L.e[k];
+        }
+        c = warp_sum(c);
+        if (lane == 0 && c != 0.0) atomicAdd(&b.cost[it], c);
+        if (it == b.max_iterations) break;
+        grid.sync();
+        double* pq = b.pq + (size_t)it * slots;
+        double* rz = b.rz + (size_t)it * slots;
+        double* rr = b.rr + (size_t)it * slots;
+        // ---- per node: g = J^T W e, H_nn = sum J_n^T W J_n, M^-1 = (H_nn + mu I)^-1, PCG start ----
+        for (int n = warp; n < b.n_nodes; n += nwarps) {
+            double H[36], g[6];
+            for (int i = 0; i < 36; i++) H[i] = 0.0;
+            for (int i = 0; i < 6; i++) g[i] = 0.0;
+            for (int k = b.node_off[n] + lane; k < b.node_off[n + 1]; k += 32) {
+                const uint32_t av = b.adj[k];
+                const int ei = (int)(av & 0x7fffffffu);
+                const EdgeLin& L = b.lin[ei];
+                const double* J = (av >> 31) ? L.B : L.A;
+                const double w = b.edges[ei].w;
+                for (int col = 0; col < 6; col++) {
+                    double gs = 0;
+                    for (int kk = 0; kk < 6; kk++) gs += J[kk * 6 + col] * wk(b, w, kk) * L.e[kk];
+                    g[col] += gs;
+                    for (int row = 0; row <= col; row++) {
+                        double hs = 0;
+                        for (int kk = 0; kk < 6; kk++) hs += J[kk * 6 + row] * wk(b, w, kk) * J[kk * 6 + col];
+                        H[row * 6 + col] += hs;
                     }
-                    Lm[i * 6 + i] = sqrt(s);
-                } else {
-                    Lm[i * 6 + j] = s / Lm[j * 6 + j];
                 }
             }
-    }
-    if (ok) {
-        for (int col = 0; col < 6; col++) {  // solve L L^T y = e_col
-            double y[6];
-            for (int i = 0; i < 6; i++) {
-                double s = i == col ? 1.0 : 0.0;
-                for (int k = 0; k < i; k++) s -= Lm[i * 6 + k] * y[k];
-                y[i] = s / Lm[i * 6 + i];
+            for (int i = 0; i < 6; i++) g[i] = warp_sum(g[i]);
+            for (int col = 0; col < 6; col++)
+                for (int row = 0; row <= col; row++) {
+                    const double v = warp_sum(H[row * 6 + col]);
+                    H[row * 6 + col] = v;
+                    H[col * 6 + row] = v;
+                }
+            if (lane == 0) {
+                const bool fixed = b.entries[n].pose.var == 0.0;
+                double Lm[36], inv[36];
+                bool ok = !fixed;
+                if (ok) {
+                    for (int i = 0; i < 6; i++) H[i * 6 + i] += b.damping;
+                    for (int i = 0; i < 6 && ok; i++)
+                        for (int j = 0; j <= i; j++) {
+                            double s = H[i * 6 + j];
+                            for (int k = 0; k < j; k++) s -= Lm[i * 6 + k] * Lm[j * 6 + k];
+                            if (i == j) {
+                                if (s <= 0.0) {
+                                    ok = false;
+                                    break;
+                                }
+                                Lm[i * 6 + i] = sqrt(s);
+                            } else {
+                                Lm[i * 6 + j] = s / Lm[j * 6 + j];
+                            }
+                        }
+                }
+                if (ok) {
+                    for (int col = 0; col < 6; col++) {  // solve L L^T y = e_col
+                        double y[6];
+                        for (int i = 0; i < 6; i++) {
+                            double s = i == col ? 1.0 : 0.0;
+                            for (int k = 0; k < i; k++) s -= Lm[i * 6 + k] * y[k];
+                            y[i] = s / Lm[i * 6 + i];
+                        }
+                        for (int i = 5; i >= 0; i--) {
+                            double s = y[i];
+                            for (int k = i + 1; k < 6; k++) s -= Lm[k * 6 + i] * y[k];
+                            y[i] = s / Lm[i * 6 + i];
+                        }
+                        for (int i = 0; i < 6; i++) inv[i * 6 + col] = y[i];
+                    }
+                } else {
+                    for (int i = 0; i < 36; i++) inv[i] = 0.0;
+                }
+                double a_rz = 0.0, a_rr = 0.0, r6[6];
+                for (int i = 0; i < 6; i++) {
+                    b.x[6 * n + i] = 0.0;
+                    r6[i] = ok ? -g[i] : 0.0;
+                    b.r[6 * n + i] = r6[i];
+                    a_rr += r6[i] * r6[i];
+                }
+                for (int i = 0; i < 6; i++) {
+                    double s = 0;
+                    for (int k = 0; k < 6; k++) s += inv[i * 6 + k] * r6[k];
+                    b.z[6 * n + i] = s;
+                    b.p[6 * n + i] = s;
+                    a_rz += r6[i] * s;
+                }
+                for (int i = 0; i < 36; i++) b.Minv[36 * n + i] = inv[i];
+                atomicAdd(&rz[0], a_rz);
+                atomicAdd(&rr[0], a_rr);
             }
-            for (int i = 5; i >= 0; i--) {
-                double s = y[i];
-                for (int k = i + 1; k < 6; k++) s -= Lm[k * 6 + i] * y[k];
-                y[i] = s / Lm[i * 6 + i];
+        }
+        grid.sync();
+        // ---- preconditioned conjugate gradient on (J^T W J + mu I) x = -g ----
+        const double rr0 = rr[0];
+        for (int k = 0; k < b.pcg_iterations; k++) {
+            if (rr[k] <= b.pcg_tol2 * rr0) break;  // grid-uniform: every thread reads the same completed sums
+            for (int i = tid; i < b.n_edges; i += nthreads) {
+                const Edge& ed = b.edges[i];
+                const EdgeLin& L = b.lin[i];
+                for (int kk = 0; kk < 6; kk++) {
+                    double s = 0;
+                    for (int cc = 0; cc < 6; cc++) s += L.A[kk * 6 + cc] * b.p[6 * ed.a + cc] + L.B[kk * 6 + cc] * b.p[6 * ed.b + cc];
+                    b.u[6 * (size_t)i + kk] = wk(b, ed.w, kk) * s;
+                }
             }
-            for (int i = 0; i < 6; i++) inv[i * 6 + col] = y[i];
+            grid.sync();
+            for (int n = warp; n < b.n_nodes; n += nwarps) {
+                double y[6] = {0, 0, 0, 0, 0, 0};
+                if (b.entries[n].pose.var != 0.0)
+                    for (int kk = b.node_off[n] + lane; kk < b.node_off[n + 1]; kk += 32) {
+                        const uint32_t av = b.adj[kk];
+                        const int ei = (int)(av & 0x7fffffffu);
+                        const double* J = (av >> 31) ? b.lin[ei].B : b.lin[ei].A;
+                        const double* ue = b.u + 6 * (size_t)ei;
+                        for (int cc = 0; cc < 6; cc++) {
+                            double s = 0;
+                            for (int r6 = 0; r6 < 6; r6++) s += J[r6 * 6 + cc] * ue[r6];
+                            y[cc] += s;
+                        }
+                    }
+                double dot = 0.0;
+                for (int cc = 0; cc < 6; cc++) {
+                    y[cc] = warp_sum(y[cc]);
+                    if (lane == 0) {
+                        const double qv = b.entries[n].pose.var != 0.0 ? y[cc] + b.damping * b.p[6 * n + cc] : 0.0;
+                        b.q[6 * n + cc] = qv;
+                        dot += b.p[6 * n + cc] * qv;
+                    }
+                }
+                if (lane == 0 && dot != 0.0) atomicAdd(&pq[k], dot);
+            }
+            grid.sync();
+            const double alpha = pq[k] > 0.0 ? rz[k] / pq[k] : 0.0;
+            for (int n = tid; n < b.n_nodes; n += nthreads) {
+                double r6[6], a_rz = 0.0, a_rr = 0.0;
+                for (int i = 0; i < 6; i++) {
+                    b.x[6 * n + i] += alpha * b.p[6 * n + i];
+                    r6[i] = b.r[6 * n + i] - alpha * b.q[6 * n + i];
+                    b.r[6 * n + i] = r6[i];
+                    a_rr += r6[i] * r6[i];
+                }
+                const double* Mi = b.Minv + 36 * n;
+                for (int i = 0; i < 6; i++) {
+                    double s = 0;
+                    for (int kk = 0; kk < 6; kk++) s += Mi[i * 6 + kk] * r6[kk];
+                    b.z[6 * n + i] = s;
+                    a_rz += r6[i] * s;
+                }
+                atomicAdd(&rz[k + 1], a_rz);
+                atomicAdd(&rr[k + 1], a_rr);
+            }
+            grid.sync();
+            const double beta = rz[k] > 0.0 ? rz[k + 1] / rz[k] : 0.0;
+            for (int i = tid; i < 6 * b.n_nodes; i += nthreads) b.p[i] = b.z[i] + beta * b.p[i];
+            grid.sync();
         }
-    } else {
-        for (int i = 0; i < 36; i++) inv[i] = 0.0;
-    }
-    double rz = 0.0, rr = 0.0;
-    for (int i = 0; i < 6; i++) {
-        b.x[6 * n + i] = 0.0;
-        b.r[6 * n + i] = ok ? -b.g[6 * n + i] : 0.0;
-    }
-    for (int i = 0; i < 6; i++) {
-        double s = 0;
-        for (int k = 0; k < 6; k++) s += inv[i * 6 + k] * b.r[6 * n + k];
-        b.z[6 * n + i] = s;
-        b.p[6 * n + i] = s;
-        rz += b.r[6 * n + i] * s;
-        rr += b.r[6 * n + i] * b.r[6 * n + i];
-    }
-    for (int i = 0; i < 36; i++) H[i] = inv[i];  // Hd now holds M^-1
-    atomicAdd(&b.scal[1], rz);
-    atomicAdd(&b.scal[4], rr);
-    atomicAdd(&b.scal[5], rr);
-}
-
-// q = (J^T W J + mu I) p over the free nodes, edge by edge; pq = p . q
-__global__ void k_gn_matvec(const RefineBufs b) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= b.n_edges) return;
-    if (b.scal[5] <= b.pcg_tol2 * b.scal[4]) return;  // converged: the remaining iterations of the fixed launch sequence are no-ops
-    const Edge& ed = b.edges[i];
-    const EdgeLin& L = b.lin[i];
-    double u[6];
-    for (int k = 0; k < 6; k++) {
-        double s = 0;
-        for (int c = 0; c < 6; c++) s += L.A[k * 6 + c] * b.p[6 * ed.a + c] + L.B[k * 6 + c] * b.p[6 * ed.b + c];
-        u[k] = wk(b, ed.w, k) * s;
-    }
-    for (int c = 0; c < 6; c++) {
-        double ya = 0, yb = 0;
-        for (int k = 0; k < 6; k++) {
-            ya += L.A[k * 6 + c] * u[k];
-            yb += L.B[k * 6 + c] * u[k];
+        // ---- apply the step: R <- R Exp(dtheta), t <- t + dt ----
+        for (int n = tid; n < b.n_nodes; n += nthreads) {
+            if (b.entries[n].pose.var == 0.0) continue;
+            double dR[9], Rn[9];
+            so3_exp(b.x + 6 * n, dR);
+            mat3_mul(b.entries[n].pose.R, dR, Rn);
+            for (int i = 0; i < 9; i++) b.entries[n].pose.R[i] = Rn[i];
+            for (int i = 0; i < 3; i++) b.entries[n].pose.t[i] += b.x[6 * n + 3 + i];
         }
-        atomicAdd(&b.q[6 * ed.a + c], ya);
-        atomicAdd(&b.q[6 * ed.b + c], yb);
+        grid.sync();
     }
-}
-// one block: finish q (damping, mask fixed nodes), pq
-__global__ void k_pcg_dot(const RefineBufs b) {
-    __shared__ double sh[32];
-    if (b.scal[5] <= b.pcg_tol2 * b.scal[4]) return;
-    double s = 0.0;
-    for (int i = threadIdx.x; i < 6 * b.n_nodes; i += blockDim.x) {
-        const bool fixed = b.entries[i / 6].pose.var == 0.0;
-        const double q = fixed ? 0.0 : b.q[i] + b.damping * b.p[i];
-        b.q[i] = q;
-        s += b.p[i] * q;
-    }
-    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double t = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += sh[w];
-        b.scal[2] = t;
-    }
-}
-// one block: x += alpha p, r -= alpha q, z = M^-1 r, rz_new, beta, p = z + beta p, clear q
-__global__ void k_pcg_update(const RefineBufs b) {
-    __shared__ double sh[2][32];
-    if (b.scal[5] <= b.pcg_tol2 * b.scal[4]) return;
-    const double alpha = b.scal[2] > 0.0 ? b.scal[1] / b.scal[2] : 0.0;
-    double rz = 0.0, rr = 0.0;
-    for (int n = threadIdx.x; n < b.n_nodes; n += blockDim.x) {
-        double r6[6];
-        for (int i = 0; i < 6; i++) {
-            b.x[6 * n + i] += alpha * b.p[6 * n + i];
-            r6[i] = b.r[6 * n + i] - alpha * b.q[6 * n + i];
-            b.r[6 * n + i] = r6[i];
-            b.q[6 * n + i] = 0.0;
-            rr += r6[i] * r6[i];
-        }
-        const double* Mi = b.Hd + 36 * n;
-        for (int i = 0; i < 6; i++) {
-            double s = 0;
-            for (int k = 0; k < 6; k++) s += Mi[i * 6 + k] * r6[k];
-            b.z[6 * n + i] = s;
-            rz += r6[i] * s;
-        }
-    }
-    for (int d = 16; d > 0; d >>= 1) {
-        rz += __shfl_xor_sync(0xffffffffu, rz, d);
-        rr += __shfl_xor_sync(0xffffffffu, rr, d);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        sh[0][threadIdx.x >> 5] = rz;
-        sh[1][threadIdx.x >> 5] = rr;
-    }
-    __syncthreads();
-    __shared__ double s_beta;
-    if (threadIdx.x == 0) {
-        double t = 0, u = 0;
-        for (int w = 0; w < (int)(blockDim.x >> 5); w++) {
-            t += sh[0][w];
-            u += sh[1][w];
-        }
-        s_beta = b.scal[1] > 0.0 ? t / b.scal[1] : 0.0;
-        b.scal[1] = t;
-        b.scal[5] = u;
-    }
-    __syncthreads();
-    const double beta = s_beta;
-    for (int i = threadIdx.x; i < 6 * b.n_nodes; i += blockDim.x) b.p[i] = b.z[i] + beta * b.p[i];
-}
-// apply the step: R <- R Exp(dtheta), t <- t + dt; reset the accumulators of the next linearisation
-__global__ void k_gn_apply(const RefineBufs b, double* cost_log, int iter) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n == 0) {
-        cost_log[iter] = b.scal[0];
-        for (int i = 0; i < 6; i++) b.scal[i] = 0.0;
-    }
-    if (n >= b.n_nodes) return;
-    if (b.entries[n].pose.var != 0.0) {
-        double dR[9], Rn[9];
-        so3_exp(b.x + 6 * n, dR);
-        mat3_mul(b.entries[n].pose.R, dR, Rn);
-        for (int i = 0; i < 9; i++) b.entries[n].pose.R[i] = Rn[i];
-        for (int i = 0; i < 3; i++) b.entries[n].pose.t[i] += b.x[6 * n + 3 + i];
-    }
-    for (int i = 0; i < 6; i++) b.g[6 * n + i] = 0.0;
-    for (int i = 0; i < 36; i++) b.Hd[36 * n + i] = 0.0;
-}
-// cost only (after the last step)
-__global__ void k_gn_cost(const RefineBufs b) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    double c = 0.0;
-    if (i < b.n_edges) {
-        const Edge ed = b.edges[i];
-        EdgeLin L;
-        edge_terms(b.entries[ed.a], b.entries[ed.b], ed, &L);
-        for (int k = 0; k < 6; k++) c += wk(b, ed.w, k) * L.e[k] * L.e[k];
-    }
-    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-    if ((threadIdx.x & 31) == 0 && c != 0.0) atomicAdd(&b.scal[0], c);
 }
 
 void host_q_to_R(const double q[4], double R[9]) { q_to_m(q, R); }
@@ -421,26 +407,49 @@ extern "C" int fid_map_refine(fid_map* m, int instance, int n_msgs, const int32_
         stats->n_free = n_free;
     }
     if (edges.empty() || n_free == 0) return FID_OK;
+    // incident-edge lists (CSR) so that J^T u is a gather per node instead of atomics per edge
+    std::vector<int32_t> node_off((size_t)n + 1, 0);
+    for (const Edge& e : edges) {
+        node_off[e.a + 1]++;
+        node_off[e.b + 1]++;
+    }
+    for (int i = 0; i < n; i++) node_off[i + 1] += node_off[i];
+    std::vector<uint32_t> adj(2 * edges.size());
+    {
+        std::vector<int32_t> fill(node_off.begin(), node_off.end() - 1);
+        for (size_t i = 0; i < edges.size(); i++) {
+            adj[fill[edges[i].a]++] = (uint32_t)i;
+            adj[fill[edges[i].b]++] = (uint32_t)i | 0x80000000u;
+        }
+    }
     // device buffers (freed on every exit path below)
     Edge* d_edges = nullptr;
     EdgeLin* d_lin = nullptr;
     double* d_vec = nullptr;
+    int32_t* d_off = nullptr;
+    uint32_t* d_adj = nullptr;
     const size_t nv = (size_t)6 * n;
-    const size_t vec_doubles = 6 * nv + 36 * (size_t)n + 8 + 72;  // g x r z p q, Hd, scal, cost log
+    const size_t slots = (size_t)P.pcg_iterations + 1;
+    const size_t n_scal = (size_t)P.max_iterations + 1 + 3 * (size_t)P.max_iterations * slots;
+    const size_t vec_doubles = 6 * nv + 36 * (size_t)n + 6 * edges.size() + n_scal;  // g x r z p q, Minv, u, scalars
     int rc = FID_OK;
     if (cudaMalloc((void**)&d_edges, sizeof(Edge) * edges.size()) != cudaSuccess || cudaMalloc((void**)&d_lin, sizeof(EdgeLin) * edges.size()) != cudaSuccess ||
-        cudaMalloc((void**)&d_vec, sizeof(double) * vec_doubles) != cudaSuccess) {
+        cudaMalloc((void**)&d_vec, sizeof(double) * vec_doubles) != cudaSuccess || cudaMalloc((void**)&d_off, sizeof(int32_t) * node_off.size()) != cudaSuccess ||
+        cudaMalloc((void**)&d_adj, sizeof(uint32_t) * adj.size()) != cudaSuccess) {
         cudaGetLastError();
         rc = FID_ERR_NO_MEMORY;
     }
-    std::vector<double> cost_log(72, 0.0);
     if (rc == FID_OK) {
         cudaStream_t s = m->stream;
         cudaMemcpyAsync(d_edges, edges.data(), sizeof(Edge) * edges.size(), cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(d_off, node_off.data(), sizeof(int32_t) * node_off.size(), cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(d_adj, adj.data(), sizeof(uint32_t) * adj.size(), cudaMemcpyHostToDevice, s);
         cudaMemsetAsync(d_vec, 0, sizeof(double) * vec_doubles, s);
         RefineBufs b{};
         b.edges = d_edges;
         b.lin = d_lin;
+        b.node_off = d_off;
+        b.adj = d_adj;
         b.n_edges = (int)edges.size();
         b.n_nodes = n;
         b.entries = m->d_entries + (size_t)instance * cap;
@@ -450,38 +459,50 @@ extern "C" int fid_map_refine(fid_map* m, int instance, int n_msgs, const int32_
         b.z = b.r + nv;
         b.p = b.z + nv;
         b.q = b.p + nv;
-        b.Hd = b.q + nv;
-        b.scal = b.Hd + 36 * (size_t)n;
-        double* d_cost_log = b.scal + 8;
+        b.Minv = b.q + nv;
+        b.u = b.Minv + 36 * (size_t)n;
+        b.cost = b.u + 6 * edges.size();
+        b.pq = b.cost + P.max_iterations + 1;
+        b.rz = b.pq + (size_t)P.max_iterations * slots;
+        b.rr = b.rz + (size_t)P.max_iterations * slots;
+        b.max_iterations = P.max_iterations;
+        b.pcg_iterations = P.pcg_iterations;
         b.lambda_t = P.translation_weight;
         b.damping = P.damping;
         b.pcg_tol2 = P.pcg_tolerance * P.pcg_tolerance;
-        const int eb = (b.n_edges + 127) / 128, nb = (n + 63) / 64;
-        for (int it = 0; it < P.max_iterations; it++) {
-            k_gn_linearize<<<eb, 128, 0, s>>>(b);
-            k_gn_precondition<<<nb, 64, 0, s>>>(b);
-            for (int k = 0; k < P.pcg_iterations; k++) {
-                k_gn_matvec<<<eb, 128, 0, s>>>(b);
-                k_pcg_dot<<<1, 512, 0, s>>>(b);
-                k_pcg_update<<<1, 512, 0, s>>>(b);
-            }
-            k_gn_apply<<<nb, 64, 0, s>>>(b, d_cost_log, it);
-        }
-        k_gn_cost<<<eb, 128, 0, s>>>(b);
-        cudaMemcpyAsync(cost_log.data(), d_cost_log, sizeof(double) * 64, cudaMemcpyDeviceToHost, s);
-        double final_cost = 0;
-        cudaMemcpyAsync(&final_cost, b.scal, sizeof(double), cudaMemcpyDeviceToHost, s);
-        const cudaError_t e = cudaStreamSynchronize(s);
-        if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) {
+        // cooperative launch: every block must be resident (one block of 256 threads per SM at most)
+        int dev_sms = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, m->device);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gn_solve, 256, 0);
+        const int want = std::max(1, std::min({dev_sms * std::max(per_sm, 0), dev_sms, (b.n_edges + 255) / 256}));
+        void* args[] = {(void*)&b};
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        cudaEventCreate(&ev0);
+        cudaEventCreate(&ev1);
+        cudaEventRecord(ev0, s);
+        cudaError_t e = per_sm > 0 ? cudaLaunchCooperativeKernel((void*)k_gn_solve, dim3(want), dim3(256), args, 0, s) : cudaErrorLaunchOutOfResources;
+        cudaEventRecord(ev1, s);
+        std::vector<double> cost_log((size_t)P.max_iterations + 1, 0.0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(cost_log.data(), b.cost, sizeof(double) * cost_log.size(), cudaMemcpyDeviceToHost, s);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
             fprintf(stderr, "[fiducials_b200] CUDA error %s in fid_map_refine\n", cudaGetErrorString(e));
             rc = FID_ERR_CUDA;
         } else if (stats) {
             stats->initial_cost = cost_log[0];
-            stats->final_cost = final_cost;
+            stats->final_cost = cost_log[P.max_iterations];
             stats->iterations = P.max_iterations;
-            stats->kernel_launches = P.max_iterations * (3 + 3 * P.pcg_iterations) + 1;
+            stats->kernel_launches = 1;
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, ev0, ev1);
+            stats->solve_ms = ms;
         }
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
     }
+    if (d_off) cudaFree(d_off);
+    if (d_adj) cudaFree(d_adj);
     if (d_edges) cudaFree(d_edges);
     if (d_lin) cudaFree(d_lin);
     if (d_vec) cudaFree(d_vec);

@@ -1,7 +1,7 @@
 // CUDA kernels, threshold stage (sm_100a):
 //   k_gray       BGR8 -> gray (cv::cvtColor BGR2GRAY, 15-bit fixed point); 4 pixels per
 //                thread, 12-byte vector loads / 4-byte store
-//   k_threshold  gray -> n_scales adaptive-threshold planes, written directly as the
+//   k_threshold  frame (BGR8/RGB8/MONO8; cvtColor fused into the load) -> n_scales adaptive-threshold planes, written directly as the
 //                bit-packed halo tiles the border walk reads (contour_walk.cuh, HaloView), plus the
 //                start-crack queues of the border walk (exact local prune) while the tiles are in registers
 //
@@ -84,11 +84,12 @@ __global__ void __launch_bounds__(256) k_gray(const GrayArgs a) {
 #define THR_FAST_R 25                      // r_max of the reference's window set
 
 struct ThreshArgs {
-    const uint8_t* gray;
+    const uint8_t* src;  // the frames as delivered (BGR8 / RGB8 / MONO8): cvtColor is fused into the region load
+    size_t src_row_stride, src_frame_stride;
+    int enc;
+    int aligned4;        // W, the base pointer and both strides are multiples of 4 -> 4-pixel groups with 32-bit loads
     uint32_t* halo;
     int W, H, n_frames;
-    int gray_pitch;
-    size_t gray_frame_stride;
     int halo_tpr, halo_tiles_y;
     size_t halo_scale_stride, halo_frame_stride;
     int n_scales;
@@ -116,50 +117,84 @@ __global__ void __launch_bounds__(THR_THREADS, 2) k_threshold(const ThreshArgs a
     const int X0 = blockIdx.x * THR_OW, Y0 = blockIdx.y * THR_OH;  // first output pixel of the CTA
     const int W = a.W, H = a.H;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint8_t* gray = a.gray + (size_t)f * a.gray_frame_stride;
+    const uint8_t* src = a.src + (size_t)f * a.src_frame_stride;
 
     for (int i = tid; i < SP; i += THR_THREADS) sat[i] = 0;
     for (int i = tid; i <= RH; i += THR_THREADS) sat[i * SP] = 0;
-    // A. gray region (replicate border): region (0,0) = image (X0-1-R, Y0-1-R)
-    const int XA = X0 - 1 - R - 2;  // 4-byte aligned when R = 25 (X0 is a multiple of 120): region column c = word column 4w - 2 + b
-    if (FAST && XA >= 0 && XA + 4 * ((RW + 2 + 3) / 4) <= a.gray_pitch && X0 - 1 - R + RW <= W) {
-        // interior CTA: 32-bit loads, all of a thread's loads in flight before the first use (the byte loop
-        // below exposes the global latency once per row group: "long scoreboard" was the top stall)
-        constexpr int WPR = (THR_OW + 2 + 2 * THR_FAST_R + 2 + 3) / 4;              // 44 words per row
-        constexpr int RHc = THR_OH + 2 + 2 * THR_FAST_R;                              // 112 rows
-        constexpr int PER = (WPR * RHc + THR_THREADS - 1) / THR_THREADS;              // 20 words per thread
-        uint32_t v[PER];
+    // A. gray region (replicate border): region (0,0) = image (X0-1-R, Y0-1-R).  cv::cvtColor BGR2GRAY happens here, on the
+    //    way from global to shared memory: the gray plane is never written to or read back from HBM.
+    const int XA = X0 - 1 - R - 2;  // multiple of 4 when R = 25 (X0 is a multiple of 120): region column c = group column 4w - 2 + b
+    if (FAST && a.aligned4) {
+        // 4-pixel groups, 32-bit loads (3 words of BGR, or 1 word of MONO8), several groups in flight per thread before the first
+        // use.  XA and W are multiples of 4, so a group lies either inside the image or entirely left / right of it: outside
+        // groups replicate the first / last pixel of the clamped group.
+        constexpr int GPR = (THR_OW + 2 + 2 * THR_FAST_R + 2 + 3) / 4;  // 44 groups per row
+        constexpr int RHc = THR_OH + 2 + 2 * THR_FAST_R;                  // 112 rows
+        constexpr int CH = 7;                                             // groups in flight per thread (21 words)
+        const int gx0 = XA >> 2, gmax = (W >> 2) - 1;
+        const bool mono = a.enc == 2, rgb = a.enc == 1;
+#pragma unroll 1
+        for (int base = 0; base < GPR * RHc; base += CH * THR_THREADS) {
+            uint32_t v[CH][3];
 #pragma unroll
-        for (int k = 0; k < PER; k++) {
-            const int u = tid + k * THR_THREADS;
-            const int ry = u / WPR, w = u - ry * WPR;
-            int y = Y0 - 1 - R + ry;
-            y = y < 0 ? 0 : (y > H - 1 ? H - 1 : y);
-            v[k] = u < WPR * RHc ? __ldg(reinterpret_cast<const uint32_t*>(gray + (size_t)y * a.gray_pitch + XA) + w) : 0u;
-        }
+            for (int k = 0; k < CH; k++) {
+                const int u = base + tid + k * THR_THREADS;
+                const int ry = u / GPR, w = u - ry * GPR;
+                int y = Y0 - 1 - R + ry;
+                y = y < 0 ? 0 : (y > H - 1 ? H - 1 : y);
+                int gx = gx0 + w;
+                gx = gx < 0 ? 0 : (gx > gmax ? gmax : gx);
+                const uint8_t* row = src + (size_t)y * a.src_row_stride;
+                if (u < GPR * RHc) {
+                    if (mono) {
+                        v[k][0] = __ldg(reinterpret_cast<const uint32_t*>(row) + gx);
+                    } else {
+                        const uint32_t* q = reinterpret_cast<const uint32_t*>(row) + 3 * gx;
+                        v[k][0] = __ldg(q);
+                        v[k][1] = __ldg(q + 1);
+                        v[k][2] = __ldg(q + 2);
+                    }
+                }
+            }
 #pragma unroll
-        for (int k = 0; k < PER; k++) {
-            const int u = tid + k * THR_THREADS;
-            const int ry = u / WPR, w = u - ry * WPR;
-            if (u < WPR * RHc) {
-                uint32_t* srow = sat + (ry + 1) * SP + 1;
+            for (int k = 0; k < CH; k++) {
+                const int u = base + tid + k * THR_THREADS;
+                const int ry = u / GPR, w = u - ry * GPR;
+                if (u < GPR * RHc) {
+                    uint32_t gr[4];
+                    if (mono) {
 #pragma unroll
-                for (int b = 0; b < 4; b++) {
-                    const int c = 4 * w - 2 + b;
-                    if (c >= 0 && c < RW) srow[c] = (v[k] >> (8 * b)) & 255u;
+                        for (int b = 0; b < 4; b++) gr[b] = (v[k][0] >> (8 * b)) & 255u;
+                    } else {
+                        const uint32_t w0 = v[k][0], w1 = v[k][1], w2 = v[k][2];  // B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3
+                        const uint32_t c0[4] = {w0 & 255u, w0 >> 24, (w1 >> 16) & 255u, (w2 >> 8) & 255u};
+                        const uint32_t c1[4] = {(w0 >> 8) & 255u, w1 & 255u, w1 >> 24, (w2 >> 16) & 255u};
+                        const uint32_t c2[4] = {(w0 >> 16) & 255u, (w1 >> 8) & 255u, w2 & 255u, w2 >> 24};
+#pragma unroll
+                        for (int b = 0; b < 4; b++) gr[b] = rgb ? gray_of_bgr(c2[b], c1[b], c0[b]) : gray_of_bgr(c0[b], c1[b], c2[b]);
+                    }
+                    const int gx = gx0 + w;
+                    if (gx < 0) gr[1] = gr[2] = gr[3] = gr[0];
+                    if (gx > gmax) gr[0] = gr[1] = gr[2] = gr[3];
+                    uint32_t* srow = sat + (ry + 1) * SP + 1;
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const int c = 4 * w - 2 + b;
+                        if (c >= 0 && c < RW) srow[c] = gr[b];
+                    }
                 }
             }
         }
     } else {
+        const FrameImg img{src, a.src_row_stride, a.enc};
         for (int ry = warp; ry < RH; ry += THR_THREADS / 32) {
             int y = Y0 - 1 - R + ry;
             y = y < 0 ? 0 : (y > H - 1 ? H - 1 : y);
-            const uint8_t* grow = gray + (size_t)y * a.gray_pitch;
             uint32_t* srow = sat + (ry + 1) * SP + 1;
             for (int rx = lane; rx < RW; rx += 32) {
                 int x = X0 - 1 - R + rx;
                 x = x < 0 ? 0 : (x > W - 1 ? W - 1 : x);
-                srow[rx] = __ldg(grow + x);
+                srow[rx] = (uint32_t)img.at(x, y);
             }
         }
     }

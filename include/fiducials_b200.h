@@ -301,6 +301,7 @@ typedef struct fid_refine_params {
 } fid_refine_params;
 typedef struct fid_refine_stats {
     double initial_cost, final_cost;
+    double solve_ms; /* device time of the solve kernel (CUDA events on the map's stream) */
     int32_t iterations, n_edges, n_free, kernel_launches;
 } fid_refine_stats;
 int fid_map_refine_default_params(fid_refine_params* p);
