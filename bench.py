@@ -556,7 +556,7 @@ def run_gpu_arm(args):
             pass
         roofline = {
             "bound": "hbm",
-            "kernel": ("k_threshold_mma (BGR->gray + 13 adaptive thresholds on the int8 tensor cores + halo tiles + start cracks, one launch)" if os.environ.get("FID_THRESH") == "mma" else "k_gray + k_threshold<FAST> (threshold stage: gray, summed-area table in shared memory, 13 thresholds, halo tiles + start cracks)"),
+            "kernel": ("k_threshold_mma (BGR->gray + 13 adaptive thresholds on the int8 tensor cores + halo tiles + start cracks, one launch)" if os.environ.get("FID_THRESH") == "mma" else "k_threshold<FAST> (threshold stage in one launch: BGR->gray fused into the region load, summed-area table in shared memory, 13 thresholds, halo tiles + start cracks)"),
             "achieved": achieved,
             "peak": peak,
             "unit": "GB/s",

@@ -477,6 +477,33 @@ static Camera make_camera(const fid_camera* c) {
     return cam;
 }
 
+// Launch with a per-launch scheduling priority (cudaLaunchAttributePriority).  Several chunks are in flight on separate streams;
+// when SM resources free up, the block scheduler serves the pending kernel with the highest priority first.  The later a stage
+// sits in a chunk's chain, the higher its priority: the latency-bound tail kernels (last walk rounds, grouping, identification,
+// pose) then slip into the gaps of the issue-bound bulk kernels (threshold, first walk rounds) of younger chunks instead of
+// queueing behind their thousands of blocks.  level: 0 = bulk ... 3 = tail.
+static int g_prio_lo = 0, g_prio_hi = 0, g_prio_mode = -1;
+template <typename... KArgs, typename... Args>
+static inline void launch_prio(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, int level, Args&&... args) {
+    if (g_prio_mode < 0) {
+        const char* e = getenv("FID_PRIO");
+        g_prio_mode = e ? atoi(e) : 1;
+        cudaDeviceGetStreamPriorityRange(&g_prio_lo, &g_prio_hi);  // lo = least (numerically largest), hi = greatest
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributePriority;
+    at[0].val.priority = g_prio_mode ? std::max(g_prio_hi, g_prio_lo - level) : g_prio_lo;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+
 // Enqueue the whole pipeline for `nf` frames resident in d_bgr (geometry g) on stream `st`.
 static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, const FrameGeom& g, const uint8_t* d_bgr, const fid_camera* cam, double fiducial_len,
                             int n_override, int stop_after /* -1 = all */, const Slot* prev = nullptr) {
@@ -568,9 +595,9 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
             for (int i = 0; i < P.n_scales; i++) a.win[i] = P.win[i];
             dim3 grid((g.halo_tpr + THR_TILES_X - 1) / THR_TILES_X, (g.halo_tiles_y + THR_TILES_Y - 1) / THR_TILES_Y, nf);
             if (fast)
-                k_threshold<true><<<grid, THR_THREADS, thresh_smem_bytes(THR_FAST_R), st>>>(a);
+                launch_prio(k_threshold<true>, grid, dim3(THR_THREADS), thresh_smem_bytes(THR_FAST_R), st, 0, a);
             else
-                k_threshold<false><<<grid, THR_THREADS, thresh_smem_bytes(a.r_max), st>>>(a);
+                launch_prio(k_threshold<false>, grid, dim3(THR_THREADS), thresh_smem_bytes(a.r_max), st, 0, a);
             launches++;
         }
     }
@@ -609,7 +636,7 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
             a.refill_min = h->walk_refill;
             a.pass_steps = h->walk_pass;
             const int blocks = r == 0 ? h->sm_count * 8 : (r == 1 ? h->sm_count * 8 : h->sm_count * 4);
-            k_walk<<<blocks, 256, 0, st>>>(a);
+            launch_prio(k_walk, dim3(blocks), dim3(256), 0, st, r == 0 ? 1 : (r == 1 ? 2 : 3), a);
             launches++;
         }
         CK(cudaEventRecord(s.ev_round[N_WALK_ROUNDS], st));
@@ -626,7 +653,7 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
         a.work_counter = &s.d_counters->emit_work;
         a.max_segs = h->max_segs;
         a.g = g;
-        k_emit<<<h->sm_count * h->emit_blocks_per_sm, 64, 0, st>>>(a);
+        launch_prio(k_emit, dim3(h->sm_count * h->emit_blocks_per_sm), dim3(64), 0, st, 3, a);
         launches++;
     }
     CK(cudaEventRecord(s.ev[ST_APPROX], st));
@@ -644,9 +671,9 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
         a.H = H;
         a.poly_accuracy_rate = P.poly_accuracy_rate;
         a.min_corner_dist_rate = P.min_corner_dist_rate;
-        k_approx_warp<<<h->sm_count * 8, APPROX_THREADS, 0, st>>>(a);
+        launch_prio(k_approx_warp, dim3(h->sm_count * 8), dim3(APPROX_THREADS), 0, st, 3, a);
         launches++;
-        k_approx<<<h->sm_count * 4, APPROX_THREADS, 0, st>>>(a);
+        launch_prio(k_approx, dim3(h->sm_count * 4), dim3(APPROX_THREADS), 0, st, 3, a);
         launches++;
     }
     CK(cudaEventRecord(s.ev[ST_GROUP], st));
@@ -669,7 +696,7 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
         a.H = H;
         a.min_dist_to_border = P.min_dist_to_border;
         a.counters = s.d_counters;
-        k_sort_group<<<nf, GROUP_THREADS, group_smem(h->max_raw), st>>>(a);
+        launch_prio(k_sort_group, dim3(nf), dim3(GROUP_THREADS), group_smem(h->max_raw), st, 4, a);
         launches++;
     }
     CK(cudaEventRecord(s.ev[ST_IDENT], st));
@@ -690,7 +717,7 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
         a.cand_id = s.d_cand_id;
         a.cand_corners = s.d_cand_corners;
         dim3 grid(h->max_sel, nf);
-        k_identify<<<grid, IDENT_WARPS * 32, ident_smem(P), st>>>(a);
+        launch_prio(k_identify, grid, dim3(IDENT_WARPS * 32), ident_smem(P), st, 4, a);
         launches++;
     }
     CK(cudaEventRecord(s.ev[ST_SUBPIX_POSE], st));
@@ -722,7 +749,7 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
         a.out_corners = s.d_out_corners;
         a.out_tf = s.d_out_tf;
         a.counters = s.d_counters;
-        k_finish<<<nf, FINISH_THREADS, 0, st>>>(a);
+        launch_prio(k_finish, dim3(nf), dim3(FINISH_THREADS), 0, st, 5, a);
         launches++;
     }
     CK(cudaEventRecord(s.ev[ST_D2H], st));
