@@ -115,6 +115,7 @@ EXPORTS = [
     "fid_debug_candidates", "fid_last_stage_ms", "fid_last_counters", "fid_map_default_params", "fid_map_create", "fid_map_destroy", "fid_map_clear",
     "fid_map_load", "fid_map_links", "fid_map_add_links", "fid_map_update", "fid_map_update_sequence", "fid_map_update_frames", "fid_map_update_frames_async", "fid_map_sync", "fid_map_entries", "fid_map_export", "fid_map_merge", "fid_map_export_device",
     "fid_map_merge_device", "fid_map_merge_device_async", "fid_map_export_async", "fid_map_stream", "fid_map_merged_entries", "fid_map_adopt_merged", "fid_map_add_fiducial", "fid_map_refine_default_params", "fid_map_refine",
+    "fid_jpeg_create", "fid_jpeg_destroy", "fid_jpeg_decode_batch", "fid_jpeg_sync", "fid_jpeg_stream", "fid_jpeg_last_stats",
 ]
 
 _lib = None
@@ -180,6 +181,12 @@ def load():
     lib.fid_map_add_fiducial.argtypes = [vp, i32, i32, C.POINTER(fid_tf)]
     lib.fid_map_refine_default_params.argtypes = [C.POINTER(fid_refine_params)]
     lib.fid_map_refine.argtypes = [vp, i32, i32, vp, vp, C.POINTER(fid_refine_params), C.POINTER(fid_refine_stats)]
+    lib.fid_jpeg_create.argtypes = [i32, i32, i32, i32, i32, C.POINTER(vp)]
+    lib.fid_jpeg_destroy.argtypes = [vp]
+    lib.fid_jpeg_decode_batch.argtypes = [vp, i32, vp, vp, i32, i32, vp, sz, sz, vp]
+    lib.fid_jpeg_sync.argtypes = [vp]
+    lib.fid_jpeg_stream.argtypes = [vp, C.POINTER(vp)]
+    lib.fid_jpeg_last_stats.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     for name in EXPORTS:
         getattr(lib, name)  # AttributeError if the build lost a symbol
     _lib = lib

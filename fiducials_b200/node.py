@@ -626,3 +626,49 @@ def _set_rpy(roll, pitch, yaw):  # tf2::Matrix3x3::setRPY
     si, sj, sh = math.sin(roll), math.sin(pitch), math.sin(yaw)
     cc, cs, sc, ss = ci * ch, ci * sh, si * ch, si * sh
     return np.array([[cj * ch, sj * sc - cs, sj * cc + ss], [cj * sh, sj * ss + cc, sj * cs - sc], [-sj, cj * si, cj * ci]])
+
+
+class JpegDecoder:
+    """fid_jpeg_*: the cv::imdecode that compressed_image_transport runs in front of imageCallback (aruco_detect.cpp:332,348;
+    launch default transport `compressed`), with the Huffman stage on host threads and everything after it on the device.
+    decode(list of bytes-like JPEG streams, device pointer) writes BGR8 frames into device memory
+    (FiducialsNode.detector_device_alloc / fid_device_alloc) for submit_batch(..., on_device=True)."""
+
+    def __init__(self, max_width, max_height, max_batch, device=0, n_threads=0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self.lib.fid_jpeg_create(device, max_width, max_height, max_batch, n_threads, C.byref(h)), "fid_jpeg_create")
+        self.h = h
+
+    def decode(self, streams, device_ptr, width, height, row_stride=None, frame_stride=None, sync=True):
+        n = len(streams)
+        bufs = [np.frombuffer(bytes(s) if not isinstance(s, np.ndarray) else s, np.uint8) for s in streams]
+        ptrs = (C.c_void_p * n)(*[b.ctypes.data for b in bufs])
+        sizes = (C.c_size_t * n)(*[b.size for b in bufs])
+        status = np.zeros(n, np.int32)
+        rs = row_stride or width * 3
+        fs = frame_stride or rs * height
+        _lib.check(self.lib.fid_jpeg_decode_batch(self.h, n, ptrs, sizes, width, height, C.c_void_p(int(device_ptr)), rs, fs, status.ctypes.data_as(C.c_void_p)), "fid_jpeg_decode_batch")
+        self._keep = bufs
+        if sync:
+            self.sync()
+        return status
+
+    def sync(self):
+        _lib.check(self.lib.fid_jpeg_sync(self.h))
+
+    def stats(self):
+        a, b, c = C.c_double(0), C.c_double(0), C.c_double(0)
+        _lib.check(self.lib.fid_jpeg_last_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"host_decode_ms": a.value, "h2d_bytes": b.value, "device_ms": c.value}
+
+    def close(self):
+        if self.h:
+            self.lib.fid_jpeg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -340,6 +340,30 @@ int fid_map_merged_entries(fid_map* m, int max_entries, int* n, fid_map_entry* e
 /* Replace an instance's fiducials by the merged view (explicit; its links are cleared). */
 int fid_map_adopt_merged(fid_map* m, int instance);
 
+/* ------------------------------------------------------------------------------------------------
+ * JPEG ingest (NEW).  Replaces the cv::imdecode that compressed_image_transport runs in front of
+ * FiducialsNode::imageCallback (aruco_detect.cpp:332,348; default transport `compressed`,
+ * aruco_detect/launch/aruco_detect.launch:6,28).  The Huffman bit stream of every image is decoded on host threads
+ * (one image per thread); the sparse quantised coefficients (typically 4-6x smaller than the frame) cross PCIe and the
+ * device performs dequantisation, the integer inverse DCT, chroma upsampling and the colour conversion, writing BGR8
+ * frames into `device_bgr` -- the buffer fid_submit_batch / fid_detect_pose_batch take with bgr_on_device = 1.
+ * Bit-exact against cv2.imdecode (libjpeg-turbo defaults).  Supported: baseline / extended-sequential 8-bit Huffman JPEG,
+ * grey or YCbCr 4:4:4 / 4:2:2 / 4:2:0, restart intervals; other streams get status FID_ERR_UNSUPPORTED (decode those with
+ * the host library and upload them as frames).  No CPU fallback: fid_jpeg_create fails with FID_ERR_NO_DEVICE.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct fid_jpeg fid_jpeg;
+int fid_jpeg_create(int device, int max_width, int max_height, int max_batch, int n_threads /* 0 = one per hardware thread, at most 64 */, fid_jpeg** out);
+int fid_jpeg_destroy(fid_jpeg* j);
+/* n images, all width x height and of one sampling layout.  status[i] (optional) = FID_OK or the reason image i was skipped (its
+ * frame is left untouched).  Returns once the device work is ENQUEUED on the decoder's stream (fid_jpeg_stream); fid_jpeg_sync
+ * waits for it.  The call itself returns an error only when no image of the batch could be decoded. */
+int fid_jpeg_decode_batch(fid_jpeg* j, int n, const uint8_t* const* data, const size_t* bytes, int width, int height, void* device_bgr, size_t row_stride,
+                          size_t frame_stride, int32_t* status);
+int fid_jpeg_sync(fid_jpeg* j);
+int fid_jpeg_stream(fid_jpeg* j, void** cuda_stream);
+/* last batch: wall time of the host entropy decoding, bytes copied to the device, device time (copies + kernels) */
+int fid_jpeg_last_stats(fid_jpeg* j, double* host_decode_ms, double* h2d_bytes, double* device_ms);
+
 #ifdef __cplusplus
 }
 #endif

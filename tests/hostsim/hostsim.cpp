@@ -20,6 +20,8 @@
 #include "../../fiducials_b200/csrc/pnp.cuh"
 #include "../../fiducials_b200/csrc/slam.cuh"
 #include "../../fiducials_b200/csrc/params_host.h"
+#include "../../fiducials_b200/csrc/jpeg_host.hpp"
+#include "../../fiducials_b200/csrc/jpeg_math.cuh"
 
 using namespace fid;
 
@@ -654,6 +656,57 @@ int hs_map_entries(void* h, double* out) {
         o[8] = e.num_obs;
     }
     return m->st.n;
+}
+
+
+// JPEG ingest: host entropy decoder (jpeg_host.hpp) + the device arithmetic (jpeg_math.cuh) in serial loops.
+// Returns 0 and fills bgr[H][W][3] / dims, or the decoder's negative status.
+int hs_jpeg_decode(const uint8_t* data, long long size, uint8_t* bgr, int max_w, int max_h, int* out_w, int* out_h, long long* n_vals) {
+    using namespace fidjpeg;
+    FrameInfo fi;
+    const size_t max_blk = (size_t)((max_w + 15) / 8 + 2) * ((max_h + 15) / 8 + 2) * 3;
+    std::vector<uint64_t> mask(max_blk);
+    std::vector<uint32_t> off(max_blk);
+    std::vector<int16_t> vals(max_blk * 64);
+    size_t nv = 0;
+    const int rc = decode_image(data, (size_t)size, &fi, mask.data(), off.data(), vals.data(), vals.size(), max_blk, &nv);
+    if (rc != JPEG_OK) return rc;
+    if (fi.W > max_w || fi.H > max_h) return JPEG_CAPACITY;
+    *out_w = fi.W;
+    *out_h = fi.H;
+    *n_vals = (long long)nv;
+    std::vector<std::vector<uint8_t>> plane(fi.ncomp);
+    for (int c = 0; c < fi.ncomp; c++) {
+        const int pitch = fi.bw[c] * 8;
+        plane[c].assign((size_t)pitch * fi.bh[c] * 8, 0);
+        for (int by = 0; by < fi.bh[c]; by++)
+            for (int bx = 0; bx < fi.bw[c]; bx++) {
+                const int b = fi.blk_base[c] + by * fi.bw[c] + bx;
+                int coef[64];
+                for (int i = 0; i < 64; i++) coef[i] = 0;
+                uint64_t m = mask[b];
+                const int16_t* v = vals.data() + off[b];
+                for (int k = 0; k < 64; k++)
+                    if ((m >> k) & 1) coef[kZigzag[k]] = (int)(*v++) * (int)fi.q[c][k];
+                uint8_t out[64];
+                jpeg_idct_block(coef, out);
+                for (int r = 0; r < 8; r++) memcpy(&plane[c][(size_t)(by * 8 + r) * pitch + bx * 8], out + r * 8, 8);
+            }
+    }
+    const int mode = fi.ncomp == 1 ? 0 : (fi.hmax == 1 ? 0 : (fi.vmax == 1 ? 1 : 2));
+    for (int y = 0; y < fi.H; y++)
+        for (int x = 0; x < fi.W; x++) {
+            uint8_t* o = bgr + ((size_t)y * fi.W + x) * 3;
+            const int Y = plane[0][(size_t)y * fi.bw[0] * 8 + x];
+            if (fi.ncomp == 1) {
+                o[0] = o[1] = o[2] = (uint8_t)Y;
+            } else {
+                const int cb = jpeg_chroma_at(plane[1].data(), fi.bw[1] * 8, fi.cw[1], fi.ch[1], mode, x, y);
+                const int cr = jpeg_chroma_at(plane[2].data(), fi.bw[2] * 8, fi.cw[2], fi.ch[2], mode, x, y);
+                jpeg_ycc_to_bgr(Y, cb, cr, o);
+            }
+        }
+    return 0;
 }
 
 }  // extern "C"
