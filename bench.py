@@ -88,6 +88,21 @@ def cpu_info():
     return model or "unknown", (len(phys) or None), os.cpu_count()
 
 
+def cpu_quota_cores():
+    """CPU time the container may use, in cores (cgroup v2 cpu.max / v1 cfs quota); None = unlimited."""
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        return None if q == "max" else float(q) / float(per)
+    except Exception:
+        pass
+    try:
+        q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        return None if q <= 0 else q / per
+    except Exception:
+        return None
+
+
 def pin_to_gpu_numa_node(index):
     """Best effort: run this rank on the cores of its GPU's NUMA node (pinned staging buffers are then first-touched there)."""
     try:
@@ -296,7 +311,7 @@ class CpuArm:
             "kind": "reference",
             "cpu_model": model,
             "physical_cores": phys,
-            "logical_cpus": logical,
+            "logical_cpus": logical, "cgroup_cpu_quota_cores": cpu_quota_cores(),
             "sample": "cv2 %s ArucoDetector(reference params)+solvePnP+projectPoints on %d frames of the %s stream (one per marker layout: frames [::%d] of rank 0's step): "
                       "reference mode (1 proc, %d OpenCV threads) %d frames %.2f fps; throughput mode (%d procs x 1 thread) %d frames %.2f fps [%s]; value = best of all; "
                       "host: %s, %s physical cores, %d logical cpus"
@@ -652,7 +667,7 @@ def run_c5(args, reference):
         val = n_obs / dt
         out = {"impl": "reference", "metric": metric, "value": val, "unit": "observations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload},
-               "cpu_baseline": {"value": val, "unit": "observations/s", "cores": 1, "kind": "port", "cpu_model": model, "physical_cores": phys, "logical_cpus": logical,
+               "cpu_baseline": {"value": val, "unit": "observations/s", "cores": 1, "kind": "port", "cpu_model": model, "physical_cores": phys, "logical_cpus": logical, "cgroup_cpu_quota_cores": cpu_quota_cores(),
                                 "sample": "the whole sequence through oracle/_ref/libslam_oracle.so (map.cpp / transform_with_variance.cpp restated, g++ -O2), one core"},
                "e2e": {"value": val, "unit": "observations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(out)
@@ -743,7 +758,7 @@ def run_c5(args, reference):
                "config": {"workload": workload, "parallelism": "replicas only: every rank folds its own copy of the sequence (the fold is sequential per map)", "map_fiducials": len(ents)},
                "e2e": {"value": val, "unit": "observations/s", "h2d_bytes_per_step": int(obs.nbytes + offsets.nbytes), "d2h_bytes_per_step": 0, "note": "value already includes the H2D of the observations"},
                "gpu_launches": args.steps, "parity": {"max_entry_diff_vs_host_fold": worst, "entries": len(ents)}, "batch_gauss_newton_refine": refine,
-               "cpu_baseline": {"value": n_obs / cpu_dt, "unit": "observations/s", "cores": 1, "kind": "port", "cpu_model": model, "physical_cores": phys, "logical_cpus": logical,
+               "cpu_baseline": {"value": n_obs / cpu_dt, "unit": "observations/s", "cores": 1, "kind": "port", "cpu_model": model, "physical_cores": phys, "logical_cpus": logical, "cgroup_cpu_quota_cores": cpu_quota_cores(),
                                 "sample": "the whole sequence through oracle/_ref/libslam_oracle.so, one core, %.2f ms" % (cpu_dt * 1e3)},
                "roofline": {"bound": "latency", "note": "sequential scalar-variance fold (SURVEY 8d): no roofline fraction is meaningful; report observations/s and ms per sequence"}}
         emit(out)

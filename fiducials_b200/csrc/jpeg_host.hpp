@@ -34,11 +34,14 @@ struct FrameInfo {
     uint16_t q[3][64];       // quantisation tables per component, ZIG-ZAG order (as stored in the file)
 };
 
+#define FIDJPEG_LOOK 10  // look-ahead bits of the symbol tables
+
 struct HuffTable {
     bool present = false;
     uint8_t vals[256];
     int mincode[17], maxcode[18], valptr[17];
-    uint16_t look[512];  // 9-bit look-ahead: (length << 8) | symbol, 0 = longer code
+    uint16_t look[1 << FIDJPEG_LOOK];    // (length << 8) | symbol, 0 = code longer than the look-ahead
+    int32_t fast_ac[1 << FIDJPEG_LOOK];  // AC tables: code AND magnitude bits inside the look-ahead -> value * 256 + run * 16 + total bits, else 0
 
     void build(const uint8_t bits[17], const uint8_t* symbols, int nsym) {
         memcpy(vals, symbols, nsym);
@@ -48,15 +51,25 @@ struct HuffTable {
             mincode[l] = code;
             valptr[l] = k;
             for (int i = 0; i < bits[l]; i++, k++, code++) {
-                if (l <= 9) {
-                    const int first = code << (9 - l), n = 1 << (9 - l);
-                    for (int j = 0; j < n && first + j < 512; j++) look[first + j] = (uint16_t)((l << 8) | vals[k]);
+                if (l <= FIDJPEG_LOOK) {
+                    const int first = code << (FIDJPEG_LOOK - l), n = 1 << (FIDJPEG_LOOK - l);
+                    for (int j = 0; j < n && first + j < (1 << FIDJPEG_LOOK); j++) look[first + j] = (uint16_t)((l << 8) | vals[k]);
                 }
             }
             maxcode[l] = bits[l] ? code - 1 : -1;
             code <<= 1;
         }
         maxcode[17] = 0x7fffffff;
+        for (int i = 0; i < (1 << FIDJPEG_LOOK); i++) {
+            fast_ac[i] = 0;
+            const int e = look[i];
+            if (!e) continue;
+            const int l = e >> 8, rs = e & 255, run = rs >> 4, mag = rs & 15;
+            if (mag == 0 || l + mag > FIDJPEG_LOOK) continue;
+            int v = ((i << l) & ((1 << FIDJPEG_LOOK) - 1)) >> (FIDJPEG_LOOK - mag);
+            if (v < (1 << (mag - 1))) v -= (1 << mag) - 1;
+            fast_ac[i] = v * 256 + run * 16 + (l + mag);  // |v| < 512: fits with room to spare
+        }
         present = true;
     }
 };
@@ -68,6 +81,19 @@ struct BitReader {
     int cnt = 0;
 
     inline void refill() {
+        if (p + 8 <= end) {  // fast path: none of the next 8 bytes is 0xFF -> take as many whole bytes as fit
+            uint64_t v;
+            memcpy(&v, p, 8);
+            if (!(((~v) - 0x0101010101010101ull) & v & 0x8080808080808080ull)) {
+                const int k = (64 - cnt) >> 3, nb = k * 8;
+                const uint64_t be = __builtin_bswap64(v);
+                const uint64_t chunk = nb == 64 ? be : (be >> (64 - nb)) << (64 - nb);
+                acc |= cnt ? chunk >> cnt : chunk;
+                cnt += nb;
+                p += k;
+                return;
+            }
+        }
         while (cnt <= 56) {
             uint32_t b = 0;
             if (p < end) {
@@ -90,14 +116,14 @@ struct BitReader {
         acc <<= n;
         cnt -= n;
     }
-    inline int decode(const HuffTable& t) {
-        if (cnt < 32) refill();
-        const uint16_t e = t.look[acc >> 55];
+    // caller guarantees cnt >= 16 (refill() beforehand)
+    inline int decode_nofill(const HuffTable& t) {
+        const uint16_t e = t.look[acc >> (64 - FIDJPEG_LOOK)];
         if (e) {
             consume(e >> 8);
             return e & 255;
         }
-        for (int l = 10; l <= 16; l++) {
+        for (int l = FIDJPEG_LOOK + 1; l <= 16; l++) {
             const int code = (int)(acc >> (64 - l));
             if (code <= t.maxcode[l]) {
                 consume(l);
@@ -106,12 +132,20 @@ struct BitReader {
         }
         return -1;
     }
-    inline int receive_extend(int s) {
+    inline int decode(const HuffTable& t) {
         if (cnt < 32) refill();
+        return decode_nofill(t);
+    }
+    // caller guarantees cnt >= s
+    inline int receive_extend_nofill(int s) {
         int v = (int)(acc >> (64 - s));
         consume(s);
         if (v < (1 << (s - 1))) v -= (1 << s) - 1;
         return v;
+    }
+    inline int receive_extend(int s) {
+        if (cnt < 32) refill();
+        return receive_extend_nofill(s);
     }
     // restart: drop the padding bits, step over RSTn
     inline bool restart() {
@@ -283,7 +317,18 @@ static inline int decode_image(const uint8_t* data, size_t size, FrameInfo* fi, 
                             vals[nv++] = (int16_t)pred[c];
                         }
                         for (int k = 1; k < 64;) {
-                            const int rs = br.decode(tac);
+                            if (br.cnt < 32) br.refill();  // one refill per coefficient: code (<= 16) + magnitude (<= 10) bits
+                            const int32_t fa = tac.fast_ac[br.acc >> (64 - FIDJPEG_LOOK)];
+                            if (fa) {  // code and magnitude inside the look-ahead
+                                k += (fa >> 4) & 15;
+                                if (k > 63) return JPEG_BAD;
+                                br.consume(fa & 15);
+                                m |= 1ull << k;
+                                vals[nv++] = (int16_t)(fa >> 8);
+                                k++;
+                                continue;
+                            }
+                            const int rs = br.decode_nofill(tac);
                             if (rs < 0) return JPEG_BAD;
                             const int r = rs >> 4;
                             s = rs & 15;
@@ -296,7 +341,7 @@ static inline int decode_image(const uint8_t* data, size_t size, FrameInfo* fi, 
                             }
                             k += r;
                             if (k > 63) return JPEG_BAD;
-                            const int val = br.receive_extend(s);
+                            const int val = br.receive_extend_nofill(s);
                             m |= 1ull << k;
                             vals[nv++] = (int16_t)val;
                             k++;

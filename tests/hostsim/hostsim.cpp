@@ -709,4 +709,21 @@ int hs_jpeg_decode(const uint8_t* data, long long size, uint8_t* bgr, int max_w,
     return 0;
 }
 
+
+// entropy stage alone, `reps` times (tools/time_jpeg_entropy.py): returns the number of values of the last pass or a negative status
+long long hs_jpeg_entropy(const uint8_t* data, long long size, int reps) {
+    using namespace fidjpeg;
+    FrameInfo fi;
+    const size_t max_blk = (size_t)(4096 / 8 + 2) * (4096 / 8 + 2) * 3;
+    static std::vector<uint64_t> mask(max_blk);
+    static std::vector<uint32_t> off(max_blk);
+    static std::vector<int16_t> vals(max_blk * 64);
+    size_t nv = 0;
+    for (int r = 0; r < reps; r++) {
+        const int rc = decode_image(data, (size_t)size, &fi, mask.data(), off.data(), vals.data(), vals.size(), max_blk, &nv);
+        if (rc != JPEG_OK) return rc;
+    }
+    return (long long)nv;
+}
+
 }  // extern "C"
