@@ -48,6 +48,7 @@ struct Slot {
     int* d_nrawc = nullptr;
     int* d_cand_id = nullptr;
     float* d_cand_corners = nullptr;
+    int* d_cand_raw = nullptr;
     int32_t* d_out_count = nullptr;
     int32_t* d_out_ids = nullptr;
     float* d_out_corners = nullptr;
@@ -258,10 +259,12 @@ static int alloc_slot(fid_detector* h, Slot& s) {
     A(dalloc(&s.fs.close_off, R));
     A(dalloc(&s.fs.selected, R));
     A(dalloc(&s.fs.sel_idx, R));
+    A(dalloc(&s.fs.raw_of_sorted, R));
     A(dalloc(&s.d_nsel, F));
     A(dalloc(&s.d_nrawc, F));
     A(dalloc(&s.d_cand_id, F * h->max_sel));
     A(dalloc(&s.d_cand_corners, F * h->max_sel * 8));
+    A(dalloc(&s.d_cand_raw, F * h->max_sel));
     const size_t M = F * h->max_markers;
     A(dalloc(&s.d_out_count, F));
     A(dalloc(&s.d_out_ids, M));
@@ -287,7 +290,7 @@ static void free_slot(Slot& s) {
                      s.d_raw,         s.d_nraw,          s.fs.quads_tmp,    s.fs.per_tmp,     s.fs.quads,       s.fs.per,         s.fs.close_bits, s.fs.group_id,
                      s.fs.group_members, s.fs.next_in_group, s.fs.group_head, s.fs.group_tail, s.fs.close_count, s.fs.close_idx,   s.fs.close_off,  s.fs.selected,
                      s.fs.sel_idx,    s.d_nsel,          s.d_nrawc,         s.d_cand_id,      s.d_cand_corners, s.d_out_count,    s.d_out_ids,     s.d_out_corners,
-                     s.d_out_tf};
+                     s.d_out_tf,      s.fs.raw_of_sorted, s.d_cand_raw};
     for (void* p : dptrs)
         if (p) cudaFree(p);
     void* hptrs[] = {s.h_out_count, s.h_out_ids, s.h_out_corners, s.h_out_tf, s.h_counters, s.h_nsel, s.h_nrawc};
@@ -716,6 +719,7 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
         a.dict = h->d_dict;
         a.cand_id = s.d_cand_id;
         a.cand_corners = s.d_cand_corners;
+        a.cand_raw = s.d_cand_raw;
         dim3 grid(h->max_sel, nf);
         launch_prio(k_identify, grid, dim3(IDENT_WARPS * 32), ident_smem(P), st, 4, a);
         launches++;
@@ -732,6 +736,9 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
         a.n_sel = s.d_nsel;
         a.cand_id = s.d_cand_id;
         a.cand_corners = s.d_cand_corners;
+        a.cand_raw = s.d_cand_raw;
+        a.raw = s.d_raw;
+        a.points = s.d_points;
         a.fs = s.fs;
         a.max_raw = h->max_raw;
         a.max_sel = h->max_sel;

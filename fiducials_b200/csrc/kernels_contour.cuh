@@ -435,6 +435,7 @@ __device__ __forceinline__ void approx_emit_quad(const ApproxArgs& a, const Chai
             r.y[k] = q[k].y;
         }
         r.n_contour = (int)c.n;
+        r.pts_off = c.offset;
         r.order_hi = (uint32_t)s;
         const uint32_t x = c.xy & 0xFFFF, y = c.xy >> 16;
         r.order_lo = 0xFFFFFFFFu - ((y * (uint32_t)a.W + x) * 2u + (uint32_t)is_right);

@@ -86,6 +86,13 @@ class FiducialsNode {
     FiducialsNode(const FiducialsNode&) = delete;
     FiducialsNode& operator=(const FiducialsNode&) = delete;
 
+    // configCallback, aruco_detect.cpp:257-298: the dynamic_reconfigure fields map one to one onto fid_params; the two booleans
+    // select the corner refinement method as the reference does (:274-281, same rule at start-up :700-711)
+    void configCallback(fid_params p, bool doCornerRefinement, bool cornerRefinementSubpix) {
+        p.cornerRefinementMethod = doCornerRefinement ? (cornerRefinementSubpix ? 1 /* SUBPIX */ : 2 /* CONTOUR */) : 0 /* NONE */;
+        check(fid_set_params(det, &p), "fid_set_params");
+    }
+
     // camInfoCallback, aruco_detect.cpp:307-330
     void camInfoCallback(const double K[9], const double* D, int nD, const std::string& frame_id) {
         if (haveCamInfo) return;

@@ -70,7 +70,7 @@ inline int make_dev_params(const fid_params& p, DevParams* dp) {
     dp->max_err_border_rate = p.maxErroneousBitsInBorderRate;
     dp->min_otsu_stddev = p.minOtsuStdDev;
     dp->error_correction_rate = p.errorCorrectionRate;
-    if (p.cornerRefinementMethod != 0 && p.cornerRefinementMethod != 1) return FID_ERR_UNSUPPORTED;
+    if (p.cornerRefinementMethod < 0 || p.cornerRefinementMethod > 2) return FID_ERR_UNSUPPORTED;  // NONE, SUBPIX, CONTOUR (APRILTAG: not in the reference)
     dp->corner_refine = p.cornerRefinementMethod;
     dp->refine_win = p.cornerRefinementWinSize;
     dp->refine_max_iter = p.cornerRefinementMaxIterations;
@@ -85,7 +85,7 @@ inline int make_dev_params(const fid_params& p, DevParams* dp) {
     if (p.markerBorderBits < 1 || p.perspectiveRemovePixelPerCell < 1) return FID_ERR_INVALID_ARG;
     const int cells = dp->marker_size + 2 * dp->marker_border_bits;
     if (cells * dp->px_per_cell > FID_MAX_WARP_SIDE || cells * cells > 128 || dp->marker_size * dp->marker_size > 64) return FID_ERR_UNSUPPORTED;
-    if (dp->corner_refine && (dp->refine_win < 1 || dp->refine_win > 5 || dp->refine_max_iter < 1 || !(dp->refine_min_acc > 0))) return FID_ERR_UNSUPPORTED;
+    if (dp->corner_refine == 1 && (dp->refine_win < 1 || dp->refine_win > 5 || dp->refine_max_iter < 1 || !(dp->refine_min_acc > 0))) return FID_ERR_UNSUPPORTED;
     return FID_OK;
 }
 

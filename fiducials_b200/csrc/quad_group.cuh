@@ -43,6 +43,7 @@ struct RawQuad {
     int32_t n_contour;   // contour length (points)
     uint32_t order_hi;   // scale index
     uint32_t order_lo;   // 0xFFFFFFFF - (2*raster(start)+is_hole): ascending == OpenCV's list order
+    uint32_t pts_off;    // the contour's points (findContours order) in the batch point buffer: CORNER_REFINE_CONTOUR fits lines to them
 };
 
 // _reorderCandidatesCorners: make the quad clockwise.

@@ -203,7 +203,9 @@ class FiducialsNode:
     """aruco_detect's node, minus ROS transport."""
 
     def __init__(self, dictionary=7, fiducial_len=0.14, ignore_fiducials: Iterable[int] = (), fiducial_len_override: Optional[Dict[int, float]] = None,
-                 do_pose_estimation=True, device=0, max_width=1920, max_height=1080, max_batch=1, **detector_params):
+                 do_pose_estimation=True, device=0, max_width=1920, max_height=1080, max_batch=1, doCornerRefinement=True, cornerRefinementSubPix=True, **detector_params):
+        # doCornerRefinement / cornerRefinementSubPix -> cornerRefinementMethod NONE / SUBPIX / CONTOUR (:700-711, configCallback :274-281)
+        detector_params.setdefault("cornerRefinementMethod", (1 if cornerRefinementSubPix else 2) if doCornerRefinement else 0)
         self.fiducial_len = float(fiducial_len)  # :615
         self.doPoseEstimation = do_pose_estimation  # :614
         self.ignoreIds = set(int(i) for i in ignore_fiducials)  # :540-571

@@ -49,7 +49,7 @@ typedef struct fid_params {
     int32_t cornerRefinementMaxIterations;     /* 30     (:694) */
     double cornerRefinementMinAccuracy;        /* 0.01   (:695) */
     int32_t cornerRefinementWinSize;           /* 5      (:696) */
-    int32_t cornerRefinementMethod;            /* 0 NONE, 1 SUBPIX (default, :700-711); CONTOUR unsupported */
+    int32_t cornerRefinementMethod;            /* 0 NONE, 1 SUBPIX (default), 2 CONTOUR (doCornerRefinement / cornerRefinementSubPix, :700-711) */
     double errorCorrectionRate;                /* 0.6    (:716) */
     double minCornerDistanceRate;              /* 0.05   (:717) */
     int32_t markerBorderBits;                  /* 1      (:718) */

@@ -17,6 +17,7 @@
 #include "../../fiducials_b200/csrc/quad_group.cuh"
 #include "../../fiducials_b200/csrc/identify.cuh"
 #include "../../fiducials_b200/csrc/subpix.cuh"
+#include "../../fiducials_b200/csrc/contour_refine.cuh"
 #include "../../fiducials_b200/csrc/pnp.cuh"
 #include "../../fiducials_b200/csrc/slam.cuh"
 #include "../../fiducials_b200/csrc/params_host.h"
@@ -372,7 +373,7 @@ int hs_is_convex(const int16_t* pts, int n) { return is_convex_int(reinterpret_c
 
 // Raw quad candidates of all scales from precomputed threshold planes (n_scales x H x W, {0,!=0}),
 // in OpenCV's concatenation order.  quads: n x 8 int32 (x0,y0,..), scale[n], clen[n].
-static void raw_candidates(const uint8_t* planes, int W, int H, const DevParams& P, std::vector<RawQuad>& out) {
+static void raw_candidates(const uint8_t* planes, int W, int H, const DevParams& P, std::vector<RawQuad>& out, std::vector<Pt16>* keep_pts = nullptr) {
     const int mx = W > H ? W : H;
     const int min_len = (int)(P.min_perimeter_rate * mx), max_len = (int)(P.max_perimeter_rate * mx);
     for (int s = 0; s < P.n_scales; s++) {
@@ -400,6 +401,11 @@ static void raw_candidates(const uint8_t* planes, int W, int H, const DevParams&
                 r.y[k] = q[k].y;
             }
             r.n_contour = n;
+            r.pts_off = 0;
+            if (keep_pts) {
+                r.pts_off = (uint32_t)keep_pts->size();
+                keep_pts->insert(keep_pts->end(), pts.begin(), pts.begin() + n);
+            }
             r.order_hi = (uint32_t)s;
             r.order_lo = 0xFFFFFFFFu - (uint32_t)(((uint32_t)st.y * (uint32_t)W + (uint32_t)st.x) * 2u + (uint32_t)st.is_right);
             found.push_back(r);
@@ -437,7 +443,8 @@ int hs_detect(const uint8_t* gray, const uint8_t* planes, int W, int H, int dict
     DevParams P;
     if (make_dev_params(fp, &P) != FID_OK) return -2;
     std::vector<RawQuad> raw;
-    raw_candidates(planes, W, H, P, raw);
+    std::vector<Pt16> contour_pts;
+    raw_candidates(planes, W, H, P, raw, &contour_pts);
     const int n = (int)raw.size();
     // stable sort by descending float perimeter
     std::vector<QuadF> q(n);
@@ -489,6 +496,7 @@ int hs_detect(const uint8_t* gray, const uint8_t* planes, int W, int H, int dict
         if (quad_near_border(sq[i], W, H, P.min_dist_to_border)) continue;
         n_sel++;
         QuadF use = sq[i];
+        int use_sorted = i;
         IdentifyResult r = identify_candidate(L, GrayPlane{gray, (size_t)W}, W, H, use, P, dict.data(), img.data(), hist);
         if (r.id < 0) {
             for (int k = 0; k < ccount[i]; k++) {
@@ -496,6 +504,7 @@ int hs_detect(const uint8_t* gray, const uint8_t* planes, int W, int H, int dict
                 r = identify_candidate(L, GrayPlane{gray, (size_t)W}, W, H, alt, P, dict.data(), img.data(), hist);
                 if (r.id >= 0) {
                     use = alt;
+                    use_sorted = cidx[coff[i] + k];
                     break;
                 }
             }
@@ -508,7 +517,10 @@ int hs_detect(const uint8_t* gray, const uint8_t* planes, int W, int H, int dict
             cx[k] = use.x[(k + 4 - r.rotation) & 3];
             cy[k] = use.y[(k + 4 - r.rotation) & 3];
         }
-        if (refine && P.corner_refine) {
+        if (refine == 2) {  // CORNER_REFINE_CONTOUR
+            const RawQuad& rw = raw[order[use_sorted]];
+            refine_candidate_lines_serial(contour_pts.data() + rw.pts_off, rw.n_contour, cx, cy);
+        } else if (refine && P.corner_refine) {
             QuadF rq;
             for (int k = 0; k < 4; k++) {
                 rq.x[k] = cx[k];

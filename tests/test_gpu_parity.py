@@ -590,3 +590,25 @@ def test_every_predefined_dictionary(dict_id):
     assert np.abs(gc[0, :nn] - oc).max() <= 1e-3
     for m in range(nn):
         assert np.abs(np.array(tfs[m].translation[:]) - fields[m]["translation"]).max() <= 1e-3
+
+
+@pytest.mark.parametrize("cfg,seed", [("C1", 0), ("C1", 3), ("C3", 1), ("C2", 0)])
+def test_corner_refine_contour(cfg, seed):
+    """CORNER_REFINE_CONTOUR: doCornerRefinement = true, cornerRefinementSubPix = false (aruco_detect.cpp:700-711, 274-281).
+    Corners = intersections of float32 least-squares lines through the candidate's contour.  OpenCV forms A^T b of the normal
+    equations with cv::gemm, which this image's build hands to OpenBLAS sgemm for 100 rows and more: the oracle's own result then
+    depends on the BLAS kernel at the 1e-3 px level (tests/test_hostsim_detect.py::test_contour_refinement_*), hence 2e-2 px for
+    large markers; sides under 100 contour points (OpenCV's own gemm) are reproduced to 1e-3 px."""
+    import cv2
+    from fiducials_b200.node import Detector, default_params
+
+    W, H, n, d = synth.CONFIGS[cfg]
+    bgr = synth.make_config_frame(cfg, seed)[0]
+    det = Detector(default_params(dictionary=d, cornerRefinementMethod=2), 0, W, H, 1)
+    ids, corners = det.detect(bgr)
+    det.close()
+    rids, rcorners = ao.detect(bgr, d, cornerRefinementMethod=cv2.aruco.CORNER_REFINE_CONTOUR)
+    assert len(rids) > 0 and ids.tolist() == rids.tolist()
+    assert np.abs(corners - rcorners).max() <= (1e-3 if cfg == "C1" else 2e-2), np.abs(corners - rcorners).max()
+    # and it is a different answer from the sub-pixel default
+    assert np.abs(rcorners - ao.detect(bgr, d)[1]).max() > 1e-2

@@ -146,3 +146,17 @@ def test_map_auto_init_matches_slam_oracle(kat):
     gold = [403, 0.7611, 0.2505, 0.4028, 1.5751, -0.014, -1.546]  # auto_init_403_test.cpp:128-137
     assert np.abs(e[:7] - np.array(gold)).max() < 1e-3
     assert np.abs(e[1:7] - np.array(m.entries()[0][1:7])).max() < 1e-10
+
+
+@pytest.mark.parametrize("cfg,seed", [("C1", 0), ("C1", 1), ("C1", 2), ("C3", 0), ("C3", 5), ("C2", 0)])
+def test_contour_refinement_matches_oracle(cfg, seed):
+    """CORNER_REFINE_CONTOUR (doCornerRefinement = true, cornerRefinementSubPix = false: aruco_detect.cpp:700-711): line fits
+    through the candidate's contour, corners = intersections.  float32 normal equations -- reproduced operation by operation."""
+    import cv2
+
+    bgr, K, D, d = _frame(cfg, seed)
+    g = ao.gray(bgr)
+    ids, corners, stats = hs.detect(g, ao.threshold_planes(g), d, refine=2)
+    rids, rcorners = ao.detect(bgr, d, cornerRefinementMethod=cv2.aruco.CORNER_REFINE_CONTOUR)
+    assert ids.tolist() == rids.tolist()
+    assert np.abs(corners - rcorners).max() <= (1e-3 if cfg == "C1" else 2e-2), np.abs(corners - rcorners).max()  # >= 100 points per side: OpenCV hands A^T b to OpenBLAS sgemm, see tests/test_gpu_parity.py::test_corner_refine_contour
