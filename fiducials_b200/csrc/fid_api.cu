@@ -725,6 +725,19 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
         launches++;
     }
     CK(cudaEventRecord(s.ev[ST_SUBPIX_POSE], st));
+    if (P.corner_refine == 2) {  // CORNER_REFINE_CONTOUR: rewrite the decoded candidates' corners before the output stage
+        ContourRefineArgs a{};
+        a.n_sel = s.d_nsel;
+        a.cand_id = s.d_cand_id;
+        a.cand_raw = s.d_cand_raw;
+        a.cand_corners = s.d_cand_corners;
+        a.raw = s.d_raw;
+        a.points = s.d_points;
+        a.max_raw = h->max_raw;
+        a.max_sel = h->max_sel;
+        launch_prio(k_contour_refine, dim3(h->max_sel, nf), dim3(CREFINE_THREADS), 0, st, 5, a);
+        launches++;
+    }
     {  // finish
         FinishArgs a{};
         a.src = d_bgr;
@@ -736,9 +749,6 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
         a.n_sel = s.d_nsel;
         a.cand_id = s.d_cand_id;
         a.cand_corners = s.d_cand_corners;
-        a.cand_raw = s.d_cand_raw;
-        a.raw = s.d_raw;
-        a.points = s.d_points;
         a.fs = s.fs;
         a.max_raw = h->max_raw;
         a.max_sel = h->max_sel;

@@ -318,6 +318,122 @@ __global__ void __launch_bounds__(IDENT_WARPS * 32) k_identify(const IdentifyArg
 }
 
 // ---------------------------------------------------------------------------------------------------
+// CORNER_REFINE_CONTOUR (contour_refine.cuh), launched only when the method is selected: one CTA per decoded candidate strides
+// over the candidate's contour.  Pass 1 finds the positions that coincide with a corner, pass 2 adds every point to the sums
+// of the corner seen last before it; the corners are rewritten in place.
+struct ContourRefineArgs {
+    const int* n_sel;      // [F]
+    const int* cand_id;    // [F][max_sel]
+    const int* cand_raw;   // [F][max_sel] raw-list index of the quad that decoded
+    float* cand_corners;   // [F][max_sel][8], rewritten
+    const RawQuad* raw;    // [F][max_raw]: pts_off, n_contour
+    const Pt16* points;    // batch point buffer
+    int max_raw, max_sel;
+};
+
+#define CREFINE_THREADS 128
+
+__global__ void __launch_bounds__(CREFINE_THREADS) k_contour_refine(const ContourRefineArgs a) {
+    __shared__ int s_nmatch, s_cidx[4];
+    __shared__ int s_mpos[32], s_mcor[32];
+    __shared__ long long s_sum[4][6];
+    __shared__ int s_ext[4][4];
+    const int f = blockIdx.y, k = blockIdx.x, tid = threadIdx.x;
+    if (k >= a.n_sel[f]) return;
+    const size_t co = (size_t)f * a.max_sel + k;
+    if (a.cand_id[co] < 0) return;
+    const RawQuad rq = a.raw[(size_t)f * a.max_raw + a.cand_raw[co]];
+    const Pt16* pts = a.points + rq.pts_off;
+    const int np = rq.n_contour;
+    float cx[4], cy[4];
+    for (int c = 0; c < 4; c++) {
+        cx[c] = a.cand_corners[co * 8 + 2 * c];
+        cy[c] = a.cand_corners[co * 8 + 2 * c + 1];
+    }
+    if (tid == 0) s_nmatch = 0;
+    if (tid < 4) s_cidx[tid] = -1;
+    if (tid < 24) s_sum[tid / 6][tid % 6] = 0;
+    if (tid < 16) s_ext[tid >> 2][tid & 3] = (tid & 1) ? -0x7fffffff : 0x7fffffff;  // min x, max x, min y, max y
+    __syncthreads();
+    for (int i = tid; i < np; i += CREFINE_THREADS) {
+        const float px = (float)pts[i].x, py = (float)pts[i].y;
+        for (int j = 0; j < 4; j++)
+            if (px == cx[j] && py == cy[j]) {
+                const int slot = atomicAdd(&s_nmatch, 1);
+                if (slot < 32) {
+                    s_mpos[slot] = i;
+                    s_mcor[slot] = j;
+                }
+                atomicMax(&s_cidx[j], i);
+            }
+    }
+    __syncthreads();
+    const int nm = s_nmatch;
+    if (s_cidx[0] < 0 || s_cidx[1] < 0 || s_cidx[2] < 0 || s_cidx[3] < 0) return;  // cannot happen for a quad of this contour (OpenCV asserts)
+    if (nm > 32) {  // a contour that revisits its corners many times: serial
+        if (tid == 0) {
+            refine_candidate_lines_serial(pts, np, cx, cy);
+            for (int c = 0; c < 4; c++) {
+                a.cand_corners[co * 8 + 2 * c] = cx[c];
+                a.cand_corners[co * 8 + 2 * c + 1] = cy[c];
+            }
+        }
+        return;
+    }
+    if (tid == 0) {  // order the matches by contour position
+        for (int i = 1; i < nm; i++) {
+            const int p = s_mpos[i], c = s_mcor[i];
+            int j = i - 1;
+            for (; j >= 0 && s_mpos[j] > p; j--) {
+                s_mpos[j + 1] = s_mpos[j];
+                s_mcor[j + 1] = s_mcor[j];
+            }
+            s_mpos[j + 1] = p;
+            s_mcor[j + 1] = c;
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < np; i += CREFINE_THREADS) {
+        int g = s_mcor[nm - 1];  // before the first corner: the corner seen last
+        for (int q = 0; q < nm && s_mpos[q] <= i; q++) g = s_mcor[q];
+        const int x = pts[i].x, y = pts[i].y;
+        atomicAdd(reinterpret_cast<unsigned long long*>(&s_sum[g][0]), 1ull);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&s_sum[g][1]), (unsigned long long)(long long)x);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&s_sum[g][2]), (unsigned long long)(long long)y);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&s_sum[g][3]), (unsigned long long)((long long)x * x));
+        atomicAdd(reinterpret_cast<unsigned long long*>(&s_sum[g][4]), (unsigned long long)((long long)y * y));
+        atomicAdd(reinterpret_cast<unsigned long long*>(&s_sum[g][5]), (unsigned long long)((long long)x * y));
+        atomicMin(&s_ext[g][0], x);
+        atomicMax(&s_ext[g][1], x);
+        atomicMin(&s_ext[g][2], y);
+        atomicMax(&s_ext[g][3], y);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        LineSums sums[4];
+        int cidx[4];
+        for (int g = 0; g < 4; g++) {
+            sums[g].n = s_sum[g][0];
+            sums[g].sx = s_sum[g][1];
+            sums[g].sy = s_sum[g][2];
+            sums[g].sxx = s_sum[g][3];
+            sums[g].syy = s_sum[g][4];
+            sums[g].sxy = s_sum[g][5];
+            sums[g].minx = s_ext[g][0];
+            sums[g].maxx = s_ext[g][1];
+            sums[g].miny = s_ext[g][2];
+            sums[g].maxy = s_ext[g][3];
+            cidx[g] = s_cidx[g];
+        }
+        corners_from_lines(sums, cidx, cx, cy);
+        for (int c = 0; c < 4; c++) {
+            a.cand_corners[co * 8 + 2 * c] = cx[c];
+            a.cand_corners[co * 8 + 2 * c + 1] = cy[c];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 struct FinishArgs {
     const uint8_t* src;
     size_t row_stride, frame_stride;
@@ -325,9 +441,6 @@ struct FinishArgs {
     const int* n_sel;
     const int* cand_id;
     const float* cand_corners;
-    const int* cand_raw;      // CORNER_REFINE_CONTOUR: raw-list index of every decoded candidate ...
-    const RawQuad* raw;       // ... its contour (pts_off, n_contour) ...
-    const Pt16* points;       // ... and the batch point buffer
     FrameScratch fs;  // selected candidates' quads (candidate hierarchy)
     int max_raw;
     int max_sel, max_markers;
@@ -444,109 +557,6 @@ __global__ void __launch_bounds__(FINISH_THREADS) k_finish(const FinishArgs a) {
         }
         oc[(size_t)m * 8 + 2 * ci] = x;
         oc[(size_t)m * 8 + 2 * ci + 1] = y;
-    }
-    if (a.P.corner_refine == 2) {
-        // CORNER_REFINE_CONTOUR (contour_refine.cuh): the CTA strides over the contour of one marker at a time.  Pass 1 finds the
-        // positions that coincide with a corner, pass 2 adds every point to the sums of the corner seen last before it.
-        __shared__ int s_nmatch, s_cidx[4];
-        __shared__ int s_mpos[32], s_mcor[32];
-        __shared__ long long s_sum[4][6];
-        __shared__ int s_ext[4][4];
-        for (int m = 0; m < n; m++) {
-            const size_t co = (size_t)f * a.max_sel + s_src[m];
-            const RawQuad rq = a.raw[(size_t)f * a.max_raw + a.cand_raw[co]];
-            const Pt16* pts = a.points + rq.pts_off;
-            const int np = rq.n_contour;
-            float cx[4], cy[4];
-            for (int k = 0; k < 4; k++) {
-                cx[k] = a.cand_corners[co * 8 + 2 * k];
-                cy[k] = a.cand_corners[co * 8 + 2 * k + 1];
-            }
-            __syncthreads();
-            if (tid == 0) s_nmatch = 0;
-            if (tid < 4) s_cidx[tid] = -1;
-            if (tid < 24) s_sum[tid / 6][tid % 6] = 0;
-            if (tid < 16) s_ext[tid >> 2][tid & 3] = (tid & 1) ? -0x7fffffff : 0x7fffffff;  // min x, max x, min y, max y
-            __syncthreads();
-            for (int i = tid; i < np; i += FINISH_THREADS) {
-                const float px = (float)pts[i].x, py = (float)pts[i].y;
-                for (int j = 0; j < 4; j++)
-                    if (px == cx[j] && py == cy[j]) {
-                        const int slot = atomicAdd(&s_nmatch, 1);
-                        if (slot < 32) {
-                            s_mpos[slot] = i;
-                            s_mcor[slot] = j;
-                        }
-                        atomicMax(&s_cidx[j], i);
-                    }
-            }
-            __syncthreads();
-            const int nm = s_nmatch;
-            const bool have_all = s_cidx[0] >= 0 && s_cidx[1] >= 0 && s_cidx[2] >= 0 && s_cidx[3] >= 0;
-            if (!have_all) continue;  // cannot happen for a quad that came from this contour; OpenCV asserts
-            if (nm > 32) {            // a contour that revisits its corners many times: serial fallback
-                if (tid == 0) {
-                    refine_candidate_lines_serial(pts, np, cx, cy);
-                    for (int k = 0; k < 4; k++) {
-                        oc[(size_t)m * 8 + 2 * k] = cx[k];
-                        oc[(size_t)m * 8 + 2 * k + 1] = cy[k];
-                    }
-                }
-                continue;
-            }
-            if (tid == 0) {  // order the matches by contour position (a corner can match several positions, a position one corner)
-                for (int i = 1; i < nm; i++) {
-                    const int p = s_mpos[i], c = s_mcor[i];
-                    int j = i - 1;
-                    for (; j >= 0 && s_mpos[j] > p; j--) {
-                        s_mpos[j + 1] = s_mpos[j];
-                        s_mcor[j + 1] = s_mcor[j];
-                    }
-                    s_mpos[j + 1] = p;
-                    s_mcor[j + 1] = c;
-                }
-            }
-            __syncthreads();
-            for (int i = tid; i < np; i += FINISH_THREADS) {
-                int g = s_mcor[nm - 1];  // before the first corner: the corner seen last
-                for (int k = 0; k < nm && s_mpos[k] <= i; k++) g = s_mcor[k];
-                const int x = pts[i].x, y = pts[i].y;
-                atomicAdd(reinterpret_cast<unsigned long long*>(&s_sum[g][0]), 1ull);
-                atomicAdd(reinterpret_cast<unsigned long long*>(&s_sum[g][1]), (unsigned long long)(long long)x);
-                atomicAdd(reinterpret_cast<unsigned long long*>(&s_sum[g][2]), (unsigned long long)(long long)y);
-                atomicAdd(reinterpret_cast<unsigned long long*>(&s_sum[g][3]), (unsigned long long)((long long)x * x));
-                atomicAdd(reinterpret_cast<unsigned long long*>(&s_sum[g][4]), (unsigned long long)((long long)y * y));
-                atomicAdd(reinterpret_cast<unsigned long long*>(&s_sum[g][5]), (unsigned long long)((long long)x * y));
-                atomicMin(&s_ext[g][0], x);
-                atomicMax(&s_ext[g][1], x);
-                atomicMin(&s_ext[g][2], y);
-                atomicMax(&s_ext[g][3], y);
-            }
-            __syncthreads();
-            if (tid == 0) {
-                LineSums sums[4];
-                int cidx[4];
-                for (int g = 0; g < 4; g++) {
-                    sums[g].n = s_sum[g][0];
-                    sums[g].sx = s_sum[g][1];
-                    sums[g].sy = s_sum[g][2];
-                    sums[g].sxx = s_sum[g][3];
-                    sums[g].syy = s_sum[g][4];
-                    sums[g].sxy = s_sum[g][5];
-                    sums[g].minx = s_ext[g][0];
-                    sums[g].maxx = s_ext[g][1];
-                    sums[g].miny = s_ext[g][2];
-                    sums[g].maxy = s_ext[g][3];
-                    cidx[g] = s_cidx[g];
-                }
-                corners_from_lines(sums, cidx, cx, cy);
-                for (int k = 0; k < 4; k++) {
-                    oc[(size_t)m * 8 + 2 * k] = cx[k];
-                    oc[(size_t)m * 8 + 2 * k + 1] = cy[k];
-                }
-            }
-        }
-        __syncthreads();
     }
     for (int m = tid; m < n; m += FINISH_THREADS) a.out_ids[(size_t)f * a.max_markers + m] = a.cand_id[(size_t)f * a.max_sel + s_src[m]];
     __syncthreads();
