@@ -40,8 +40,8 @@ FID_HD bool quad_inside_quad(const QuadF& inner, const QuadF& outer) {
 // Raw candidate emitted by the approximation kernel.
 struct RawQuad {
     int16_t x[4], y[4];  // approxPolyDP vertex order
-    int32_t n_contour;   // contour length (points)
-    uint32_t order_hi;   // scale index
+    uint32_t n_contour : 24;  // contour length (points)
+    uint32_t order_hi : 8;    // scale index  (one word with n_contour: the record stays 28 bytes)
     uint32_t order_lo;   // 0xFFFFFFFF - (2*raster(start)+is_hole): ascending == OpenCV's list order
     uint32_t pts_off;    // the contour's points (findContours order) in the batch point buffer: CORNER_REFINE_CONTOUR fits lines to them
 };
