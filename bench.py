@@ -228,8 +228,8 @@ def _cpu_worker_frame(i):
 class CpuArm:
     """The reference's CPU path on a bounded sample, in both modes:
     reference mode  = one process, OpenCV threads = all cores (what the single-threaded node does);
-    throughput mode = single-threaded worker processes, frames round-robin: one per logical core and one per
-                      physical core (half of them on an SMT box -- the detector is memory bound and ran 30 % faster
+    throughput mode = single-threaded worker processes, frames round-robin: one per logical core, one per
+                      physical core, and -- under a cgroup CPU quota -- one and two per core of the quota (half of them on an SMT box -- the detector is memory bound and ran 30 % faster
                       that way on the 128-thread host of the B200 box).
     The worker pools are spawned once (spawn, so OpenCV's thread pool is never forked) and reused by every
     measure() call: --impl reference times K steps without paying K pool start-ups."""
@@ -246,7 +246,13 @@ class CpuArm:
         self.tmp.close()
         try:
             ctx = mp.get_context("spawn")
-            for npr in [max(1, self.ncores)] + ([self.ncores // 2] if self.ncores >= 8 else []):
+            counts = [max(1, self.ncores)] + ([self.ncores // 2] if self.ncores >= 8 else [])
+            quota = cpu_quota_cores()
+            if quota and quota < self.ncores:  # a cgroup CPU quota below the CPU count: oversubscribed pools are throttled, so also
+                for c in (int(round(quota)), int(round(2 * quota))):  # try one worker (and two) per core of CPU time the container owns
+                    if 1 <= c < self.ncores and c not in counts:
+                        counts.append(c)
+            for npr in counts:
                 pool = ctx.Pool(npr, initializer=_cpu_worker_init, initargs=(1, self.tmp.name, dict_id, K, D))
                 pool.map(_cpu_worker_frame, range(npr), chunksize=1)  # warm-up (imports, first-call setup)
                 self.pools.append((npr, pool))
@@ -593,6 +599,8 @@ def run_gpu_arm(args):
         }
         if os.environ.get("FID_BENCH_SKIP_CPU"):  # profiling runs (ncu) only
             cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "skipped (FID_BENCH_SKIP_CPU set)"}
+        elif world > 1:  # the CPU baseline is a rank-0, N = 1 measurement (the host cores do not multiply with the GPUs)
+            cpu = {"value": None, "unit": "frames/s", "cores": 0, "kind": "reference", "sample": "measured at N = 1 only: see the 1-GPU line / --impl reference"}
         else:
             cpu = cpu_reference_fps(np.ascontiguousarray(frames[::REALIZATIONS]), dict_id, K, D, budget_s=16.0)
         d2h = nf * (4 + MAXM * 4 + MAXM * 32 + MAXM * C.sizeof(_lib.fid_transform))
