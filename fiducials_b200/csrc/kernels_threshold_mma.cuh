@@ -64,12 +64,13 @@ static_assert(TM_REGS_CTRL + TM_REGS_CONV + 2 * TM_REGS_EPI <= 4 * 128, "setmaxn
 #define TM_BOXH 16
 #define TM_NBANDS 7
 #define TM_STAGE_BYTES (TM_BOXW * TM_BOXH * 4)
+#define TM_STAGE_STRIDE (TM_STAGE_BYTES + 128)  // the converters read up to 5 words past the last row of a box (columns nobody uses): keep them inside the stage
 #define TM_NSTAGES 4
 #define TM_COLW_WORDS (13 * 2 * 128)
 #define TM_OFF_A 0
 #define TM_OFF_B (TM_OFF_A + TM_NTAB * TM_A_BYTES)
 #define TM_OFF_STAGE (TM_OFF_B + 2 * TM_B_BYTES)
-#define TM_OFF_COLW (TM_OFF_STAGE + TM_NSTAGES * TM_STAGE_BYTES)
+#define TM_OFF_COLW (TM_OFF_STAGE + TM_NSTAGES * TM_STAGE_STRIDE)
 #define TM_OFF_BAR (TM_OFF_COLW + 2 * TM_COLW_WORDS * 4)
 #define TM_SMEM_BYTES (TM_OFF_BAR + 256)
 
@@ -344,7 +345,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_threshold_mma(const ThreshMma
                 if (tm_elect()) {
                     tm_mbar_expect_tx(&bar[TMB_STAGE_FULL + st], TM_STAGE_BYTES);
                     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
-                                     tm_smem(sStage + st * TM_STAGE_BYTES)),
+                                     tm_smem(sStage + st * TM_STAGE_STRIDE)),
                                  "l"((uint64_t)&tmap), "r"(c0), "r"(c1 + band * TM_BOXH), "r"(f), "r"(tm_smem(&bar[TMB_STAGE_FULL + st]))
                                  : "memory");
                 }
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(TM_THREADS, 1) k_threshold_mma(const ThreshMma
                     for (int band = 0; band < TM_NBANDS; band++, n_consumed++) {
                         const uint32_t st = n_consumed % TM_NSTAGES, use = n_consumed / TM_NSTAGES;
                         TM_WAIT(1, &bar[TMB_STAGE_FULL + st], use & 1u);
-                        const uint32_t* stage = reinterpret_cast<const uint32_t*>(sStage + st * TM_STAGE_BYTES);
+                        const uint32_t* stage = reinterpret_cast<const uint32_t*>(sStage + st * TM_STAGE_STRIDE);
 #pragma unroll 1
                         for (int blk = 0; blk < 6; blk++) {
                             const int b = cw + blk * TM_NCONV;       // 24 blocks of 8 rows x 16 columns per band
