@@ -110,8 +110,11 @@ __host__ __device__ inline size_t thresh_smem_bytes(int r_max) {
 }
 
 // FAST: windows 3 + 4*s (s = 0..12), r_max = 25 -> everything below is compile-time.
+#ifndef THR_MAXNREG
+#define THR_MAXNREG 96  // 2 CTAs per SM leave a quarter of the register file to the kernels of other chunks (+1 % pipelined, no spills)
+#endif
 template <bool FAST>
-__global__ void __launch_bounds__(THR_THREADS, 2) k_threshold(const ThreshArgs a) {
+__global__ void __maxnreg__(THR_MAXNREG) k_threshold(const ThreshArgs a) {
     extern __shared__ uint32_t sat[];
     const int R = FAST ? THR_FAST_R : a.r_max;
     const int RW = THR_OW + 2 + 2 * R, RH = THR_OH + 2 + 2 * R;
