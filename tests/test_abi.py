@@ -58,6 +58,8 @@ def test_no_cpu_fallback(lib):
     lib.fid_map_default_params(C.byref(mp))
     m = C.c_void_p()
     assert lib.fid_map_create(C.byref(mp), 0, C.byref(m)) == -2
+    j = C.c_void_p()
+    assert lib.fid_jpeg_create(0, 640, 480, 4, 0, C.byref(j)) == -2  # the JPEG ingest has no host decoder to fall back to either
 
 
 def test_argument_validation(lib):
