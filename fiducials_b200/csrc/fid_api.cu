@@ -699,6 +699,8 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
         a.H = H;
         a.min_dist_to_border = P.min_dist_to_border;
         a.counters = s.d_counters;
+        static const int group_prof = getenv("FID_GROUP_PROF") ? atoi(getenv("FID_GROUP_PROF")) : 0;
+        a.prof = group_prof;
         launch_prio(k_sort_group, dim3(nf), dim3(GROUP_THREADS), group_smem(h->max_raw), st, 4, a);
         launches++;
     }

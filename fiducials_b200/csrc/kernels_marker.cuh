@@ -52,6 +52,7 @@ struct GroupArgs {
     float min_marker_dist_rate, min_group_dist;
     int W, H, min_dist_to_border;
     Counters* counters;
+    int prof;  // FID_GROUP_PROF=1: frame 0 prints its phase clocks (debug aid)
 };
 
 // One warp as a lane group (identify.cuh, quad_group.cuh); tests/hostsim plugs SerialLanes (one lane).
@@ -83,7 +84,7 @@ struct WarpLanes {
     __device__ int atomic_add(int* p, int v) const { return atomicAdd(p, v); }
 };
 
-#define GROUP_THREADS 256
+#define GROUP_THREADS 1024
 #define FID_GROUP_MAX_RAW 4096  // >= fid_detector::max_raw
 #define GROUP_CLOSE_SMEM_WORDS 12288  // 48 KB of the close-pair matrix in shared memory
 
@@ -98,21 +99,33 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_sort_group(const GroupArgs a)
     float* pt = a.fs.per_tmp + fo;
     QuadF* qs = a.fs.quads + fo;
     float* ps = a.fs.per + fo;
+    long long t_[7] = {0, 0, 0, 0, 0, 0, 0};
+#define GROUP_TICK(k) if (a.prof && tid == 0 && f == 0) t_[k] = clock64()
+    GROUP_TICK(0);
     if (tid == 0) a.n_raw_clamped[f] = n;
+    extern __shared__ int sm_group[];  // 6 * max_raw ints + max_raw bytes (+ the close-pair matrix when it fits)
+    // the grouping scratch is idle until pass 1: phases a-c keep their per-candidate scalars there (perimeters for the rank
+    // sort, then centroids and distance thresholds for the close-pair pre-filter) instead of re-reading them from L2 in the
+    // inner loops
+    float* s_f0 = reinterpret_cast<float*>(sm_group);
+    float* s_f1 = s_f0 + a.max_raw;
+    float* s_f2 = s_f1 + a.max_raw;
     // a. clockwise + perimeter
     for (int i = tid; i < n; i += GROUP_THREADS) {
         const QuadF q = quad_clockwise(raw[i]);
         qt[i] = q;
-        pt[i] = quad_perimeter(q);
+        const float p = quad_perimeter(q);
+        pt[i] = p;
+        s_f0[i] = p;
     }
     __syncthreads();
     // b. rank = position under std::stable_sort(descending perimeter) of OpenCV's candidate order
     for (int i = tid; i < n; i += GROUP_THREADS) {
-        const float pi = pt[i];
+        const float pi = s_f0[i];
         const uint32_t hi = raw[i].order_hi, lo = raw[i].order_lo;
         int rank = 0;
         for (int j = 0; j < n; j++) {
-            const float pj = pt[j];
+            const float pj = s_f0[j];
             const bool before = pj > pi || (pj == pi && (raw[j].order_hi < hi || (raw[j].order_hi == hi && raw[j].order_lo < lo)));
             rank += before ? 1 : 0;
         }
@@ -121,11 +134,21 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_sort_group(const GroupArgs a)
         a.fs.raw_of_sorted[fo + rank] = i;
     }
     __syncthreads();
+    QuadF* s_quads = reinterpret_cast<QuadF*>(s_f2 + a.max_raw);  // the other half of the scratch: up to 3 * max_raw / 8 quads
+    const bool quads_in_smem = (size_t)n * sizeof(QuadF) <= (size_t)3 * a.max_raw * sizeof(int);
+    for (int i = tid; i < n; i += GROUP_THREADS) {  // sorted order: centroid and "too close" threshold of every candidate
+        const QuadF q = qs[i];
+        s_f0[i] = (q.x[0] + q.x[1] + q.x[2] + q.x[3]) * 0.25f;
+        s_f1[i] = (q.y[0] + q.y[1] + q.y[2] + q.y[3]) * 0.25f;
+        s_f2[i] = ps[i] * a.min_marker_dist_rate;
+        if (quads_in_smem) s_quads[i] = q;
+    }
+    __syncthreads();
+    GROUP_TICK(1);
     // c. close-pair matrix, upper triangle; unit = (row i, 32-column word).  The matrix is very sparse (a
     //    marker scene has a few dozen close pairs among ~10^5): rows with at least one pair are flagged in
     //    shared memory so that the serial pass below does not pay an L2 round trip per empty word.
     __shared__ uint32_t row_any[(FID_GROUP_MAX_RAW + 31) / 32], grouped[(FID_GROUP_MAX_RAW + 31) / 32];
-    extern __shared__ int sm_group[];  // 6 * max_raw ints + max_raw bytes
     int* sm_group_id = sm_group;
     int* sm_members = sm_group + a.max_raw;  // 2 * max_raw: members + accepted ids of every group
     int* sm_next = sm_group + 3 * a.max_raw;
@@ -144,49 +167,105 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_sort_group(const GroupArgs a)
     const bool close_in_smem = n * wpr <= GROUP_CLOSE_SMEM_WORDS;
     uint32_t* cb = close_in_smem ? sm_close : a.fs.close_bits + fo * a.close_wpr;
     const int cb_pitch = close_in_smem ? wpr : a.close_wpr;
-    for (int u = tid; u < n * wpr; u += GROUP_THREADS) {
-        const int i = u / wpr, w = u - i * wpr;
-        uint32_t bits = 0;
-        const int j0 = w << 5;
-        if (j0 + 31 > i) {
-            const QuadF qi = qs[i];
-            const float cix = (qi.x[0] + qi.x[1] + qi.x[2] + qi.x[3]) * 0.25f, ciy = (qi.y[0] + qi.y[1] + qi.y[2] + qi.y[3]) * 0.25f;
-            for (int b = 0; b < 32; b++) {
-                const int j = j0 + b;
-                if (j <= i || j >= n) continue;
-                const QuadF qj = qs[j];
-                const float thr = ps[j] * a.min_marker_dist_rate;
-                // the mean squared corner distance is >= the squared centroid distance for every
-                // corner alignment, so a far centroid can never be "close" (conservative margin)
-                const float cjx = (qj.x[0] + qj.x[1] + qj.x[2] + qj.x[3]) * 0.25f, cjy = (qj.y[0] + qj.y[1] + qj.y[2] + qj.y[3]) * 0.25f;
-                const float cd2 = (cix - cjx) * (cix - cjx) + (ciy - cjy) * (ciy - cjy);
-                const float lim = thr * 1.01f + 1.0f;
-                if (cd2 > lim * lim) continue;
-                if (quad_avg_distance(qi, qj) < thr) bits |= 1u << b;
+    // one warp per (row i, word w): lane = column j0 + lane, the word is a ballot.  The pre-filter -- the mean squared corner
+    // distance is >= the squared centroid distance for every corner alignment, so a far centroid can never be "close"
+    // (conservative margin) -- runs on shared memory; only the few near pairs load the two quads.
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        for (int u = warp; u < n * wpr; u += GROUP_THREADS / 32) {
+            const int i = u / wpr, w = u - i * wpr;
+            const int j0 = w << 5;
+            uint32_t bits = 0;
+            if (j0 + 31 > i) {
+                const int j = j0 + lane;
+                bool close = false;
+                if (j > i && j < n) {
+                    const float thr = s_f2[j];
+                    const float dx = s_f0[i] - s_f0[j], dy = s_f1[i] - s_f1[j];
+                    const float cd2 = dx * dx + dy * dy;
+                    const float lim = thr * 1.01f + 1.0f;
+                    if (cd2 <= lim * lim) close = (quads_in_smem ? quad_avg_distance(s_quads[i], s_quads[j]) : quad_avg_distance(qs[i], qs[j])) < thr;
+                }
+                bits = __ballot_sync(0xffffffffu, close);
+            }
+            if (lane == 0) {
+                cb[(size_t)i * cb_pitch + w] = bits;
+                if (bits) atomicOr(&row_any[i >> 5], 1u << (i & 31));
             }
         }
-        cb[(size_t)i * cb_pitch + w] = bits;
-        if (bits) atomicOr(&row_any[i >> 5], 1u << (i & 31));
     }
     __syncthreads();
+    GROUP_TICK(2);
     // d. order-dependent grouping.  Pass 1 (the close pairs in row-major order -> groups) is inherently serial
     //    and runs in one thread on shared-memory scratch; pass 2 (per group: sort, pick the leader, collect the
     //    close contours that differ from the running reference) runs one warp per group.
     __shared__ int s_n_groups, s_total_close, s_members_used;
-    if (tid == 0) {
-        struct CloseWordDev {
-            const uint32_t* cb;
-            int cw;
-            const uint32_t* ra;
-            __device__ uint32_t operator()(int i, int w) const { return cb[(size_t)i * cw + w]; }
-            __device__ bool row_any(int i) const { return (ra[i >> 5] >> (i & 31)) & 1u; }
-        } close_word{cb, cb_pitch, row_any};
-        s_n_groups = group_pairs(n, close_word, sm_selected, sm_group_id, sm_next, sm_head, sm_tail, a.fs.close_count + fo, grouped);
-        s_total_close = 0;
-        s_members_used = 0;
-        s_base = 0;
+    __shared__ uint32_t s_row[2][FID_GROUP_MAX_RAW / 32], s_rowmask[2][4];
+    if (tid < 32) {
+        // warp 0: the lanes stage row i of the matrix (one coalesced load, the next row's load already in flight), lane 0
+        // applies the sequential rule from shared memory.  A large frame (C4: ~1400 candidates, matrix in global memory) used
+        // to pay one dependent L2 round trip per word of every row -- 20 ms per 4K frame.
+        struct RowPtr {
+            const uint32_t* p;
+            __device__ uint32_t operator()(int w) const { return p[w]; }
+        };
+        const int lane = tid;
+        int n_groups = 0;
+        if (lane == 0) group_pairs_init(n, sm_selected, sm_group_id, sm_next, a.fs.close_count + fo, grouped);
+        __syncwarp();
+        auto next_row = [&](int i) {  // first row >= i with a close pair (warp uniform)
+            while (i < n && !((row_any[i >> 5] >> (i & 31)) & 1u)) i++;
+            return i;
+        };
+        if (close_in_smem) {
+            if (lane == 0)
+                for (int i = next_row(0); i < n; i = next_row(i + 1))
+                    group_pairs_row(n, i, RowPtr{sm_close + (size_t)i * wpr}, nullptr, &n_groups, sm_selected, sm_group_id, sm_next, sm_head, sm_tail, grouped);
+        } else {
+            // three rows in flight: the L2 latency of a row hides behind the sequential work on the rows before it
+            uint32_t v[3][4];
+            int rows[3];
+            rows[0] = next_row(0);
+            rows[1] = rows[0] < n ? next_row(rows[0] + 1) : n;
+            rows[2] = rows[1] < n ? next_row(rows[1] + 1) : n;
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) v[r][k] = (rows[r] < n && lane + 32 * k < wpr) ? cb[(size_t)rows[r] * cb_pitch + lane + 32 * k] : 0u;
+            int buf = 0;
+            while (rows[0] < n) {
+                const int i = rows[0];
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (lane + 32 * k < wpr) s_row[buf][lane + 32 * k] = v[0][k];
+                    const uint32_t nz = __ballot_sync(0xffffffffu, v[0][k] != 0u);
+                    if (lane == 0) s_rowmask[buf][k] = nz;
+                }
+                __syncwarp();
+                const int inext = rows[2] < n ? next_row(rows[2] + 1) : n;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    v[0][k] = v[1][k];
+                    v[1][k] = v[2][k];
+                    v[2][k] = (inext < n && lane + 32 * k < wpr) ? cb[(size_t)inext * cb_pitch + lane + 32 * k] : 0u;
+                }
+                rows[0] = rows[1];
+                rows[1] = rows[2];
+                rows[2] = inext;
+                if (lane == 0) group_pairs_row(n, i, RowPtr{s_row[buf]}, s_rowmask[buf], &n_groups, sm_selected, sm_group_id, sm_next, sm_head, sm_tail, grouped);
+                __syncwarp();
+                buf ^= 1;
+            }
+        }
+        if (lane == 0) {
+            s_n_groups = n_groups;
+            s_total_close = 0;
+            s_members_used = 0;
+            s_base = 0;
+        }
     }
     __syncthreads();
+    GROUP_TICK(3);
     {
         const WarpLanes L;
         for (int g = tid >> 5; g < s_n_groups; g += GROUP_THREADS / 32)
@@ -194,6 +273,7 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_sort_group(const GroupArgs a)
                                a.fs.close_idx + fo, a.fs.close_off + fo, &s_total_close);
     }
     __syncthreads();
+    GROUP_TICK(4);
     // e. selected candidates, in order, minus the ones near the frame border (dropped silently, with their group)
     for (int c0 = 0; c0 < n; c0 += GROUP_THREADS) {
         const int i = c0 + tid;
@@ -220,6 +300,10 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_sort_group(const GroupArgs a)
         __syncthreads();
     }
     if (tid == 0) a.n_sel[f] = s_base < a.max_sel ? s_base : a.max_sel;
+    GROUP_TICK(5);
+    if (a.prof && tid == 0 && f == 0)
+        printf("[group prof] n=%d groups=%d clocks: sort %lld close %lld pass1 %lld pass2 %lld select %lld\n", n, s_n_groups, t_[1] - t_[0], t_[2] - t_[1], t_[3] - t_[2], t_[4] - t_[3], t_[5] - t_[4]);
+#undef GROUP_TICK
 }
 
 // ---------------------------------------------------------------------------------------------------

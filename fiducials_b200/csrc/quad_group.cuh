@@ -108,11 +108,9 @@ FID_HD float quad_module_size(const QuadF& q, int marker_size, int border_bits) 
 }
 
 // Pass 1 (order dependent, serial): the close pairs in row-major order -> groups as linked lists.
-// Returns the number of groups.  selected[i] = 1 for candidates that are in no group.
-template <class CloseWord>
-FID_HD int group_pairs(int n, const CloseWord& close_word, uint8_t* selected, int* group_id, int* next_in_group, int* group_head, int* group_tail, int* close_count,
-                       uint32_t* grouped) {
-    int n_groups = 0;
+// selected[i] = 1 for candidates that are in no group.  Split into init + one call per matrix row so that the device can stage
+// a row with a whole warp (one coalesced load) while a single lane applies the sequential rule.
+FID_HD void group_pairs_init(int n, uint8_t* selected, int* group_id, int* next_in_group, int* close_count, uint32_t* grouped) {
     for (int i = 0; i < n; i++) {
         selected[i] = 1;
         group_id[i] = -1;
@@ -121,48 +119,78 @@ FID_HD int group_pairs(int n, const CloseWord& close_word, uint8_t* selected, in
     }
     const int n_words = (n + 31) >> 5;
     for (int w = 0; w < n_words; w++) grouped[w] = 0;
-    // OpenCV visits the close pairs (i, j > i) in row-major order: both ungrouped -> new group; one
-    // grouped -> the other joins it; both grouped -> nothing (groups never merge).  The same marker seen at
-    // 13 scales gives hundreds of "both grouped" pairs per marker; the `grouped` bit mask skips them a
-    // word at a time (such a pair changes nothing: selected[] is already 0 for every grouped candidate).
-    for (int i = 0; i < n; i++) {
-        if (!close_word.row_any(i)) continue;
-        for (int w = (i + 1) >> 5; w < n_words; w++) {
-            uint32_t bits = close_word(i, w);
-            if (w == ((i + 1) >> 5)) bits &= (i & 31) == 31 ? 0xFFFFFFFFu : ~((2u << (i & 31)) - 1u);  // j > i only
-            if (w == n_words - 1 && (n & 31)) bits &= (1u << (n & 31)) - 1u;                            // j < n only
-            while (bits) {
-                if (group_id[i] >= 0) {
-                    bits &= ~grouped[w];
-                    if (!bits) break;
-                }
-                const int j = (w << 5) + fid_ctz(bits);
-                bits &= bits - 1;
-                selected[i] = 0;
-                selected[j] = 0;
-                if (group_id[i] < 0 && group_id[j] < 0) {
-                    const int g = n_groups++;
-                    group_id[i] = group_id[j] = g;
-                    group_head[g] = i;
-                    next_in_group[i] = j;
-                    group_tail[g] = j;
-                    grouped[i >> 5] |= 1u << (i & 31);
-                    grouped[j >> 5] |= 1u << (j & 31);
-                } else if (group_id[i] > -1 && group_id[j] == -1) {
-                    const int g = group_id[i];
-                    group_id[j] = g;
-                    next_in_group[group_tail[g]] = j;
-                    group_tail[g] = j;
-                    grouped[j >> 5] |= 1u << (j & 31);
-                } else if (group_id[j] > -1 && group_id[i] == -1) {
-                    const int g = group_id[j];
-                    group_id[i] = g;
-                    next_in_group[group_tail[g]] = i;
-                    group_tail[g] = i;
-                    grouped[i >> 5] |= 1u << (i & 31);
-                }
+}
+
+// OpenCV visits the close pairs (i, j > i) in row-major order: both ungrouped -> new group; one
+// grouped -> the other joins it; both grouped -> nothing (groups never merge).  The same marker seen at
+// 13 scales gives hundreds of "both grouped" pairs per marker; the `grouped` bit mask skips them a
+// word at a time (such a pair changes nothing: selected[] is already 0 for every grouped candidate).
+// row(w) = word w of row i of the close-pair matrix; nonempty (optional, 4 words = 128 bits) flags the words of the row that are
+// not zero, so that a sparse row costs a few iterations instead of one per word.
+template <class Row>
+FID_HD void group_pairs_row(int n, int i, const Row& row, const uint32_t* nonempty, int* n_groups, uint8_t* selected, int* group_id, int* next_in_group, int* group_head,
+                            int* group_tail, uint32_t* grouped) {
+    const int n_words = (n + 31) >> 5;
+    for (int w = (i + 1) >> 5; w < n_words; w++) {
+        if (nonempty) {  // jump to the next flagged word
+            uint32_t m = nonempty[w >> 5] & (0xFFFFFFFFu << (w & 31));
+            int q = w >> 5;
+            while (!m && ++q < 4) m = nonempty[q];
+            if (!m) break;
+            w = (q << 5) + fid_ctz(m);
+            if (w >= n_words) break;
+        }
+        uint32_t bits = row(w);
+        if (w == ((i + 1) >> 5)) bits &= (i & 31) == 31 ? 0xFFFFFFFFu : ~((2u << (i & 31)) - 1u);  // j > i only
+        if (w == n_words - 1 && (n & 31)) bits &= (1u << (n & 31)) - 1u;                            // j < n only
+        while (bits) {
+            if (group_id[i] >= 0) {
+                bits &= ~grouped[w];
+                if (!bits) break;
+            }
+            const int j = (w << 5) + fid_ctz(bits);
+            bits &= bits - 1;
+            selected[i] = 0;
+            selected[j] = 0;
+            if (group_id[i] < 0 && group_id[j] < 0) {
+                const int g = (*n_groups)++;
+                group_id[i] = group_id[j] = g;
+                group_head[g] = i;
+                next_in_group[i] = j;
+                group_tail[g] = j;
+                grouped[i >> 5] |= 1u << (i & 31);
+                grouped[j >> 5] |= 1u << (j & 31);
+            } else if (group_id[i] > -1 && group_id[j] == -1) {
+                const int g = group_id[i];
+                group_id[j] = g;
+                next_in_group[group_tail[g]] = j;
+                group_tail[g] = j;
+                grouped[j >> 5] |= 1u << (j & 31);
+            } else if (group_id[j] > -1 && group_id[i] == -1) {
+                const int g = group_id[j];
+                group_id[i] = g;
+                next_in_group[group_tail[g]] = i;
+                group_tail[g] = i;
+                grouped[i >> 5] |= 1u << (i & 31);
             }
         }
+    }
+}
+
+// Returns the number of groups.
+template <class CloseWord>
+FID_HD int group_pairs(int n, const CloseWord& close_word, uint8_t* selected, int* group_id, int* next_in_group, int* group_head, int* group_tail, int* close_count,
+                       uint32_t* grouped) {
+    int n_groups = 0;
+    group_pairs_init(n, selected, group_id, next_in_group, close_count, grouped);
+    struct RowOf {
+        const CloseWord& cw;
+        int i;
+        FID_HD uint32_t operator()(int w) const { return cw(i, w); }
+    };
+    for (int i = 0; i < n; i++) {
+        if (!close_word.row_any(i)) continue;
+        group_pairs_row(n, i, RowOf{close_word, i}, nullptr, &n_groups, selected, group_id, next_in_group, group_head, group_tail, grouped);
     }
     return n_groups;
 }
