@@ -177,7 +177,7 @@ static int upload_dictionary(fid_detector* h) {
 }
 
 static size_t group_smem(int max_raw) { return (size_t)max_raw * 6 * sizeof(int) + (((size_t)max_raw + 15) & ~(size_t)15) + GROUP_CLOSE_SMEM_WORDS * sizeof(uint32_t); }
-static size_t ident_smem(const DevParams& P) { return (size_t)P.n_markers * 4 * 8 + IDENT_WARPS * 256 * 4 + IDENT_WARPS * FID_MAX_WARP_SIDE_SQ; }
+static size_t ident_smem(const DevParams& P, int warps) { return (size_t)P.n_markers * 4 * 8 + (size_t)warps * 256 * 4 + (size_t)warps * FID_MAX_WARP_SIDE_SQ; }
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -219,7 +219,8 @@ static int configure_kernels(fid_detector* h) {
     CK(cudaFuncSetAttribute(k_threshold_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_threshold_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_sort_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)group_smem(FID_GROUP_MAX_RAW)));
-    CK(cudaFuncSetAttribute(k_identify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxDictMarkers * 4 * 8 + IDENT_WARPS * 256 * 4 + IDENT_WARPS * FID_MAX_WARP_SIDE_SQ)));
+    CK(cudaFuncSetAttribute(k_identify_retry, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxDictMarkers * 4 * 8 + IDENT_WARPS * 256 * 4 + IDENT_WARPS * FID_MAX_WARP_SIDE_SQ)));
+    CK(cudaFuncSetAttribute(k_identify_first, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kMaxDictMarkers * 4 * 8 + IDENT0_WARPS * 256 * 4 + IDENT0_WARPS * FID_MAX_WARP_SIDE_SQ)));
     return FID_OK;
 }
 
@@ -722,9 +723,9 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
         a.cand_id = s.d_cand_id;
         a.cand_corners = s.d_cand_corners;
         a.cand_raw = s.d_cand_raw;
-        dim3 grid(h->max_sel, nf);
-        launch_prio(k_identify, grid, dim3(IDENT_WARPS * 32), ident_smem(P), st, 4, a);
-        launches++;
+        launch_prio(k_identify_first, dim3((h->max_sel + IDENT0_WARPS - 1) / IDENT0_WARPS, nf), dim3(IDENT0_WARPS * 32), ident_smem(P, IDENT0_WARPS), st, 4, a);
+        launch_prio(k_identify_retry, dim3(h->max_sel, nf), dim3(IDENT_WARPS * 32), ident_smem(P, IDENT_WARPS), st, 4, a);
+        launches += 2;
     }
     CK(cudaEventRecord(s.ev[ST_SUBPIX_POSE], st));
     if (P.corner_refine == 2) {  // CORNER_REFINE_CONTOUR: rewrite the decoded candidates' corners before the output stage

@@ -1,7 +1,7 @@
 // CUDA kernels, back half of the per-frame pipeline (sm_100a):
 //   k_sort_group  one block per frame: clockwise fix, stable descending-perimeter order, pairwise
 //                 "too close" matrix, OpenCV's order-dependent grouping                  
-//   k_identify    one warp per selected candidate: perspective removal, Otsu, cell votes, border
+//   k_identify_first / k_identify_retry   one warp per selected candidate, one block per failed first attempt: perspective removal, Otsu, cell votes, border
 //                 check, first-match dictionary search (+ close-contour retry)           (A.6, A.7)
 //   k_finish      one block per frame: compaction in OpenCV's output order, cornerSubPix (A.8),
 //                 solvePnP(ITERATIVE) + FiducialTransform arithmetic                     (A.9)
@@ -323,19 +323,60 @@ struct IdentifyArgs {
     int* cand_raw;       // [F][max_sel] raw-list index of the quad that decoded
 };
 
-#define IDENT_WARPS 8
+#define IDENT_WARPS 8    // retry kernel: warps per candidate
+#define IDENT0_WARPS 4   // first-attempt kernel: candidates per block (one warp each)
 
-// One block per selected candidate.  cv::aruco tries the selected quad first and then, in order, the
-// "close contours" of its group until one decodes; a non-marker group of a dozen nested
-// outlines used to cost a dozen identifications back to back in one warp -- the longest chain of the
-// launch.  Here warp w tries attempts w, w + 8, ... concurrently; the lowest successful attempt wins,
-// which is exactly the sequential first-success rule.
-__global__ void __launch_bounds__(IDENT_WARPS * 32) k_identify(const IdentifyArgs a) {
+__device__ __forceinline__ void identify_write(const IdentifyArgs& a, size_t fo, size_t o, int id, int rot, int used) {
+    a.cand_id[o] = id;
+    a.cand_raw[o] = a.fs.raw_of_sorted[fo + used];
+    const QuadF use = a.fs.quads[fo + used];
+    for (int c = 0; c < 4; c++) {  // correctCornerPosition: std::rotate(begin, begin + 4 - rotation, end)
+        a.cand_corners[o * 8 + 2 * c] = use.x[(c + 4 - rot) & 3];
+        a.cand_corners[o * 8 + 2 * c + 1] = use.y[(c + 4 - rot) & 3];
+    }
+}
+
+// cv::aruco tries the selected quad first and then, in order, the "close contours" of its group until one decodes
+// (SURVEY A.6).  The first attempt decodes for every real marker, so it gets a kernel of its own with ONE WARP per selected
+// candidate -- every candidate of the chunk is in flight at once (a block of 8 warps per candidate held 7 idle warps' worth of
+// registers and ran the chunk in five waves).  cand_id = -2 marks the candidates whose first attempt failed and that have
+// close contours left to try.
+__global__ void __launch_bounds__(IDENT0_WARPS * 32) k_identify_first(const IdentifyArgs a) {
+    extern __shared__ unsigned long long sm_dict[];  // n_markers*4 words, then per-warp scratch
+    const int f = blockIdx.y;
+    if ((int)blockIdx.x * IDENT0_WARPS >= a.n_sel[f]) return;
+    const int n_words = a.P.n_markers * 4;
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) sm_dict[i] = __ldg(a.dict + i);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int* hist = reinterpret_cast<int*>(sm_dict + n_words) + warp * 256;
+    uint8_t* img = reinterpret_cast<uint8_t*>(reinterpret_cast<int*>(sm_dict + n_words) + IDENT0_WARPS * 256) + warp * (FID_MAX_WARP_SIDE_SQ);
+    __syncthreads();
+    const int k = blockIdx.x * IDENT0_WARPS + warp;
+    if (k >= a.n_sel[f]) return;
+    const size_t fo = (size_t)f * a.max_raw, o = (size_t)f * a.max_sel + k;
+    const int si = a.fs.sel_idx[fo + k];
+    const FrameImg gray{a.src + (size_t)f * a.frame_stride, a.row_stride, a.enc};
+    WarpLanes L;
+    const IdentifyResult r = identify_candidate(L, gray, a.W, a.H, a.fs.quads[fo + si], a.P, sm_dict, img, hist);
+    if (lane == 0) {
+        if (r.id >= 0)
+            identify_write(a, fo, o, r.id, r.rotation, si);
+        else
+            a.cand_id[o] = a.fs.close_count[fo + si] > 0 ? -2 : -1;
+    }
+}
+
+// One block per candidate whose first attempt failed.  A non-marker group of a dozen nested outlines used to cost a dozen
+// identifications back to back in one warp -- the longest chain of the launch.  Here warp w tries attempts 1 + w, 1 + w + 8, ...
+// concurrently; the lowest successful attempt wins, which is exactly the sequential first-success rule.
+__global__ void __launch_bounds__(IDENT_WARPS * 32) k_identify_retry(const IdentifyArgs a) {
     extern __shared__ unsigned long long sm_dict[];  // n_markers*4 words, then per-warp scratch
     __shared__ int s_best;                            // lowest successful attempt so far
     __shared__ int s_id[IDENT_WARPS], s_rot[IDENT_WARPS], s_att[IDENT_WARPS];
     const int f = blockIdx.y, k = blockIdx.x;
     if (k >= a.n_sel[f]) return;
+    const size_t o = (size_t)f * a.max_sel + k;
+    if (a.cand_id[o] != -2) return;
     const int n_words = a.P.n_markers * 4;
     for (int i = threadIdx.x; i < n_words; i += blockDim.x) sm_dict[i] = __ldg(a.dict + i);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -349,38 +390,23 @@ __global__ void __launch_bounds__(IDENT_WARPS * 32) k_identify(const IdentifyArg
     const FrameImg gray{a.src + (size_t)f * a.frame_stride, a.row_stride, a.enc};
     const int nc = a.fs.close_count[fo + si], co = a.fs.close_off[fo + si];
     WarpLanes L;
-    // attempt 0 (the selected quad) decodes for every real marker: warp 0 tries it alone, and only when it
-    // fails do all warps share the close contours (attempts 1 + w, 1 + w + 8, ...)
-    if (warp == 0) {
-        const IdentifyResult r = identify_candidate(L, gray, a.W, a.H, a.fs.quads[fo + si], a.P, sm_dict, img, hist);
-        if (r.id >= 0 && lane == 0) {
-            s_id[0] = r.id;
-            s_rot[0] = r.rotation;
-            s_att[0] = 0;
-            s_best = 0;
-        }
-    }
-    __syncthreads();
-    if (s_best != 0) {
-        for (int t = 1 + warp; t <= nc; t += IDENT_WARPS) {
-            if (t > *reinterpret_cast<volatile int*>(&s_best)) break;  // an earlier attempt already decoded
-            const QuadF quad = a.fs.quads[fo + a.fs.close_idx[fo + co + t - 1]];
-            const IdentifyResult r = identify_candidate(L, gray, a.W, a.H, quad, a.P, sm_dict, img, hist);
-            __syncwarp();
-            if (r.id >= 0) {
-                if (lane == 0) {
-                    s_id[warp] = r.id;
-                    s_rot[warp] = r.rotation;
-                    s_att[warp] = t;
-                    atomicMin(&s_best, t);
-                }
-                break;  // later attempts of this warp cannot win
+    for (int t = 1 + warp; t <= nc; t += IDENT_WARPS) {
+        if (t > *reinterpret_cast<volatile int*>(&s_best)) break;  // an earlier attempt already decoded
+        const QuadF quad = a.fs.quads[fo + a.fs.close_idx[fo + co + t - 1]];
+        const IdentifyResult r = identify_candidate(L, gray, a.W, a.H, quad, a.P, sm_dict, img, hist);
+        __syncwarp();
+        if (r.id >= 0) {
+            if (lane == 0) {
+                s_id[warp] = r.id;
+                s_rot[warp] = r.rotation;
+                s_att[warp] = t;
+                atomicMin(&s_best, t);
             }
+            break;  // later attempts of this warp cannot win
         }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        const size_t o = (size_t)f * a.max_sel + k;
         int id = -1, rot = 0, att = 0;
         for (int w = 0; w < IDENT_WARPS; w++)
             if (s_att[w] == s_best && s_best != 0x7fffffff) {
@@ -388,16 +414,10 @@ __global__ void __launch_bounds__(IDENT_WARPS * 32) k_identify(const IdentifyArg
                 rot = s_rot[w];
                 att = s_att[w];
             }
-        a.cand_id[o] = id;
-        if (id >= 0) {
-            const int used = att == 0 ? si : a.fs.close_idx[fo + co + att - 1];
-            a.cand_raw[o] = a.fs.raw_of_sorted[fo + used];
-            const QuadF use = a.fs.quads[fo + used];
-            for (int c = 0; c < 4; c++) {  // correctCornerPosition: std::rotate(begin, begin + 4 - rotation, end)
-                a.cand_corners[o * 8 + 2 * c] = use.x[(c + 4 - rot) & 3];
-                a.cand_corners[o * 8 + 2 * c + 1] = use.y[(c + 4 - rot) & 3];
-            }
-        }
+        if (id >= 0)
+            identify_write(a, fo, o, id, rot, a.fs.close_idx[fo + co + att - 1]);
+        else
+            a.cand_id[o] = -1;
     }
 }
 
