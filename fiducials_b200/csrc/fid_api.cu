@@ -49,6 +49,8 @@ struct Slot {
     int* d_cand_id = nullptr;
     float* d_cand_corners = nullptr;
     int* d_cand_raw = nullptr;
+    uint32_t* d_first_list = nullptr;  // work lists of the identification kernels, F * max_sel records each
+    uint32_t* d_retry_list = nullptr;
     int32_t* d_out_count = nullptr;
     int32_t* d_out_ids = nullptr;
     float* d_out_corners = nullptr;
@@ -266,6 +268,8 @@ static int alloc_slot(fid_detector* h, Slot& s) {
     A(dalloc(&s.d_cand_id, F * h->max_sel));
     A(dalloc(&s.d_cand_corners, F * h->max_sel * 8));
     A(dalloc(&s.d_cand_raw, F * h->max_sel));
+    A(dalloc(&s.d_first_list, F * h->max_sel));
+    A(dalloc(&s.d_retry_list, F * h->max_sel));
     const size_t M = F * h->max_markers;
     A(dalloc(&s.d_out_count, F));
     A(dalloc(&s.d_out_ids, M));
@@ -291,7 +295,7 @@ static void free_slot(Slot& s) {
                      s.d_raw,         s.d_nraw,          s.fs.quads_tmp,    s.fs.per_tmp,     s.fs.quads,       s.fs.per,         s.fs.close_bits, s.fs.group_id,
                      s.fs.group_members, s.fs.next_in_group, s.fs.group_head, s.fs.group_tail, s.fs.close_count, s.fs.close_idx,   s.fs.close_off,  s.fs.selected,
                      s.fs.sel_idx,    s.d_nsel,          s.d_nrawc,         s.d_cand_id,      s.d_cand_corners, s.d_out_count,    s.d_out_ids,     s.d_out_corners,
-                     s.d_out_tf,      s.fs.raw_of_sorted, s.d_cand_raw};
+                     s.d_out_tf,      s.fs.raw_of_sorted, s.d_cand_raw,     s.d_first_list,   s.d_retry_list};
     for (void* p : dptrs)
         if (p) cudaFree(p);
     void* hptrs[] = {s.h_out_count, s.h_out_ids, s.h_out_corners, s.h_out_tf, s.h_counters, s.h_nsel, s.h_nrawc};
@@ -700,6 +704,7 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
         a.H = H;
         a.min_dist_to_border = P.min_dist_to_border;
         a.counters = s.d_counters;
+        a.first_list = s.d_first_list;
         static const int group_prof = getenv("FID_GROUP_PROF") ? atoi(getenv("FID_GROUP_PROF")) : 0;
         a.prof = group_prof;
         launch_prio(k_sort_group, dim3(nf), dim3(GROUP_THREADS), group_smem(h->max_raw), st, 4, a);
@@ -723,8 +728,12 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
         a.cand_id = s.d_cand_id;
         a.cand_corners = s.d_cand_corners;
         a.cand_raw = s.d_cand_raw;
-        launch_prio(k_identify_first, dim3((h->max_sel + IDENT0_WARPS - 1) / IDENT0_WARPS, nf), dim3(IDENT0_WARPS * 32), ident_smem(P, IDENT0_WARPS), st, 4, a);
-        launch_prio(k_identify_retry, dim3(h->max_sel, nf), dim3(IDENT_WARPS * 32), ident_smem(P, IDENT_WARPS), st, 4, a);
+        a.first_list = s.d_first_list;
+        a.retry_list = s.d_retry_list;
+        a.counters = s.d_counters;
+        // fixed grids over work lists: a grid of one block per (frame, candidate slot) is 32 768 blocks of which 1 500 have work
+        launch_prio(k_identify_first, dim3(h->sm_count * 4), dim3(IDENT0_WARPS * 32), ident_smem(P, IDENT0_WARPS), st, 4, a);
+        launch_prio(k_identify_retry, dim3(h->sm_count * 2), dim3(IDENT_WARPS * 32), ident_smem(P, IDENT_WARPS), st, 4, a);
         launches += 2;
     }
     CK(cudaEventRecord(s.ev[ST_SUBPIX_POSE], st));

@@ -29,6 +29,8 @@ struct Counters {
     unsigned int emit_work;
     unsigned int n_segs;       // contour segments queued for k_emit
     unsigned int approx_work;  // k_approx_warp work counter
+    unsigned int n_first;      // selected candidates of the chunk (k_sort_group -> k_identify_first work list)
+    unsigned int n_retry;      // candidates whose first identification attempt failed (-> k_identify_retry work list)
 };
 
 struct WalkRec {       // a bidirectional border walk suspended between rounds (contour_walk.cuh, WalkState2)

@@ -52,6 +52,7 @@ struct GroupArgs {
     float min_marker_dist_rate, min_group_dist;
     int W, H, min_dist_to_border;
     Counters* counters;
+    uint32_t* first_list;  // [F * max_sel] frame << 16 | k of every selected candidate of the chunk, any order
     int prof;  // FID_GROUP_PROF=1: frame 0 prints its phase clocks (debug aid)
 };
 
@@ -299,7 +300,16 @@ __global__ void __launch_bounds__(GROUP_THREADS) k_sort_group(const GroupArgs a)
         }
         __syncthreads();
     }
-    if (tid == 0) a.n_sel[f] = s_base < a.max_sel ? s_base : a.max_sel;
+    {
+        const int ns = s_base < a.max_sel ? s_base : a.max_sel;
+        __shared__ unsigned int s_first_base;
+        if (tid == 0) {
+            a.n_sel[f] = ns;
+            s_first_base = ns ? atomicAdd(&a.counters->n_first, (unsigned int)ns) : 0u;
+        }
+        __syncthreads();
+        for (int j = tid; j < ns; j += GROUP_THREADS) a.first_list[s_first_base + j] = ((uint32_t)f << 16) | (uint32_t)j;
+    }
     GROUP_TICK(5);
     if (a.prof && tid == 0 && f == 0)
         printf("[group prof] n=%d groups=%d clocks: sort %lld close %lld pass1 %lld pass2 %lld select %lld\n", n, s_n_groups, t_[1] - t_[0], t_[2] - t_[1], t_[3] - t_[2], t_[4] - t_[3], t_[5] - t_[4]);
@@ -321,6 +331,9 @@ struct IdentifyArgs {
     int* cand_id;        // [F][max_sel]  -1 rejected
     float* cand_corners; // [F][max_sel][8] rotated to marker order
     int* cand_raw;       // [F][max_sel] raw-list index of the quad that decoded
+    const uint32_t* first_list;  // work list of k_identify_first (frame << 16 | k)
+    uint32_t* retry_list;        // work list of k_identify_retry, filled by k_identify_first
+    Counters* counters;          // n_first, n_retry
 };
 
 #define IDENT_WARPS 8    // retry kernel: warps per candidate
@@ -343,26 +356,33 @@ __device__ __forceinline__ void identify_write(const IdentifyArgs& a, size_t fo,
 // close contours left to try.
 __global__ void __launch_bounds__(IDENT0_WARPS * 32) k_identify_first(const IdentifyArgs a) {
     extern __shared__ unsigned long long sm_dict[];  // n_markers*4 words, then per-warp scratch
-    const int f = blockIdx.y;
-    if ((int)blockIdx.x * IDENT0_WARPS >= a.n_sel[f]) return;
+    const unsigned int n_first = a.counters->n_first;
+    if (blockIdx.x * IDENT0_WARPS >= n_first) return;  // fixed grid, work list: no empty blocks worth mentioning
     const int n_words = a.P.n_markers * 4;
     for (int i = threadIdx.x; i < n_words; i += blockDim.x) sm_dict[i] = __ldg(a.dict + i);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int* hist = reinterpret_cast<int*>(sm_dict + n_words) + warp * 256;
     uint8_t* img = reinterpret_cast<uint8_t*>(reinterpret_cast<int*>(sm_dict + n_words) + IDENT0_WARPS * 256) + warp * (FID_MAX_WARP_SIDE_SQ);
     __syncthreads();
-    const int k = blockIdx.x * IDENT0_WARPS + warp;
-    if (k >= a.n_sel[f]) return;
-    const size_t fo = (size_t)f * a.max_raw, o = (size_t)f * a.max_sel + k;
-    const int si = a.fs.sel_idx[fo + k];
-    const FrameImg gray{a.src + (size_t)f * a.frame_stride, a.row_stride, a.enc};
     WarpLanes L;
-    const IdentifyResult r = identify_candidate(L, gray, a.W, a.H, a.fs.quads[fo + si], a.P, sm_dict, img, hist);
-    if (lane == 0) {
-        if (r.id >= 0)
-            identify_write(a, fo, o, r.id, r.rotation, si);
-        else
-            a.cand_id[o] = a.fs.close_count[fo + si] > 0 ? -2 : -1;
+    for (unsigned int i = blockIdx.x * IDENT0_WARPS + warp; i < n_first; i += gridDim.x * IDENT0_WARPS) {
+        const uint32_t rec = a.first_list[i];
+        const int f = (int)(rec >> 16), k = (int)(rec & 0xFFFFu);
+        const size_t fo = (size_t)f * a.max_raw, o = (size_t)f * a.max_sel + k;
+        const int si = a.fs.sel_idx[fo + k];
+        const FrameImg gray{a.src + (size_t)f * a.frame_stride, a.row_stride, a.enc};
+        const IdentifyResult r = identify_candidate(L, gray, a.W, a.H, a.fs.quads[fo + si], a.P, sm_dict, img, hist);
+        __syncwarp();
+        if (lane == 0) {
+            if (r.id >= 0) {
+                identify_write(a, fo, o, r.id, r.rotation, si);
+            } else if (a.fs.close_count[fo + si] > 0) {
+                a.cand_id[o] = -2;
+                a.retry_list[atomicAdd(&a.counters->n_retry, 1u)] = rec;
+            } else {
+                a.cand_id[o] = -1;
+            }
+        }
     }
 }
 
@@ -373,51 +393,54 @@ __global__ void __launch_bounds__(IDENT_WARPS * 32) k_identify_retry(const Ident
     extern __shared__ unsigned long long sm_dict[];  // n_markers*4 words, then per-warp scratch
     __shared__ int s_best;                            // lowest successful attempt so far
     __shared__ int s_id[IDENT_WARPS], s_rot[IDENT_WARPS], s_att[IDENT_WARPS];
-    const int f = blockIdx.y, k = blockIdx.x;
-    if (k >= a.n_sel[f]) return;
-    const size_t o = (size_t)f * a.max_sel + k;
-    if (a.cand_id[o] != -2) return;
+    const unsigned int n_retry = a.counters->n_retry;
+    if (blockIdx.x >= n_retry) return;
     const int n_words = a.P.n_markers * 4;
     for (int i = threadIdx.x; i < n_words; i += blockDim.x) sm_dict[i] = __ldg(a.dict + i);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int* hist = reinterpret_cast<int*>(sm_dict + n_words) + warp * 256;
     uint8_t* img = reinterpret_cast<uint8_t*>(reinterpret_cast<int*>(sm_dict + n_words) + IDENT_WARPS * 256) + warp * (FID_MAX_WARP_SIDE_SQ);
-    if (threadIdx.x == 0) s_best = 0x7fffffff;
-    if (lane == 0) s_att[warp] = 0x7fffffff;
-    __syncthreads();
-    const size_t fo = (size_t)f * a.max_raw;
-    const int si = a.fs.sel_idx[fo + k];
-    const FrameImg gray{a.src + (size_t)f * a.frame_stride, a.row_stride, a.enc};
-    const int nc = a.fs.close_count[fo + si], co = a.fs.close_off[fo + si];
     WarpLanes L;
-    for (int t = 1 + warp; t <= nc; t += IDENT_WARPS) {
-        if (t > *reinterpret_cast<volatile int*>(&s_best)) break;  // an earlier attempt already decoded
-        const QuadF quad = a.fs.quads[fo + a.fs.close_idx[fo + co + t - 1]];
-        const IdentifyResult r = identify_candidate(L, gray, a.W, a.H, quad, a.P, sm_dict, img, hist);
-        __syncwarp();
-        if (r.id >= 0) {
-            if (lane == 0) {
-                s_id[warp] = r.id;
-                s_rot[warp] = r.rotation;
-                s_att[warp] = t;
-                atomicMin(&s_best, t);
+    for (unsigned int i = blockIdx.x; i < n_retry; i += gridDim.x) {
+        const uint32_t rec = a.retry_list[i];
+        const int f = (int)(rec >> 16), k = (int)(rec & 0xFFFFu);
+        const size_t fo = (size_t)f * a.max_raw, o = (size_t)f * a.max_sel + k;
+        __syncthreads();  // the previous candidate's result has been read
+        if (threadIdx.x == 0) s_best = 0x7fffffff;
+        if (lane == 0) s_att[warp] = 0x7fffffff;
+        __syncthreads();
+        const int si = a.fs.sel_idx[fo + k];
+        const FrameImg gray{a.src + (size_t)f * a.frame_stride, a.row_stride, a.enc};
+        const int nc = a.fs.close_count[fo + si], co = a.fs.close_off[fo + si];
+        for (int t = 1 + warp; t <= nc; t += IDENT_WARPS) {
+            if (t > *reinterpret_cast<volatile int*>(&s_best)) break;  // an earlier attempt already decoded
+            const QuadF quad = a.fs.quads[fo + a.fs.close_idx[fo + co + t - 1]];
+            const IdentifyResult r = identify_candidate(L, gray, a.W, a.H, quad, a.P, sm_dict, img, hist);
+            __syncwarp();
+            if (r.id >= 0) {
+                if (lane == 0) {
+                    s_id[warp] = r.id;
+                    s_rot[warp] = r.rotation;
+                    s_att[warp] = t;
+                    atomicMin(&s_best, t);
+                }
+                break;  // later attempts of this warp cannot win
             }
-            break;  // later attempts of this warp cannot win
         }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int id = -1, rot = 0, att = 0;
-        for (int w = 0; w < IDENT_WARPS; w++)
-            if (s_att[w] == s_best && s_best != 0x7fffffff) {
-                id = s_id[w];
-                rot = s_rot[w];
-                att = s_att[w];
-            }
-        if (id >= 0)
-            identify_write(a, fo, o, id, rot, a.fs.close_idx[fo + co + att - 1]);
-        else
-            a.cand_id[o] = -1;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int id = -1, rot = 0, att = 0;
+            for (int w = 0; w < IDENT_WARPS; w++)
+                if (s_att[w] == s_best && s_best != 0x7fffffff) {
+                    id = s_id[w];
+                    rot = s_rot[w];
+                    att = s_att[w];
+                }
+            if (id >= 0)
+                identify_write(a, fo, o, id, rot, a.fs.close_idx[fo + co + att - 1]);
+            else
+                a.cand_id[o] = -1;
+        }
     }
 }
 
