@@ -643,7 +643,8 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
             a.chunk = r == 0 ? 256u : 32u;
             a.refill_min = h->walk_refill;
             a.pass_steps = h->walk_pass;
-            const int blocks = r == 0 ? h->sm_count * 8 : (r == 1 ? h->sm_count * 8 : h->sm_count * 4);
+            static const int wb2 = getenv("FID_WALK_BLOCKS_R2") ? atoi(getenv("FID_WALK_BLOCKS_R2")) : 4, wb3 = getenv("FID_WALK_BLOCKS_R3") ? atoi(getenv("FID_WALK_BLOCKS_R3")) : 4;
+            const int blocks = r == 0 ? h->sm_count * 8 : (r == 1 ? h->sm_count * 8 : h->sm_count * (r == 2 ? wb2 : wb3));
             launch_prio(k_walk, dim3(blocks), dim3(256), 0, st, r == 0 ? 1 : (r == 1 ? 2 : 3), a);
             launches++;
         }
