@@ -43,11 +43,14 @@ struct HuffTable {
     uint16_t look[1 << FIDJPEG_LOOK];    // (length << 8) | symbol, 0 = code longer than the look-ahead
     int32_t fast_ac[1 << FIDJPEG_LOOK];  // AC tables: code AND magnitude bits inside the look-ahead -> value * 256 + run * 16 + total bits, else 0
 
-    void build(const uint8_t bits[17], const uint8_t* symbols, int nsym) {
+    // false = not a prefix code (more codes of some length than the code space holds): the stream is rejected
+    bool build(const uint8_t bits[17], const uint8_t* symbols, int nsym) {
+        memset(vals, 0, sizeof(vals));
         memcpy(vals, symbols, nsym);
         memset(look, 0, sizeof(look));
         int code = 0, k = 0;
         for (int l = 1; l <= 16; l++) {
+            if (code + bits[l] > (1 << l)) return false;
             mincode[l] = code;
             valptr[l] = k;
             for (int i = 0; i < bits[l]; i++, k++, code++) {
@@ -71,6 +74,7 @@ struct HuffTable {
             fast_ac[i] = v * 256 + run * 16 + (l + mag);  // |v| < 512: fits with room to spare
         }
         present = true;
+        return true;
     }
 };
 
@@ -127,7 +131,7 @@ struct BitReader {
             const int code = (int)(acc >> (64 - l));
             if (code <= t.maxcode[l]) {
                 consume(l);
-                return t.vals[t.valptr[l] + code - t.mincode[l]];
+                return t.vals[(t.valptr[l] + code - t.mincode[l]) & 255];
             }
         }
         return -1;
@@ -230,7 +234,7 @@ static inline int parse_headers(const uint8_t* data, size_t size, FrameInfo* fi,
                 }
                 o += 17;
                 if (nsym > 256 || o + nsym > n) return JPEG_BAD;
-                (tc ? ac : dc)[th].build(bits, seg + o, nsym);
+                if (!(tc ? ac : dc)[th].build(bits, seg + o, nsym)) return JPEG_BAD;
                 o += nsym;
             }
         } else if (m == 0xDD) {  // DRI

@@ -88,3 +88,33 @@ def test_sparse_coefficients_are_smaller_than_the_frame():
     nblk = (1920 // 8) * (1088 // 8) * 3 // 2
     sparse_bytes = nblk * 12 + nv * 2
     assert sparse_bytes < frames[0].nbytes / 3, (sparse_bytes, frames[0].nbytes)
+
+
+def test_corrupted_streams_never_crash_the_entropy_decoder():
+    """Robustness of the host half (it parses bytes that arrive over the network in the reference's deployment): random byte
+    flips, truncations and garbage tables must end in a status code or a decoded image, never in an out-of-bounds access."""
+    rng = np.random.default_rng(7)
+    base = []
+    for q, samp in [(40, "420"), (90, "444"), (75, "422")]:
+        ok, buf = cv2.imencode(".jpg", scene(48, 80, q), [cv2.IMWRITE_JPEG_QUALITY, q, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, SAMPLING[samp], cv2.IMWRITE_JPEG_RST_INTERVAL, 2])
+        base.append(np.frombuffer(bytes(buf), np.uint8))
+    n_ok = 0
+    for it in range(1500):
+        b = base[it % 3].copy()
+        mode = it % 4
+        if mode == 0:  # flips anywhere (headers included)
+            for _ in range(int(rng.integers(1, 6))):
+                b[int(rng.integers(2, b.size))] = int(rng.integers(0, 256))
+        elif mode == 1:  # flips in the entropy-coded part only
+            for _ in range(int(rng.integers(1, 20))):
+                b[int(rng.integers(b.size // 2, b.size))] = int(rng.integers(0, 256))
+        elif mode == 2:  # truncation
+            b = b[: int(rng.integers(4, b.size))]
+        else:  # a run of 0xFF (markers in the middle of the scan)
+            p = int(rng.integers(2, b.size - 8))
+            b[p : p + int(rng.integers(1, 8))] = 0xFF
+        rc, img, _ = hs_decode(b, max_w=128, max_h=128)
+        if rc == 0:
+            n_ok += 1
+            assert img.shape[2] == 3 and img.shape[0] <= 128 and img.shape[1] <= 128
+    assert n_ok > 0  # damage in the scan usually still decodes (to a damaged picture), like libjpeg
