@@ -675,8 +675,9 @@ def run_c5(args, reference):
         val = n_obs / dt
         out = {"impl": "reference", "metric": metric, "value": val, "unit": "observations/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": workload},
-               "cpu_baseline": {"value": val, "unit": "observations/s", "cores": 1, "kind": "port", "cpu_model": model, "physical_cores": phys, "logical_cpus": logical, "cgroup_cpu_quota_cores": cpu_quota_cores(),
-                                "sample": "the whole sequence through oracle/_ref/libslam_oracle.so (map.cpp / transform_with_variance.cpp restated, g++ -O2), one core"},
+               "cpu_baseline": {"value": val, "unit": "observations/s", "cores": 1, "kind": bench_c5.cpu_fold_kind()[0], "cpu_model": model, "physical_cores": phys, "logical_cpus": logical, "cgroup_cpu_quota_cores": cpu_quota_cores(),
+                                "sample": "the whole sequence through " + bench_c5.cpu_fold_kind()[1] + ", one core",
+                                "arithmetic_only_port": bench_c5.cpu_port_info(msgs, seed_entry)},
                "e2e": {"value": val, "unit": "observations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(out)
         return
@@ -766,8 +767,9 @@ def run_c5(args, reference):
                "config": {"workload": workload, "parallelism": "replicas only: every rank folds its own copy of the sequence (the fold is sequential per map)", "map_fiducials": len(ents)},
                "e2e": {"value": val, "unit": "observations/s", "h2d_bytes_per_step": int(obs.nbytes + offsets.nbytes), "d2h_bytes_per_step": 0, "note": "value already includes the H2D of the observations"},
                "gpu_launches": args.steps, "parity": {"max_entry_diff_vs_host_fold": worst, "entries": len(ents)}, "batch_gauss_newton_refine": refine,
-               "cpu_baseline": {"value": n_obs / cpu_dt, "unit": "observations/s", "cores": 1, "kind": "port", "cpu_model": model, "physical_cores": phys, "logical_cpus": logical, "cgroup_cpu_quota_cores": cpu_quota_cores(),
-                                "sample": "the whole sequence through oracle/_ref/libslam_oracle.so, one core, %.2f ms" % (cpu_dt * 1e3)},
+               "cpu_baseline": {"value": n_obs / cpu_dt, "unit": "observations/s", "cores": 1, "kind": bench_c5.cpu_fold_kind()[0], "cpu_model": model, "physical_cores": phys, "logical_cpus": logical, "cgroup_cpu_quota_cores": cpu_quota_cores(),
+                                "sample": "the whole sequence through " + bench_c5.cpu_fold_kind()[1] + ", one core, %.2f ms" % (cpu_dt * 1e3),
+                                "arithmetic_only_port": bench_c5.cpu_port_info(msgs, seed_entry)},
                "roofline": {"bound": "latency", "note": "sequential scalar-variance fold (SURVEY 8d): no roofline fraction is meaningful; report observations/s and ms per sequence"}}
         emit(out)
     slam.close()

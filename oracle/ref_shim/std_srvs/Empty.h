@@ -1,0 +1,7 @@
+#pragma once
+namespace std_srvs {
+struct Empty {
+    struct Request {};
+    struct Response {};
+};
+}  // namespace std_srvs

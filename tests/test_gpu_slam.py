@@ -426,3 +426,48 @@ def test_batch_gauss_newton_refine_matches_oracle():
     # the reference's map-quality metric (fiducial_slam/scripts/fit_plane.py) stays at the noise level of the observations
     assert ro.plane_fit_residual([[e.x, e.y, e.z] for e in after]) < 0.05
     slam.close()
+
+
+def test_device_map_matches_the_reference_compiled_code():
+    """The CUDA map update against the REFERENCE'S OWN Map class (oracle/_ref/libmap_ref.so: fiducial_slam/src/map.cpp +
+    transform_with_variance.cpp compiled unmodified against stand-in ROS / tf2 headers; built by oracle/Makefile in the authoring
+    container, shipped prebuilt) -- no restatement in between: per-message robot pose, the full C5 map, links and the map file."""
+    from fiducials_b200 import synth
+    from fiducials_b200.node import FiducialSlam
+    from oracle import map_ref
+
+    if not map_ref.available():
+        pytest.skip("oracle/_ref/libmap_ref.so was not built (needs the reference checkout: make -C oracle)")
+    msgs, seed_entry = synth.make_c5_sequence(1000, seed=0)
+    text = "%d %.17g %.17g %.17g %.17g %.17g %.17g %.17g 0\n" % tuple(seed_entry[:8])
+    T_bc = [0.1, -0.02, 0.3, *so.q_from_rpy(0.02, -0.6, 0.1)]
+    inv = so.TWV.from_qt(T_bc[3:], T_bc[:3]).inverse()
+    T_cb = [*inv.t, *so.m_to_q(inv.R)]
+    # message by message, with a camera offset: robot pose and variance of every update
+    ref = map_ref.RefMap(initial_map_text=text)
+    slam = FiducialSlam(max_fiducials=512)
+    slam.loadMap([seed_entry])
+    for m in msgs[:120]:
+        pub, t, q, cov = ref.update(m, T_bc, T_cb)
+        r = slam.transformCallback(m, np.array(T_bc), np.array(T_cb))
+        assert bool(r.valid) == pub
+        if pub:
+            assert np.abs(np.array(r.t) - t).max() < 1e-9
+            rq = np.array(r.q)
+            assert min(np.abs(rq - q).max(), np.abs(rq + q).max()) < 1e-9
+            assert abs(r.variance - cov[0]) <= 1e-9 * max(1.0, cov[0])
+    re = ref.entries()
+    _cmp_entries(slam.entries(), [(int(x[0]), *x[1:7]) for x in re], 1e-9)
+    assert {k: set(v) for k, v in slam.links().items()} == ref.links()
+    ref.close()
+    # the whole sequence in one launch against one replay inside the compiled reference
+    ref = map_ref.RefMap(initial_map_text=text)
+    ref.replay(msgs, [0, 0, 0, 0, 0, 0, 1], [0, 0, 0, 0, 0, 0, 1])
+    one = FiducialSlam(max_fiducials=512)
+    one.loadMap([seed_entry])
+    ident = so.TWV.identity()
+    one.replay([msgs], _tf7(ident), _tf7(ident))
+    re = ref.entries()
+    assert len(re) == 500
+    _cmp_entries(one.entries(0), [(int(x[0]), *x[1:7]) for x in re], 1e-8)
+    ref.close()

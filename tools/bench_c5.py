@@ -36,13 +36,60 @@ def cpu_replay(msgs, seed_entry, reps=5):
     return best, n
 
 
+def _ref_map(seed_entry):
+    """The reference's own Map (oracle/_ref/libmap_ref.so: map.cpp + transform_with_variance.cpp compiled from the reference
+    checkout) seeded with the pinned fiducial, or None when the library was not built."""
+    from oracle import map_ref
+
+    if not map_ref.available():
+        return None
+    text = "%d %.17g %.17g %.17g %.17g %.17g %.17g %.17g 0\n" % tuple(seed_entry[:8])
+    return map_ref.RefMap(initial_map_text=text)
+
+
+IDENT7 = [0, 0, 0, 0, 0, 0, 1]
+
+
+def cpu_fold_kind():
+    """("reference" | "port", description) of what cpu_fold_seconds times."""
+    from oracle import map_ref
+
+    if map_ref.available():
+        return "reference", "oracle/_ref/libmap_ref.so = the reference's fiducial_slam/src/map.cpp + transform_with_variance.cpp compiled unmodified (g++ -O2) against stand-in ROS/tf2 headers, Map::update per message incl. its publishMap / marker messages"
+    return "port", "oracle/_ref/libslam_oracle.so (map.cpp / transform_with_variance.cpp restated, g++ -O2)"
+
+
 def cpu_fold_seconds(msgs, seed_entry, reps=3):
     """Seconds for the whole sequence on one host core (bench.py --workload C5 cpu_baseline)."""
-    return cpu_replay(msgs, seed_entry, reps)[0]
+    best = 1e9
+    for _ in range(reps):
+        ref = _ref_map(seed_entry)
+        if ref is None:
+            return cpu_replay(msgs, seed_entry, reps)[0]
+        t0 = time.perf_counter()
+        ref.replay(msgs, IDENT7, IDENT7)
+        best = min(best, time.perf_counter() - t0)
+        ref.close()
+    return best
+
+
+def cpu_port_info(msgs, seed_entry):
+    """The arithmetic-only restatement (oracle/_ref/libslam_oracle.so) beside the compiled reference: the reference's Map::update
+    also rebuilds and publishes the whole FiducialMapEntryArray and four rviz markers per observation on every message."""
+    t, n = cpu_replay(msgs, seed_entry, 3)
+    n_obs = sum(len(m) for m in msgs)
+    return {"value": n_obs / t, "unit": "observations/s", "ms_per_sequence": t * 1e3,
+            "what": "oracle/_ref/libslam_oracle.so: the same fold without the reference's per-message publishMap / marker messages (map.cpp:629-654, 669-775)"}
 
 
 def cpu_fold_entries(msgs, seed_entry):
     """Map after the sequence as rows (id, x, y, z, roll, pitch, yaw), ids ascending (publishMap read-out)."""
+    ref = _ref_map(seed_entry)
+    if ref is not None:
+        ref.replay(msgs, IDENT7, IDENT7)
+        rows = [(int(r[0]), *r[1:7]) for r in ref.entries()]
+        ref.close()
+        return sorted(rows)
     from oracle import slam_oracle as so
 
     cpu_replay(msgs, seed_entry, 1)
