@@ -571,4 +571,22 @@ FID_HD void halo_row_starts(uint32_t up, uint32_t mid, uint32_t dn, uint32_t* L,
     *R = r & interior;
 }
 
+// Second, optional pruning stage (start_prune_table.h, tools/gen_prune_table.py): the 3 x 5 neighbourhood of a surviving start
+// indexes a table of the patterns for which the start's walk provably aborts within 3 steps whatever lies outside the
+// neighbourhood (exhaustively enumerated with the walk code itself).  tab = kStartPruneTable laid out [2][FID_START_PRUNE_WORDS].
+// Columns 1 and 30 of a tile are left alone: their neighbourhood reaches beyond the halo.
+FID_HD void halo_prune_starts(uint32_t up, uint32_t mid, uint32_t dn, uint32_t* L, uint32_t* R, const uint32_t* tab) {
+    for (int side = 0; side < 2; side++) {
+        uint32_t* S = side ? R : L;
+        uint32_t todo = *S & 0x3FFFFFFCu;  // columns 2..29
+        const uint32_t* t = tab + side * 1024;
+        while (todo) {
+            const int i = fid_ctz(todo);
+            todo &= todo - 1;
+            const uint32_t pat = ((up >> (i - 2)) & 31u) | (((mid >> (i - 2)) & 31u) << 5) | (((dn >> (i - 2)) & 31u) << 10);
+            if ((lut_load(t + (pat >> 5)) >> (pat & 31u)) & 1u) *S &= ~(1u << i);
+        }
+    }
+}
+
 }  // namespace fid

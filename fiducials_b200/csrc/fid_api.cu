@@ -12,6 +12,7 @@
 #include "../../include/fiducials_b200.h"
 #include "kernels_contour.cuh"
 #include "kernels_threshold.cuh"
+#include "start_prune_table.h"
 #include "kernels_threshold_mma.cuh"
 #include "kernels_marker.cuh"
 #include "params_host.h"
@@ -100,6 +101,8 @@ struct fid_detector {
     int pf_idx = 0, pf_frames = 0, pf_w = 0, pf_h = 0;
     float* d_subpix_masks = nullptr;
     unsigned long long* d_dict = nullptr;  // active dictionary, kMaxDictMarkers * 4 words
+    uint32_t* d_prune = nullptr;           // start_prune_table.h on the device; used when start_prune is set (FID_START_PRUNE=1, default off)
+    int start_prune = 0;
     uint32_t* d_lut_prev = nullptr;
     uint32_t* d_lut_next = nullptr;
     int thresh_mode = 0;  // 0 = summed-area-table kernel (kernels_threshold.cuh, default: faster end to end), 1 = tensor-core kernel (kernels_threshold_mma.cuh; FID_THRESH=mma)
@@ -218,6 +221,8 @@ static int r_max_of(const DevParams& P) {
 static int configure_kernels(fid_detector* h) {
     CK(cudaFuncSetAttribute(k_threshold<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thresh_smem_bytes(THR_FAST_R)));
     CK(cudaFuncSetAttribute(k_threshold<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thresh_smem_bytes(FID_MAX_WIN_RADIUS)));
+    CK(cudaFuncSetAttribute(k_threshold<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thresh_smem_bytes(THR_FAST_R)));
+    CK(cudaFuncSetAttribute(k_threshold<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)thresh_smem_bytes(FID_MAX_WIN_RADIUS)));
     CK(cudaFuncSetAttribute(k_threshold_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_threshold_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TM_SMEM_BYTES));
     CK(cudaFuncSetAttribute(k_sort_group, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)group_smem(FID_GROUP_MAX_RAW)));
@@ -359,6 +364,14 @@ extern "C" int fid_create(const fid_params* params, int device, int max_width, i
         fid_destroy(h);
         return rc;
     }
+    if (const char* e = getenv("FID_START_PRUNE")) h->start_prune = atoi(e) != 0;  // table stage of the start pruning: proven on the CPU
+    if (h->start_prune) {                                                            // (tests/test_hostsim_contours.py), off by default
+        if ((rc = dalloc(&h->d_prune, (size_t)2 * FID_START_PRUNE_WORDS)) != FID_OK) {
+            fid_destroy(h);
+            return rc;
+        }
+        CKH(cudaMemcpy(h->d_prune, kStartPruneTable, sizeof(kStartPruneTable), cudaMemcpyHostToDevice));
+    }
     for (int i = 0; i < h->n_slots; i++)
         if ((rc = alloc_slot(h, h->slot[i])) != FID_OK) {
             fid_destroy(h);
@@ -440,7 +453,7 @@ extern "C" int fid_destroy(fid_detector* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (int i = 0; i < MAX_SLOTS; i++) free_slot(h->slot[i]);
-    void* ptrs[] = {h->d_dict, h->d_pf[0], h->d_pf[1], h->d_lut_prev, h->d_lut_next, h->d_subpix_masks, h->d_override_ids, h->d_override_lens, h->d_pose_ids, h->d_pose_corners, h->d_pose_out};
+    void* ptrs[] = {h->d_prune, h->d_dict, h->d_pf[0], h->d_pf[1], h->d_lut_prev, h->d_lut_next, h->d_subpix_masks, h->d_override_ids, h->d_override_lens, h->d_pose_ids, h->d_pose_corners, h->d_pose_out};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     for (int i = 0; i < 2; i++)
@@ -600,12 +613,19 @@ static int enqueue_pipeline(fid_detector* h, Slot& s, cudaStream_t st, int nf, c
             a.starts = s.d_starts;
             a.counters = s.d_counters;
             a.max_starts = h->max_starts;
+            a.prune = h->start_prune ? h->d_prune : nullptr;
             for (int i = 0; i < P.n_scales; i++) a.win[i] = P.win[i];
             dim3 grid((g.halo_tpr + THR_TILES_X - 1) / THR_TILES_X, (g.halo_tiles_y + THR_TILES_Y - 1) / THR_TILES_Y, nf);
-            if (fast)
+            if (a.prune) {
+                if (fast)
+                    launch_prio(k_threshold<true, true>, grid, dim3(THR_THREADS), thresh_smem_bytes(THR_FAST_R), st, 0, a);
+                else
+                    launch_prio(k_threshold<false, true>, grid, dim3(THR_THREADS), thresh_smem_bytes(a.r_max), st, 0, a);
+            } else if (fast) {
                 launch_prio(k_threshold<true>, grid, dim3(THR_THREADS), thresh_smem_bytes(THR_FAST_R), st, 0, a);
-            else
+            } else {
                 launch_prio(k_threshold<false>, grid, dim3(THR_THREADS), thresh_smem_bytes(a.r_max), st, 0, a);
+            }
             launches++;
         }
     }

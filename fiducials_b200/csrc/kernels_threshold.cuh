@@ -99,6 +99,7 @@ struct ThreshArgs {
     StartRec* starts;      // start-crack queue: left cracks at [0, nL), right cracks at [max_starts-1 ...]
     Counters* counters;
     unsigned int max_starts;
+    const uint32_t* prune;  // kStartPruneTable on the device (FID_START_PRUNE=1) or NULL
 };
 
 // gray byte tile: region column rx lives at byte rx + 2 of its row (the 4-pixel groups of the fast load start 2 columns left of the
@@ -113,7 +114,9 @@ __host__ __device__ inline size_t thresh_smem_bytes(int r_max) {
 #ifndef THR_MAXNREG
 #define THR_MAXNREG 96  // 2 CTAs per SM leave a quarter of the register file to the kernels of other chunks (+1 % pipelined, no spills)
 #endif
-template <bool FAST>
+// PRUNE: the opt-in table stage of the start pruning (FID_START_PRUNE=1) is its own instantiation, so that the default kernel is
+// instruction for instruction the one that was measured.
+template <bool FAST, bool PRUNE = false>
 __global__ void __maxnreg__(THR_MAXNREG) k_threshold(const ThreshArgs a) {
     extern __shared__ uint32_t sat[];
     const int R = FAST ? THR_FAST_R : a.r_max;
@@ -309,8 +312,8 @@ __global__ void __maxnreg__(THR_MAXNREG) k_threshold(const ThreshArgs a) {
 #pragma unroll
         for (int s = 0; s < NS; s++) acc[s] &= colmask;
     }
-    thr_store_tile_and_starts<NS>(acc, FAST ? 13 : a.n_scales, f, tx, ty, lane, a.halo, a.halo_frame_stride, a.halo_scale_stride, a.halo_tpr, a.halo_tiles_y, a.starts, a.counters,
-                                  a.max_starts);
+    thr_store_tile_and_starts<NS, PRUNE>(acc, FAST ? 13 : a.n_scales, f, tx, ty, lane, a.halo, a.halo_frame_stride, a.halo_scale_stride, a.halo_tpr, a.halo_tiles_y, a.starts, a.counters,
+                                  a.max_starts, a.prune);
 }
 
 }  // namespace fid

@@ -10,9 +10,10 @@
 namespace fid {
 
 // stores the 13 tiles (one 128-byte transaction each) and queues the start cracks of the border walk
-template <int NS>
+template <int NS, bool PRUNE = false>
 __device__ __forceinline__ void thr_store_tile_and_starts(const uint32_t (&acc)[NS], int n_scales, int f, int tx, int ty, int lane, uint32_t* halo, size_t halo_frame_stride,
-                                                          size_t halo_scale_stride, int halo_tpr, int halo_tiles_y, StartRec* starts, Counters* counters, unsigned int max_starts) {
+                                                          size_t halo_scale_stride, int halo_tpr, int halo_tiles_y, StartRec* starts, Counters* counters, unsigned int max_starts,
+                                                          const uint32_t* prune = nullptr /* start_prune_table.h on the device, or off */) {
     uint32_t* out = halo + (size_t)f * halo_frame_stride + ((size_t)ty * halo_tpr + tx) * 32 + lane;
     int cnt_l = 0, cnt_r = 0;
     const bool row_ok = lane >= 1 && lane <= FID_HALO_T;
@@ -24,6 +25,7 @@ __device__ __forceinline__ void thr_store_tile_and_starts(const uint32_t (&acc)[
         out[(size_t)s * halo_scale_stride] = acc[s];
         const uint32_t up = __shfl_up_sync(0xffffffffu, acc[s], 1), dn = __shfl_down_sync(0xffffffffu, acc[s], 1);
         if (row_ok && acc[s]) halo_row_starts(up, acc[s], dn, &Lm[s], &Rm[s]);
+        if (PRUNE && (Lm[s] | Rm[s])) halo_prune_starts(up, acc[s], dn, &Lm[s], &Rm[s], prune);  // opt-in second stage (FID_START_PRUNE=1)
         cnt_l += __popc(Lm[s]);
         cnt_r += __popc(Rm[s]);
     }

@@ -13,6 +13,7 @@
 
 #include "../../fiducials_b200/csrc/common.cuh"
 #include "../../fiducials_b200/csrc/contour_walk.cuh"
+#include "../../fiducials_b200/csrc/start_prune_table.h"
 #include "../../fiducials_b200/csrc/approx_quad.cuh"
 #include "../../fiducials_b200/csrc/quad_group.cuh"
 #include "../../fiducials_b200/csrc/identify.cuh"
@@ -66,6 +67,8 @@ static void pack_plane(const uint8_t* plane, int W, int H, HostPlane& hp) {
             }
 }
 
+static int g_start_prune = 0;  // hs_set_start_prune: apply the table stage (halo_prune_starts) as the device does with FID_START_PRUNE=1
+
 static void find_starts(const HostPlane& hp, std::vector<Start>& starts) {
     for (int ty = 0; ty < hp.tiles_y; ty++)
         for (int r = 1; r <= FID_HALO_T; r++)
@@ -73,6 +76,7 @@ static void find_starts(const HostPlane& hp, std::vector<Start>& starts) {
                 const uint32_t* t = hp.halo.data() + ((size_t)ty * hp.tpr + tx) * 32 + r;
                 uint32_t L = 0, R = 0;
                 if (t[0]) halo_row_starts(t[-1], t[0], t[1], &L, &R);
+                if (g_start_prune && (L | R)) halo_prune_starts(t[-1], t[0], t[1], &L, &R, &kStartPruneTable[0][0]);
                 const int y = FID_HALO_T * ty - 1 + r;
                 for (int i = 1; i <= FID_HALO_T; i++) {
                     if ((L >> i) & 1) starts.push_back({FID_HALO_T * tx - 1 + i, y, 0});
@@ -736,6 +740,119 @@ long long hs_jpeg_entropy(const uint8_t* data, long long size, int reps) {
         if (rc != JPEG_OK) return rc;
     }
     return (long long)nv;
+}
+
+
+void hs_set_start_prune(int on) { g_start_prune = on; }
+void hs_committed_prune_table(uint32_t* out) { memcpy(out, kStartPruneTable, sizeof(kStartPruneTable)); }
+
+// ---- start-prune table (tools/gen_prune_table.py) ------------------------------------------------------------
+// For every 3-row x `cols`-column neighbourhood of a start crack: does the walk of that start abort within K steps for EVERY
+// completion of the pixels outside the neighbourhood?  Pixels are assigned lazily: the walk only reads the 3x3 around the
+// pixels it visits, so only unknown pixels inside those read sets are branched on.
+namespace {
+struct PruneSim {
+    static const int N = 40, CX = 20, CY = 20;
+    int8_t val[N][N];  // -1 unknown, 0, 1
+    int K, is_right;
+    long nodes = 0;
+    bool all_abort() {
+        nodes++;
+        std::vector<uint8_t> img((size_t)N * N);
+        for (int y = 0; y < N; y++)
+            for (int x = 0; x < N; x++) img[(size_t)y * N + x] = val[y][x] == 1 ? 1 : 0;
+        HostPlane hp;
+        pack_plane(img.data(), N, N, hp);
+        const WalkCtx c = hp.ctx();
+        int vx[16], vy[16], nv = 0;
+        vx[nv] = CX;
+        vy[nv++] = CY;
+        WalkState st;
+        int r = walk_init(c, CX, CY, is_right, &st);
+        int steps = 0;
+        while (r == WALK_CONTINUE && steps < K) {
+            r = is_right ? walk_uni_fast<true>(c, CX, CY, 1 << 20, 1, &st) : walk_uni_fast<false>(c, CX, CY, 1 << 20, 1, &st);
+            steps++;
+            vx[nv] = st.x;
+            vy[nv++] = st.y;
+        }
+        // unknown pixels inside the read sets of this run
+        int ux[64], uy[64], nu = 0;
+        for (int k = 0; k < nv; k++)
+            for (int dy = -1; dy <= 1; dy++)
+                for (int dx = -1; dx <= 1; dx++) {
+                    const int x = vx[k] + dx, y = vy[k] + dy;
+                    if (val[y][x] != -1) continue;
+                    bool seen = false;
+                    for (int q = 0; q < nu; q++) seen = seen || (ux[q] == x && uy[q] == y);
+                    if (!seen && nu < 64) {
+                        ux[nu] = x;
+                        uy[nu++] = y;
+                    }
+                }
+        if (nu == 0) return r == WALK_ABORT;
+        if (nu > 16) return false;  // give up on patterns that fan out this far
+        for (uint32_t a = 0; a < (1u << nu); a++) {
+            for (int q = 0; q < nu; q++) val[uy[q]][ux[q]] = (int8_t)((a >> q) & 1);
+            const bool ok = all_abort();
+            if (!ok) {
+                for (int q = 0; q < nu; q++) val[uy[q]][ux[q]] = -1;
+                return false;
+            }
+        }
+        for (int q = 0; q < nu; q++) val[uy[q]][ux[q]] = -1;
+        return true;
+    }
+};
+}  // namespace
+
+// out[pattern] = 1 when a start with this neighbourhood can be dropped.  pattern bit (row * cols + col), row 0 = the row above the
+// start, col cols/2 = the start's column.  Returns the number of prunable patterns.
+long hs_prune_table(int cols, int K, int is_right, uint8_t* out) {
+    const int half = cols / 2, nbits = 3 * cols;
+    long n_prunable = 0;
+    PruneSim sim;
+    sim.K = K;
+    sim.is_right = is_right;
+    for (uint32_t pat = 0; pat < (1u << nbits); pat++) {
+        out[pat] = 0;
+        const int centre = (int)((pat >> (cols + half)) & 1u);
+        const int side = (int)((pat >> (cols + half + (is_right ? 1 : -1))) & 1u);
+        if (!centre || side) continue;  // not a left / right crack
+        for (int y = 0; y < PruneSim::N; y++)
+            for (int x = 0; x < PruneSim::N; x++) sim.val[y][x] = -1;
+        for (int r = 0; r < 3; r++)
+            for (int cc = 0; cc < cols; cc++) sim.val[PruneSim::CY - 1 + r][PruneSim::CX - half + cc] = (int8_t)((pat >> (r * cols + cc)) & 1u);
+        if (sim.all_abort()) {
+            out[pat] = 1;
+            n_prunable++;
+        }
+    }
+    return n_prunable;
+}
+
+// how many of the starts halo_row_starts leaves on this plane would the table drop (cols as above)?  out[0] = starts, out[1] = dropped
+void hs_prune_gain(const uint8_t* plane, int W, int H, int cols, const uint8_t* tabL, const uint8_t* tabR, int64_t* out) {
+    HostPlane hp;
+    pack_plane(plane, W, H, hp);
+    const int half = cols / 2;
+    const uint32_t cm = (1u << cols) - 1u;
+    out[0] = out[1] = 0;
+    for (int ty = 0; ty < hp.tiles_y; ty++)
+        for (int r = 1; r <= FID_HALO_T; r++)
+            for (int tx = 0; tx < hp.tpr; tx++) {
+                const uint32_t* t = hp.halo.data() + ((size_t)ty * hp.tpr + tx) * 32 + r;
+                uint32_t L = 0, R = 0;
+                if (t[0]) halo_row_starts(t[-1], t[0], t[1], &L, &R);
+                for (int i = 1; i <= FID_HALO_T; i++)
+                    for (int side = 0; side < 2; side++) {
+                        if (!(((side ? R : L) >> i) & 1)) continue;
+                        out[0]++;
+                        if (i - half < 0 || i + half > 31) continue;
+                        const uint32_t pat = ((t[-1] >> (i - half)) & cm) | (((t[0] >> (i - half)) & cm) << cols) | (((t[1] >> (i - half)) & cm) << (2 * cols));
+                        if ((side ? tabR : tabL)[pat]) out[1]++;
+                    }
+            }
 }
 
 }  // extern "C"

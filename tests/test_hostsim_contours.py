@@ -189,3 +189,61 @@ def test_approx_poly_fuzz_spurred_marker_outlines():
             else:
                 assert k != 4, (trial, n, len(ref))
     assert total > 300 and quads > 100 and touching > 100, (total, quads, touching)
+
+
+# ---- table stage of the start pruning (start_prune_table.h) ------------------------------------------------------------------
+def test_start_prune_table_is_what_the_generator_proves():
+    """The committed table equals a fresh exhaustive enumeration (tools/gen_prune_table.py: every completion of the pixels outside
+    the 3 x 5 neighbourhood, walked with the real walk code)."""
+    import ctypes as C
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import gen_prune_table
+
+    words, counts = gen_prune_table.generate()
+    committed = np.zeros((2, 1024), np.uint32)
+    hs.load().hs_committed_prune_table(committed.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(words, committed)
+    assert counts[0] > 6000 and counts[1] > 5000
+
+
+@pytest.mark.parametrize("kind", ["noise", "blobs", "threshold"])
+def test_table_pruned_starts_give_identical_contours(kind):
+    """With the table stage on, every contour (points, order, list order) still equals cv2.findContours -- only starts that can never
+    be canonical disappear -- and a third of the starts are gone."""
+    import cv2
+
+    rng = np.random.default_rng(5)
+    if kind == "noise":
+        planes = [(rng.random((97, 131)) < p).astype(np.uint8) for p in (0.3, 0.5, 0.7)]
+    elif kind == "blobs":
+        planes = []
+        for s in range(3):
+            img = np.zeros((160, 200), np.uint8)
+            for _ in range(60):
+                cv2.circle(img, (int(rng.integers(0, 200)), int(rng.integers(0, 160))), int(rng.integers(1, 14)), 1, -1 if rng.random() < 0.7 else 1)
+            planes.append(img ^ (rng.random(img.shape) < 0.02).astype(np.uint8))
+    else:
+        from fiducials_b200 import synth
+        from oracle import aruco_oracle as ao
+
+        g = ao.gray(synth.make_config_frame("C3", 1)[0])
+        tp = ao.threshold_planes(g)
+        planes = [(tp[s] > 0).astype(np.uint8) for s in (0, 5, 12)]
+    lib = hs.load()
+    try:
+        for pl in planes:
+            lib.hs_set_start_prune(0)
+            _, n0 = hs.find_contours(pl)
+            lib.hs_set_start_prune(1)
+            ref, _ = cv2.findContours(pl, cv2.RETR_LIST, cv2.CHAIN_APPROX_NONE)
+            for mode in (0, 1, 2):  # one-directional walk, the GPU's round structure, tiny passes / checkpoints
+                got, n1 = hs.find_contours(pl, mode=mode)
+                assert len(got) == len(ref)
+                for a, b in zip(got, ref):
+                    assert np.array_equal(a, b.reshape(-1, 2))
+            assert n1 < 0.8 * n0, (n0, n1)
+    finally:
+        lib.hs_set_start_prune(0)
