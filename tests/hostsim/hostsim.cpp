@@ -855,4 +855,52 @@ void hs_prune_gain(const uint8_t* plane, int W, int H, int cols, const uint8_t* 
             }
 }
 
+
+// Experiment only: the same proof for a neighbourhood with `above` rows above the start and one below, 5 columns.
+// out has 2^((above+2)*5) entries; pattern bit (row * 5 + col), row 0 = the topmost row.  Returns the number of prunable patterns.
+long hs_prune_table_rows(int above, int K, int is_right, uint8_t* out) {
+    const int cols = 5, half = 2, rows = above + 2, nbits = rows * cols;
+    long n_prunable = 0;
+    PruneSim sim;
+    sim.K = K;
+    sim.is_right = is_right;
+    for (uint32_t pat = 0; pat < (1u << nbits); pat++) {
+        out[pat] = 0;
+        const int centre = (int)((pat >> (above * cols + half)) & 1u);
+        const int side = (int)((pat >> (above * cols + half + (is_right ? 1 : -1))) & 1u);
+        if (!centre || side) continue;
+        for (int y = 0; y < PruneSim::N; y++)
+            for (int x = 0; x < PruneSim::N; x++) sim.val[y][x] = -1;
+        for (int r = 0; r < rows; r++)
+            for (int cc = 0; cc < cols; cc++) sim.val[PruneSim::CY - above + r][PruneSim::CX - half + cc] = (int8_t)((pat >> (r * cols + cc)) & 1u);
+        if (sim.all_abort()) {
+            out[pat] = 1;
+            n_prunable++;
+        }
+    }
+    return n_prunable;
+}
+
+void hs_prune_gain_rows(const uint8_t* plane, int W, int H, int above, const uint8_t* tabL, const uint8_t* tabR, int64_t* out) {
+    HostPlane hp;
+    pack_plane(plane, W, H, hp);
+    out[0] = out[1] = 0;
+    for (int ty = 0; ty < hp.tiles_y; ty++)
+        for (int r = 1; r <= FID_HALO_T; r++)
+            for (int tx = 0; tx < hp.tpr; tx++) {
+                const uint32_t* t = hp.halo.data() + ((size_t)ty * hp.tpr + tx) * 32 + r;
+                uint32_t L = 0, R = 0;
+                if (t[0]) halo_row_starts(t[-1], t[0], t[1], &L, &R);
+                for (int i = 1; i <= FID_HALO_T; i++)
+                    for (int side = 0; side < 2; side++) {
+                        if (!(((side ? R : L) >> i) & 1)) continue;
+                        out[0]++;
+                        if (i - 2 < 0 || i + 2 > 31 || r - above < 0) continue;
+                        uint32_t pat = 0;
+                        for (int k = 0; k < above + 2; k++) pat |= ((t[k - above] >> (i - 2)) & 31u) << (5 * k);
+                        if ((side ? tabR : tabL)[pat]) out[1]++;
+                    }
+            }
+}
+
 }  // extern "C"
