@@ -36,9 +36,19 @@ def _load():
         lib.mapref_load_map.argtypes = [C.c_void_p, C.c_char_p]
         lib.mapref_save_map.argtypes = [C.c_void_p, C.c_char_p]
         lib.mapref_state.argtypes = [C.c_void_p, C.c_void_p]
+        lib.twvref_apply.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.mapref_replay.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_double, C.c_char_p]
         _lib = lib
     return _lib
+
+
+def twv_apply(op, a, b=None):
+    """The reference's TransformWithVariance, directly.  a, b: x y z qx qy qz qw variance.  op: 'update', 'average', 'mul', 'inverse'."""
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b if b is not None else a, np.float64)
+    out = np.zeros(8, np.float64)
+    _load().twvref_apply({"update": 0, "average": 1, "mul": 2, "inverse": 3}[op], a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return out
 
 
 CAMERA, BASE, MAP, ODOM = b"camera", b"base_link", b"map", b"odom"

@@ -185,4 +185,30 @@ int mapref_replay(void* p, int n_msgs, const int* offsets, const double* obs, do
     return n;
 }
 
+// TransformWithVariance::update / operator* of the reference, directly (transform_with_variance.cpp:43-85, .h:26-59).
+// a, b: x y z qx qy qz qw variance; out the same layout.  op 0: a.update(b)  1: averageTransforms(a, b)  2: a * b  3: a.inverse composed: a^-1 (variance kept)
+void twvref_apply(int op, const double* a, const double* b, double* out) {
+    auto mk = [](const double* v) { return TransformWithVariance(tf2::Vector3(v[0], v[1], v[2]), tf2::Quaternion(v[3], v[4], v[5], v[6]), v[7]); };
+    TransformWithVariance r = mk(a);
+    if (op == 0) {
+        r.update(mk(b));
+    } else if (op == 1) {
+        r = averageTransforms(mk(a), mk(b));
+    } else if (op == 2) {
+        r = mk(a) * mk(b);
+    } else {
+        r.transform = r.transform.inverse();
+    }
+    const tf2::Vector3 t = r.transform.getOrigin();
+    const tf2::Quaternion q = r.transform.getRotation();
+    out[0] = t.x();
+    out[1] = t.y();
+    out[2] = t.z();
+    out[3] = q.x();
+    out[4] = q.y();
+    out[5] = q.z();
+    out[6] = q.w();
+    out[7] = r.variance;
+}
+
 }  // extern "C"

@@ -23,6 +23,8 @@ passed in by the caller, exactly as the C-ABI does (include/fiducials_b200.h).
 from __future__ import annotations
 
 import math
+
+import numpy as np
 from dataclasses import dataclass, field
 
 SYSTEMATIC_ERROR = 0.01  # map.cpp:50
@@ -172,21 +174,22 @@ class TWV:
 
 
 def probability_at_point(x, u, var):
-    """probabiltyAtPoint, transform_with_variance.cpp:14-17."""
-    return (1.0 / (math.sqrt(var) * math.sqrt(2.0 * math.pi))) * math.exp(-((x - u) * (x - u)) / (2.0 * var))
+    """probabiltyAtPoint, transform_with_variance.cpp:14-17 -- IEEE semantics (a zero variance gives inf / NaN, not an exception)."""
+    with np.errstate(all="ignore"):
+        x, u, var = np.float64(x), np.float64(u), np.float64(var)
+        return float((np.float64(1.0) / (np.sqrt(var) * np.sqrt(np.float64(2.0 * math.pi)))) * np.exp(-((x - u) * (x - u)) / (np.float64(2.0) * var)))
 
 
 def normalize_david(new_mean, mean1, var1, mean2, var2):
     """normalizeDavid, transform_with_variance.cpp:23-38."""
     p1 = probability_at_point(new_mean, mean1, var1)
     p2 = probability_at_point(new_mean, mean2, var2)
-    p = math.sqrt(p1 * p1 + p2 * p2)
-    if p == 0.0:
-        nv = math.inf
-    else:
-        nv = (1.0 / (p * math.sqrt(2.0 * math.pi))) ** 2
-    nv = min(nv, 1e3)
-    nv = max(nv, 1e-8)
+    with np.errstate(all="ignore"):  # std::pow / division overflow to +inf, NaN propagates (found by tests/test_map_ref.py)
+        p = np.sqrt(np.float64(p1) * np.float64(p1) + np.float64(p2) * np.float64(p2))
+        x = np.float64(1.0) / (p * np.sqrt(np.float64(2.0 * math.pi)))
+        nv = float(x * x)
+    nv = 1e3 if 1e3 < nv else nv    # std::min(newVar, 1e3): NaN stays NaN
+    nv = 1e-8 if nv < 1e-8 else nv  # std::max(newVar, 1e-8)
     return nv
 
 

@@ -203,3 +203,85 @@ def test_create_map_expectations_with_the_reference_code(kat):
     for fid, g in expect.items():
         assert np.abs(ents[fid][1:4] - g).max() < 0.1
     ref.close()
+
+
+# ---- the fusion operator itself (a10) ----------------------------------------------------------------------------------------
+def _rand_twv(rng, spread=2.0):
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    return [*rng.uniform(-spread, spread, 3), *q, float(10 ** rng.uniform(-6, 2))]
+
+
+def _to_so(v):
+    return so.TWV.from_qt(list(v[3:7]), list(v[0:3]), v[7])
+
+
+def _close(ref8, twv, tol=1e-12):
+    assert np.allclose(ref8[:3], twv.t, rtol=0, atol=tol * 10)
+    q = np.array(so.m_to_q(twv.R))
+    assert min(np.abs(ref8[3:7] - q).max(), np.abs(ref8[3:7] + q).max()) < 1e-9
+    assert abs(ref8[7] - twv.var) <= 1e-12 * max(1.0, abs(ref8[7]))
+
+
+def test_transform_with_variance_operators_match_the_reference_code():
+    """TransformWithVariance::update / averageTransforms / operator* / inverse of the compiled reference against the restatement the
+    whole map oracle is built from, 2000 random pairs incl. equal rotations (slerp's theta == 0 branch) and opposite quaternion signs."""
+    rng = np.random.default_rng(0)
+    for it in range(2000):
+        a, b = _rand_twv(rng), _rand_twv(rng)
+        if it % 7 == 0:
+            b[3:7] = a[3:7]  # identical rotation
+        if it % 11 == 0:
+            b[3:7] = [-x for x in b[3:7]]  # same rotation, other sign
+        if it % 13 == 0:
+            b[0:3] = a[0:3]  # identical position: zero-length line between the means
+        A, B = _to_so(a), _to_so(b)
+        u = A.copy()
+        u.update(B)
+        _close(map_ref.twv_apply("update", a, b), u)
+        _close(map_ref.twv_apply("average", a, b), so.average_transforms(A, B))
+        _close(map_ref.twv_apply("mul", a, b), A.mul(B))
+        inv = A.inverse()
+        inv.var = A.var
+        _close(map_ref.twv_apply("inverse", a), inv)
+
+
+def test_reference_property_tests_through_the_compiled_reference():
+    """fiducial_slam/test/transform_var_test.cpp (five inequalities) evaluated with the reference's own operator."""
+    def tv(x, var, yaw=0.0):
+        return [x, 0, 0, *so.q_from_rpy(0, 0, yaw), var]
+
+    def angle(v):
+        return 2.0 * math.acos(max(-1.0, min(1.0, abs(v[6]))))
+
+    # simple fusion: equal variances meet in the middle, variance shrinks (:15-31)
+    r = map_ref.twv_apply("update", tv(0.0, 1.0), tv(1.0, 1.0))
+    assert abs(r[0] - 0.5) < 1e-12 and r[7] < 1.0
+    # simple rotation fusion (:33-49)
+    r = map_ref.twv_apply("update", tv(0.0, 1.0, 0.0), tv(0.0, 1.0, 1.0))
+    assert abs(angle(r) - 0.5) < 1e-9
+    # same fusion iterated: the estimate stays, the variance falls monotonically (:51-77)
+    cur, last = tv(1.0, 1.0), 1.0
+    for _ in range(10):
+        cur = map_ref.twv_apply("update", cur, tv(1.0, 1.0)).tolist()
+        assert abs(cur[0] - 1.0) < 1e-12 and cur[7] <= last
+        last = cur[7]
+    # an outlier with a large variance barely moves the estimate (:79-107)
+    r = map_ref.twv_apply("update", tv(0.0, 0.01), tv(10.0, 100.0))
+    assert abs(r[0]) < 0.01
+    # different estimates with similar variance end up between them (:109-126)
+    r = map_ref.twv_apply("update", tv(0.0, 1.0), tv(1.0, 1.2))
+    assert 0.4 < r[0] < 0.6
+
+
+def test_zero_variance_observation_gives_nan_like_the_reference():
+    """object_error == 0 exactly: the reference divides by zero inside probabiltyAtPoint and publishes a NaN variance
+    (std::min / std::max let NaN through).  The restatement follows it.  (The device code clamps that NaN to the 1e3 bound --
+    slam.cuh normalize_david -- a deliberate difference in a case the detector cannot produce: a reprojection error of exactly 0.)"""
+    a = [0, 0, 0, 0, 0, 0, 1, 1.0]
+    b = [1, 0, 0, 0, 0, 0, 1, 0.0]
+    r = map_ref.twv_apply("update", a, b)
+    A = _to_so(a)
+    A.update(_to_so(b))
+    assert math.isnan(r[7]) and math.isnan(A.var)
+    assert np.allclose(r[:3], A.t)
